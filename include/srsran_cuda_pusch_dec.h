@@ -1,0 +1,220 @@
+/*
+ * srsran_cuda_pusch_dec.h - C ABI of the B200 (sm_100a) PUSCH channel-decoding accelerator.
+ *
+ * Drop-in boundary for srsRAN Project's du_low PUSCH decoding path: LDPC rate dematching with HARQ soft combining,
+ * layered normalized min-sum LDPC decoding (BG1/BG2, 51 lifting sizes) and the code-block / transport-block CRC check.
+ * Plain pointers and sizes only; the library owns all device memory; the caller owns every pointer it passes. No
+ * exceptions cross this boundary: every function returns a status (SRSRAN_CUDA_*) or a documented value.
+ * A handle is thread-compatible (one thread at a time), like one hal::hw_accelerator_pusch_dec instance
+ * (reference: include/srsran/hal/phy/upper/channel_processors/pusch/hw_accelerator_pusch_dec.h:36-115).
+ *
+ * There is no CPU fallback: every entry point fails with SRSRAN_CUDA_ERR_NO_DEVICE if no CUDA device is usable.
+ *
+ * Arithmetic contract: bit-exact to the reference's AVX2/AVX-512 flavour (ldpc_decoder_avx512.cpp,
+ * ldpc_rate_dematcher_avx512_impl.cpp, crc_calculator_*): decoded bits, CRC verdict, iteration count and the combined
+ * soft-buffer bytes. Valid LLR domain: [-120, 120] and +-127 (include/srsran/phy/upper/log_likelihood_ratio.h:46-51).
+ */
+#ifndef SRSRAN_CUDA_PUSCH_DEC_H
+#define SRSRAN_CUDA_PUSCH_DEC_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Status codes. */
+#define SRSRAN_CUDA_OK 0
+#define SRSRAN_CUDA_ERR_NO_DEVICE (-1)   /* no usable CUDA device / driver */
+#define SRSRAN_CUDA_ERR_INVALID (-2)     /* invalid argument or configuration */
+#define SRSRAN_CUDA_ERR_NO_MEMORY (-3)   /* device or pinned host allocation failed */
+#define SRSRAN_CUDA_ERR_CUDA (-4)        /* CUDA runtime error (see srsran_cuda_pusch_dec_last_error) */
+#define SRSRAN_CUDA_ERR_STATE (-5)       /* call sequence violated (e.g. dequeue of an operation never enqueued) */
+
+/* CRC polynomial selectors (crc_generator_poly of include/srsran/phy/upper/channel_coding/crc_calculator.h:31-39). */
+#define SRSRAN_CUDA_CRC_NONE 0
+#define SRSRAN_CUDA_CRC24A 1
+#define SRSRAN_CUDA_CRC24B 2
+#define SRSRAN_CUDA_CRC16 3
+
+/* Code-block CRC type as hal::hw_dec_cb_crc_type (hw_accelerator_pusch_dec.h:39). */
+#define SRSRAN_CUDA_CB_CRC16 0
+#define SRSRAN_CUDA_CB_CRC24B 1
+#define SRSRAN_CUDA_CB_CRC24A 2
+
+#define SRSRAN_CUDA_MAX_NOF_SEGMENTS 162 /* MAX_NOF_SEGMENTS, include/srsran/ran/sch/sch_constants.h:33-44 */
+#define SRSRAN_CUDA_MAX_CB_LENGTH 25344  /* 66 * 384 */
+
+typedef struct srsran_cuda_pusch_dec srsran_cuda_pusch_dec_t;
+
+/* Field-for-field image of hal::hw_pusch_decoder_configuration (hw_accelerator_pusch_dec.h:42-77). */
+typedef struct {
+  uint32_t base_graph;              /* 1 = BG1, 2 = BG2 */
+  uint32_t modulation;              /* bits per symbol: 1, 2, 4, 6, 8 (0 = pi/2-BPSK, handled as 1) */
+  uint32_t nof_segments;            /* code blocks in the TB */
+  uint32_t rv;                      /* redundancy version 0..3 */
+  uint32_t cw_length;               /* rate-matched length E of this code block */
+  uint32_t lifting_size;            /* Z */
+  uint32_t Ncb;                     /* 66 Z (BG1) or 50 Z (BG2) */
+  uint32_t Nref;                    /* limited-buffer rate matching length, 0 = unlimited */
+  uint32_t nof_segment_bits;        /* payload bits of this code block that go into the TB */
+  uint32_t nof_filler_bits;
+  uint32_t max_nof_ldpc_iterations;
+  uint32_t use_early_stop;
+  uint32_t new_data;
+  uint32_t cb_crc_len;              /* 16 or 24 */
+  uint32_t cb_crc_type;             /* SRSRAN_CUDA_CB_CRC16 / CRC24B / CRC24A */
+  uint32_t absolute_cb_id;          /* HARQ soft-buffer slot, < nof_harq_cb_slots */
+} srsran_cuda_pusch_dec_cb_config;
+
+/* Image of pusch_decoder::configuration (include/srsran/phy/upper/channel_processors/pusch/pusch_decoder.h:57-77) plus
+ * what new_data()/on_end_softbits() derive from their arguments. */
+typedef struct {
+  uint32_t tbs_bits;                /* transport block size in bits (multiple of 8) */
+  uint32_t base_graph;              /* 1 or 2 */
+  uint32_t rv;
+  uint32_t modulation;              /* bits per symbol */
+  uint32_t Nref;
+  uint32_t nof_layers;
+  uint32_t nof_ldpc_iterations;
+  uint32_t use_early_stop;
+  uint32_t new_data;
+  uint32_t harq_first_slot;         /* absolute_cb_id of code block 0; code block i uses harq_first_slot + i */
+} srsran_cuda_pusch_dec_tb_config;
+
+/* Image of pusch_decoder_result (pusch_decoder_result.h:30-41) + per-TB bookkeeping. */
+typedef struct {
+  int32_t  tb_crc_ok;
+  uint32_t nof_codeblocks_total;
+  uint32_t nof_observations;        /* code blocks decoded in this transmission (those not already CRC-ok) */
+  uint32_t iter_min;
+  uint32_t iter_max;
+  float    iter_mean;
+} srsran_cuda_pusch_dec_tb_result;
+
+/* Segmentation metadata of one code block (codeblock_metadata, include/srsran/phy/upper/codeblock_metadata.h). */
+typedef struct {
+  uint32_t base_graph, lifting_size, full_length, rm_length, nof_filler_bits, cw_offset, nof_crc_bits;
+} srsran_cuda_pusch_dec_cb_meta;
+
+/* ---- Lifetime ---------------------------------------------------------------------------------------------------- */
+
+/* Creates an accelerator on CUDA device `device` with room for `max_cbs_in_flight` queued code-block operations and
+ * `nof_harq_cb_slots` HBM-resident HARQ code-block slots (25344 soft bits + 1056 data bytes each, zero-initialised and
+ * never cleared afterwards, like rx_buffer_pool: include/srsran/phy/upper/rx_buffer_pool.h:62-63).
+ * Replaces: hal::create_hw_accelerator_pusch_dec_factory(...)->create() (lib/hal/.../hw_accelerator_factories.cpp:32-84). */
+int srsran_cuda_pusch_dec_create(int device, uint32_t max_cbs_in_flight, uint32_t nof_harq_cb_slots,
+                                 srsran_cuda_pusch_dec_t** handle);
+void srsran_cuda_pusch_dec_destroy(srsran_cuda_pusch_dec_t* handle);
+/* Text of the last CUDA/runtime error seen by this handle (or by create when handle is NULL). */
+const char* srsran_cuda_pusch_dec_last_error(const srsran_cuda_pusch_dec_t* handle);
+/* Number of kernels this handle has launched so far (evidence for bench.py's gpu_launches). */
+uint64_t srsran_cuda_pusch_dec_launch_count(const srsran_cuda_pusch_dec_t* handle);
+
+/* Selects which flavour of the reference's HARQ combine is reproduced for NON-FINITE inputs (finite LLRs combine
+ * identically in all flavours): 64 = AVX-512 (default; ldpc_rate_dematcher_avx512_impl.cpp:29-64), 32 = AVX2
+ * (ldpc_rate_dematcher_avx2_impl.cpp), 0 = generic (ldpc_rate_dematcher_impl.cpp:116-126). */
+int srsran_cuda_pusch_dec_set_combine_flavour(srsran_cuda_pusch_dec_t* handle, uint32_t simd_block);
+/* Page-locked host memory for LLR buffers (what pusch_decoder_buffer::get_next_block_view hands to the demodulator,
+ * include/srsran/phy/upper/channel_processors/pusch/pusch_decoder_buffer.h:47): LLRs passed from such memory are copied
+ * to the device without an intermediate staging copy. */
+void* srsran_cuda_pusch_dec_host_alloc(size_t bytes);
+void  srsran_cuda_pusch_dec_host_free(void* ptr);
+
+/* ---- hal::hw_accelerator_pusch_dec, one call per method ------------------------------------------------------------ */
+
+/* hw_accelerator_pusch_dec::reserve_queue / free_queue (hw_accelerator_pusch_dec.h:87-90). */
+int srsran_cuda_pusch_dec_reserve_queue(srsran_cuda_pusch_dec_t* handle);
+int srsran_cuda_pusch_dec_free_queue(srsran_cuda_pusch_dec_t* handle);
+/* hw_accelerator_pusch_dec::configure_operation (:95). */
+int srsran_cuda_pusch_dec_configure(srsran_cuda_pusch_dec_t* handle, uint32_t cb_index,
+                                    const srsran_cuda_pusch_dec_cb_config* config);
+/* hw_accelerator<int8_t,uint8_t>::enqueue_operation (include/srsran/hal/hw_accelerator.h:47). `softbuf` is ignored
+ * (may be NULL): HARQ soft bits live in HBM (is_external_harq_supported() == true). Returns 1 if enqueued, 0 if the
+ * queue is full (caller retries after dequeuing), < 0 on error. */
+int srsran_cuda_pusch_dec_enqueue(srsran_cuda_pusch_dec_t* handle, uint32_t cb_index, const int8_t* llrs, uint32_t E,
+                                  const int8_t* softbuf, uint32_t N);
+/* hw_accelerator::dequeue_operation (:56). The first dequeue after a run of enqueues launches everything queued as one
+ * batch. Returns 1 and fills `bits` (K_bg * Z bits, MSB-first, `bits_size` >= ceil(K/8) bytes) when the operation has
+ * completed, 0 if it is not ready yet, < 0 on error. If `softbuf_out` is not NULL it receives the N combined soft bits. */
+int srsran_cuda_pusch_dec_dequeue(srsran_cuda_pusch_dec_t* handle, uint32_t cb_index, uint8_t* bits, uint32_t bits_size,
+                                  int8_t* softbuf_out, uint32_t N);
+/* hw_accelerator_pusch_dec::read_operation_outputs (:100-101). Valid after a successful dequeue of cb_index. */
+int srsran_cuda_pusch_dec_read_outputs(srsran_cuda_pusch_dec_t* handle, uint32_t cb_index, int* crc_pass,
+                                       uint32_t* nof_ldpc_iterations);
+/* hw_accelerator_pusch_dec::free_harq_context_entry (:105). The slot content is kept (the reference never clears it). */
+int srsran_cuda_pusch_dec_free_harq(srsran_cuda_pusch_dec_t* handle, uint32_t absolute_cb_id);
+/* hw_accelerator_pusch_dec::is_external_harq_supported (:109): always 1. */
+int srsran_cuda_pusch_dec_is_external_harq_supported(const srsran_cuda_pusch_dec_t* handle);
+
+/* ---- pusch_decoder, one transport block per call ------------------------------------------------------------------- */
+
+/* ldpc_segmenter_rx::segment metadata (lib/phy/upper/channel_coding/ldpc/ldpc_segmenter_impl.cpp:254-331). Writes up to
+ * SRSRAN_CUDA_MAX_NOF_SEGMENTS entries; returns the number of code blocks or < 0. Host-only arithmetic. */
+int srsran_cuda_pusch_dec_segment(uint32_t tbs_bits, uint32_t base_graph, uint32_t modulation, uint32_t nof_layers,
+                                  uint32_t nof_llrs, srsran_cuda_pusch_dec_cb_meta* out);
+
+/* pusch_decoder::new_data + on_new_softbits + on_end_softbits for a whole TB (pusch_decoder_impl.cpp:89-307): copies
+ * `nof_llrs` LLRs from HOST memory, runs dematch + LDPC + CB CRC for every code block, assembles the TB and checks its
+ * CRC on the device. Asynchronous: returns a ticket >= 0 (or < 0 on error); the CRC flags of the HARQ slots are kept by
+ * the handle across transmissions (rx_buffer::get_codeblocks_crc). */
+int srsran_cuda_pusch_dec_submit_tb(srsran_cuda_pusch_dec_t* handle, const srsran_cuda_pusch_dec_tb_config* config,
+                                    const int8_t* llrs, uint32_t nof_llrs);
+/* Completion of a ticket: returns 1 and fills `tb` (tbs_bits / 8 bytes; written only when the reference writes it) and
+ * `result` when done, 0 if `block` is 0 and the TB is still in flight, < 0 on error. Replaces
+ * pusch_decoder_notifier::on_sch_data (pusch_decoder_notifier.h:38). */
+int srsran_cuda_pusch_dec_poll_tb(srsran_cuda_pusch_dec_t* handle, int ticket, int block, uint8_t* tb,
+                                  srsran_cuda_pusch_dec_tb_result* result);
+
+/* Same as submit_tb for a batch of TBs whose LLRs are ALREADY RESIDENT in device memory (`llrs_dev[i]` points to
+ * `nof_llrs[i]` int8 LLRs in HBM); used when the demodulator runs on the device, and by the benchmark's device-resident
+ * leg. One ticket per TB is written to `tickets`. `stream` is a cudaStream_t (NULL = the handle's own stream). */
+int srsran_cuda_pusch_dec_submit_tbs_device(srsran_cuda_pusch_dec_t* handle, uint32_t nof_tbs,
+                                            const srsran_cuda_pusch_dec_tb_config* configs,
+                                            const int8_t* const* llrs_dev, const uint32_t* nof_llrs, int* tickets);
+/* Same as submit_tb for a batch of TBs with HOST LLRs: one staging copy, one set of launches. */
+int srsran_cuda_pusch_dec_submit_tbs(srsran_cuda_pusch_dec_t* handle, uint32_t nof_tbs,
+                                     const srsran_cuda_pusch_dec_tb_config* configs, const int8_t* const* llrs,
+                                     const uint32_t* nof_llrs, int* tickets);
+/* Blocks until everything submitted on this handle has completed. */
+int srsran_cuda_pusch_dec_synchronize(srsran_cuda_pusch_dec_t* handle);
+
+/* ---- unit-level interfaces (synchronous, host buffers) -------------------------------------------------------------- */
+
+/* ldpc_rate_dematcher::rate_dematch (include/srsran/phy/upper/channel_coding/ldpc/ldpc_rate_dematcher.h:52-55):
+ * `softbuf` (N = 66Z / 50Z soft bits) is read and updated in place. */
+int srsran_cuda_ldpc_rate_dematch(srsran_cuda_pusch_dec_t* handle, int8_t* softbuf, uint32_t N, const int8_t* llrs,
+                                  uint32_t E, int new_data, uint32_t rv, uint32_t modulation, uint32_t Nref,
+                                  uint32_t nof_filler_bits);
+/* ldpc_decoder::decode (include/srsran/phy/upper/channel_coding/ldpc/ldpc_decoder.h:73-75). `crc_poly` =
+ * SRSRAN_CUDA_CRC_NONE mirrors crc == nullptr. `bits` (ceil(K/8) bytes) is read and written like the reference's
+ * bit_buffer (left untouched when the reference leaves it untouched). `*nof_iterations` = iteration count, or -1 for
+ * std::nullopt. LLRs past the end of a partially filled last node are taken as zero (a fresh reference instance). */
+int srsran_cuda_ldpc_decode(srsran_cuda_pusch_dec_t* handle, uint8_t* bits, const int8_t* llrs, uint32_t nof_llrs,
+                            uint32_t base_graph, uint32_t lifting_size, uint32_t nof_filler_bits, uint32_t crc_poly,
+                            uint32_t max_iterations, float scaling_factor, int* nof_iterations);
+/* Batched variant on identical shapes (BASELINE config 1): `nof_cbs` code blocks of `nof_llrs` LLRs each, contiguous. */
+int srsran_cuda_ldpc_decode_batch(srsran_cuda_pusch_dec_t* handle, uint8_t* bits, const int8_t* llrs, uint32_t nof_cbs,
+                                  uint32_t nof_llrs, uint32_t base_graph, uint32_t lifting_size,
+                                  uint32_t nof_filler_bits, uint32_t crc_poly, uint32_t max_iterations,
+                                  float scaling_factor, int* nof_iterations);
+/* crc_calculator::calculate / calculate_byte (include/srsran/phy/upper/channel_coding/crc_calculator.h:70-80) over the
+ * first `nof_bits` bits of an MSB-first packed buffer. */
+int srsran_cuda_crc_calculate(srsran_cuda_pusch_dec_t* handle, uint32_t crc_poly, const uint8_t* packed,
+                              uint32_t nof_bits, uint32_t* checksum);
+
+/* ---- inspection (tests, HARQ migration) ----------------------------------------------------------------------------- */
+
+/* Copies `N` soft bits of HARQ slot `absolute_cb_id` to / from host memory. */
+int srsran_cuda_pusch_dec_read_softbuffer(srsran_cuda_pusch_dec_t* handle, uint32_t absolute_cb_id, int8_t* out,
+                                          uint32_t N);
+int srsran_cuda_pusch_dec_write_softbuffer(srsran_cuda_pusch_dec_t* handle, uint32_t absolute_cb_id, const int8_t* in,
+                                           uint32_t N);
+/* CRC flag of a HARQ slot as kept by the TB-level API (rx_buffer::get_codeblocks_crc). */
+int srsran_cuda_pusch_dec_read_cb_crc(srsran_cuda_pusch_dec_t* handle, uint32_t absolute_cb_id, int* crc_ok);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SRSRAN_CUDA_PUSCH_DEC_H */

@@ -1,0 +1,127 @@
+"""ctypes binding of the C ABI declared in include/srsran_cuda_pusch_dec.h.
+
+This is the only way Python reaches the product: the shared library libsrsran_cuda_pusch_dec.so (hand-written sm_100a
+kernels + host runtime, built in-tree by ``csrc/Makefile``). There is NO CPU fallback: if the library is missing or no
+CUDA device is usable, every entry point raises.
+"""
+import ctypes as C
+import subprocess
+from pathlib import Path
+
+HERE = Path(__file__).resolve().parent
+LIB_PATH = HERE / "libsrsran_cuda_pusch_dec.so"
+
+OK, ERR_NO_DEVICE, ERR_INVALID, ERR_NO_MEMORY, ERR_CUDA, ERR_STATE = 0, -1, -2, -3, -4, -5
+CRC_NONE, CRC24A, CRC24B, CRC16 = 0, 1, 2, 3
+CB_CRC16, CB_CRC24B, CB_CRC24A = 0, 1, 2
+MAX_NOF_SEGMENTS = 162
+MAX_CB_LENGTH = 25344
+
+u8p = C.POINTER(C.c_uint8)
+i8p = C.POINTER(C.c_int8)
+u32p = C.POINTER(C.c_uint32)
+intp = C.POINTER(C.c_int)
+
+
+class CbConfig(C.Structure):
+    """srsran_cuda_pusch_dec_cb_config == hal::hw_pusch_decoder_configuration."""
+    _fields_ = [(n, C.c_uint32) for n in (
+        "base_graph", "modulation", "nof_segments", "rv", "cw_length", "lifting_size", "Ncb", "Nref",
+        "nof_segment_bits", "nof_filler_bits", "max_nof_ldpc_iterations", "use_early_stop", "new_data", "cb_crc_len",
+        "cb_crc_type", "absolute_cb_id")]
+
+
+class TbConfig(C.Structure):
+    """srsran_cuda_pusch_dec_tb_config == pusch_decoder::configuration + TBS + HARQ slot."""
+    _fields_ = [(n, C.c_uint32) for n in (
+        "tbs_bits", "base_graph", "rv", "modulation", "Nref", "nof_layers", "nof_ldpc_iterations", "use_early_stop",
+        "new_data", "harq_first_slot")]
+
+
+class TbResult(C.Structure):
+    _fields_ = [("tb_crc_ok", C.c_int32), ("nof_codeblocks_total", C.c_uint32), ("nof_observations", C.c_uint32),
+                ("iter_min", C.c_uint32), ("iter_max", C.c_uint32), ("iter_mean", C.c_float)]
+
+
+class CbMeta(C.Structure):
+    _fields_ = [(n, C.c_uint32) for n in
+                ("base_graph", "lifting_size", "full_length", "rm_length", "nof_filler_bits", "cw_offset",
+                 "nof_crc_bits")]
+
+
+# Every symbol include/srsran_cuda_pusch_dec.h declares: name -> (restype, argtypes).
+SYMBOLS = {
+    "srsran_cuda_pusch_dec_create": (C.c_int, [C.c_int, C.c_uint32, C.c_uint32, C.POINTER(C.c_void_p)]),
+    "srsran_cuda_pusch_dec_destroy": (None, [C.c_void_p]),
+    "srsran_cuda_pusch_dec_last_error": (C.c_char_p, [C.c_void_p]),
+    "srsran_cuda_pusch_dec_launch_count": (C.c_uint64, [C.c_void_p]),
+    "srsran_cuda_pusch_dec_set_combine_flavour": (C.c_int, [C.c_void_p, C.c_uint32]),
+    "srsran_cuda_pusch_dec_host_alloc": (C.c_void_p, [C.c_size_t]),
+    "srsran_cuda_pusch_dec_host_free": (None, [C.c_void_p]),
+    "srsran_cuda_pusch_dec_reserve_queue": (C.c_int, [C.c_void_p]),
+    "srsran_cuda_pusch_dec_free_queue": (C.c_int, [C.c_void_p]),
+    "srsran_cuda_pusch_dec_configure": (C.c_int, [C.c_void_p, C.c_uint32, C.POINTER(CbConfig)]),
+    "srsran_cuda_pusch_dec_enqueue": (C.c_int, [C.c_void_p, C.c_uint32, i8p, C.c_uint32, i8p, C.c_uint32]),
+    "srsran_cuda_pusch_dec_dequeue": (C.c_int, [C.c_void_p, C.c_uint32, u8p, C.c_uint32, i8p, C.c_uint32]),
+    "srsran_cuda_pusch_dec_read_outputs": (C.c_int, [C.c_void_p, C.c_uint32, intp, u32p]),
+    "srsran_cuda_pusch_dec_free_harq": (C.c_int, [C.c_void_p, C.c_uint32]),
+    "srsran_cuda_pusch_dec_is_external_harq_supported": (C.c_int, [C.c_void_p]),
+    "srsran_cuda_pusch_dec_segment": (C.c_int, [C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32,
+                                                 C.POINTER(CbMeta)]),
+    "srsran_cuda_pusch_dec_submit_tb": (C.c_int, [C.c_void_p, C.POINTER(TbConfig), i8p, C.c_uint32]),
+    "srsran_cuda_pusch_dec_poll_tb": (C.c_int, [C.c_void_p, C.c_int, C.c_int, u8p, C.POINTER(TbResult)]),
+    "srsran_cuda_pusch_dec_submit_tbs_device": (C.c_int, [C.c_void_p, C.c_uint32, C.POINTER(TbConfig),
+                                                           C.POINTER(C.c_void_p), u32p, intp]),
+    "srsran_cuda_pusch_dec_submit_tbs": (C.c_int, [C.c_void_p, C.c_uint32, C.POINTER(TbConfig),
+                                                    C.POINTER(C.c_void_p), u32p, intp]),
+    "srsran_cuda_pusch_dec_synchronize": (C.c_int, [C.c_void_p]),
+    "srsran_cuda_ldpc_rate_dematch": (C.c_int, [C.c_void_p, i8p, C.c_uint32, i8p, C.c_uint32, C.c_int, C.c_uint32,
+                                                 C.c_uint32, C.c_uint32, C.c_uint32]),
+    "srsran_cuda_ldpc_decode": (C.c_int, [C.c_void_p, u8p, i8p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32,
+                                           C.c_uint32, C.c_uint32, C.c_float, intp]),
+    "srsran_cuda_ldpc_decode_batch": (C.c_int, [C.c_void_p, u8p, i8p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32,
+                                                 C.c_uint32, C.c_uint32, C.c_uint32, C.c_float, intp]),
+    "srsran_cuda_crc_calculate": (C.c_int, [C.c_void_p, C.c_uint32, u8p, C.c_uint32, u32p]),
+    "srsran_cuda_pusch_dec_read_softbuffer": (C.c_int, [C.c_void_p, C.c_uint32, i8p, C.c_uint32]),
+    "srsran_cuda_pusch_dec_write_softbuffer": (C.c_int, [C.c_void_p, C.c_uint32, i8p, C.c_uint32]),
+    "srsran_cuda_pusch_dec_read_cb_crc": (C.c_int, [C.c_void_p, C.c_uint32, intp]),
+}
+
+
+class CudaPuschDecError(RuntimeError):
+    pass
+
+
+def build(verbose=False):
+    """Compiles the CUDA library in-tree for sm_100a (nvcc cross-compiles without a GPU)."""
+    r = subprocess.run(["make", "-C", str(HERE / "csrc")], capture_output=not verbose, text=True)
+    if r.returncode != 0:
+        raise CudaPuschDecError("building libsrsran_cuda_pusch_dec.so failed:\n" + (r.stdout or "") + (r.stderr or ""))
+    return LIB_PATH
+
+
+_lib = None
+
+
+def lib():
+    """Loads the shared library (never a fallback) and binds every declared symbol."""
+    global _lib
+    if _lib is None:
+        if not LIB_PATH.exists():
+            raise CudaPuschDecError(
+                f"{LIB_PATH} is missing: build it with `make -C srsran_projectvtlmo_b200/csrc` "
+                "(or __graft_entry__.build()). There is no CPU fallback.")
+        handle = C.CDLL(str(LIB_PATH))
+        for name, (restype, argtypes) in SYMBOLS.items():
+            fn = getattr(handle, name)  # AttributeError if a declared symbol is not exported
+            fn.restype = restype
+            fn.argtypes = argtypes
+        _lib = handle
+    return _lib
+
+
+def check(handle, status, what):
+    if status < 0:
+        msg = lib().srsran_cuda_pusch_dec_last_error(handle)
+        raise CudaPuschDecError(f"{what} failed with status {status}: {msg.decode() if msg else ''}")
+    return status

@@ -1,0 +1,1539 @@
+// C ABI (include/srsran_cuda_pusch_dec.h) of the B200 PUSCH channel-decoding accelerator: batch contexts, HARQ state in
+// HBM, launch sequencing. No CPU fallback: every entry point needs a CUDA device.
+#include "../../include/srsran_cuda_pusch_dec.h"
+#include "pusch_dec_kernels.cuh"
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+using namespace pusch_dec;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+constexpr int      NOF_CONTEXTS   = 4;
+constexpr uint32_t MAX_TBS_PER_CTX = 1024;
+
+template <typename T>
+struct pinned_buf {
+  T*     p   = nullptr;
+  size_t cap = 0;
+  cudaError_t reserve(size_t n)
+  {
+    if (n <= cap) {
+      return cudaSuccess;
+    }
+    if (p != nullptr) {
+      cudaFreeHost(p);
+      p = nullptr;
+    }
+    cap            = 0;
+    cudaError_t e  = cudaMallocHost(reinterpret_cast<void**>(&p), n * sizeof(T));
+    if (e == cudaSuccess) {
+      cap = n;
+    }
+    return e;
+  }
+  void release()
+  {
+    if (p != nullptr) {
+      cudaFreeHost(p);
+    }
+    p   = nullptr;
+    cap = 0;
+  }
+};
+
+template <typename T>
+struct device_buf {
+  T*     p   = nullptr;
+  size_t cap = 0;
+  cudaError_t reserve(size_t n)
+  {
+    if (n <= cap) {
+      return cudaSuccess;
+    }
+    if (p != nullptr) {
+      cudaFree(p);
+      p = nullptr;
+    }
+    cap           = 0;
+    cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&p), n * sizeof(T));
+    if (e == cudaSuccess) {
+      cap = n;
+    }
+    return e;
+  }
+  void release()
+  {
+    if (p != nullptr) {
+      cudaFree(p);
+    }
+    p   = nullptr;
+    cap = 0;
+  }
+};
+
+struct cb_host_meta {
+  uint32_t K;       // message length in bits
+  uint32_t max_it;
+  uint32_t slot;
+};
+
+struct tb_host_meta {
+  uint32_t first_cb, nof_cbs, tbs_bits, out_offset, max_it;
+  bool     polled;
+};
+
+/// One batch in flight: staging buffers, descriptors and results.
+struct batch_context {
+  cudaStream_t stream     = nullptr;
+  cudaEvent_t  done       = nullptr; // everything (incl. D2H) complete
+  cudaEvent_t  kernels    = nullptr; // kernels complete (HARQ ordering between contexts)
+  bool         open       = false;   // accepting operations, not launched
+  bool         in_flight  = false;   // launched, results not yet consumed
+  uint32_t     generation = 0;
+
+  pinned_buf<int8_t>        h_llr;
+  device_buf<int8_t>        d_llr;
+  size_t                    llr_used = 0;
+  pinned_buf<cb_desc>       h_desc;
+  device_buf<cb_desc>       d_desc;
+  pinned_buf<uint32_t>      h_order;
+  device_buf<uint32_t>      d_order;
+  pinned_buf<cb_result>     h_res;
+  device_buf<cb_result>     d_res;
+  pinned_buf<uint8_t>       h_bits;
+  device_buf<uint8_t>       d_bits;
+  pinned_buf<tb_desc>       h_tb;
+  device_buf<tb_desc>       d_tb;
+  pinned_buf<tb_result_dev> h_tbres;
+  device_buf<tb_result_dev> d_tbres;
+  pinned_buf<uint8_t>       h_tbout;
+  device_buf<uint8_t>       d_tbout;
+  size_t                    tbout_used = 0;
+  bool                      want_bits  = false; // per-CB decoded bits are copied back (HAL path, unit-level decode)
+  device_buf<uint8_t>       d_unit_bits;        // scratch data-bit slots of unit-level decodes (not HARQ state)
+  uint8_t*                  bits_base  = nullptr; // data-bit slots the decoder writes: HARQ slots or d_unit_bits
+
+  std::vector<cb_host_meta> cb_meta;
+  std::vector<tb_host_meta> tb_meta;
+  struct copy_job {
+    const int8_t* src;
+    size_t        dst_off;
+    size_t        bytes;
+  };
+  std::vector<copy_job> copies;
+};
+
+struct hal_op {
+  srsran_cuda_pusch_dec_cb_config cfg;
+  bool                            configured = false;
+  int                             ctx        = -1;
+  uint32_t                        idx        = 0;
+  uint32_t                        generation = 0;
+  bool                            enqueued   = false;
+};
+
+} // namespace
+
+struct srsran_cuda_pusch_dec {
+  int      device            = 0;
+  uint32_t max_cbs           = 0;
+  uint32_t nof_slots         = 0;
+  uint32_t combine_block     = 64; // AVX-512 flavour of the reference's combine (32 = AVX2, 0 = generic)
+  uint64_t launches          = 0;
+  int      max_smem_optin    = 0;
+  std::string last_error;
+
+  device_buf<int8_t>   d_soft;
+  device_buf<uint8_t>  d_bits;
+  device_buf<uint32_t> d_crc_flags;
+  std::vector<uint32_t> extent; // per slot: upper bound of the non-zero extent of the soft buffer
+
+  batch_context ctx[NOF_CONTEXTS];
+  int           open_ctx      = -1;
+  int           last_launched = -1;
+
+  hal_op hal[SRSRAN_CUDA_MAX_NOF_SEGMENTS];
+
+  // unit-level scratch
+  device_buf<crc_job>  d_crc_jobs;
+  device_buf<uint32_t> d_crc_out;
+  device_buf<uint8_t>  d_crc_msg;
+};
+
+namespace {
+
+#define CUDA_TRY(h, expr)                                                                                              \
+  do {                                                                                                                 \
+    cudaError_t e__ = (expr);                                                                                          \
+    if (e__ != cudaSuccess) {                                                                                          \
+      (h)->last_error = std::string(#expr) + ": " + cudaGetErrorString(e__);                                           \
+      return SRSRAN_CUDA_ERR_CUDA;                                                                                     \
+    }                                                                                                                  \
+  } while (0)
+
+int ls_index(uint32_t Z)
+{
+  static const uint32_t a[8] = {2, 3, 5, 7, 9, 11, 13, 15};
+  for (int i = 0; i != 8; ++i) {
+    for (uint32_t z = a[i]; z <= 384; z *= 2) {
+      if (z == Z) {
+        return i;
+      }
+    }
+  }
+  return -1;
+}
+
+const double K0_FACTOR[2][4] = {{0, 17, 33, 56}, {0, 13, 25, 43}};
+
+uint32_t compute_k0(uint32_t bg, uint32_t rv, uint32_t Ncb, uint32_t N, uint32_t Z)
+{
+  // ldpc_rate_dematcher_impl.cpp:104-105: floor((shift_factor * buffer_length) / block_length) * lifting_size.
+  double tmp = (K0_FACTOR[bg - 1][rv] * Ncb) / N;
+  return static_cast<uint32_t>(static_cast<uint16_t>(std::floor(tmp))) * Z;
+}
+
+/// Upper bound of the non-zero extent of a soft buffer after one dematching operation (see DESIGN.md "extent").
+uint32_t extent_after_dematch(uint32_t prev, uint32_t N, uint32_t Ncb, uint32_t k0, uint32_t E, uint32_t info,
+                              uint32_t sys, bool new_data)
+{
+  uint32_t D         = info + (Ncb - sys);
+  uint32_t s0        = (k0 < info) ? k0 : ((k0 < sys) ? info : info + (k0 - sys));
+  uint32_t first_len = D - s0;
+  if (E > first_len) {
+    return std::max(prev, Ncb);
+  }
+  uint32_t end_slot = s0 + E;
+  uint32_t idx_end  = (end_slot <= info) ? sys : sys + (end_slot - info);
+  if (!new_data) {
+    return std::max(prev, idx_end);
+  }
+  if (idx_end >= Ncb) {
+    return std::max(prev, Ncb);
+  }
+  uint32_t tail_start = N - (Ncb - idx_end);
+  return std::max(idx_end, std::min(prev, tail_start));
+}
+
+uint32_t layers_for_extent(uint32_t ext, uint32_t bg, uint32_t Z)
+{
+  uint32_t Kb  = (bg == 1) ? 22 : 10;
+  uint32_t cbl = std::max(ext + 2 * Z, (Kb + 4) * Z);
+  cbl          = ((cbl + Z - 1) / Z) * Z;
+  uint32_t L   = cbl / Z - Kb;
+  return std::min(L, (bg == 1) ? 46U : 42U);
+}
+
+uint16_t scale_mult(float sf)
+{
+  // mm512::scale_epi8 (avx512_support.h:69-83): identity for sf >= .9999, else (uint16)(sf * 65536).
+  if (sf >= .9999) {
+    return 0;
+  }
+  constexpr unsigned FLOAT2INT = 1U << 16U;
+  return static_cast<uint16_t>(sf * FLOAT2INT);
+}
+
+int tpc_class(uint32_t Z)
+{
+  return Z <= 32 ? 0 : (Z <= 64 ? 1 : (Z <= 128 ? 2 : (Z <= 256 ? 3 : 4)));
+}
+
+template <int TPC, int CBS>
+cudaError_t launch_decode(srsran_cuda_pusch_dec* h, cudaStream_t s, const cb_desc* descs, const uint32_t* order,
+                          cb_result* res, uint8_t* bits_base, uint32_t n, uint32_t smem_per_cb)
+{
+  uint32_t grid = (n + CBS - 1) / CBS;
+  ldpc_decode_kernel<TPC, CBS><<<grid, TPC * CBS, smem_per_cb * CBS, s>>>(
+      descs, order, res, h->d_soft.p, bits_base, h->d_crc_flags.p, n, smem_per_cb);
+  ++h->launches;
+  return cudaGetLastError();
+}
+
+template <int TPC, int CBS>
+cudaError_t set_smem_attr(int bytes)
+{
+  return cudaFuncSetAttribute(ldpc_decode_kernel<TPC, CBS>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+}
+
+int upload_tables(srsran_cuda_pusch_dec* h)
+{
+  uint16_t row_ptr[2][48] = {};
+  uint8_t  col[2][MAX_EDGES] = {};
+  static uint16_t shift[2][8][MAX_EDGES];
+  std::memset(shift, 0, sizeof(shift));
+  std::memcpy(row_ptr[0], NR_BG1_ROW_PTR, sizeof(NR_BG1_ROW_PTR));
+  std::memcpy(row_ptr[1], NR_BG2_ROW_PTR, sizeof(NR_BG2_ROW_PTR));
+  std::memcpy(col[0], NR_BG1_COL, sizeof(NR_BG1_COL));
+  std::memcpy(col[1], NR_BG2_COL, sizeof(NR_BG2_COL));
+  for (int i = 0; i != 8; ++i) {
+    std::memcpy(shift[0][i], NR_BG1_SHIFT[i], sizeof(NR_BG1_SHIFT[i]));
+    std::memcpy(shift[1][i], NR_BG2_SHIFT[i], sizeof(NR_BG2_SHIFT[i]));
+  }
+  static uint32_t xp32[3][272], xp128[3][1024];
+  for (int poly = 1; poly <= 3; ++poly) {
+    uint32_t gen = crc_gen(poly), order = crc_order(poly);
+    uint32_t x32  = crc_push_bits(1, 0, 32, gen, order);  // x^32 mod g
+    uint32_t x128 = crc_push_bits(1, 0, 32, gen, order);
+    x128          = gf2_mulmod(x128, x128, gen, order);    // x^64
+    x128          = gf2_mulmod(x128, x128, gen, order);    // x^128
+    uint32_t v    = 1;
+    for (int i = 0; i != 272; ++i) {
+      xp32[poly - 1][i] = v;
+      v                 = gf2_mulmod(v, x32, gen, order);
+    }
+    v = 1;
+    for (int i = 0; i != 1024; ++i) {
+      xp128[poly - 1][i] = v;
+      v                  = gf2_mulmod(v, x128, gen, order);
+    }
+  }
+  CUDA_TRY(h, cudaMemcpyToSymbol(c_row_ptr, row_ptr, sizeof(row_ptr)));
+  CUDA_TRY(h, cudaMemcpyToSymbol(c_col, col, sizeof(col)));
+  CUDA_TRY(h, cudaMemcpyToSymbol(c_shift, shift, sizeof(shift)));
+  CUDA_TRY(h, cudaMemcpyToSymbol(c_xpow32, xp32, sizeof(xp32)));
+  CUDA_TRY(h, cudaMemcpyToSymbol(c_xpow128, xp128, sizeof(xp128)));
+  return SRSRAN_CUDA_OK;
+}
+
+bool is_pinned(const void* p)
+{
+  cudaPointerAttributes attr;
+  cudaError_t           e = cudaPointerGetAttributes(&attr, p);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return attr.type == cudaMemoryTypeHost;
+}
+
+/// Waits for a context's results and marks it reusable.
+int finish_context(srsran_cuda_pusch_dec* h, batch_context& c)
+{
+  if (c.in_flight) {
+    CUDA_TRY(h, cudaEventSynchronize(c.done));
+  }
+  return SRSRAN_CUDA_OK;
+}
+
+bool context_has_unpolled(const batch_context& c)
+{
+  for (const tb_host_meta& t : c.tb_meta) {
+    if (!t.polled) {
+      return true;
+    }
+  }
+  return false;
+}
+
+/// Opens a fresh context (waiting for the oldest one if necessary). Returns its index or < 0.
+int open_context(srsran_cuda_pusch_dec* h, uint32_t min_cbs)
+{
+  if (h->open_ctx >= 0) {
+    return h->open_ctx;
+  }
+  int pick = -1;
+  for (int k = 1; k <= NOF_CONTEXTS; ++k) {
+    int i = (h->last_launched + k) % NOF_CONTEXTS;
+    if (i < 0) {
+      i = 0;
+    }
+    batch_context& c = h->ctx[i];
+    if (c.in_flight && context_has_unpolled(c)) {
+      continue;
+    }
+    pick = i;
+    break;
+  }
+  if (pick < 0) {
+    h->last_error = "all batch contexts hold unpolled transport blocks";
+    return SRSRAN_CUDA_ERR_STATE;
+  }
+  batch_context& c = h->ctx[pick];
+  if (c.in_flight) {
+    int r = finish_context(h, c);
+    if (r != SRSRAN_CUDA_OK) {
+      return r;
+    }
+    c.in_flight = false;
+  }
+  uint32_t ncb = std::max(min_cbs, h->max_cbs);
+  CUDA_TRY(h, c.h_desc.reserve(ncb));
+  CUDA_TRY(h, c.d_desc.reserve(ncb));
+  CUDA_TRY(h, c.h_order.reserve(ncb));
+  CUDA_TRY(h, c.d_order.reserve(ncb));
+  CUDA_TRY(h, c.h_res.reserve(ncb));
+  CUDA_TRY(h, c.d_res.reserve(ncb));
+  c.open       = true;
+  c.llr_used   = 0;
+  c.tbout_used = 0;
+  c.want_bits  = false;
+  c.bits_base  = h->d_bits.p;
+  c.cb_meta.clear();
+  c.tb_meta.clear();
+  c.copies.clear();
+  ++c.generation;
+  h->open_ctx = pick;
+  return pick;
+}
+
+/// Reserves `bytes` (rounded to 16) of LLR staging in the open context; returns the offset.
+int stage_llrs(srsran_cuda_pusch_dec* h, batch_context& c, const int8_t* src, size_t bytes, size_t* off_out)
+{
+  size_t off    = c.llr_used;
+  size_t padded = (bytes + 15) & ~size_t(15);
+  size_t need   = off + padded;
+  if (need > c.d_llr.cap) {
+    // Grow (keeps what has been staged so far).
+    size_t             ncap = std::max(need, c.d_llr.cap * 2 + (size_t(1) << 20));
+    device_buf<int8_t> nd;
+    CUDA_TRY(h, nd.reserve(ncap));
+    if (c.d_llr.p != nullptr) {
+      // Nothing has been copied to the device yet for this context (copies happen at launch), so no device copy.
+      c.d_llr.release();
+    }
+    c.d_llr = nd;
+    pinned_buf<int8_t> nh;
+    CUDA_TRY(h, nh.reserve(ncap));
+    if (c.h_llr.p != nullptr) {
+      std::memcpy(nh.p, c.h_llr.p, off);
+      c.h_llr.release();
+    }
+    c.h_llr = nh;
+  }
+  if (is_pinned(src)) {
+    // Caller memory is page-locked: copy straight from it at launch.
+    c.copies.push_back({src, off, bytes});
+  } else {
+    // Pageable caller memory: stage through the context's pinned buffer (src == nullptr), merging adjacent pieces.
+    std::memcpy(c.h_llr.p + off, src, bytes);
+    if (!c.copies.empty() && c.copies.back().src == nullptr &&
+        c.copies.back().dst_off + ((c.copies.back().bytes + 15) & ~size_t(15)) == off) {
+      c.copies.back().bytes = off + bytes - c.copies.back().dst_off;
+    } else {
+      c.copies.push_back({nullptr, off, bytes});
+    }
+  }
+  c.llr_used = need;
+  *off_out   = off;
+  return SRSRAN_CUDA_OK;
+}
+
+struct cb_params {
+  uint32_t bg, Z, E, rv, Qm, Nref, F, crc_poly, max_it, mode, new_data, slot, flags, n_in;
+  float    scaling;
+};
+
+/// Appends one code-block operation to the open context. `llr_dev` is the device address of its LLRs.
+int add_cb(srsran_cuda_pusch_dec* h, batch_context& c, const cb_params& p, const int8_t* llr_dev, bool want_bits,
+           uint32_t* idx_out)
+{
+  int ils = ls_index(p.Z);
+  if (ils < 0 || (p.bg != 1 && p.bg != 2) || p.rv > 3 || p.max_it == 0 || p.max_it > 255) {
+    h->last_error = "invalid code-block parameters";
+    return SRSRAN_CUDA_ERR_INVALID;
+  }
+  uint32_t Kb = (p.bg == 1) ? 22 : 10, Ns = (p.bg == 1) ? 66 : 50;
+  uint32_t N = Ns * p.Z, K = Kb * p.Z, sys = (Kb - 2) * p.Z;
+  uint32_t idx = static_cast<uint32_t>(c.cb_meta.size());
+  if (idx >= c.h_desc.cap) {
+    h->last_error = "batch context full";
+    return SRSRAN_CUDA_ERR_STATE;
+  }
+  cb_desc d     = {};
+  d.llr         = llr_dev;
+  d.E           = p.E;
+  d.slot        = p.slot;
+  d.N           = N;
+  d.Z           = static_cast<uint16_t>(p.Z);
+  d.bg          = static_cast<uint8_t>(p.bg);
+  d.ils         = static_cast<uint8_t>(ils);
+  d.nof_filler  = p.F;
+  d.crc_poly    = static_cast<uint8_t>(p.crc_poly);
+  d.max_it      = static_cast<uint8_t>(p.max_it);
+  d.mode        = static_cast<uint8_t>(p.mode);
+  d.new_data    = static_cast<uint8_t>(p.new_data ? 1 : 0);
+  d.flags       = static_cast<uint8_t>(p.flags);
+  d.scale_mult  = scale_mult(p.scaling);
+  d.Qm          = static_cast<uint8_t>(p.Qm == 0 ? 1 : p.Qm);
+  if (p.flags & FLAG_DEMATCH) {
+    if (p.slot > h->nof_slots || (p.slot == h->nof_slots && (p.flags & FLAG_DECODE))) {
+      h->last_error = "HARQ slot out of range";
+      return SRSRAN_CUDA_ERR_INVALID;
+    }
+    uint32_t Ncb = p.Nref ? std::min(p.Nref, N) : N;
+    if (p.F >= sys || Ncb <= sys || p.E == 0 || (p.E % d.Qm) != 0) {
+      h->last_error = "invalid rate-dematching parameters";
+      return SRSRAN_CUDA_ERR_INVALID;
+    }
+    d.Ncb = Ncb;
+    d.k0  = compute_k0(p.bg, p.rv, Ncb, N, p.Z);
+    h->extent[p.slot] =
+        extent_after_dematch(h->extent[p.slot], N, Ncb, d.k0, p.E, sys - p.F, sys, p.new_data != 0);
+  }
+  if (p.flags & FLAG_USE_HARQ) {
+    d.n_in     = N;
+    d.scan_len = std::min(N, (h->extent[p.slot] + 15) & ~15U);
+  } else {
+    if (p.n_in > N || p.n_in < K + 2 * p.Z) {
+      h->last_error = "invalid decoder input length";
+      return SRSRAN_CUDA_ERR_INVALID;
+    }
+    d.n_in     = p.n_in;
+    d.scan_len = p.n_in;
+  }
+  d.layer_cap = layers_for_extent(d.scan_len, p.bg, p.Z);
+  if (want_bits) {
+    d.bits_out  = c.d_bits.p + static_cast<size_t>(idx) * BITS_STRIDE;
+    c.want_bits = true;
+  }
+  c.h_desc.p[idx] = d;
+  c.cb_meta.push_back({K, p.max_it, p.slot});
+  *idx_out = idx;
+  return SRSRAN_CUDA_OK;
+}
+
+int launch_context(srsran_cuda_pusch_dec* h, int ci)
+{
+  batch_context& c   = h->ctx[ci];
+  uint32_t       ncb = static_cast<uint32_t>(c.cb_meta.size());
+  uint32_t       ntb = static_cast<uint32_t>(c.tb_meta.size());
+  cudaStream_t   s   = c.stream;
+  c.open             = false;
+  h->open_ctx        = -1;
+  if (ncb == 0) {
+    return SRSRAN_CUDA_OK;
+  }
+  // 1. Host -> device: LLRs (direct from pinned caller memory when possible), descriptors.
+  for (const batch_context::copy_job& j : c.copies) {
+    const int8_t* src = (j.src != nullptr) ? j.src : c.h_llr.p + j.dst_off;
+    CUDA_TRY(h, cudaMemcpyAsync(c.d_llr.p + j.dst_off, src, j.bytes, cudaMemcpyHostToDevice, s));
+  }
+  // 2. Group the decode operations into launch classes (threads per code block x shared-memory bucket).
+  struct klass {
+    int                   tpc;
+    uint32_t              smem;
+    std::vector<uint32_t> idx;
+  };
+  std::vector<klass> classes;
+  bool               any_dematch = false;
+  for (uint32_t i = 0; i != ncb; ++i) {
+    const cb_desc& d = c.h_desc.p[i];
+    any_dematch |= (d.flags & FLAG_DEMATCH) != 0;
+    if (!(d.flags & FLAG_DECODE)) {
+      continue;
+    }
+    dec_smem_layout lay  = dec_layout(d.bg, d.Z, d.layer_cap);
+    uint32_t        need = (lay.total + 1023) & ~1023U;
+    // Buckets: 16, 24, 32, 48, 64, 96, 128, 227 KB - coarse enough for few launches, fine enough for occupancy.
+    static const uint32_t buckets[] = {16, 24, 32, 40, 48, 64, 80, 96, 112, 128, 160, 192, 227};
+    uint32_t              bsz       = 227 * 1024;
+    for (uint32_t b : buckets) {
+      if (need <= b * 1024) {
+        bsz = b * 1024;
+        break;
+      }
+    }
+    if (need > 227 * 1024) {
+      h->last_error = "code block does not fit in shared memory";
+      return SRSRAN_CUDA_ERR_INVALID;
+    }
+    int    tc    = tpc_class(d.Z);
+    klass* found = nullptr;
+    for (klass& k : classes) {
+      if (k.tpc == tc && k.smem == bsz) {
+        found = &k;
+        break;
+      }
+    }
+    if (found == nullptr) {
+      classes.push_back({tc, bsz, {}});
+      found = &classes.back();
+    }
+    found->idx.push_back(i);
+  }
+  uint32_t pos = 0;
+  for (klass& k : classes) {
+    for (uint32_t i : k.idx) {
+      c.h_order.p[pos++] = i;
+    }
+  }
+  CUDA_TRY(h, cudaMemcpyAsync(c.d_desc.p, c.h_desc.p, ncb * sizeof(cb_desc), cudaMemcpyHostToDevice, s));
+  if (pos != 0) {
+    CUDA_TRY(h, cudaMemcpyAsync(c.d_order.p, c.h_order.p, pos * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
+  }
+  if (ntb != 0) {
+    CUDA_TRY(h, cudaMemcpyAsync(c.d_tb.p, c.h_tb.p, ntb * sizeof(tb_desc), cudaMemcpyHostToDevice, s));
+  }
+  // 3. HARQ ordering: kernels of this context run after the kernels of the previously launched context.
+  if (h->last_launched >= 0 && h->last_launched != ci) {
+    CUDA_TRY(h, cudaStreamWaitEvent(s, h->ctx[h->last_launched].kernels, 0));
+  }
+  // 4. Kernels.
+  if (any_dematch) {
+    rate_dematch_kernel<<<ncb, 256, 0, s>>>(c.d_desc.p, h->d_soft.p, h->combine_block);
+    ++h->launches;
+    CUDA_TRY(h, cudaGetLastError());
+  }
+  pos = 0;
+  for (klass& k : classes) {
+    uint32_t        n   = static_cast<uint32_t>(k.idx.size());
+    const uint32_t* ord = c.d_order.p + pos;
+    cudaError_t     e   = cudaSuccess;
+    switch (k.tpc) {
+      case 0:
+        e = launch_decode<32, 4>(h, s, c.d_desc.p, ord, c.d_res.p, c.bits_base, n, k.smem);
+        break;
+      case 1:
+        e = launch_decode<64, 2>(h, s, c.d_desc.p, ord, c.d_res.p, c.bits_base, n, k.smem);
+        break;
+      case 2:
+        e = launch_decode<128, 1>(h, s, c.d_desc.p, ord, c.d_res.p, c.bits_base, n, k.smem);
+        break;
+      case 3:
+        e = launch_decode<256, 1>(h, s, c.d_desc.p, ord, c.d_res.p, c.bits_base, n, k.smem);
+        break;
+      default:
+        e = launch_decode<384, 1>(h, s, c.d_desc.p, ord, c.d_res.p, c.bits_base, n, k.smem);
+        break;
+    }
+    CUDA_TRY(h, e);
+    pos += n;
+  }
+  if (ntb != 0) {
+    tb_assemble_crc_kernel<<<ntb, CRC_THREADS, 0, s>>>(c.d_tb.p, c.d_tbres.p, h->d_bits.p, h->d_crc_flags.p, c.d_tbout.p);
+    ++h->launches;
+    CUDA_TRY(h, cudaGetLastError());
+  }
+  CUDA_TRY(h, cudaEventRecord(c.kernels, s));
+  // 5. Device -> host.
+  CUDA_TRY(h, cudaMemcpyAsync(c.h_res.p, c.d_res.p, ncb * sizeof(cb_result), cudaMemcpyDeviceToHost, s));
+  if (c.want_bits) {
+    CUDA_TRY(h, cudaMemcpyAsync(c.h_bits.p, c.d_bits.p, static_cast<size_t>(ncb) * BITS_STRIDE, cudaMemcpyDeviceToHost, s));
+  }
+  if (ntb != 0) {
+    CUDA_TRY(h, cudaMemcpyAsync(c.h_tbres.p, c.d_tbres.p, ntb * sizeof(tb_result_dev), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(h, cudaMemcpyAsync(c.h_tbout.p, c.d_tbout.p, c.tbout_used, cudaMemcpyDeviceToHost, s));
+  }
+  CUDA_TRY(h, cudaEventRecord(c.done, s));
+  c.in_flight      = true;
+  h->last_launched = ci;
+  return SRSRAN_CUDA_OK;
+}
+
+int ensure_bits_buffers(srsran_cuda_pusch_dec* h, batch_context& c)
+{
+  CUDA_TRY(h, c.h_bits.reserve(c.h_desc.cap * BITS_STRIDE));
+  CUDA_TRY(h, c.d_bits.reserve(c.h_desc.cap * BITS_STRIDE + 16));
+  return SRSRAN_CUDA_OK;
+}
+
+/// Segmentation (ldpc_segmenter_impl.cpp:58-68,254-331 and ldpc.h:128-228), host arithmetic.
+int segment(uint32_t tbs, uint32_t bg, uint32_t Qm, uint32_t nof_layers, uint32_t nof_llrs,
+            srsran_cuda_pusch_dec_cb_meta* out)
+{
+  static const uint16_t ALL_Z[51] = {2,  3,  4,  5,  6,  7,  8,  9,   10,  11,  12,  13,  14,  15,  16,  18,  20,
+                                     22, 24, 26, 28, 30, 32, 36, 40,  44,  48,  52,  56,  60,  64,  72,  80,  88,
+                                     96, 104, 112, 120, 128, 144, 160, 176, 192, 208, 224, 240, 256, 288, 320, 352, 384};
+  if ((bg != 1 && bg != 2) || Qm == 0 || nof_layers == 0 || tbs == 0) {
+    return SRSRAN_CUDA_ERR_INVALID;
+  }
+  uint32_t tb_crc  = (tbs <= 3824) ? 16 : 24;
+  uint32_t B       = tbs + tb_crc;
+  uint32_t max_seg = (bg == 1) ? 8448 : 3840;
+  uint32_t C       = (B <= max_seg) ? 1 : (B + (max_seg - 24) - 1) / (max_seg - 24);
+  if (C > SRSRAN_CUDA_MAX_NOF_SEGMENTS) {
+    return SRSRAN_CUDA_ERR_INVALID;
+  }
+  uint32_t Bp      = B + ((C > 1) ? 24 * C : 0);
+  uint32_t ref_len = 22;
+  if (bg == 2) {
+    ref_len = (B > 640) ? 10 : (B > 560) ? 9 : (B > 192) ? 8 : 6;
+  }
+  uint32_t Z = 0;
+  for (uint16_t z : ALL_Z) {
+    if (z * C * ref_len >= Bp) {
+      Z = z;
+      break;
+    }
+  }
+  if (Z == 0) {
+    return SRSRAN_CUDA_ERR_INVALID;
+  }
+  uint32_t K        = ((bg == 1) ? 22 : 10) * Z;
+  uint32_t cb_crc   = (C > 1) ? 24 : 0;
+  uint32_t max_info = (Bp + C - 1) / C - cb_crc;
+  uint32_t nsl      = (nof_llrs / Qm) / nof_layers;
+  uint32_t nshort   = C - (nsl % C);
+  uint32_t off      = 0;
+  for (uint32_t i = 0; i != C; ++i) {
+    uint32_t per = (i < nshort) ? nsl / C : (nsl + C - 1) / C;
+    uint32_t E   = per * nof_layers * Qm;
+    out[i]       = {bg, Z, K * ((bg == 1) ? 3U : 5U), E, K - (max_info + cb_crc), off, (C == 1) ? tb_crc : cb_crc};
+    off += E;
+  }
+  return (off == nof_llrs) ? static_cast<int>(C) : SRSRAN_CUDA_ERR_INVALID;
+}
+
+/// Adds all code blocks of one TB to the open context. `llr_dev` = device address of the TB's LLRs.
+int add_tb(srsran_cuda_pusch_dec* h, batch_context& c, const srsran_cuda_pusch_dec_tb_config& cfg, const int8_t* llr_dev,
+           uint32_t nof_llrs)
+{
+  srsran_cuda_pusch_dec_cb_meta metas[SRSRAN_CUDA_MAX_NOF_SEGMENTS];
+  if (cfg.tbs_bits % 8 != 0) {
+    h->last_error = "TBS must be a multiple of 8";
+    return SRSRAN_CUDA_ERR_INVALID;
+  }
+  uint32_t Qm = cfg.modulation == 0 ? 1 : cfg.modulation;
+  int      C  = segment(cfg.tbs_bits, cfg.base_graph, Qm, cfg.nof_layers, nof_llrs, metas);
+  if (C < 0) {
+    h->last_error = "segmentation failed (inconsistent TBS / number of LLRs)";
+    return SRSRAN_CUDA_ERR_INVALID;
+  }
+  if (c.tb_meta.size() >= MAX_TBS_PER_CTX) {
+    h->last_error = "too many transport blocks in one batch";
+    return SRSRAN_CUDA_ERR_STATE;
+  }
+  // pusch_decoder_impl.cpp:35-46.
+  uint32_t crc_poly = (C > 1) ? SRSRAN_CUDA_CRC24B : ((cfg.tbs_bits > 3824) ? SRSRAN_CUDA_CRC24A : SRSRAN_CUDA_CRC16);
+  uint32_t first_cb = static_cast<uint32_t>(c.cb_meta.size());
+  for (int i = 0; i != C; ++i) {
+    cb_params p = {};
+    p.bg        = cfg.base_graph;
+    p.Z         = metas[i].lifting_size;
+    p.E         = metas[i].rm_length;
+    p.rv        = cfg.rv;
+    p.Qm        = Qm;
+    p.Nref      = cfg.Nref;
+    p.F         = metas[i].nof_filler_bits;
+    p.crc_poly  = crc_poly;
+    p.max_it    = cfg.nof_ldpc_iterations;
+    p.mode      = cfg.use_early_stop ? MODE_EARLY_STOP : MODE_CRC_AT_END;
+    p.new_data  = cfg.new_data;
+    p.slot      = cfg.harq_first_slot + i;
+    p.flags     = FLAG_DEMATCH | FLAG_DECODE | FLAG_USE_HARQ | FLAG_TRACK_CRC;
+    p.scaling   = 0.8F; // pusch_codeblock_decoder.cpp:47-50 keeps the default scaling factor
+    uint32_t idx;
+    int      r = add_cb(h, c, p, llr_dev + metas[i].cw_offset, false, &idx);
+    if (r != SRSRAN_CUDA_OK) {
+      return r;
+    }
+  }
+  uint32_t K        = metas[0].full_length / ((cfg.base_graph == 1) ? 3 : 5);
+  tb_desc  t        = {};
+  t.first_cb        = first_cb;
+  t.nof_cbs         = C;
+  t.first_slot      = cfg.harq_first_slot;
+  t.tbs_bits        = cfg.tbs_bits;
+  t.cb_data_bits    = K - metas[0].nof_crc_bits - metas[0].nof_filler_bits;
+  t.out_offset      = static_cast<uint32_t>(c.tbout_used);
+  uint32_t ti       = static_cast<uint32_t>(c.tb_meta.size());
+  c.h_tb.p[ti]      = t;
+  c.tb_meta.push_back({first_cb, static_cast<uint32_t>(C), cfg.tbs_bits, t.out_offset, cfg.nof_ldpc_iterations, false});
+  c.tbout_used += (cfg.tbs_bits / 8 + 3 + 15) & ~size_t(15);
+  return SRSRAN_CUDA_OK;
+}
+
+int prepare_tb_buffers(srsran_cuda_pusch_dec* h, batch_context& c, uint32_t nof_tbs, size_t tb_bytes_total)
+{
+  CUDA_TRY(h, c.h_tb.reserve(MAX_TBS_PER_CTX));
+  CUDA_TRY(h, c.d_tb.reserve(MAX_TBS_PER_CTX));
+  CUDA_TRY(h, c.h_tbres.reserve(MAX_TBS_PER_CTX));
+  CUDA_TRY(h, c.d_tbres.reserve(MAX_TBS_PER_CTX));
+  size_t need = c.tbout_used + tb_bytes_total + 32 * static_cast<size_t>(nof_tbs);
+  if (need > c.h_tbout.cap) {
+    if (c.tbout_used != 0) {
+      h->last_error = "TB output staging exhausted";
+      return SRSRAN_CUDA_ERR_STATE;
+    }
+    CUDA_TRY(h, c.h_tbout.reserve(need));
+    CUDA_TRY(h, c.d_tbout.reserve(need));
+  }
+  return SRSRAN_CUDA_OK;
+}
+
+int make_ticket(int ctx, uint32_t tb_index, uint32_t generation)
+{
+  return static_cast<int>(((generation & 0x3ff) << 20) | (static_cast<uint32_t>(ctx) << 16) | tb_index);
+}
+
+} // namespace
+
+// =====================================================================================================================
+// C ABI
+// =====================================================================================================================
+extern "C" {
+
+int srsran_cuda_pusch_dec_create(int device, uint32_t max_cbs_in_flight, uint32_t nof_harq_cb_slots,
+                                 srsran_cuda_pusch_dec_t** handle)
+{
+  if (handle == nullptr || max_cbs_in_flight == 0 || nof_harq_cb_slots == 0) {
+    g_create_error = "invalid arguments";
+    return SRSRAN_CUDA_ERR_INVALID;
+  }
+  *handle   = nullptr;
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0 || device < 0 || device >= count) {
+    g_create_error = std::string("no usable CUDA device: ") + (e != cudaSuccess ? cudaGetErrorString(e) : "bad index");
+    cudaGetLastError();
+    return SRSRAN_CUDA_ERR_NO_DEVICE;
+  }
+  if (cudaSetDevice(device) != cudaSuccess) {
+    g_create_error = "cudaSetDevice failed";
+    return SRSRAN_CUDA_ERR_NO_DEVICE;
+  }
+  srsran_cuda_pusch_dec* h = new (std::nothrow) srsran_cuda_pusch_dec();
+  if (h == nullptr) {
+    return SRSRAN_CUDA_ERR_NO_MEMORY;
+  }
+  h->device    = device;
+  h->max_cbs   = max_cbs_in_flight;
+  h->nof_slots = nof_harq_cb_slots;
+  auto fail    = [&](int code) {
+    g_create_error = h->last_error;
+    srsran_cuda_pusch_dec_destroy(h);
+    return code;
+  };
+  cudaDeviceGetAttribute(&h->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
+  if (upload_tables(h) != SRSRAN_CUDA_OK) {
+    return fail(SRSRAN_CUDA_ERR_CUDA);
+  }
+  int smem = std::min(h->max_smem_optin, 227 * 1024);
+  if (set_smem_attr<32, 4>(smem) != cudaSuccess || set_smem_attr<64, 2>(smem) != cudaSuccess ||
+      set_smem_attr<128, 1>(smem) != cudaSuccess || set_smem_attr<256, 1>(smem) != cudaSuccess ||
+      set_smem_attr<384, 1>(smem) != cudaSuccess) {
+    h->last_error = "cudaFuncSetAttribute(MaxDynamicSharedMemorySize) failed";
+    return fail(SRSRAN_CUDA_ERR_CUDA);
+  }
+  size_t soft_bytes = (static_cast<size_t>(nof_harq_cb_slots) + 1) * SOFT_STRIDE; // + 1 scratch slot (unit-level)
+  size_t bits_bytes = static_cast<size_t>(nof_harq_cb_slots) * BITS_STRIDE + 16;
+  if (h->d_soft.reserve(soft_bytes) != cudaSuccess || h->d_bits.reserve(bits_bytes) != cudaSuccess ||
+      h->d_crc_flags.reserve(nof_harq_cb_slots) != cudaSuccess) {
+    h->last_error = "HARQ buffer allocation failed";
+    cudaGetLastError();
+    return fail(SRSRAN_CUDA_ERR_NO_MEMORY);
+  }
+  // Zero-initialised once, never cleared afterwards (rx_buffer_pool.h:62-63).
+  if (cudaMemset(h->d_soft.p, 0, soft_bytes) != cudaSuccess || cudaMemset(h->d_bits.p, 0, bits_bytes) != cudaSuccess ||
+      cudaMemset(h->d_crc_flags.p, 0, nof_harq_cb_slots * sizeof(uint32_t)) != cudaSuccess) {
+    h->last_error = "HARQ buffer initialisation failed";
+    return fail(SRSRAN_CUDA_ERR_CUDA);
+  }
+  h->extent.assign(nof_harq_cb_slots + 1, 0);
+  for (batch_context& c : h->ctx) {
+    if (cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&c.done, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&c.kernels, cudaEventDisableTiming) != cudaSuccess) {
+      h->last_error = "stream / event creation failed";
+      return fail(SRSRAN_CUDA_ERR_CUDA);
+    }
+  }
+  if (cudaDeviceSynchronize() != cudaSuccess) {
+    h->last_error = "device synchronisation failed";
+    return fail(SRSRAN_CUDA_ERR_CUDA);
+  }
+  *handle = h;
+  return SRSRAN_CUDA_OK;
+}
+
+void srsran_cuda_pusch_dec_destroy(srsran_cuda_pusch_dec_t* h)
+{
+  if (h == nullptr) {
+    return;
+  }
+  cudaSetDevice(h->device);
+  cudaDeviceSynchronize();
+  for (batch_context& c : h->ctx) {
+    c.h_llr.release();
+    c.d_llr.release();
+    c.h_desc.release();
+    c.d_desc.release();
+    c.h_order.release();
+    c.d_order.release();
+    c.h_res.release();
+    c.d_res.release();
+    c.h_bits.release();
+    c.d_bits.release();
+    c.h_tb.release();
+    c.d_tb.release();
+    c.h_tbres.release();
+    c.d_tbres.release();
+    c.h_tbout.release();
+    c.d_tbout.release();
+    c.d_unit_bits.release();
+    if (c.done != nullptr) {
+      cudaEventDestroy(c.done);
+    }
+    if (c.kernels != nullptr) {
+      cudaEventDestroy(c.kernels);
+    }
+    if (c.stream != nullptr) {
+      cudaStreamDestroy(c.stream);
+    }
+  }
+  h->d_soft.release();
+  h->d_bits.release();
+  h->d_crc_flags.release();
+  h->d_crc_jobs.release();
+  h->d_crc_out.release();
+  h->d_crc_msg.release();
+  delete h;
+}
+
+const char* srsran_cuda_pusch_dec_last_error(const srsran_cuda_pusch_dec_t* h)
+{
+  return (h == nullptr) ? g_create_error.c_str() : h->last_error.c_str();
+}
+
+uint64_t srsran_cuda_pusch_dec_launch_count(const srsran_cuda_pusch_dec_t* h)
+{
+  return (h == nullptr) ? 0 : h->launches;
+}
+
+int srsran_cuda_pusch_dec_set_combine_flavour(srsran_cuda_pusch_dec_t* h, uint32_t simd_block)
+{
+  if (h == nullptr || (simd_block != 0 && simd_block != 32 && simd_block != 64)) {
+    return SRSRAN_CUDA_ERR_INVALID;
+  }
+  h->combine_block = simd_block;
+  return SRSRAN_CUDA_OK;
+}
+
+void* srsran_cuda_pusch_dec_host_alloc(size_t bytes)
+{
+  void* p = nullptr;
+  if (cudaMallocHost(&p, bytes) != cudaSuccess) {
+    cudaGetLastError();
+    return nullptr;
+  }
+  return p;
+}
+
+void srsran_cuda_pusch_dec_host_free(void* p)
+{
+  if (p != nullptr) {
+    cudaFreeHost(p);
+  }
+}
+
+// ---- HAL-style ------------------------------------------------------------------------------------------------------
+
+int srsran_cuda_pusch_dec_reserve_queue(srsran_cuda_pusch_dec_t* h)
+{
+  return (h == nullptr) ? SRSRAN_CUDA_ERR_INVALID : SRSRAN_CUDA_OK;
+}
+
+int srsran_cuda_pusch_dec_free_queue(srsran_cuda_pusch_dec_t* h)
+{
+  if (h == nullptr) {
+    return SRSRAN_CUDA_ERR_INVALID;
+  }
+  for (hal_op& op : h->hal) {
+    op.configured = false;
+    op.enqueued   = false;
+  }
+  return SRSRAN_CUDA_OK;
+}
+
+int srsran_cuda_pusch_dec_configure(srsran_cuda_pusch_dec_t* h, uint32_t cb_index,
+                                    const srsran_cuda_pusch_dec_cb_config* config)
+{
+  if (h == nullptr || config == nullptr || cb_index >= SRSRAN_CUDA_MAX_NOF_SEGMENTS) {
+    return SRSRAN_CUDA_ERR_INVALID;
+  }
+  h->hal[cb_index].cfg        = *config;
+  h->hal[cb_index].configured = true;
+  h->hal[cb_index].enqueued   = false;
+  return SRSRAN_CUDA_OK;
+}
+
+int srsran_cuda_pusch_dec_enqueue(srsran_cuda_pusch_dec_t* h, uint32_t cb_index, const int8_t* llrs, uint32_t E,
+                                  const int8_t* /*softbuf*/, uint32_t /*N*/)
+{
+  if (h == nullptr || llrs == nullptr || cb_index >= SRSRAN_CUDA_MAX_NOF_SEGMENTS) {
+    return SRSRAN_CUDA_ERR_INVALID;
+  }
+  hal_op& op = h->hal[cb_index];
+  if (!op.configured || op.cfg.cw_length != E) {
+    h->last_error = "enqueue without matching configure";
+    return SRSRAN_CUDA_ERR_STATE;
+  }
+  cudaSetDevice(h->device);
+  int ci = open_context(h, 0);
+  if (ci < 0) {
+    return ci;
+  }
+  batch_context& c = h->ctx[ci];
+  if (c.cb_meta.size() >= h->max_cbs) {
+    return 0; // queue full: the caller dequeues first
+  }
+  int r = ensure_bits_buffers(h, c);
+  if (r != SRSRAN_CUDA_OK) {
+    return r;
+  }
+  size_t off;
+  r = stage_llrs(h, c, llrs, E, &off);
+  if (r != SRSRAN_CUDA_OK) {
+    return r;
+  }
+  const srsran_cuda_pusch_dec_cb_config& cfg = op.cfg;
+  cb_params                              p   = {};
+  p.bg       = cfg.base_graph;
+  p.Z        = cfg.lifting_size;
+  p.E        = E;
+  p.rv       = cfg.rv;
+  p.Qm       = cfg.modulation == 0 ? 1 : cfg.modulation;
+  p.Nref     = cfg.Nref;
+  p.F        = cfg.nof_filler_bits;
+  p.crc_poly = cfg.cb_crc_type == SRSRAN_CUDA_CB_CRC16 ? SRSRAN_CUDA_CRC16
+                                                       : (cfg.cb_crc_type == SRSRAN_CUDA_CB_CRC24B ? SRSRAN_CUDA_CRC24B : SRSRAN_CUDA_CRC24A);
+  p.max_it   = cfg.max_nof_ldpc_iterations;
+  p.mode     = cfg.use_early_stop ? MODE_EARLY_STOP : MODE_CRC_AT_END;
+  p.new_data = cfg.new_data;
+  p.slot     = cfg.absolute_cb_id;
+  p.flags    = FLAG_DEMATCH | FLAG_DECODE | FLAG_USE_HARQ;
+  p.scaling  = 0.8F;
+  uint32_t idx;
+  // The device address is fixed up at launch (the staging buffer may still grow): store the offset for now.
+  r = add_cb(h, c, p, reinterpret_cast<const int8_t*>(off), true, &idx);
+  if (r != SRSRAN_CUDA_OK) {
+    return r;
+  }
+  op.ctx        = ci;
+  op.idx        = idx;
+  op.generation = c.generation;
+  op.enqueued   = true;
+  return 1;
+}
+
+static int fixup_and_launch(srsran_cuda_pusch_dec_t* h, int ci)
+{
+  batch_context& c = h->ctx[ci];
+  for (size_t i = 0; i != c.cb_meta.size(); ++i) {
+    cb_desc& d = c.h_desc.p[i];
+    d.llr      = c.d_llr.p + reinterpret_cast<size_t>(d.llr);
+    if (d.bits_out != nullptr) {
+      d.bits_out = c.d_bits.p + i * BITS_STRIDE;
+    }
+  }
+  return launch_context(h, ci);
+}
+
+int srsran_cuda_pusch_dec_dequeue(srsran_cuda_pusch_dec_t* h, uint32_t cb_index, uint8_t* bits, uint32_t bits_size,
+                                  int8_t* softbuf_out, uint32_t N)
+{
+  if (h == nullptr || bits == nullptr || cb_index >= SRSRAN_CUDA_MAX_NOF_SEGMENTS) {
+    return SRSRAN_CUDA_ERR_INVALID;
+  }
+  hal_op& op = h->hal[cb_index];
+  if (!op.enqueued) {
+    h->last_error = "dequeue of an operation that was not enqueued";
+    return SRSRAN_CUDA_ERR_STATE;
+  }
+  cudaSetDevice(h->device);
+  batch_context& c = h->ctx[op.ctx];
+  if (c.generation != op.generation) {
+    h->last_error = "operation result was overwritten";
+    return SRSRAN_CUDA_ERR_STATE;
+  }
+  if (c.open) {
+    int r = fixup_and_launch(h, op.ctx);
+    if (r != SRSRAN_CUDA_OK) {
+      return r;
+    }
+  }
+  cudaError_t q = cudaEventQuery(c.done);
+  if (q == cudaErrorNotReady) {
+    return 0;
+  }
+  if (q != cudaSuccess) {
+    h->last_error = std::string("batch failed: ") + cudaGetErrorString(q);
+    return SRSRAN_CUDA_ERR_CUDA;
+  }
+  const cb_host_meta& m      = c.cb_meta[op.idx];
+  uint32_t            nbytes = (m.K + 7) / 8;
+  if (bits_size < nbytes) {
+    h->last_error = "bits buffer too small";
+    return SRSRAN_CUDA_ERR_INVALID;
+  }
+  const uint8_t* src = c.h_bits.p + static_cast<size_t>(op.idx) * BITS_STRIDE;
+  std::memcpy(bits, src, m.K / 8);
+  if (m.K % 8 != 0) {
+    // bit_buffer semantics: only the first K bits belong to the message.
+    uint8_t mask    = static_cast<uint8_t>(0xff00U >> (m.K % 8));
+    bits[m.K / 8]   = static_cast<uint8_t>((bits[m.K / 8] & ~mask) | (src[m.K / 8] & mask));
+  }
+  if (softbuf_out != nullptr && N != 0) {
+    CUDA_TRY(h, cudaMemcpy(softbuf_out, h->d_soft.p + static_cast<size_t>(m.slot) * SOFT_STRIDE,
+                           std::min(N, SOFT_STRIDE), cudaMemcpyDeviceToHost));
+  }
+  return 1;
+}
+
+int srsran_cuda_pusch_dec_read_outputs(srsran_cuda_pusch_dec_t* h, uint32_t cb_index, int* crc_pass,
+                                       uint32_t* nof_ldpc_iterations)
+{
+  if (h == nullptr || cb_index >= SRSRAN_CUDA_MAX_NOF_SEGMENTS) {
+    return SRSRAN_CUDA_ERR_INVALID;
+  }
+  hal_op& op = h->hal[cb_index];
+  if (!op.enqueued || h->ctx[op.ctx].generation != op.generation || h->ctx[op.ctx].open) {
+    h->last_error = "read_outputs before a successful dequeue";
+    return SRSRAN_CUDA_ERR_STATE;
+  }
+  batch_context& c = h->ctx[op.ctx];
+  if (cudaEventQuery(c.done) != cudaSuccess) {
+    h->last_error = "read_outputs before completion";
+    return SRSRAN_CUDA_ERR_STATE;
+  }
+  const cb_result& r = c.h_res.p[op.idx];
+  if (r.status == 1) {
+    h->last_error = "internal: shared-memory layer capacity exceeded";
+    return SRSRAN_CUDA_ERR_STATE;
+  }
+  if (crc_pass != nullptr) {
+    *crc_pass = r.crc_ok ? 1 : 0;
+  }
+  if (nof_ldpc_iterations != nullptr) {
+    // Like the software path's statistics (pusch_decoder_impl.cpp:357-363): iterations on success, else the maximum.
+    *nof_ldpc_iterations = (r.iters >= 0) ? static_cast<uint32_t>(r.iters) : c.cb_meta[op.idx].max_it;
+  }
+  return SRSRAN_CUDA_OK;
+}
+
+int srsran_cuda_pusch_dec_free_harq(srsran_cuda_pusch_dec_t* h, uint32_t absolute_cb_id)
+{
+  if (h == nullptr || absolute_cb_id >= h->nof_slots) {
+    return SRSRAN_CUDA_ERR_INVALID;
+  }
+  return SRSRAN_CUDA_OK;
+}
+
+int srsran_cuda_pusch_dec_is_external_harq_supported(const srsran_cuda_pusch_dec_t*)
+{
+  return 1;
+}
+
+// ---- TB-level -------------------------------------------------------------------------------------------------------
+
+int srsran_cuda_pusch_dec_segment(uint32_t tbs_bits, uint32_t base_graph, uint32_t modulation, uint32_t nof_layers,
+                                  uint32_t nof_llrs, srsran_cuda_pusch_dec_cb_meta* out)
+{
+  if (out == nullptr) {
+    return SRSRAN_CUDA_ERR_INVALID;
+  }
+  return segment(tbs_bits, base_graph, modulation == 0 ? 1 : modulation, nof_layers, nof_llrs, out);
+}
+
+static int submit_common(srsran_cuda_pusch_dec_t* h, uint32_t nof_tbs, const srsran_cuda_pusch_dec_tb_config* configs,
+                         const int8_t* const* llrs, const uint32_t* nof_llrs, int* tickets, bool device_resident)
+{
+  if (h == nullptr || configs == nullptr || llrs == nullptr || nof_llrs == nullptr || tickets == nullptr ||
+      nof_tbs == 0 || nof_tbs > MAX_TBS_PER_CTX) {
+    return SRSRAN_CUDA_ERR_INVALID;
+  }
+  cudaSetDevice(h->device);
+  if (h->open_ctx >= 0) {
+    // A HAL-style batch is still open: launch it first to keep HARQ ordering.
+    int r = fixup_and_launch(h, h->open_ctx);
+    if (r != SRSRAN_CUDA_OK) {
+      return r;
+    }
+  }
+  uint32_t total_cbs = 0;
+  size_t   tb_bytes  = 0;
+  for (uint32_t i = 0; i != nof_tbs; ++i) {
+    uint32_t B = configs[i].tbs_bits + ((configs[i].tbs_bits <= 3824) ? 16 : 24);
+    uint32_t m = (configs[i].base_graph == 1) ? 8448 : 3840;
+    total_cbs += (B <= m) ? 1 : (B + m - 25) / (m - 24);
+    tb_bytes += configs[i].tbs_bits / 8 + 32;
+  }
+  int ci = open_context(h, total_cbs);
+  if (ci < 0) {
+    return ci;
+  }
+  batch_context& c = h->ctx[ci];
+  int            r = prepare_tb_buffers(h, c, nof_tbs, tb_bytes);
+  if (r != SRSRAN_CUDA_OK) {
+    c.open      = false;
+    h->open_ctx = -1;
+    return r;
+  }
+  // Stage first (the device staging buffer may be reallocated while growing), then build the descriptors.
+  std::vector<size_t> offs(nof_tbs, 0);
+  if (!device_resident) {
+    for (uint32_t i = 0; i != nof_tbs; ++i) {
+      r = stage_llrs(h, c, llrs[i], nof_llrs[i], &offs[i]);
+      if (r != SRSRAN_CUDA_OK) {
+        c.open      = false;
+        h->open_ctx = -1;
+        return r;
+      }
+    }
+  }
+  for (uint32_t i = 0; i != nof_tbs; ++i) {
+    const int8_t* dev = device_resident ? llrs[i] : c.d_llr.p + offs[i];
+    r                 = add_tb(h, c, configs[i], dev, nof_llrs[i]);
+    if (r != SRSRAN_CUDA_OK) {
+      c.open      = false;
+      h->open_ctx = -1;
+      return r;
+    }
+    tickets[i] = make_ticket(ci, static_cast<uint32_t>(c.tb_meta.size() - 1), c.generation);
+  }
+  return launch_context(h, ci);
+}
+
+int srsran_cuda_pusch_dec_submit_tbs(srsran_cuda_pusch_dec_t* h, uint32_t nof_tbs,
+                                     const srsran_cuda_pusch_dec_tb_config* configs, const int8_t* const* llrs,
+                                     const uint32_t* nof_llrs, int* tickets)
+{
+  return submit_common(h, nof_tbs, configs, llrs, nof_llrs, tickets, false);
+}
+
+int srsran_cuda_pusch_dec_submit_tbs_device(srsran_cuda_pusch_dec_t* h, uint32_t nof_tbs,
+                                            const srsran_cuda_pusch_dec_tb_config* configs,
+                                            const int8_t* const* llrs_dev, const uint32_t* nof_llrs, int* tickets)
+{
+  return submit_common(h, nof_tbs, configs, llrs_dev, nof_llrs, tickets, true);
+}
+
+int srsran_cuda_pusch_dec_submit_tb(srsran_cuda_pusch_dec_t* h, const srsran_cuda_pusch_dec_tb_config* config,
+                                    const int8_t* llrs, uint32_t nof_llrs)
+{
+  int ticket = -1;
+  int r      = submit_common(h, 1, config, &llrs, &nof_llrs, &ticket, false);
+  return (r == SRSRAN_CUDA_OK) ? ticket : r;
+}
+
+int srsran_cuda_pusch_dec_poll_tb(srsran_cuda_pusch_dec_t* h, int ticket, int block, uint8_t* tb,
+                                  srsran_cuda_pusch_dec_tb_result* result)
+{
+  if (h == nullptr || ticket < 0) {
+    return SRSRAN_CUDA_ERR_INVALID;
+  }
+  int      ci  = (ticket >> 16) & 0xf;
+  uint32_t ti  = static_cast<uint32_t>(ticket) & 0xffff;
+  uint32_t gen = (static_cast<uint32_t>(ticket) >> 20) & 0x3ff;
+  if (ci >= NOF_CONTEXTS) {
+    return SRSRAN_CUDA_ERR_INVALID;
+  }
+  batch_context& c = h->ctx[ci];
+  if ((c.generation & 0x3ff) != gen || ti >= c.tb_meta.size() || !c.in_flight) {
+    h->last_error = "stale or unknown ticket";
+    return SRSRAN_CUDA_ERR_STATE;
+  }
+  cudaSetDevice(h->device);
+  if (block) {
+    CUDA_TRY(h, cudaEventSynchronize(c.done));
+  } else {
+    cudaError_t q = cudaEventQuery(c.done);
+    if (q == cudaErrorNotReady) {
+      return 0;
+    }
+    if (q != cudaSuccess) {
+      h->last_error = std::string("batch failed: ") + cudaGetErrorString(q);
+      return SRSRAN_CUDA_ERR_CUDA;
+    }
+  }
+  tb_host_meta&        m  = c.tb_meta[ti];
+  const tb_result_dev& tr = c.h_tbres.p[ti];
+  if (tb != nullptr && tr.written) {
+    std::memcpy(tb, c.h_tbout.p + m.out_offset, m.tbs_bits / 8);
+  }
+  if (result != nullptr) {
+    // sample_statistics<unsigned>::update (include/srsran/support/stats.h:49-53), code blocks in order.
+    uint32_t nobs = 0, imin = 0xffffffffU, imax = 0;
+    float    mean = 0;
+    for (uint32_t i = 0; i != m.nof_cbs; ++i) {
+      const cb_result& r = c.h_res.p[m.first_cb + i];
+      if (r.status == 1) {
+        h->last_error = "internal: shared-memory layer capacity exceeded";
+        return SRSRAN_CUDA_ERR_STATE;
+      }
+      if (r.status == 2) {
+        continue;
+      }
+      uint32_t obs   = (r.iters >= 0) ? static_cast<uint32_t>(r.iters) : m.max_it;
+      float    delta = obs - mean;
+      ++nobs;
+      mean += delta / nobs;
+      imin = std::min(imin, obs);
+      imax = std::max(imax, obs);
+    }
+    result->tb_crc_ok            = tr.tb_crc_ok ? 1 : 0;
+    result->nof_codeblocks_total = m.nof_cbs;
+    result->nof_observations     = nobs;
+    result->iter_min             = nobs ? imin : 0;
+    result->iter_max             = nobs ? imax : 0;
+    result->iter_mean            = nobs ? mean : 0;
+  }
+  m.polled = true;
+  return 1;
+}
+
+int srsran_cuda_pusch_dec_synchronize(srsran_cuda_pusch_dec_t* h)
+{
+  if (h == nullptr) {
+    return SRSRAN_CUDA_ERR_INVALID;
+  }
+  cudaSetDevice(h->device);
+  if (h->open_ctx >= 0) {
+    int r = fixup_and_launch(h, h->open_ctx);
+    if (r != SRSRAN_CUDA_OK) {
+      return r;
+    }
+  }
+  for (batch_context& c : h->ctx) {
+    if (c.in_flight) {
+      CUDA_TRY(h, cudaEventSynchronize(c.done));
+    }
+  }
+  return SRSRAN_CUDA_OK;
+}
+
+// ---- unit-level -----------------------------------------------------------------------------------------------------
+
+/// Runs one standalone batch (waits for everything before and after).
+static int run_unit_batch(srsran_cuda_pusch_dec_t* h, int ci)
+{
+  int r = launch_context(h, ci);
+  if (r != SRSRAN_CUDA_OK) {
+    return r;
+  }
+  CUDA_TRY(h, cudaEventSynchronize(h->ctx[ci].done));
+  h->ctx[ci].in_flight = false;
+  return SRSRAN_CUDA_OK;
+}
+
+int srsran_cuda_ldpc_rate_dematch(srsran_cuda_pusch_dec_t* h, int8_t* softbuf, uint32_t N, const int8_t* llrs, uint32_t E,
+                                  int new_data, uint32_t rv, uint32_t modulation, uint32_t Nref, uint32_t nof_filler_bits)
+{
+  if (h == nullptr || softbuf == nullptr || llrs == nullptr) {
+    return SRSRAN_CUDA_ERR_INVALID;
+  }
+  uint32_t bg = (N % 66 == 0) ? 1 : ((N % 50 == 0) ? 2 : 0);
+  if (bg == 0) {
+    h->last_error = "invalid soft buffer length";
+    return SRSRAN_CUDA_ERR_INVALID;
+  }
+  uint32_t Z = N / ((bg == 1) ? 66 : 50);
+  int      r = srsran_cuda_pusch_dec_synchronize(h);
+  if (r != SRSRAN_CUDA_OK) {
+    return r;
+  }
+  // The unit-level interface works on a caller-owned buffer: it is staged through a hidden scratch slot.
+  uint32_t slot = h->nof_slots;
+  CUDA_TRY(h, cudaMemcpy(h->d_soft.p + static_cast<size_t>(slot) * SOFT_STRIDE, softbuf, N, cudaMemcpyHostToDevice));
+  int ci = open_context(h, 1);
+  if (ci < 0) {
+    return ci;
+  }
+  batch_context& c = h->ctx[ci];
+  size_t         off;
+  r = stage_llrs(h, c, llrs, E, &off);
+  if (r != SRSRAN_CUDA_OK) {
+    return r;
+  }
+  cb_params p = {};
+  p.bg        = bg;
+  p.Z         = Z;
+  p.E         = E;
+  p.rv        = rv;
+  p.Qm        = modulation == 0 ? 1 : modulation;
+  p.Nref      = Nref;
+  p.F         = nof_filler_bits;
+  p.max_it    = 1;
+  p.new_data  = new_data;
+  p.slot      = slot;
+  p.flags     = FLAG_DEMATCH;
+  p.scaling   = 0.8F;
+  uint32_t idx;
+  r = add_cb(h, c, p, c.d_llr.p + off, false, &idx);
+  if (r != SRSRAN_CUDA_OK) {
+    c.open      = false;
+    h->open_ctx = -1;
+    return r;
+  }
+  r = run_unit_batch(h, ci);
+  if (r != SRSRAN_CUDA_OK) {
+    return r;
+  }
+  CUDA_TRY(h, cudaMemcpy(softbuf, h->d_soft.p + static_cast<size_t>(slot) * SOFT_STRIDE, N, cudaMemcpyDeviceToHost));
+  return SRSRAN_CUDA_OK;
+}
+
+int srsran_cuda_ldpc_decode_batch(srsran_cuda_pusch_dec_t* h, uint8_t* bits, const int8_t* llrs, uint32_t nof_cbs,
+                                  uint32_t nof_llrs, uint32_t base_graph, uint32_t lifting_size,
+                                  uint32_t nof_filler_bits, uint32_t crc_poly, uint32_t max_iterations,
+                                  float scaling_factor, int* nof_iterations)
+{
+  if (h == nullptr || bits == nullptr || llrs == nullptr || nof_cbs == 0 || (base_graph != 1 && base_graph != 2)) {
+    return SRSRAN_CUDA_ERR_INVALID;
+  }
+  if (!(scaling_factor > 0 && scaling_factor <= 1)) {
+    h->last_error = "scaling factor out of range";
+    return SRSRAN_CUDA_ERR_INVALID;
+  }
+  int r = srsran_cuda_pusch_dec_synchronize(h);
+  if (r != SRSRAN_CUDA_OK) {
+    return r;
+  }
+  uint32_t K      = ((base_graph == 1) ? 22 : 10) * lifting_size;
+  uint32_t nbytes = (K + 7) / 8;
+  uint32_t done   = 0;
+  while (done != nof_cbs) {
+    uint32_t n  = std::min(nof_cbs - done, std::max<uint32_t>(h->max_cbs, 1));
+    int      ci = open_context(h, n);
+    if (ci < 0) {
+      return ci;
+    }
+    batch_context& c = h->ctx[ci];
+    r                = ensure_bits_buffers(h, c);
+    if (r != SRSRAN_CUDA_OK) {
+      return r;
+    }
+    // The decoder reads and (conditionally) writes the caller's bit buffer: seed scratch data-bit slots [0, n) with it.
+    CUDA_TRY(h, c.d_unit_bits.reserve(static_cast<size_t>(c.h_desc.cap) * BITS_STRIDE + 16));
+    c.bits_base = c.d_unit_bits.p;
+    std::vector<size_t> offs(n);
+    for (uint32_t i = 0; i != n; ++i) {
+      r = stage_llrs(h, c, llrs + static_cast<size_t>(done + i) * nof_llrs, nof_llrs, &offs[i]);
+      if (r != SRSRAN_CUDA_OK) {
+        return r;
+      }
+      CUDA_TRY(h, cudaMemcpy(c.d_unit_bits.p + static_cast<size_t>(i) * BITS_STRIDE,
+                             bits + static_cast<size_t>(done + i) * nbytes, nbytes, cudaMemcpyHostToDevice));
+    }
+    for (uint32_t i = 0; i != n; ++i) {
+      cb_params p = {};
+      p.bg        = base_graph;
+      p.Z         = lifting_size;
+      p.F         = nof_filler_bits;
+      p.crc_poly  = crc_poly;
+      p.max_it    = max_iterations;
+      p.mode      = (crc_poly == SRSRAN_CUDA_CRC_NONE) ? MODE_NO_CRC : MODE_EARLY_STOP;
+      p.slot      = i;
+      p.flags     = FLAG_DECODE;
+      p.n_in      = nof_llrs;
+      p.scaling   = scaling_factor;
+      uint32_t idx;
+      r = add_cb(h, c, p, c.d_llr.p + offs[i], true, &idx);
+      if (r != SRSRAN_CUDA_OK) {
+        c.open      = false;
+        h->open_ctx = -1;
+        return r;
+      }
+    }
+    r = run_unit_batch(h, ci);
+    if (r != SRSRAN_CUDA_OK) {
+      return r;
+    }
+    for (uint32_t i = 0; i != n; ++i) {
+      const cb_result& res = c.h_res.p[i];
+      if (res.status == 1) {
+        h->last_error = "internal: shared-memory layer capacity exceeded";
+        return SRSRAN_CUDA_ERR_STATE;
+      }
+      uint8_t*       dst = bits + static_cast<size_t>(done + i) * nbytes;
+      const uint8_t* src = c.h_bits.p + static_cast<size_t>(i) * BITS_STRIDE;
+      std::memcpy(dst, src, K / 8);
+      if (K % 8 != 0) {
+        uint8_t mask = static_cast<uint8_t>(0xff00U >> (K % 8));
+        dst[K / 8]   = static_cast<uint8_t>((dst[K / 8] & ~mask) | (src[K / 8] & mask));
+      }
+      if (nof_iterations != nullptr) {
+        nof_iterations[done + i] = res.iters;
+      }
+    }
+    done += n;
+  }
+  return SRSRAN_CUDA_OK;
+}
+
+int srsran_cuda_ldpc_decode(srsran_cuda_pusch_dec_t* h, uint8_t* bits, const int8_t* llrs, uint32_t nof_llrs,
+                            uint32_t base_graph, uint32_t lifting_size, uint32_t nof_filler_bits, uint32_t crc_poly,
+                            uint32_t max_iterations, float scaling_factor, int* nof_iterations)
+{
+  return srsran_cuda_ldpc_decode_batch(h, bits, llrs, 1, nof_llrs, base_graph, lifting_size, nof_filler_bits, crc_poly,
+                                       max_iterations, scaling_factor, nof_iterations);
+}
+
+int srsran_cuda_crc_calculate(srsran_cuda_pusch_dec_t* h, uint32_t crc_poly, const uint8_t* packed, uint32_t nof_bits,
+                              uint32_t* checksum)
+{
+  if (h == nullptr || packed == nullptr || checksum == nullptr || crc_poly < 1 || crc_poly > 3) {
+    return SRSRAN_CUDA_ERR_INVALID;
+  }
+  cudaSetDevice(h->device);
+  size_t nbytes = (nof_bits + 7) / 8;
+  CUDA_TRY(h, h->d_crc_msg.reserve(nbytes + 16));
+  CUDA_TRY(h, h->d_crc_jobs.reserve(1));
+  CUDA_TRY(h, h->d_crc_out.reserve(1));
+  cudaStream_t s = h->ctx[0].stream;
+  crc_job      job{h->d_crc_msg.p, nof_bits, crc_poly};
+  CUDA_TRY(h, cudaMemcpyAsync(h->d_crc_msg.p, packed, nbytes, cudaMemcpyHostToDevice, s));
+  CUDA_TRY(h, cudaMemcpyAsync(h->d_crc_jobs.p, &job, sizeof(job), cudaMemcpyHostToDevice, s));
+  crc_kernel<<<1, CRC_THREADS, 0, s>>>(h->d_crc_jobs.p, h->d_crc_out.p);
+  ++h->launches;
+  CUDA_TRY(h, cudaGetLastError());
+  CUDA_TRY(h, cudaMemcpyAsync(checksum, h->d_crc_out.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(h, cudaStreamSynchronize(s));
+  return SRSRAN_CUDA_OK;
+}
+
+// ---- inspection -----------------------------------------------------------------------------------------------------
+
+int srsran_cuda_pusch_dec_read_softbuffer(srsran_cuda_pusch_dec_t* h, uint32_t absolute_cb_id, int8_t* out, uint32_t N)
+{
+  if (h == nullptr || out == nullptr || absolute_cb_id >= h->nof_slots || N > SOFT_STRIDE) {
+    return SRSRAN_CUDA_ERR_INVALID;
+  }
+  int r = srsran_cuda_pusch_dec_synchronize(h);
+  if (r != SRSRAN_CUDA_OK) {
+    return r;
+  }
+  CUDA_TRY(h, cudaMemcpy(out, h->d_soft.p + static_cast<size_t>(absolute_cb_id) * SOFT_STRIDE, N, cudaMemcpyDeviceToHost));
+  return SRSRAN_CUDA_OK;
+}
+
+int srsran_cuda_pusch_dec_write_softbuffer(srsran_cuda_pusch_dec_t* h, uint32_t absolute_cb_id, const int8_t* in,
+                                           uint32_t N)
+{
+  if (h == nullptr || in == nullptr || absolute_cb_id >= h->nof_slots || N > SOFT_STRIDE) {
+    return SRSRAN_CUDA_ERR_INVALID;
+  }
+  int r = srsran_cuda_pusch_dec_synchronize(h);
+  if (r != SRSRAN_CUDA_OK) {
+    return r;
+  }
+  CUDA_TRY(h, cudaMemcpy(h->d_soft.p + static_cast<size_t>(absolute_cb_id) * SOFT_STRIDE, in, N, cudaMemcpyHostToDevice));
+  h->extent[absolute_cb_id] = std::max(h->extent[absolute_cb_id], N);
+  return SRSRAN_CUDA_OK;
+}
+
+int srsran_cuda_pusch_dec_read_cb_crc(srsran_cuda_pusch_dec_t* h, uint32_t absolute_cb_id, int* crc_ok)
+{
+  if (h == nullptr || crc_ok == nullptr || absolute_cb_id >= h->nof_slots) {
+    return SRSRAN_CUDA_ERR_INVALID;
+  }
+  int r = srsran_cuda_pusch_dec_synchronize(h);
+  if (r != SRSRAN_CUDA_OK) {
+    return r;
+  }
+  uint32_t v = 0;
+  CUDA_TRY(h, cudaMemcpy(&v, h->d_crc_flags.p + absolute_cb_id, sizeof(v), cudaMemcpyDeviceToHost));
+  *crc_ok = v ? 1 : 0;
+  return SRSRAN_CUDA_OK;
+}
+
+} // extern "C"

@@ -1,0 +1,900 @@
+// Hand-written sm_100a kernels of the PUSCH channel-decoding path:
+//   1. rate_dematch_kernel   - fused de-interleave + circular-buffer placement + HARQ soft combining, HBM-resident buffers
+//   2. ldpc_decode_kernel    - batched layered normalized min-sum LDPC decoder with in-kernel CRC early stop
+//   3. tb_assemble_crc_kernel / crc_kernel - transport-block assembly and CRC24A/B/16 by carry-less folding
+//
+// Arithmetic follows the reference's AVX2/AVX-512 flavour bit for bit (see DESIGN.md for the derivations):
+//   rate dematcher : lib/phy/upper/channel_coding/ldpc/ldpc_rate_dematcher_impl.cpp:46-201,
+//                    ldpc_rate_dematcher_avx512_impl.cpp:29-64
+//   LDPC decoder   : lib/phy/upper/channel_coding/ldpc/ldpc_decoder_impl.cpp:60-308, ldpc_decoder_avx512.cpp:81-290,
+//                    avx512_support.h:65-107
+//   CRC            : lib/phy/upper/channel_coding/crc_calculator_lut_impl.cpp:33-38,66-152
+#pragma once
+#include "nr_ldpc_bg_tables.h"
+#include "pusch_dec_types.h"
+#include <cuda_runtime.h>
+
+namespace pusch_dec {
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Constant tables (filled once per device by upload_tables()).
+// ---------------------------------------------------------------------------------------------------------------------
+__constant__ uint16_t c_row_ptr[2][48];
+__constant__ uint8_t  c_col[2][MAX_EDGES];
+__constant__ uint16_t c_shift[2][8][MAX_EDGES];
+/// x^(32 i) mod g, i = 0..271, for CRC24A, CRC24B, CRC16 (index poly - 1).
+__constant__ uint32_t c_xpow32[3][272];
+/// x^(128 i) mod g, i = 0..1023.
+__constant__ uint32_t c_xpow128[3][1024];
+
+__host__ __device__ __forceinline__ uint32_t crc_gen(int poly)
+{
+  return poly == 1 ? 0x1864CFBU : (poly == 2 ? 0x1800063U : 0x11021U);
+}
+__host__ __device__ __forceinline__ uint32_t crc_order(int poly)
+{
+  return poly == 3 ? 16U : 24U;
+}
+
+/// (a(x) * b(x)) mod g over GF(2); a, b of degree < order.
+__host__ __device__ __forceinline__ uint32_t gf2_mulmod(uint32_t a, uint32_t b, uint32_t gen, uint32_t order)
+{
+  uint32_t top = 1U << order;
+  uint32_t acc = 0;
+  for (int i = (int)order - 1; i >= 0; --i) {
+    acc <<= 1;
+    if (acc & top) {
+      acc ^= gen;
+    }
+    if ((b >> i) & 1U) {
+      acc ^= a;
+    }
+  }
+  return acc;
+}
+
+/// Remainder update with `nbits` message bits taken from the top of `word` (MSB first): reg <- (reg * x^nbits + m * x^order) mod g.
+__host__ __device__ __forceinline__ uint32_t crc_push_bits(uint32_t reg, uint32_t word, uint32_t nbits, uint32_t gen,
+                                                           uint32_t order)
+{
+  uint32_t top = 1U << order;
+  for (uint32_t i = 0; i != nbits; ++i) {
+    uint32_t bit = (word >> (31 - i)) & 1U;
+    reg          = (reg << 1) ^ (bit << order);
+    if (reg & top) {
+      reg ^= gen;
+    }
+  }
+  return reg;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Kernel 1: rate dematching + HARQ combining.
+// One CTA per code block. Every thread owns 16-byte chunks of the N-byte soft buffer (aligned 16-byte vector stores);
+// for every byte it derives, in closed form, the ordered list of rate-matched positions that land on it, so the
+// result is independent of scheduling and reproduces the reference's write set exactly (untouched bytes stay untouched).
+// ---------------------------------------------------------------------------------------------------------------------
+struct dm_geom {
+  uint32_t N, Ncb, E, F, info, sys, D, s0, first_len, S, Qm, new_data, zero_head, tail_start, copy_at_end, blk;
+};
+
+__device__ __forceinline__ int llr_add_scalar(int a_new, int b_old)
+{
+  // log_likelihood_ratio::operator+ (lib/phy/upper/log_likelihood_ratio.cpp:39-75), new value tested first.
+  if (a_new == -b_old) {
+    return 0;
+  }
+  if (a_new == 127 || a_new == -127) {
+    return a_new;
+  }
+  if (b_old == 127 || b_old == -127) {
+    return b_old;
+  }
+  return max(-120, min(120, a_new + b_old));
+}
+
+__device__ __forceinline__ int llr_add_simd(int a_new, int b_old)
+{
+  // clamp(adds_epi8(a, b), +-120) (ldpc_rate_dematcher_avx512_impl.cpp:45-58).
+  int s = max(-128, min(127, a_new + b_old));
+  return max(-120, min(120, s));
+}
+
+/// True if position p of the rate-matched stream is combined by the SIMD loop of the reference (the first
+/// floor(n / blk) * blk elements of each contiguous combine call), false if by its scalar tail.
+__device__ __forceinline__ bool dm_simd_rule(const dm_geom& g, uint32_t p)
+{
+  if (g.blk == 0) {
+    return false;
+  }
+  uint32_t start, maxlen;
+  if (p < g.first_len) {
+    uint32_t info_part = (g.s0 < g.info) ? g.info - g.s0 : 0;
+    if (p < info_part) {
+      start  = 0;
+      maxlen = info_part;
+    } else {
+      start  = info_part;
+      maxlen = g.first_len - info_part;
+    }
+  } else {
+    uint32_t rel = p - g.first_len;
+    uint32_t lap = rel / g.D;
+    uint32_t lp  = rel - lap * g.D;
+    if (lp < g.info) {
+      start  = g.first_len + lap * g.D;
+      maxlen = g.info;
+    } else {
+      start  = g.first_len + lap * g.D + g.info;
+      maxlen = g.D - g.info;
+    }
+  }
+  uint32_t len = min(maxlen, g.E - start);
+  return (p - start) < (len / g.blk) * g.blk;
+}
+
+__global__ void __launch_bounds__(256) rate_dematch_kernel(const cb_desc* __restrict__ descs, int8_t* __restrict__ soft_base,
+                                                           uint32_t combine_block)
+{
+  const cb_desc& d = descs[blockIdx.x];
+  if (!(d.flags & FLAG_DEMATCH)) {
+    return;
+  }
+  dm_geom g;
+  g.N        = d.N;
+  g.Ncb      = d.Ncb;
+  g.E        = d.E;
+  g.F        = d.nof_filler;
+  uint32_t Kb = (d.bg == 1) ? 22 : 10;
+  g.sys      = (Kb - 2) * d.Z;
+  g.info     = g.sys - g.F;
+  g.D        = g.info + (g.Ncb - g.sys);
+  uint32_t k0 = d.k0;
+  g.s0        = (k0 < g.info) ? k0 : ((k0 < g.sys) ? g.info : g.info + (k0 - g.sys));
+  g.first_len = g.D - g.s0;
+  g.Qm        = d.Qm ? d.Qm : 1;
+  g.S         = g.E / g.Qm;
+  g.new_data  = d.new_data;
+  g.zero_head = min(k0, g.info);
+  g.copy_at_end = (g.new_data && g.E <= g.first_len) ? 1 : 0;
+  g.blk       = combine_block;
+  g.tail_start = g.N; // none
+  if (g.copy_at_end) {
+    uint32_t end_slot = g.s0 + g.E;
+    uint32_t idx_end  = (end_slot <= g.info) ? g.sys : g.sys + (end_slot - g.info);
+    if (idx_end >= g.Ncb) {
+      idx_end -= g.Ncb;
+    }
+    if (idx_end != 0) {
+      g.tail_start = g.N - (g.Ncb - idx_end);
+    }
+  }
+
+  const int8_t* __restrict__ in  = d.llr;
+  int8_t*                    out = soft_base + (size_t)d.slot * SOFT_STRIDE;
+  uint32_t nchunks = (g.N + 15) / 16;
+
+  for (uint32_t c = threadIdx.x; c < nchunks; c += blockDim.x) {
+    uint32_t i0 = c * 16;
+    // Pass A: classify the chunk (no memory traffic): is any byte modified, and is every byte fully determined without
+    // its old value (copied, zeroed or filler)?
+    bool any_touched = false, all_known = true;
+#pragma unroll
+    for (uint32_t b = 0; b != 16; ++b) {
+      uint32_t i = i0 + b;
+      if (i >= g.N) {
+        break;
+      }
+      bool     is_data = (i < g.info) || (i >= g.sys && i < g.Ncb);
+      uint32_t slot    = (i < g.info) ? i : g.info + (i - g.sys);
+      uint32_t p0      = (slot >= g.s0) ? slot - g.s0 : slot + g.D - g.s0;
+      bool     visited = is_data && (p0 < g.E);
+      bool     known   = g.new_data && ((visited && p0 < g.first_len) || (i < g.zero_head) ||
+                                      (i >= g.info && i < g.sys) || (i >= g.tail_start));
+      any_touched |= (visited || known);
+      all_known &= known;
+    }
+    if (!any_touched) {
+      continue;
+    }
+    uint4 oldv = make_uint4(0, 0, 0, 0);
+    bool  full = (i0 + 16 <= g.N);
+    int8_t vals[16];
+    if (!all_known) {
+      if (full) {
+        oldv = *reinterpret_cast<const uint4*>(out + i0);
+      } else {
+        uint8_t* ob = reinterpret_cast<uint8_t*>(&oldv);
+        for (uint32_t b = 0; i0 + b < g.N; ++b) {
+          ob[b] = (uint8_t)out[i0 + b];
+        }
+      }
+    }
+    {
+      const int8_t* ob = reinterpret_cast<const int8_t*>(&oldv);
+#pragma unroll
+      for (uint32_t b = 0; b != 16; ++b) {
+        vals[b] = ob[b];
+      }
+    }
+    // Pass B: values. (q, r) = (p / S, p % S) carried incrementally along consecutive positions.
+    uint32_t prev_p = 0xfffffffeU, q1 = 0, r1 = 0;
+#pragma unroll 4
+    for (uint32_t b = 0; b != 16; ++b) {
+      uint32_t i = i0 + b;
+      if (i >= g.N) {
+        break;
+      }
+      bool     is_data = (i < g.info) || (i >= g.sys && i < g.Ncb);
+      uint32_t slot    = (i < g.info) ? i : g.info + (i - g.sys);
+      uint32_t p0      = (slot >= g.s0) ? slot - g.s0 : slot + g.D - g.s0;
+      bool     visited = is_data && (p0 < g.E);
+      int      val     = vals[b];
+      if (g.new_data) {
+        if (i < g.zero_head || i >= g.tail_start) {
+          val = 0;
+        } else if (i >= g.info && i < g.sys) {
+          val = 127;
+        }
+      }
+      if (visited) {
+        uint32_t p = p0;
+        bool     first = true;
+        for (; p < g.E; p += g.D) {
+          int x;
+          if (g.Qm > 1) {
+            uint32_t q, r;
+            if (first) {
+              if (p == prev_p + 1) {
+                if (++r1 == g.S) {
+                  r1 = 0;
+                  ++q1;
+                }
+              } else {
+                q1 = p / g.S;
+                r1 = p - q1 * g.S;
+              }
+              prev_p = p;
+              q      = q1;
+              r      = r1;
+            } else {
+              q = p / g.S;
+              r = p - q * g.S;
+            }
+            x = __ldg(in + (size_t)r * g.Qm + q);
+          } else {
+            x = __ldg(in + p);
+          }
+          if (g.new_data && p < g.first_len) {
+            val = x;
+          } else {
+            val = dm_simd_rule(g, p) ? llr_add_simd(x, val) : llr_add_scalar(x, val);
+          }
+          first = false;
+        }
+      }
+      vals[b] = (int8_t)val;
+    }
+    if (full) {
+      uint4 nv;
+      int8_t* nb = reinterpret_cast<int8_t*>(&nv);
+#pragma unroll
+      for (uint32_t b = 0; b != 16; ++b) {
+        nb[b] = vals[b];
+      }
+      *reinterpret_cast<uint4*>(out + i0) = nv;
+    } else {
+      for (uint32_t b = 0; i0 + b < g.N; ++b) {
+        out[i0 + b] = vals[b];
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Kernel 2: batched layered normalized min-sum LDPC decoder.
+//
+// One group of TPC threads per code block (TPC = 32, 64, 128, 256 or 384 >= Z), CBS groups per CTA. Thread j owns lifted
+// check j of every layer. Shared memory per code block:
+//   tab  : per edge of the processed layers, node base (col * Z) and shift (V mod Z)
+//   soft : (K_b + L) * Z int8 a-posteriori LLRs in natural order; the circulant shift is an index rotation
+//   c2v  : one int8 per lifted edge, stored in CHECK order (thread-private column), zero before the first visit so that
+//          v2c = f(soft, 0) = soft reproduces the reference's "row not initialised" copy (ldpc_decoder_impl.cpp:196-200)
+// ---------------------------------------------------------------------------------------------------------------------
+struct dec_smem_layout {
+  uint32_t tab_off, soft_off, c2v_off, misc_off, total;
+};
+
+__host__ __device__ inline dec_smem_layout dec_layout(uint32_t bg, uint32_t Z, uint32_t layer_cap)
+{
+#ifdef __CUDA_ARCH__
+  uint32_t nedges = c_row_ptr[bg - 1][layer_cap];
+#else
+  uint32_t nedges = ((bg == 1) ? NR_BG1_ROW_PTR : NR_BG2_ROW_PTR)[layer_cap];
+#endif
+  uint32_t        Kb = (bg == 1) ? 22 : 10;
+  dec_smem_layout l;
+  l.tab_off  = 0;
+  l.soft_off = (nedges * 4 + 15) & ~15U;
+  l.c2v_off  = l.soft_off + (((Kb + layer_cap) * Z + 15) & ~15U);
+  l.misc_off = l.c2v_off + ((nedges * Z + 15) & ~15U);
+  l.total    = l.misc_off + 64;
+  return l;
+}
+
+template <int TPC>
+__device__ __forceinline__ void group_sync(int group)
+{
+  if (TPC == 32) {
+    __syncwarp();
+  } else {
+    asm volatile("bar.sync %0, %1;" ::"r"(group + 1), "r"(TPC) : "memory");
+  }
+}
+
+/// One layer for one lifted check, degree known at compile time so the v2c messages stay in registers.
+template <int DEG>
+__device__ __forceinline__ void
+process_check(int8_t* __restrict__ soft, int8_t* __restrict__ c2v, const uint32_t* __restrict__ tab, int j, int Z, uint32_t mult)
+{
+  int      pk[DEG];
+  int      m1 = 120, m2 = 120, amin = 0;
+  unsigned sg = 0;
+#pragma unroll
+  for (int e = 0; e != DEG; ++e) {
+    uint32_t te = tab[e];
+    int      k  = j + (int)(te >> 16);
+    k           = (k >= Z) ? k - Z : k;
+    int addr    = (int)(te & 0xffffU) + k;
+    int s       = soft[addr];
+    int c       = c2v[e * Z + j];
+    // compute_var_to_check_msgs (ldpc_decoder_avx512.cpp:81-121): clamp(soft - c2v, +-120); +-infinity is sticky.
+    int x = max(-120, min(120, s - c));
+    x     = (s >= 127) ? 127 : x;
+    x     = (s <= -127) ? -127 : x;
+    pk[e] = (addr << 8) | (x & 0xff);
+    // analyze_var_to_check_msgs (:123-165): min1 / min2 / argmin with strict '<', both minima start at 120.
+    int a = abs(x);
+    sg ^= (unsigned)x;
+    m2   = min(m2, max(m1, a));
+    amin = (a < m1) ? e : amin;
+    m1   = min(m1, a);
+  }
+  // mm512::scale_epi8 (avx512_support.h:65-107): (m * (uint16)(sf * 65536)) >> 16 on magnitudes in [0, 120].
+  int M1 = mult ? (int)(((uint32_t)m1 * mult) >> 16) : m1;
+  int M2 = mult ? (int)(((uint32_t)m2 * mult) >> 16) : m2;
+#pragma unroll
+  for (int e = 0; e != DEG; ++e) {
+    int x    = (int)(int8_t)(pk[e] & 0xff);
+    int addr = pk[e] >> 8;
+    // compute_check_to_var_msgs (:167-216): magnitude excluding self, sign = parity xor own sign (0 counts as +).
+    int mag = (e == amin) ? M2 : M1;
+    int c   = ((int)(sg ^ (unsigned)x) < 0) ? -mag : mag;
+    c2v[e * Z + j] = (int8_t)c;
+    // compute_soft_bits (:218-259): promotion sum; |c| <= 95 is never infinite, an infinite v2c is sticky.
+    int sum = c + x;
+    int r   = (sum > 120) ? 127 : ((sum < -120) ? -127 : sum);
+    r       = (x >= 127) ? 127 : r;
+    r       = (x <= -127) ? -127 : r;
+    soft[addr] = (int8_t)r;
+  }
+}
+
+/// Fallback with a run-time degree (two passes, recomputing v2c); never needed for the 3GPP graphs but kept for safety.
+__device__ __noinline__ void
+process_check_generic(int deg, int8_t* soft, int8_t* c2v, const uint32_t* tab, int j, int Z, uint32_t mult)
+{
+  int      m1 = 120, m2 = 120, amin = 0;
+  unsigned sg = 0;
+  for (int e = 0; e != deg; ++e) {
+    uint32_t te = tab[e];
+    int      k  = j + (int)(te >> 16);
+    k           = (k >= Z) ? k - Z : k;
+    int s       = soft[(int)(te & 0xffffU) + k];
+    int c       = c2v[e * Z + j];
+    int x       = max(-120, min(120, s - c));
+    x           = (s >= 127) ? 127 : x;
+    x           = (s <= -127) ? -127 : x;
+    int a       = abs(x);
+    sg ^= (unsigned)x;
+    m2   = min(m2, max(m1, a));
+    amin = (a < m1) ? e : amin;
+    m1   = min(m1, a);
+  }
+  int M1 = mult ? (int)(((uint32_t)m1 * mult) >> 16) : m1;
+  int M2 = mult ? (int)(((uint32_t)m2 * mult) >> 16) : m2;
+  for (int e = 0; e != deg; ++e) {
+    uint32_t te   = tab[e];
+    int      k    = j + (int)(te >> 16);
+    k             = (k >= Z) ? k - Z : k;
+    int      addr = (int)(te & 0xffffU) + k;
+    int      s    = soft[addr];
+    int      cold = c2v[e * Z + j];
+    int      x    = max(-120, min(120, s - cold));
+    x             = (s >= 127) ? 127 : x;
+    x             = (s <= -127) ? -127 : x;
+    int mag       = (e == amin) ? M2 : M1;
+    int c         = ((int)(sg ^ (unsigned)x) < 0) ? -mag : mag;
+    c2v[e * Z + j] = (int8_t)c;
+    int sum = c + x;
+    int r   = (sum > 120) ? 127 : ((sum < -120) ? -127 : sum);
+    r       = (x >= 127) ? 127 : r;
+    r       = (x <= -127) ? -127 : r;
+    soft[addr] = (int8_t)r;
+  }
+}
+
+/// Hard decision of the first K soft bits (MSB-first, bit = (llr <= 0)), "no zero LLR" test and CRC of the first
+/// K - F bits, cooperatively by the TPC threads of a group. Returns (to every thread of the group) 1 if the CRC is zero
+/// and no LLR is zero. get_hard_bits + hard_decision + crc->calculate (ldpc_decoder_impl.cpp:126-134).
+template <int TPC>
+__device__ __forceinline__ uint32_t hard_decision_crc(const int8_t* soft,
+                                                      uint8_t*      bits_out,
+                                                      uint32_t      K,
+                                                      uint32_t      nb,
+                                                      int           poly,
+                                                      uint32_t*     misc,
+                                                      int           t,
+                                                      int           group)
+{
+  const int      lane   = t & 31;
+  const int      warp   = t >> 5;
+  constexpr int  NW     = TPC / 32;
+  const uint32_t nwords = (K + 31) / 32;
+  const uint32_t gen = crc_gen(poly), order = crc_order(poly);
+  const uint32_t nfull = nb / 32, rem = nb % 32;
+
+  if (t == 0) {
+    misc[0] = 0; // xor of CRC contributions
+    misc[1] = 0; // any zero LLR
+    misc[2] = 0; // partial word
+  }
+  group_sync<TPC>(group);
+
+  uint32_t my_word = 0, my_idx = 0xffffffffU, zero_any = 0;
+  uint32_t slot_in_warp = 0;
+  uint32_t acc = 0;
+  for (uint32_t w = warp; w < nwords; w += NW) {
+    uint32_t idx = w * 32 + lane;
+    int      s   = (idx < K) ? (int)soft[idx] : 1;
+    uint32_t b   = __ballot_sync(0xffffffffU, s <= 0);
+    uint32_t z   = __ballot_sync(0xffffffffU, s == 0);
+    uint32_t word = __brev(b);
+    zero_any |= z;
+    if (lane == 0) {
+      // MSB-first packed bytes, written as one 32-bit store (bits_out is 4-byte aligned, slot stride 1056).
+      reinterpret_cast<uint32_t*>(bits_out)[w] = __byte_perm(word, 0, 0x0123);
+    }
+    if ((uint32_t)lane == (slot_in_warp & 31)) {
+      my_word = word;
+      my_idx  = w;
+    }
+    ++slot_in_warp;
+    if ((slot_in_warp & 31) == 0 || w + NW >= nwords) {
+      // Every lane that holds a word folds it: contribution = (word(x) * x^order mod g) * x^(32 * (nfull - 1 - idx)).
+      if (poly != 0 && my_idx != 0xffffffffU) {
+        if (my_idx < nfull) {
+          uint32_t rr = crc_push_bits(0, my_word, 32, gen, order);
+          acc ^= gf2_mulmod(rr, c_xpow32[poly - 1][nfull - 1 - my_idx], gen, order);
+        } else if (my_idx == nfull && rem != 0) {
+          misc[2] = my_word;
+        }
+      }
+      my_idx = 0xffffffffU;
+    }
+  }
+  if (poly != 0) {
+    acc = __reduce_xor_sync(0xffffffffU, acc);
+    if (lane == 0 && acc != 0) {
+      atomicXor(&misc[0], acc);
+    }
+  }
+  if (lane == 0 && zero_any != 0) {
+    atomicOr(&misc[1], 1U);
+  }
+  group_sync<TPC>(group);
+  uint32_t ok = 0;
+  if (poly != 0) {
+    uint32_t total = misc[0];
+    if (rem != 0) {
+      // total * x^rem + partial bits: continue the division over the last `rem` bits.
+      total = crc_push_bits(total, misc[2], rem, gen, order);
+    }
+    ok = (total == 0 && misc[1] == 0) ? 1U : 0U;
+  }
+  group_sync<TPC>(group);
+  return ok;
+}
+
+template <int TPC, int CBS>
+__global__ void __launch_bounds__(TPC* CBS, (TPC * CBS >= 256) ? 2 : 4) ldpc_decode_kernel(const cb_desc* __restrict__ descs,
+                                                               const uint32_t* __restrict__ order,
+                                                               cb_result* __restrict__ results,
+                                                               const int8_t* __restrict__ soft_base,
+                                                               uint8_t* __restrict__ bits_base,
+                                                               uint32_t* __restrict__ crc_flags,
+                                                               uint32_t nof_cbs,
+                                                               uint32_t smem_per_cb)
+{
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  const int      group = threadIdx.x / TPC;
+  const int      t     = threadIdx.x % TPC;
+  if (blockIdx.x * CBS + group >= nof_cbs) {
+    return;
+  }
+  const uint32_t cb = order[blockIdx.x * CBS + group];
+  const cb_desc& d  = descs[cb];
+  if (!(d.flags & FLAG_DECODE)) {
+    return;
+  }
+  uint8_t* bits_slot = bits_base + (size_t)d.slot * BITS_STRIDE;
+  const uint32_t Z  = d.Z;
+  const uint32_t bg = d.bg;
+  const uint32_t Kb = (bg == 1) ? 22 : 10;
+  const uint32_t K  = Kb * Z;
+
+  // Code blocks whose CRC is already ok are only dematched (pusch_decoder_impl.cpp:335-345).
+  if ((d.flags & FLAG_TRACK_CRC) && !d.new_data && crc_flags[d.slot] != 0) {
+    if (t == 0) {
+      results[cb] = {0, 1U, 0U, 2U};
+    }
+    if (d.bits_out != nullptr) {
+      for (uint32_t i = t; i < (K + 31) / 32; i += TPC) {
+        reinterpret_cast<uint32_t*>(d.bits_out)[i] = reinterpret_cast<const uint32_t*>(bits_slot)[i];
+      }
+    }
+    return;
+  }
+
+  uint8_t*              smem = smem_raw + (size_t)group * smem_per_cb;
+  const dec_smem_layout lay  = dec_layout(bg, Z, d.layer_cap);
+  uint32_t*             tab  = reinterpret_cast<uint32_t*>(smem + lay.tab_off);
+  int8_t*               soft = reinterpret_cast<int8_t*>(smem + lay.soft_off);
+  int8_t*               c2v  = reinterpret_cast<int8_t*>(smem + lay.c2v_off);
+  uint32_t*             misc = reinterpret_cast<uint32_t*>(smem + lay.misc_off);
+
+  // ---- prologue: clear soft + c2v, load the decoder input, find the last non-zero LLR ------------------------------
+  {
+    uint4*   z4 = reinterpret_cast<uint4*>(smem + lay.soft_off);
+    uint32_t n4 = (lay.misc_off - lay.soft_off) / 16;
+    for (uint32_t i = t; i < n4; i += TPC) {
+      z4[i] = make_uint4(0, 0, 0, 0);
+    }
+    if (t < 16) {
+      misc[t] = 0;
+    }
+  }
+  group_sync<TPC>(group);
+
+  const int8_t* src    = (d.flags & FLAG_USE_HARQ) ? soft_base + (size_t)d.slot * SOFT_STRIDE : d.llr;
+  uint32_t      cap_in = (Kb + d.layer_cap) * Z - 2 * Z;
+  uint32_t      n_load = min(min(d.n_in, d.scan_len), cap_in);
+  uint32_t      last   = 0;
+  {
+    int8_t*  dst = soft + 2 * Z;
+    uint32_t nv  = n_load / 16;
+    bool     al  = ((2 * Z) % 4) == 0;
+    for (uint32_t i = t; i < nv; i += TPC) {
+      uint4 v = __ldg(reinterpret_cast<const uint4*>(src) + i);
+      if (v.x | v.y | v.z | v.w) {
+        uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int q = 3; q >= 0; --q) {
+          if (w[q] != 0) {
+            // index of the last non-zero byte (little endian: highest byte = highest index)
+            uint32_t hb = 3 - (__clz(w[q]) >> 3);
+            last        = max(last, i * 16 + q * 4 + hb + 1);
+            break;
+          }
+        }
+        if (al) {
+          uint32_t* d32 = reinterpret_cast<uint32_t*>(dst + i * 16);
+          d32[0] = v.x;
+          d32[1] = v.y;
+          d32[2] = v.z;
+          d32[3] = v.w;
+        } else {
+          const int8_t* vb = reinterpret_cast<const int8_t*>(&v);
+#pragma unroll
+          for (int q = 0; q != 16; ++q) {
+            dst[i * 16 + q] = vb[q];
+          }
+        }
+      }
+    }
+    for (uint32_t i = nv * 16 + t; i < n_load; i += TPC) {
+      int8_t x = src[i];
+      if (x != 0) {
+        dst[i] = x;
+        last   = max(last, i + 1);
+      }
+    }
+    last = __reduce_max_sync(0xffffffffU, last);
+    if ((t & 31) == 0 && last != 0) {
+      atomicMax(&misc[8], last);
+    }
+  }
+  group_sync<TPC>(group);
+  last = misc[8];
+
+  const uint32_t nb      = K - d.nof_filler;
+  const int      poly    = d.crc_poly;
+  const uint32_t mode    = d.mode;
+  int            iters   = -1;
+  uint32_t       crc_ok  = 0;
+  uint32_t       L       = 0;
+  uint32_t       status  = 0;
+
+  if (last == 0) {
+    // All-zero input (ldpc_decoder_impl.cpp:88-94): without a CRC calculator the output becomes all ones.
+    if (mode != MODE_EARLY_STOP) {
+      for (uint32_t i = t; i < K; i += TPC) {
+        soft[i] = -1;
+      }
+      group_sync<TPC>(group);
+      crc_ok = hard_decision_crc<TPC>(soft, bits_slot, K, nb, (mode == MODE_CRC_AT_END) ? poly : 0, misc, t, group);
+      if (mode == MODE_CRC_AT_END && crc_ok) {
+        iters = d.max_it;
+      }
+    }
+  } else {
+    uint32_t cbl = max(last + 2 * Z, K + 4 * Z);
+    cbl          = ((cbl + Z - 1) / Z) * Z;
+    L            = cbl / Z - Kb;
+    if (L > d.layer_cap) {
+      status = 1;
+      L      = 0;
+    }
+    // Edge table of the processed layers.
+    const uint32_t nedges = c_row_ptr[bg - 1][L];
+    for (uint32_t e = t; e < nedges; e += TPC) {
+      uint32_t sh = c_shift[bg - 1][d.ils][e] % Z;
+      tab[e]      = ((uint32_t)c_col[bg - 1][e] * Z) | (sh << 16);
+    }
+    group_sync<TPC>(group);
+
+    const uint32_t mult = d.scale_mult;
+    const int      j    = t;
+    for (uint32_t it = 0; it != d.max_it && L != 0; ++it) {
+      for (uint32_t l = 0; l != L; ++l) {
+        uint32_t e0  = c_row_ptr[bg - 1][l];
+        int      deg = (int)c_row_ptr[bg - 1][l + 1] - (int)e0;
+        if (j < (int)Z) {
+          int8_t*         c2v_row = c2v + (size_t)e0 * Z;
+          const uint32_t* tab_row = tab + e0;
+          switch (deg) {
+            case 3:
+              process_check<3>(soft, c2v_row, tab_row, j, Z, mult);
+              break;
+            case 4:
+              process_check<4>(soft, c2v_row, tab_row, j, Z, mult);
+              break;
+            case 5:
+              process_check<5>(soft, c2v_row, tab_row, j, Z, mult);
+              break;
+            case 6:
+              process_check<6>(soft, c2v_row, tab_row, j, Z, mult);
+              break;
+            case 7:
+              process_check<7>(soft, c2v_row, tab_row, j, Z, mult);
+              break;
+            case 8:
+              process_check<8>(soft, c2v_row, tab_row, j, Z, mult);
+              break;
+            case 9:
+              process_check<9>(soft, c2v_row, tab_row, j, Z, mult);
+              break;
+            case 10:
+              process_check<10>(soft, c2v_row, tab_row, j, Z, mult);
+              break;
+            case 19:
+              process_check<19>(soft, c2v_row, tab_row, j, Z, mult);
+              break;
+            default:
+              process_check_generic(deg, soft, c2v_row, tab_row, j, Z, mult);
+              break;
+          }
+        }
+        group_sync<TPC>(group);
+      }
+      if (mode == MODE_EARLY_STOP) {
+        if (hard_decision_crc<TPC>(soft, bits_slot, K, nb, poly, misc, t, group)) {
+          iters  = (int)it + 1;
+          crc_ok = 1;
+          break;
+        }
+      }
+    }
+    if (status == 0 && mode != MODE_EARLY_STOP) {
+      crc_ok = hard_decision_crc<TPC>(soft, bits_slot, K, nb, (mode == MODE_CRC_AT_END) ? poly : 0, misc, t, group);
+      if (mode == MODE_CRC_AT_END && crc_ok) {
+        iters = d.max_it;
+      }
+    }
+  }
+
+  if (t == 0) {
+    results[cb] = {iters, crc_ok, L, status};
+    if (d.flags & FLAG_TRACK_CRC) {
+      crc_flags[d.slot] = crc_ok;
+    }
+  }
+  if (d.bits_out != nullptr) {
+    // hard_decision_crc ended with a group barrier, so the slot bytes written by lane 0 of each warp are visible
+    // to the group (global memory, same CTA) after a fence.
+    __threadfence_block();
+    group_sync<TPC>(group);
+    for (uint32_t i = t; i < (K + 31) / 32; i += TPC) {
+      reinterpret_cast<uint32_t*>(d.bits_out)[i] = reinterpret_cast<const uint32_t*>(bits_slot)[i];
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Kernel 3: CRC by carry-less folding. One CTA per message. Thread t folds the 16-byte chunks c' = t, t + T, ... counted
+// from the END of the message (so leading zero padding is free), Horner-style across passes; lanes are then aligned with
+// x^(128 t) and XOR-reduced (warp shuffles, then shared memory).
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int CRC_THREADS = 1024;
+
+__device__ __forceinline__ uint32_t block_crc_bytes(const uint8_t* __restrict__ msg, uint32_t nbytes, int poly, uint32_t* lut /*256*/,
+                                                    uint32_t* red /*33*/)
+{
+  const uint32_t gen = crc_gen(poly), order = crc_order(poly);
+  const uint32_t mask = (1U << order) - 1;
+  const int      t    = threadIdx.x;
+  // Byte table: lut[b] = (b(x) * x^order) mod g.
+  if (t < 256) {
+    lut[t] = crc_push_bits(0, (uint32_t)t << 24, 8, gen, order);
+  }
+  if (t < 33) {
+    red[t] = 0;
+  }
+  __syncthreads();
+  const uint32_t nchunks = (nbytes + 15) / 16;
+  const uint32_t npass   = (nchunks + CRC_THREADS - 1) / CRC_THREADS;
+  const uint32_t xpass   = gf2_mulmod(c_xpow128[poly - 1][CRC_THREADS / 2], c_xpow128[poly - 1][CRC_THREADS / 2], gen, order);
+  uint32_t       acc     = 0;
+  bool           any     = false;
+  for (int p = (int)npass - 1; p >= 0; --p) {
+    uint32_t cp = (uint32_t)t + (uint32_t)p * CRC_THREADS; // chunk index from the end
+    if (cp >= nchunks) {
+      continue;
+    }
+    if (any) {
+      acc = gf2_mulmod(acc, xpass, gen, order);
+    }
+    any          = true;
+    long long b0 = (long long)nbytes - 16LL * (cp + 1);
+    uint32_t  r  = 0;
+#pragma unroll
+    for (int i = 0; i != 16; ++i) {
+      long long b    = b0 + i;
+      uint32_t  byte = (b >= 0) ? msg[b] : 0U;
+      r              = ((r << 8) & mask) ^ lut[((r >> (order - 8)) ^ byte) & 0xff];
+    }
+    acc ^= r;
+  }
+  if (any && t != 0) {
+    acc = gf2_mulmod(acc, c_xpow128[poly - 1][t], gen, order);
+  }
+  acc = __reduce_xor_sync(0xffffffffU, acc);
+  if ((t & 31) == 0) {
+    red[t >> 5] = acc;
+  }
+  __syncthreads();
+  if (t < 32) {
+    uint32_t v = red[t];
+    v          = __reduce_xor_sync(0xffffffffU, v);
+    if (t == 0) {
+      red[32] = v;
+    }
+  }
+  __syncthreads();
+  return red[32];
+}
+
+struct crc_job {
+  const uint8_t* msg;
+  uint32_t       nbits;
+  uint32_t       poly;
+};
+
+__global__ void __launch_bounds__(CRC_THREADS) crc_kernel(const crc_job* __restrict__ jobs, uint32_t* __restrict__ out)
+{
+  __shared__ uint32_t lut[256];
+  __shared__ uint32_t red[33];
+  const crc_job       job    = jobs[blockIdx.x];
+  uint32_t            nbytes = job.nbits / 8, rem = job.nbits % 8;
+  uint32_t            crc    = block_crc_bytes(job.msg, nbytes, (int)job.poly, lut, red);
+  if (threadIdx.x == 0) {
+    if (rem != 0) {
+      crc = crc_push_bits(crc, (uint32_t)job.msg[nbytes] << 24, rem, crc_gen((int)job.poly), crc_order((int)job.poly));
+    }
+    out[blockIdx.x] = crc;
+  }
+}
+
+/// TB assembly (pusch_decoder_impl.cpp:384-497): concatenates the payload bits of every code block (dropping CB CRC,
+/// filler and zero padding), then checks CRC24A over TBS + 24 bits. One CTA per TB.
+__global__ void __launch_bounds__(CRC_THREADS) tb_assemble_crc_kernel(const tb_desc* __restrict__ tbs,
+                                                                      tb_result_dev* __restrict__ tb_results,
+                                                                      const uint8_t* __restrict__ bits_base,
+                                                                      uint32_t* __restrict__ crc_flags,
+                                                                      uint8_t* __restrict__ tb_out)
+{
+  __shared__ uint32_t lut[256];
+  __shared__ uint32_t red[33];
+  __shared__ uint32_t all_ok;
+  const tb_desc       tb = tbs[blockIdx.x];
+  const int           t  = threadIdx.x;
+  if (t == 0) {
+    all_ok = 1;
+  }
+  __syncthreads();
+  for (uint32_t i = t; i < tb.nof_cbs; i += CRC_THREADS) {
+    if (crc_flags[tb.first_slot + i] == 0) {
+      all_ok = 0;
+    }
+  }
+  __syncthreads();
+  uint8_t*       out       = tb_out + tb.out_offset;
+  const uint32_t tb_bytes  = tb.tbs_bits / 8;
+  if (tb.nof_cbs == 1) {
+    // The code-block CRC is the TB CRC; copy the payload only if it is ok.
+    if (all_ok) {
+      const uint8_t* src = bits_base + (size_t)tb.first_slot * BITS_STRIDE;
+      for (uint32_t i = t; i < tb_bytes; i += CRC_THREADS) {
+        out[i] = src[i];
+      }
+    }
+    if (t == 0) {
+      tb_results[blockIdx.x] = {all_ok, all_ok};
+    }
+    return;
+  }
+  if (!all_ok) {
+    if (t == 0) {
+      tb_results[blockIdx.x] = {0U, 0U};
+    }
+    return;
+  }
+  // Gather TBS + 24 bits. Output byte b holds TB bits [8b, 8b+8): bit o lives in code block o / Lp at offset o % Lp.
+  const uint32_t Lp     = tb.cb_data_bits;
+  const uint32_t nbytes = tb_bytes + 3;
+  for (uint32_t b = t; b < nbytes; b += CRC_THREADS) {
+    uint32_t o    = 8 * b;
+    uint32_t cb   = o / Lp;
+    uint32_t w    = o - cb * Lp;
+    uint32_t byte = 0;
+    uint32_t got  = 0;
+    while (got < 8) {
+      const uint8_t* src  = bits_base + (size_t)(tb.first_slot + cb) * BITS_STRIDE;
+      uint32_t       take = min(8 - got, Lp - w);
+      // `take` bits starting at bit w of src.
+      uint32_t two = ((uint32_t)src[w >> 3] << 8) | (uint32_t)src[(w >> 3) + 1];
+      uint32_t v   = (two >> (16 - (w & 7) - take)) & ((1U << take) - 1);
+      byte |= v << (8 - got - take);
+      got += take;
+      w += take;
+      if (w == Lp) {
+        w = 0;
+        ++cb;
+      }
+    }
+    out[b] = (uint8_t)byte;
+  }
+  __syncthreads();
+  uint32_t crc = block_crc_bytes(out, nbytes, 1, lut, red);
+  if (t == 0) {
+    tb_results[blockIdx.x] = {crc == 0 ? 1U : 0U, 1U};
+  }
+  if (crc != 0) {
+    // At least one code block is a false positive: reset them all (pusch_decoder_impl.cpp:425-428).
+    for (uint32_t i = t; i < tb.nof_cbs; i += CRC_THREADS) {
+      crc_flags[tb.first_slot + i] = 0;
+    }
+  }
+}
+
+} // namespace pusch_dec
