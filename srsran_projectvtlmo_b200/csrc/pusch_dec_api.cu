@@ -479,7 +479,10 @@ int add_cb(srsran_cuda_pusch_dec* h, batch_context& c, const cb_params& p, const
     h->extent[p.slot] =
         extent_after_dematch(h->extent[p.slot], N, Ncb, d.k0, p.E, sys - p.F, sys, p.new_data != 0);
   }
-  if (p.flags & FLAG_USE_HARQ) {
+  if (!(p.flags & FLAG_DECODE)) {
+    d.n_in     = 0;
+    d.scan_len = 0;
+  } else if (p.flags & FLAG_USE_HARQ) {
     d.n_in     = N;
     d.scan_len = std::min(N, (h->extent[p.slot] + 15) & ~15U);
   } else {

@@ -29,7 +29,7 @@ def acc():
     """One accelerator handle (GPU 0) shared by the GPU tests. Fails loudly if the CUDA library is missing."""
     from srsran_projectvtlmo_b200 import pusch
 
-    a = pusch.Accelerator(device=0, max_cbs_in_flight=4096, nof_harq_cb_slots=2048)
+    a = pusch.Accelerator(device=0, max_cbs_in_flight=4096, nof_harq_cb_slots=8192)
     yield a
     a.close()
 

@@ -186,18 +186,17 @@ TB_CASES = [
 ]
 
 
-def _tb_sequence(acc, rng, prb, qm, R, nl, bg, nref, mu, slot0, early_stop, max_it, rvs=(0, 2, 3, 1)):
+def _tb_sequence(acc, port, rng, prb, qm, R, nl, bg, nref, mu, slot0, early_stop, max_it, rvs=(0, 2, 3, 1)):
     tbs = synth.tbs_for(prb, qm, R, nl)
     nllr = prb * 156 * qm * nl
     tb = rng.integers(0, 256, tbs // 8, dtype=np.uint8)
-    port = ob.PortPusch()
     gdec = pusch.pusch_decoder_cuda(acc)
     metas = pusch.segment(tbs, bg, qm, nl, nllr)
     tb_g = np.zeros(tbs // 8, np.uint8)
     for i, rv in enumerate(rvs):
         cw = synth.encode_tb(tb, bg, rv, qm, nref, nl, nllr)
         llr = awgn_llrs(rng, cw, mu)
-        tb_p, res_p = port.decode(7, tbs // 8, llr, bg, rv, qm, nref, nl, max_it, early_stop, i == 0)
+        tb_p, res_p = port.decode(slot0, tbs // 8, llr, bg, rv, qm, nref, nl, max_it, early_stop, i == 0)
         cfg = pusch.pusch_decoder_configuration(bg, rv, qm, nref, nl, max_it, early_stop, i == 0)
         gdec.new_data(tb_g, slot0, None, cfg)
         gdec.on_new_softbits(llr)
@@ -212,7 +211,7 @@ def _tb_sequence(acc, rng, prb, qm, R, nl, bg, nref, mu, slot0, early_stop, max_
             assert np.array_equal(tb_g, tb_p), key
             assert np.array_equal(tb_g, tb), key
         # Combined soft buffers, byte for byte.
-        hb = C.cast(port.harq[7][0], C.POINTER(ob_harq_struct())).contents
+        hb = C.cast(port.harq[slot0][0], C.POINTER(ob_harq_struct())).contents
         for cb, m in enumerate(metas):
             soft_p = np.ctypeslib.as_array(hb.soft, shape=(len(metas) * 25344,))[cb * 25344:cb * 25344 + m.full_length]
             soft_g = acc.read_softbuffer(slot0 + cb, m.full_length)
@@ -235,11 +234,15 @@ def ob_harq_struct():
 def test_pusch_tb_harq_sequences(acc, case):
     prb, qm, R, nl, bg, nref = case
     rng = np.random.default_rng(prb * 1000 + qm)
-    # Low SNR first (several retransmissions, soft combining), then a clean decode in the same HARQ slots.
-    base = {8: 9.0, 4: 3.5, 2: 1.0}[qm]
-    _tb_sequence(acc, rng, prb, qm, R, nl, bg, nref, base * 0.55, 0, True, 6)
-    _tb_sequence(acc, rng, prb, qm, R, nl, bg, nref, base * 1.6, 0, True, 6)
-    _tb_sequence(acc, rng, prb, qm, R, nl, bg, nref, base * 0.8, 200, False, 4)
+    # Low SNR first (several retransmissions, soft combining), then new TBs in the SAME HARQ slots: the reference never
+    # clears a slot, so the new transmission decodes with the stale LLRs the old one left (SURVEY.md 8(a) trap 3).
+    base = {8: 14.0, 4: 5.0, 2: 1.6}[qm]
+    slot0 = 1000 + 400 * TB_CASES.index(case)  # slots no other test touches: the port starts from the same zeros
+    port = ob.PortPusch()
+    _tb_sequence(acc, port, rng, prb, qm, R, nl, bg, nref, base * 0.55, slot0, True, 6)
+    _tb_sequence(acc, port, rng, prb, qm, R, nl, bg, nref, base * 1.6, slot0, True, 6)
+    _tb_sequence(acc, port, rng, prb, qm, R, nl, bg, nref, base * 0.8, slot0, False, 4)
+    _tb_sequence(acc, port, rng, prb, qm, R, nl, bg, nref, base * 1.0, slot0 + 200, True, 6)
 
 
 def test_pusch_tb_random_llrs_never_converge(acc):
