@@ -1,0 +1,398 @@
+#!/usr/bin/env python3
+"""PUSCH channel-decoding benchmark (BASELINE.json metric: decoded info Gbit/s, BG1 Z=384).
+
+  python bench.py --gpus 1 --steps 10 --warmup 3            our arm (CUDA path through the C ABI)
+  python bench.py --impl reference --steps 3 --warmup 1     the reference's own CPU implementation on the host cores
+  python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...   one rank per GPU, no collective on the
+                                                                                  data path (TBs are independent)
+
+A step = one pass of the hot path (rate dematch + HARQ combine -> layered LDPC -> CB CRC -> TB assembly + CRC24A) over
+one batch of `--tbs-per-step` synthetic transport blocks of BASELINE config 2 (273 PRB, 256QAM, R=948/1024, 4 layers,
+TBS 1 277 992, 152 code blocks BG1 Z=384, Nref 12611, rv0, early stop, <= 6 iterations), encoded by the numpy
+transmitter (srsran_projectvtlmo_b200/synth.py), AWGN LLRs.
+
+One JSON line on stdout (rank 0). `value` = device-resident inputs (LLRs already in HBM), timed with CUDA events on the
+stream the kernels run on; `e2e` = the same through the host-buffer C ABI with H2D/D2H inside the timed region.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+WORKLOAD = {"name": "pusch_273prb_256qam_r948_4layer_rv0", "prb": 273, "qm": 8, "rate": 948, "layers": 4, "bg": 1,
+            "nref": 12611, "max_it": 6, "early_stop": 1}
+BG1_DEG = [19, 19, 19, 19, 3, 8, 9, 7, 10, 9, 7, 8, 7, 6, 7, 7, 6, 6, 6, 6, 6, 6, 5, 5, 6, 5, 5, 4, 5, 5, 5, 5, 5, 5, 5,
+           5, 5, 4, 5, 5, 4, 5, 4, 5, 5, 4]
+
+
+def measured_peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        return d, "MEASURED_PEAKS.json"
+    return {"hbm_gbs": 6650.0, "sm_max_mhz": 1965.0}, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            if len(r) < 7:
+                continue
+            try:
+                sm.append(float(r[0]))
+                smax.append(float(r[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def make_inputs(tbs_per_step, nsets, mu, seed):
+    """`nsets` batches of `tbs_per_step` TBs: a few distinct payloads, an independent noise realisation per TB."""
+    from srsran_projectvtlmo_b200 import synth
+
+    w = WORKLOAD
+    tbs = synth.tbs_for(w["prb"], w["qm"], w["rate"], w["layers"])
+    nllr = w["prb"] * 156 * w["qm"] * w["layers"]
+    rng = np.random.default_rng(seed)
+    payloads, cws = [], []
+    for _ in range(min(4, tbs_per_step)):
+        tb = rng.integers(0, 256, tbs // 8, dtype=np.uint8)
+        payloads.append(tb)
+        cws.append(synth.encode_tb(tb, w["bg"], 0, w["qm"], w["nref"], w["layers"], nllr))
+    sets = []
+    for _ in range(nsets):
+        llrs = np.empty((tbs_per_step, nllr), np.int8)
+        for i in range(tbs_per_step):
+            llrs[i] = synth.awgn_llrs(rng, cws[i % len(cws)], mu)
+        sets.append(llrs)
+    return tbs, nllr, payloads, sets
+
+
+def reference_arm(args, rank, world):
+    """The reference's own CPU implementation of the path on the host cores (oracle/_ref when compiled, else the port)."""
+    if rank != 0:
+        return
+    from oracle import bindings as ob
+
+    w = WORKLOAD
+    tbs, nllr, payloads, sets = make_inputs(1, 1, args.mu, 1234)
+    llr = np.ascontiguousarray(sets[0][0])
+    threads = ob.host_threads()
+    lib = ob.ref()
+    ok = C.c_int(0)
+    if lib is not None and ob.ref_flavour() is not None:
+        kind, flavour = "reference", ob.ref_flavour()
+
+        def run(reps):
+            return lib.ref_pusch_bench_mt(b"auto", threads, tbs // 8, ob._pi(llr), nllr, w["bg"], w["qm"], w["nref"],
+                                          w["layers"], w["max_it"], w["early_stop"], reps, C.byref(ok))
+    else:
+        kind, flavour, threads = "port", "scalar C restatement", 1
+
+        def run(reps):
+            return ob.port().oracle_pusch_bench(tbs // 8, ob._pi(llr), nllr, w["bg"], w["qm"], w["nref"], w["layers"],
+                                                w["max_it"], w["early_stop"], reps, C.byref(ok))
+    t1 = run(1)
+    reps = max(1, int(args.ref_seconds / max(t1, 1e-3)))
+    for _ in range(args.warmup):
+        run(1)
+    times = [run(reps) for _ in range(args.steps)]
+    t = float(np.mean(times))
+    gbps = threads * reps * tbs / t / 1e9
+    line = {
+        "impl": "reference", "metric": "pusch_decoded_info_gbit_per_s", "value": gbps, "unit": "Gbit/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int8", "data": "synthetic",
+        "config": {"workload": w["name"], "tbs_bits": tbs, "codeblocks_per_tb": 152, "mu": args.mu,
+                   "tbs_per_step": threads * reps},
+        "cpu_baseline": {"value": gbps, "unit": "Gbit/s", "cores": threads, "kind": kind,
+                         "sample": f"{threads} threads x {reps} TBs per step, {flavour} decoder/dematcher, all TB CRC ok: "
+                                   f"{ok.value == threads * reps}"},
+        "e2e": {"value": gbps, "unit": "Gbit/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def cpu_baseline(args, tbs, nllr, llr):
+    """Bounded CPU sample on rank 0: the compiled reference on all host threads (kind "reference") or the port."""
+    try:
+        from oracle import bindings as ob
+    except Exception as e:  # pragma: no cover
+        return {"value": None, "unit": "Gbit/s", "cores": 0, "kind": "port", "sample": f"oracle unavailable: {e}"}
+    w = WORKLOAD
+    ok = C.c_int(0)
+    llr = np.ascontiguousarray(llr)
+    lib = ob.ref()
+    if lib is not None and ob.ref_flavour() is not None:
+        threads = ob.host_threads()
+        t1 = lib.ref_pusch_bench_mt(b"auto", threads, tbs // 8, ob._pi(llr), nllr, w["bg"], w["qm"], w["nref"],
+                                    w["layers"], w["max_it"], w["early_stop"], 1, C.byref(ok))
+        reps = max(1, int(args.cpu_seconds / max(t1, 1e-3)))
+        t = lib.ref_pusch_bench_mt(b"auto", threads, tbs // 8, ob._pi(llr), nllr, w["bg"], w["qm"], w["nref"],
+                                   w["layers"], w["max_it"], w["early_stop"], reps, C.byref(ok))
+        t1c = lib.ref_pusch_bench_mt(b"auto", 1, tbs // 8, ob._pi(llr), nllr, w["bg"], w["qm"], w["nref"], w["layers"],
+                                     w["max_it"], w["early_stop"], max(1, reps // 2), C.byref(ok))
+        return {"value": threads * reps * tbs / t / 1e9, "unit": "Gbit/s", "cores": threads, "kind": "reference",
+                "sample": f"{threads} threads x {reps} TBs of the same workload, {ob.ref_flavour()} flavour "
+                          f"({lib.ref_info().decode()})",
+                "single_core_value": max(1, reps // 2) * tbs / t1c / 1e9}
+    t1 = ob.port().oracle_pusch_bench(tbs // 8, ob._pi(llr), nllr, w["bg"], w["qm"], w["nref"], w["layers"], w["max_it"],
+                                      w["early_stop"], 1, C.byref(ok))
+    reps = max(1, int(args.cpu_seconds / max(t1, 1e-3)))
+    t = ob.port().oracle_pusch_bench(tbs // 8, ob._pi(llr), nllr, w["bg"], w["qm"], w["nref"], w["layers"], w["max_it"],
+                                     w["early_stop"], reps, C.byref(ok))
+    return {"value": reps * tbs / t / 1e9, "unit": "Gbit/s", "cores": 1, "kind": "port",
+            "sample": f"1 thread x {reps} TBs of the same workload, scalar C restatement"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--tbs-per-step", type=int, default=64)
+    ap.add_argument("--mu", type=float, default=18.0, help="AWGN operating point of the synthetic LLRs")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--ref-seconds", type=float, default=20.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--latency-reps", type=int, default=200)
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 0)
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        reference_arm(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    from srsran_projectvtlmo_b200 import capi, pusch
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    w = WORKLOAD
+    B = args.tbs_per_step
+    tbs, nllr, payloads, sets = make_inputs(B, 2, args.mu, 1000 + rank)
+    ncb = 152
+    acc = pusch.Accelerator(device=local_rank, max_cbs_in_flight=B * ncb, nof_harq_cb_slots=B * ncb)
+    cfgs = [capi.TbConfig(tbs, w["bg"], 0, w["qm"], w["nref"], w["layers"], w["max_it"], w["early_stop"], 1, i * ncb)
+            for i in range(B)]
+
+    # Device-resident inputs (value leg) and page-locked host inputs (e2e leg).
+    dev_sets = [torch.from_numpy(s).cuda() for s in sets]
+    lib = capi.lib()
+    host_sets = []
+    for s in sets:
+        p = lib.srsran_cuda_pusch_dec_host_alloc(s.size)
+        if not p:
+            raise SystemExit("pinned host allocation failed")
+        buf = np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_int8)), shape=s.shape)
+        buf[...] = s
+        host_sets.append((p, buf))
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+
+    def step_device(i):
+        d = dev_sets[i % 2]
+        lst = [(d[k].data_ptr(), nllr) for k in range(B)]
+        return pusch.submit_tbs(acc, cfgs, lst, device_resident=True)
+
+    def step_host(i):
+        buf = host_sets[i % 2][1]
+        return pusch.submit_tbs(acc, cfgs, [buf[k] for k in range(B)])
+
+    tb_out = np.zeros(tbs // 8, np.uint8)
+
+    def drain(tickets, check=False):
+        ok = 0
+        for t in tickets:
+            r = pusch.poll_tb(acc, t, tb_out)
+            ok += r.tb_crc_ok
+        return ok
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- warm-up + correctness gate: every TB of the warm-up must decode to its payload -------------------------------
+    for i in range(max(args.warmup, 1)):
+        tk = step_device(i)
+        for k, t in enumerate(tk):
+            r = pusch.poll_tb(acc, t, tb_out)
+            if i == 0 and r.tb_crc_ok and not np.array_equal(tb_out, payloads[k % len(payloads)]):
+                raise SystemExit("decoded TB differs from the transmitted payload")
+    for i in range(max(args.warmup, 1)):
+        drain(step_host(i))
+
+    # ---- value: device-resident, CUDA-event timed per stage on the library's stream ------------------------------------
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    launches0 = acc.launch_count
+    stage = np.zeros(5)
+    ok_tbs = 0
+    iters = []
+    for i in range(args.steps):
+        flush.fill_(i & 0xFF)  # L2 flush between timed iterations (256 MiB > 126 MB L2), outside the timed events
+        torch.cuda.synchronize()
+        tk = step_device(i)
+        ms = pusch.ticket_timing(acc, tk[0])
+        stage += np.array(ms)
+        for t in tk:
+            r = pusch.poll_tb(acc, t, None)
+            ok_tbs += r.tb_crc_ok
+            iters.append(r.iter_mean)
+    launches = acc.launch_count - launches0
+    clocks = sampler.stop()
+    barrier()
+    step_ms = float(stage.sum() / args.steps)
+    stage_ms = (stage / args.steps).tolist()
+
+    # ---- e2e: host LLRs in pinned memory, H2D + kernels + D2H of TB bytes and results, two batches in flight ---------
+    barrier()
+    t0 = time.perf_counter()
+    pending = None
+    for i in range(args.steps):
+        tk = step_host(i)
+        if pending is not None:
+            drain(pending)
+        pending = tk
+    drain(pending)
+    acc.synchronize()
+    e2e_s = time.perf_counter() - t0
+    barrier()
+
+    # ---- single-TB latency through the host API on an otherwise idle GPU ---------------------------------------------
+    lat = []
+    one = host_sets[0][1][0]
+    for i in range(args.latency_reps):
+        t1 = time.perf_counter()
+        tk = pusch.submit_tbs(acc, cfgs[:1], [one])
+        pusch.poll_tb(acc, tk[0], tb_out)
+        lat.append((time.perf_counter() - t1) * 1e6)
+    lat = np.array(lat[10:]) if len(lat) > 20 else np.array(lat)
+
+    # ---- max over ranks ------------------------------------------------------------------------------------------------
+    red = torch.tensor([step_ms, e2e_s], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(red, op=dist.ReduceOp.MAX)
+    step_ms_max, e2e_s_max = float(red[0]), float(red[1])
+    n_gpus = world
+    value = n_gpus * B * tbs / (step_ms_max * 1e-3) / 1e9
+    e2e = n_gpus * B * tbs * args.steps / e2e_s_max / 1e9
+
+    if rank == 0:
+        peaks, peak_src = measured_peaks()
+        mean_it = float(np.mean(iters)) if iters else 0.0
+        # Algorithmic work of the decoder: edge updates U = iterations * Z * sum(deg of processed layers),
+        # 4 bytes of shared-memory traffic per edge update. Layers processed here: 4 (E = 8960/8992 <= 8976 + ...).
+        edges = sum(BG1_DEG[:4])
+        U = mean_it * 384 * edges * ncb * B
+        dec_s = stage_ms[2] * 1e-3
+        sm_clk = (clocks.get("sm_mhz") or peaks.get("sm_max_mhz", 1965.0)) * 1e6
+        smem_peak = 128.0 * 148 * sm_clk / 1e9
+        smem_ach = 4.0 * U / dec_s / 1e9 if dec_s > 0 else 0.0
+        # Dematch: read E, write the reference's write set W = 12611 bytes per code block.
+        dm_bytes = B * (nllr + ncb * 12611)
+        dm_s = stage_ms[1] * 1e-3
+        hbm_ach = dm_bytes / dm_s / 1e9 if dm_s > 0 else 0.0
+        line = {
+            "metric": "pusch_decoded_info_gbit_per_s", "value": value, "unit": "Gbit/s", "n_gpus": n_gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_ms_max, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "int8", "data": "synthetic",
+            "config": {"workload": w["name"], "tbs_bits": tbs, "codeblocks_per_tb": ncb, "tbs_per_step_per_gpu": B,
+                       "lifting_size": 384, "base_graph": 1, "max_iterations": w["max_it"], "early_stop": True,
+                       "mu": args.mu, "mean_iterations": mean_it, "tb_crc_ok_fraction": ok_tbs / (B * args.steps),
+                       "timing": "CUDA events per stage on the library stream; L2 flushed (256 MiB write) between steps"},
+            "e2e": {"value": e2e, "unit": "Gbit/s", "h2d_bytes_per_step": B * nllr,
+                    "d2h_bytes_per_step": B * (tbs // 8 + 3 + 8 + ncb * 16),
+                    "note": "pinned host LLRs -> submit_tbs -> poll_tb (TB bytes + results), 2 batches in flight, wall clock"},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "stage_ms": {"h2d_descriptors": stage_ms[0], "rate_dematch": stage_ms[1], "ldpc_decode": stage_ms[2],
+                         "tb_assemble_crc": stage_ms[3], "d2h_results": stage_ms[4]},
+            "roofline": {"kernel": "ldpc_decode_kernel", "bound": "smem", "achieved": smem_ach, "peak": smem_peak,
+                         "unit": "GB/s", "frac": smem_ach / smem_peak if smem_peak else None, "traffic": None,
+                         "peak_source": "128 B/clk/SM x 148 SMs x SM clock sampled during the run (B300_MICROARCH.md: "
+                                        "smem crossbar 128 B/cyc/SM)",
+                         "algorithmic": f"4 B per edge update, U = {mean_it:.2f} it x 384 x {edges} edges x {ncb * B} CBs",
+                         "share_of_step": stage_ms[2] / step_ms if step_ms else None},
+            "roofline_dematch": {"kernel": "rate_dematch_kernel", "bound": "hbm", "achieved": hbm_ach,
+                                 "peak": peaks.get("hbm_gbs"), "unit": "GB/s",
+                                 "frac": hbm_ach / peaks["hbm_gbs"] if peaks.get("hbm_gbs") else None, "traffic": None,
+                                 "peak_source": peak_src, "algorithmic": "E + 12611 B per code block"},
+            "tb_latency_us": {"p50": float(np.percentile(lat, 50)), "p99": float(np.percentile(lat, 99)),
+                              "max": float(lat.max()), "n": int(lat.size),
+                              "what": "one TB, host LLRs -> TB bytes, idle GPU, wall clock; slot budget 500 us"},
+        }
+        if n_gpus == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline(args, tbs, nllr, sets[0][0])
+        print(json.dumps(line), flush=True)
+
+    for p, _ in host_sets:
+        lib.srsran_cuda_pusch_dec_host_free(p)
+    acc.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -177,6 +177,10 @@ int srsran_cuda_pusch_dec_submit_tbs_device(srsran_cuda_pusch_dec_t* handle, uin
 int srsran_cuda_pusch_dec_submit_tbs(srsran_cuda_pusch_dec_t* handle, uint32_t nof_tbs,
                                      const srsran_cuda_pusch_dec_tb_config* configs, const int8_t* const* llrs,
                                      const uint32_t* nof_llrs, int* tickets);
+/* Device-side duration (CUDA events on the stream the batch ran on) of the five stages of the batch a ticket belongs
+ * to, in milliseconds: [0] host->device copies, [1] rate-dematch kernel, [2] LDPC decode kernels, [3] TB assembly + CRC
+ * kernel, [4] device->host copies. Waits for the batch to complete. Used by the benchmark's roofline accounting. */
+int srsran_cuda_pusch_dec_ticket_timing(srsran_cuda_pusch_dec_t* handle, int ticket, float* stage_ms);
 /* Blocks until everything submitted on this handle has completed. */
 int srsran_cuda_pusch_dec_synchronize(srsran_cuda_pusch_dec_t* handle);
 

@@ -95,6 +95,7 @@ struct batch_context {
   cudaStream_t stream     = nullptr;
   cudaEvent_t  done       = nullptr; // everything (incl. D2H) complete
   cudaEvent_t  kernels    = nullptr; // kernels complete (HARQ ordering between contexts)
+  cudaEvent_t  stage[4]   = {nullptr, nullptr, nullptr, nullptr}; // begin, copies in, dematch done, decode done
   bool         open       = false;   // accepting operations, not launched
   bool         in_flight  = false;   // launched, results not yet consumed
   uint32_t     generation = 0;
@@ -516,6 +517,7 @@ int launch_context(srsran_cuda_pusch_dec* h, int ci)
     return SRSRAN_CUDA_OK;
   }
   // 1. Host -> device: LLRs (direct from pinned caller memory when possible), descriptors.
+  CUDA_TRY(h, cudaEventRecord(c.stage[0], s));
   for (const batch_context::copy_job& j : c.copies) {
     const int8_t* src = (j.src != nullptr) ? j.src : c.h_llr.p + j.dst_off;
     CUDA_TRY(h, cudaMemcpyAsync(c.d_llr.p + j.dst_off, src, j.bytes, cudaMemcpyHostToDevice, s));
@@ -581,11 +583,13 @@ int launch_context(srsran_cuda_pusch_dec* h, int ci)
     CUDA_TRY(h, cudaStreamWaitEvent(s, h->ctx[h->last_launched].kernels, 0));
   }
   // 4. Kernels.
+  CUDA_TRY(h, cudaEventRecord(c.stage[1], s));
   if (any_dematch) {
     rate_dematch_kernel<<<ncb, 256, 0, s>>>(c.d_desc.p, h->d_soft.p, h->combine_block);
     ++h->launches;
     CUDA_TRY(h, cudaGetLastError());
   }
+  CUDA_TRY(h, cudaEventRecord(c.stage[2], s));
   pos = 0;
   for (klass& k : classes) {
     uint32_t        n   = static_cast<uint32_t>(k.idx.size());
@@ -611,6 +615,7 @@ int launch_context(srsran_cuda_pusch_dec* h, int ci)
     CUDA_TRY(h, e);
     pos += n;
   }
+  CUDA_TRY(h, cudaEventRecord(c.stage[3], s));
   if (ntb != 0) {
     tb_assemble_crc_kernel<<<ntb, CRC_THREADS, 0, s>>>(c.d_tb.p, c.d_tbres.p, h->d_bits.p, h->d_crc_flags.p, c.d_tbout.p);
     ++h->launches;
@@ -833,9 +838,12 @@ int srsran_cuda_pusch_dec_create(int device, uint32_t max_cbs_in_flight, uint32_
   }
   h->extent.assign(nof_harq_cb_slots + 1, 0);
   for (batch_context& c : h->ctx) {
-    if (cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaEventCreateWithFlags(&c.done, cudaEventDisableTiming) != cudaSuccess ||
-        cudaEventCreateWithFlags(&c.kernels, cudaEventDisableTiming) != cudaSuccess) {
+    bool ok = cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking) == cudaSuccess &&
+              cudaEventCreate(&c.done) == cudaSuccess && cudaEventCreate(&c.kernels) == cudaSuccess;
+    for (cudaEvent_t& e : c.stage) {
+      ok = ok && cudaEventCreate(&e) == cudaSuccess;
+    }
+    if (!ok) {
       h->last_error = "stream / event creation failed";
       return fail(SRSRAN_CUDA_ERR_CUDA);
     }
@@ -878,6 +886,11 @@ void srsran_cuda_pusch_dec_destroy(srsran_cuda_pusch_dec_t* h)
     }
     if (c.kernels != nullptr) {
       cudaEventDestroy(c.kernels);
+    }
+    for (cudaEvent_t e : c.stage) {
+      if (e != nullptr) {
+        cudaEventDestroy(e);
+      }
     }
     if (c.stream != nullptr) {
       cudaStreamDestroy(c.stream);
@@ -1282,6 +1295,27 @@ int srsran_cuda_pusch_dec_poll_tb(srsran_cuda_pusch_dec_t* h, int ticket, int bl
   }
   m.polled = true;
   return 1;
+}
+
+int srsran_cuda_pusch_dec_ticket_timing(srsran_cuda_pusch_dec_t* h, int ticket, float* stage_ms)
+{
+  if (h == nullptr || ticket < 0 || stage_ms == nullptr) {
+    return SRSRAN_CUDA_ERR_INVALID;
+  }
+  int      ci  = (ticket >> 16) & 0xf;
+  uint32_t gen = (static_cast<uint32_t>(ticket) >> 20) & 0x3ff;
+  if (ci >= NOF_CONTEXTS || (h->ctx[ci].generation & 0x3ff) != gen) {
+    h->last_error = "stale or unknown ticket";
+    return SRSRAN_CUDA_ERR_STATE;
+  }
+  batch_context& c = h->ctx[ci];
+  cudaSetDevice(h->device);
+  CUDA_TRY(h, cudaEventSynchronize(c.done));
+  cudaEvent_t ev[6] = {c.stage[0], c.stage[1], c.stage[2], c.stage[3], c.kernels, c.done};
+  for (int i = 0; i != 5; ++i) {
+    CUDA_TRY(h, cudaEventElapsedTime(&stage_ms[i], ev[i], ev[i + 1]));
+  }
+  return SRSRAN_CUDA_OK;
 }
 
 int srsran_cuda_pusch_dec_synchronize(srsran_cuda_pusch_dec_t* h)

@@ -290,3 +290,10 @@ def poll_tb(acc: Accelerator, ticket, tb_out=None, block=True):
     st = acc._lib.srsran_cuda_pusch_dec_poll_tb(acc.h, ticket, int(block), p, C.byref(res))
     acc._check(st, "poll_tb")
     return (res if st == 1 else None)
+
+
+def ticket_timing(acc: Accelerator, ticket):
+    """Device-side stage durations [h2d, dematch, decode, tb_crc, d2h] in ms of the batch `ticket` belongs to."""
+    ms = (C.c_float * 5)()
+    acc._check(acc._lib.srsran_cuda_pusch_dec_ticket_timing(acc.h, ticket, ms), "ticket_timing")
+    return [float(v) for v in ms]
