@@ -116,6 +116,11 @@ uint64_t srsran_cuda_pusch_dec_launch_count(const srsran_cuda_pusch_dec_t* handl
  * identically in all flavours): 64 = AVX-512 (default; ldpc_rate_dematcher_avx512_impl.cpp:29-64), 32 = AVX2
  * (ldpc_rate_dematcher_avx2_impl.cpp), 0 = generic (ldpc_rate_dematcher_impl.cpp:116-126). */
 int srsran_cuda_pusch_dec_set_combine_flavour(srsran_cuda_pusch_dec_t* handle, uint32_t simd_block);
+/* Selects the LDPC decoder kernel: 0 (default) = automatic - groups of four same-shape code blocks with few layers
+ * (high-rate PUSCH, Z >= 144) run on the packed kernel (four code blocks per CTA, 16-bit SIMD lanes), the rest on the
+ * one-code-block-per-CTA kernel; 1 = one-code-block-per-CTA kernel only. Results are identical (both are bit-exact to
+ * the reference, ldpc_decoder_avx512.cpp); the switch exists for A/B measurements. */
+int srsran_cuda_pusch_dec_set_decoder_variant(srsran_cuda_pusch_dec_t* handle, uint32_t variant);
 /* Page-locked host memory for LLR buffers (what pusch_decoder_buffer::get_next_block_view hands to the demodulator,
  * include/srsran/phy/upper/channel_processors/pusch/pusch_decoder_buffer.h:47): LLRs passed from such memory are copied
  * to the device without an intermediate staging copy. */

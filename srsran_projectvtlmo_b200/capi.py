@@ -56,6 +56,7 @@ SYMBOLS = {
     "srsran_cuda_pusch_dec_last_error": (C.c_char_p, [C.c_void_p]),
     "srsran_cuda_pusch_dec_launch_count": (C.c_uint64, [C.c_void_p]),
     "srsran_cuda_pusch_dec_set_combine_flavour": (C.c_int, [C.c_void_p, C.c_uint32]),
+    "srsran_cuda_pusch_dec_set_decoder_variant": (C.c_int, [C.c_void_p, C.c_uint32]),
     "srsran_cuda_pusch_dec_host_alloc": (C.c_void_p, [C.c_size_t]),
     "srsran_cuda_pusch_dec_host_free": (None, [C.c_void_p]),
     "srsran_cuda_pusch_dec_reserve_queue": (C.c_int, [C.c_void_p]),

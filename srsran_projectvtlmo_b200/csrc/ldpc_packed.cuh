@@ -1,0 +1,376 @@
+// Kernel 2b: packed layered LDPC decoder - FOUR code blocks per CTA, one thread per lifted check, the four code blocks
+// in the 16-bit lanes of two registers (arithmetic: ldpc_packed_math.h, verified on the CPU against the oracle by
+// tests/test_packed_math_cpu.py). Used for groups of code blocks that share base graph, lifting size (Z >= 144,
+// Z % 16 == 0), CRC, mode, iteration limit and scaling, whose state fits in shared memory - i.e. the high-rate PUSCH
+// transport blocks of BASELINE config 2 (BG1, Z = 384, 4 layers). Everything else runs on ldpc_decode_kernel.
+//
+// The number of layers is NOT derived from the data here (ldpc_decoder_impl.cpp:86-114 trims trailing zero LLRs): the
+// host's upper bound (layer_cap) is processed, because a layer whose extension node holds only zero LLRs is a no-op
+// for every other node (min1 = 0 => all its messages are 0, soft' = clamp(soft - 0) + 0), see DESIGN.md.
+//
+// Shared memory per CTA:  tab   per edge: node base | shift << 16
+//                         soft  (K_b + L) * Z x 8 bytes: 4 biased u16 lanes per variable node lift
+//                         c2v   edges * Z x 4 bytes: 4 biased u8 lanes per lifted edge, check order (thread-private)
+//                         hb    4 x K/32 words of hard decisions, crc tables 4 x 256 words, misc
+#pragma once
+#include "ldpc_packed_math.h"
+
+namespace pusch_dec {
+
+struct grp_desc {
+  uint32_t cb[4];     ///< indices into the batch's cb_desc array
+  uint32_t n;         ///< number of valid entries (1..4)
+  uint32_t layer_cap; ///< layers processed (max over the members' bounds)
+  uint32_t pad[2];
+};
+
+struct dec4_layout {
+  uint32_t tab_off, soft_off, c2v_off, hb_off, crc_off, misc_off, total;
+};
+
+__host__ __device__ inline dec4_layout dec4_smem_layout(uint32_t bg, uint32_t Z, uint32_t layer_cap)
+{
+#ifdef __CUDA_ARCH__
+  uint32_t nedges = c_row_ptr[bg - 1][layer_cap];
+#else
+  uint32_t nedges = ((bg == 1) ? NR_BG1_ROW_PTR : NR_BG2_ROW_PTR)[layer_cap];
+#endif
+  uint32_t    Kb = (bg == 1) ? 22 : 10;
+  dec4_layout l;
+  l.tab_off  = 0;
+  l.soft_off = (nedges * 4 + 15) & ~15U;
+  l.c2v_off  = l.soft_off + (Kb + layer_cap) * Z * 8;
+  l.hb_off   = l.c2v_off + nedges * Z * 4;
+  l.crc_off  = l.hb_off + 4 * (Kb * Z / 32) * 4;
+  l.misc_off = l.crc_off + 4 * 256 * 4;
+  l.total    = l.misc_off + 128;
+  return l;
+}
+
+template <int DEG>
+__device__ __forceinline__ void
+process_check4(uint2* __restrict__ soft, uint32_t* __restrict__ c2v_row, const uint32_t* __restrict__ tab_row, int j, int Z, uint32_t mult)
+{
+  pk::check4<DEG> ck;
+  int             addr[DEG];
+  ck.begin();
+#pragma unroll
+  for (int e = 0; e != DEG; ++e) {
+    uint32_t te = tab_row[e];
+    int      k  = j + (int)(te >> 16);
+    k           = (k >= Z) ? k - Z : k;
+    addr[e]     = (int)(te & 0xffffU) + k;
+    uint2 s     = soft[addr[e]];
+    ck.gather(e, s.x, s.y, c2v_row[e * Z + j]);
+  }
+  ck.reduce(mult);
+#pragma unroll
+  for (int e = 0; e != DEG; ++e) {
+    uint32_t s0, s1;
+    c2v_row[e * Z + j] = ck.scatter(e, s0, s1);
+    soft[addr[e]]      = make_uint2(s0, s1);
+  }
+}
+
+/// CRC of the first nb bits of hb (MSB-first 32-bit words) by ONE warp. tabs[k][b] = (b(x) x^(8k) x^order) mod g.
+__device__ __forceinline__ uint32_t warp_crc_words(const uint32_t* hb, uint32_t nb, int poly, const uint32_t* tabs, int lane)
+{
+  const uint32_t gen = crc_gen(poly), order = crc_order(poly);
+  const uint32_t nfull = nb / 32, rem = nb % 32;
+  const uint32_t per   = (nfull + 31) / 32;
+  uint32_t       w0 = min(nfull, (uint32_t)lane * per), w1 = min(nfull, w0 + per);
+  uint32_t       acc = 0;
+  const uint32_t sh  = (32 - order) / 8; // tables that multiply a register byte by x^32
+  for (uint32_t w = w0; w < w1; ++w) {
+    uint32_t word = hb[w];
+    uint32_t r    = tabs[3 * 256 + (word >> 24)] ^ tabs[2 * 256 + ((word >> 16) & 0xff)] ^ tabs[256 + ((word >> 8) & 0xff)] ^
+                 tabs[word & 0xff];
+    uint32_t m = tabs[sh * 256 + (acc & 0xff)] ^ tabs[(sh + 1) * 256 + ((acc >> 8) & 0xff)];
+    if (order == 24) {
+      m ^= tabs[(sh + 2) * 256 + (acc >> 16)];
+    }
+    acc = m ^ r;
+  }
+  if (w1 > w0 && w1 != nfull) {
+    acc = gf2_mulmod(acc, c_xpow32[poly - 1][nfull - w1], gen, order);
+  }
+  acc = __reduce_xor_sync(0xffffffffU, acc);
+  if (rem != 0) {
+    acc = crc_push_bits(acc, hb[nfull], rem, gen, order);
+  }
+  return acc;
+}
+
+template <int TPC>
+__global__ void __launch_bounds__(TPC, 1) ldpc_decode4_kernel(const cb_desc* __restrict__ descs,
+                                                               const grp_desc* __restrict__ groups,
+                                                               cb_result* __restrict__ results,
+                                                               const int8_t* __restrict__ soft_base,
+                                                               uint8_t* __restrict__ bits_base,
+                                                               uint32_t* __restrict__ crc_flags)
+{
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  const int      t    = threadIdx.x;
+  const int      lane = t & 31;
+  const int      warp = t >> 5;
+  constexpr int  NW   = TPC / 32;
+  const grp_desc g    = groups[blockIdx.x];
+  const cb_desc& d0   = descs[g.cb[0]];
+  const uint32_t Z = d0.Z, bg = d0.bg, Kb = (bg == 1) ? 22 : 10, K = Kb * Z, L = g.layer_cap;
+  const uint32_t mode = d0.mode, max_it = d0.max_it, mult = d0.scale_mult;
+  const int      poly = d0.crc_poly;
+  const uint32_t HBW  = K / 32;
+
+  const dec4_layout lay  = dec4_smem_layout(bg, Z, L);
+  uint32_t*         tab  = reinterpret_cast<uint32_t*>(smem_raw + lay.tab_off);
+  uint2*            soft = reinterpret_cast<uint2*>(smem_raw + lay.soft_off);
+  uint32_t*         c2v  = reinterpret_cast<uint32_t*>(smem_raw + lay.c2v_off);
+  uint32_t*         hb   = reinterpret_cast<uint32_t*>(smem_raw + lay.hb_off);
+  uint32_t*         tabs = reinterpret_cast<uint32_t*>(smem_raw + lay.crc_off);
+  uint32_t*         misc = reinterpret_cast<uint32_t*>(smem_raw + lay.misc_off);
+  // misc: [0..3] any non-zero input, [4..7] any zero soft bit, [8..11] crc ok of this round
+
+  // ---- per-lane (code block) setup: uniform across the CTA ---------------------------------------------------------------
+  const int8_t* src[4];
+  uint32_t      n_load[4], nbits[4], cbi[4];
+  bool          live[4]; // takes part in decoding (valid, not skipped)
+  const uint32_t cap_in = (Kb + L) * Z - 2 * Z;
+#pragma unroll
+  for (int c = 0; c != 4; ++c) {
+    cbi[c]  = g.cb[c < (int)g.n ? c : 0];
+    live[c] = c < (int)g.n;
+    const cb_desc& d = descs[cbi[c]];
+    src[c]    = soft_base + (size_t)d.slot * SOFT_STRIDE;
+    n_load[c] = live[c] ? min(min(d.n_in, d.scan_len), cap_in) : 0U;
+    nbits[c]  = K - d.nof_filler;
+    if (live[c] && (d.flags & FLAG_TRACK_CRC) && !d.new_data && crc_flags[d.slot] != 0) {
+      // Already decoded in an earlier transmission: only dematched (pusch_decoder_impl.cpp:335-345).
+      live[c]   = false;
+      n_load[c] = 0;
+      if (t == 0) {
+        results[cbi[c]] = {0, 1U, 0U, 2U};
+      }
+      if (d.bits_out != nullptr) {
+        const uint32_t* from = reinterpret_cast<const uint32_t*>(bits_base + (size_t)d.slot * BITS_STRIDE);
+        for (uint32_t i = t; i < HBW; i += TPC) {
+          reinterpret_cast<uint32_t*>(d.bits_out)[i] = from[i];
+        }
+      }
+    }
+  }
+
+  // ---- prologue ----------------------------------------------------------------------------------------------------------
+  const uint32_t nedges = c_row_ptr[bg - 1][L];
+  for (uint32_t e = t; e < nedges; e += TPC) {
+    uint32_t sh = c_shift[bg - 1][d0.ils][e] % Z;
+    tab[e]      = ((uint32_t)c_col[bg - 1][e] * Z) | (sh << 16);
+  }
+  {
+    uint4*         c4 = reinterpret_cast<uint4*>(c2v);
+    const uint32_t n4 = nedges * Z / 4;
+    const uint4    zz = make_uint4(pk::C2V_ZERO4, pk::C2V_ZERO4, pk::C2V_ZERO4, pk::C2V_ZERO4);
+    for (uint32_t i = t; i < n4; i += TPC) {
+      c4[i] = zz;
+    }
+  }
+  if (poly != 0) {
+    const uint32_t gen = crc_gen(poly), order = crc_order(poly);
+    for (uint32_t i = t; i < 1024; i += TPC) {
+      // (b(x) x^(8k) x^order) mod g, k = i / 256: push the byte followed by k zero bytes.
+      uint32_t r = crc_push_bits(0, (i & 0xffU) << 24, 8, gen, order);
+      r          = crc_push_bits(r, 0, 8 * (i >> 8), gen, order);
+      tabs[i]    = r;
+    }
+  }
+  if (t < 32) {
+    misc[t] = 0;
+  }
+  __syncthreads();
+  {
+    const uint32_t nq    = (Kb + L) * Z / 4; // quads of variable nodes
+    const uint32_t punct = 2 * Z / 4;
+    uint32_t       nz[4] = {0, 0, 0, 0};
+    for (uint32_t v = t; v < nq; v += TPC) {
+      uint32_t w[4] = {0, 0, 0, 0};
+      if (v >= punct) {
+        uint32_t p = (v - punct) * 4;
+#pragma unroll
+        for (int c = 0; c != 4; ++c) {
+          if (p < n_load[c]) {
+            w[c] = __ldg(reinterpret_cast<const uint32_t*>(src[c] + p));
+          }
+          nz[c] |= w[c];
+        }
+      }
+#pragma unroll
+      for (int c = 0; c != 4; ++c) {
+        w[c] ^= 0x80808080U;
+      }
+#pragma unroll
+      for (int b = 0; b != 4; ++b) {
+        uint32_t selb = (uint32_t)b * 0x11U + 0x4400U + (uint32_t)b * 0x1100U; // byte b of x -> bytes 0,1; of y -> 2,3
+        uint32_t r0   = __byte_perm(w[0], w[2], selb) & 0x00ff00ffU;
+        uint32_t r1   = __byte_perm(w[1], w[3], selb) & 0x00ff00ffU;
+        soft[v * 4 + b] = make_uint2(pk::soft_from_biased_bytes(r0), pk::soft_from_biased_bytes(r1));
+      }
+    }
+#pragma unroll
+    for (int c = 0; c != 4; ++c) {
+      uint32_t any = __reduce_or_sync(0xffffffffU, nz[c]);
+      if (lane == 0 && any != 0) {
+        atomicOr(&misc[c], 1U);
+      }
+    }
+  }
+  __syncthreads();
+  bool allzero[4];
+#pragma unroll
+  for (int c = 0; c != 4; ++c) {
+    allzero[c] = (misc[c] == 0);
+  }
+
+  // ---- iterations --------------------------------------------------------------------------------------------------------
+  int      iters[4]  = {-1, -1, -1, -1};
+  uint32_t crc_ok[4] = {0, 0, 0, 0};
+  bool     done[4];
+#pragma unroll
+  for (int c = 0; c != 4; ++c) {
+    // All-zero input with early stop: the reference returns before touching the output (ldpc_decoder_impl.cpp:88-94).
+    done[c] = !live[c] || (allzero[c] && mode == MODE_EARLY_STOP);
+  }
+  const int j = t;
+  for (uint32_t it = 0; it != max_it; ++it) {
+    for (uint32_t l = 0; l != L; ++l) {
+      uint32_t e0  = c_row_ptr[bg - 1][l];
+      int      deg = (int)c_row_ptr[bg - 1][l + 1] - (int)e0;
+      if (j < (int)Z) {
+        uint32_t*       c2v_row = c2v + (size_t)e0 * Z;
+        const uint32_t* tab_row = tab + e0;
+        switch (deg) {
+          case 3:
+            process_check4<3>(soft, c2v_row, tab_row, j, Z, mult);
+            break;
+          case 4:
+            process_check4<4>(soft, c2v_row, tab_row, j, Z, mult);
+            break;
+          case 5:
+            process_check4<5>(soft, c2v_row, tab_row, j, Z, mult);
+            break;
+          case 6:
+            process_check4<6>(soft, c2v_row, tab_row, j, Z, mult);
+            break;
+          case 7:
+            process_check4<7>(soft, c2v_row, tab_row, j, Z, mult);
+            break;
+          case 8:
+            process_check4<8>(soft, c2v_row, tab_row, j, Z, mult);
+            break;
+          case 9:
+            process_check4<9>(soft, c2v_row, tab_row, j, Z, mult);
+            break;
+          case 10:
+            process_check4<10>(soft, c2v_row, tab_row, j, Z, mult);
+            break;
+          default:
+            process_check4<19>(soft, c2v_row, tab_row, j, Z, mult);
+            break;
+        }
+      }
+      __syncthreads();
+    }
+    const bool last_it = (it + 1 == max_it);
+    if (mode != MODE_EARLY_STOP && !last_it) {
+      continue;
+    }
+    // Hard decision of the first K soft bits of every code block: bit = (llr <= 0), MSB first; "any zero" flags.
+    if (t < 8) {
+      misc[4 + t] = 0;
+    }
+    __syncthreads();
+    {
+      uint32_t zany[4] = {0, 0, 0, 0};
+      for (uint32_t w = warp; w < HBW; w += NW) {
+        uint2    s    = soft[w * 32 + lane];
+        uint32_t v[4] = {s.x & 0xffffU, s.y & 0xffffU, s.x >> 16, s.y >> 16};
+#pragma unroll
+        for (int c = 0; c != 4; ++c) {
+          uint32_t b = __ballot_sync(0xffffffffU, v[c] <= pk::BS);
+          zany[c] |= __ballot_sync(0xffffffffU, v[c] == pk::BS);
+          if (lane == 0) {
+            hb[c * HBW + w] = __brev(b);
+          }
+        }
+      }
+      if (lane == 0) {
+#pragma unroll
+        for (int c = 0; c != 4; ++c) {
+          if (zany[c] != 0) {
+            atomicOr(&misc[4 + c], 1U);
+          }
+        }
+      }
+    }
+    __syncthreads();
+    if (warp < 4) {
+      uint32_t ok = 0;
+#pragma unroll
+      for (int c = 0; c != 4; ++c) {
+        if (c == warp && !done[c]) {
+          uint32_t crc = warp_crc_words(hb + c * HBW, nbits[c], poly, tabs, lane);
+          ok           = (crc == 0 && (mode != MODE_EARLY_STOP || misc[4 + c] == 0)) ? 1U : 0U;
+        }
+      }
+      if (lane == 0) {
+        misc[8 + warp] = ok;
+      }
+    }
+    __syncthreads();
+    bool all_done = true;
+#pragma unroll
+    for (int c = 0; c != 4; ++c) {
+      if (done[c]) {
+        continue;
+      }
+      bool ok = misc[8 + c] != 0;
+      if (ok || last_it) {
+        // The output holds the hard decision of the last iteration run (ldpc_decoder_impl.cpp:126-146).
+        const cb_desc& d    = descs[cbi[c]];
+        uint32_t*      slot = reinterpret_cast<uint32_t*>(bits_base + (size_t)d.slot * BITS_STRIDE);
+        for (uint32_t i = t; i < HBW; i += TPC) {
+          uint32_t wd = __byte_perm(hb[c * HBW + i], 0, 0x0123);
+          slot[i]     = wd;
+          if (d.bits_out != nullptr) {
+            reinterpret_cast<uint32_t*>(d.bits_out)[i] = wd;
+          }
+        }
+      }
+      if (ok) {
+        done[c]   = true;
+        crc_ok[c] = 1;
+        iters[c]  = (mode == MODE_EARLY_STOP) ? (int)it + 1 : (int)max_it;
+      } else {
+        all_done = false;
+      }
+    }
+    __syncthreads(); // hb and misc are rewritten by the next round
+    if (all_done) {
+      break;
+    }
+  }
+
+  if (t == 0) {
+#pragma unroll
+    for (int c = 0; c != 4; ++c) {
+      if (!live[c]) {
+        continue;
+      }
+      const cb_desc& d = descs[cbi[c]];
+      results[cbi[c]]  = {iters[c], crc_ok[c], L, 0U};
+      if (d.flags & FLAG_TRACK_CRC) {
+        crc_flags[d.slot] = crc_ok[c];
+      }
+    }
+  }
+}
+
+} // namespace pusch_dec

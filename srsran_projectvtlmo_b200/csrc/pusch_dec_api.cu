@@ -2,6 +2,7 @@
 // HBM, launch sequencing. No CPU fallback: every entry point needs a CUDA device.
 #include "../../include/srsran_cuda_pusch_dec.h"
 #include "pusch_dec_kernels.cuh"
+#include "ldpc_packed.cuh"
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
@@ -107,6 +108,8 @@ struct batch_context {
   device_buf<cb_desc>       d_desc;
   pinned_buf<uint32_t>      h_order;
   device_buf<uint32_t>      d_order;
+  pinned_buf<grp_desc>      h_grp; // packed-decoder groups (four code blocks per CTA)
+  device_buf<grp_desc>      d_grp;
   pinned_buf<cb_result>     h_res;
   device_buf<cb_result>     d_res;
   pinned_buf<uint8_t>       h_bits;
@@ -149,6 +152,7 @@ struct srsran_cuda_pusch_dec {
   uint32_t nof_slots         = 0;
   uint32_t combine_block     = 64; // AVX-512 flavour of the reference's combine (32 = AVX2, 0 = generic)
   uint64_t launches          = 0;
+  bool     use_packed        = true; // route eligible code blocks to the packed (4 per CTA) decoder
   int      max_smem_optin    = 0;
   std::string last_error;
 
@@ -257,6 +261,25 @@ cudaError_t launch_decode(srsran_cuda_pusch_dec* h, cudaStream_t s, const cb_des
       descs, order, res, h->d_soft.p, bits_base, h->d_crc_flags.p, n, smem_per_cb);
   ++h->launches;
   return cudaGetLastError();
+}
+
+template <int TPC>
+cudaError_t launch_decode4(srsran_cuda_pusch_dec* h, cudaStream_t s, const cb_desc* descs, const grp_desc* groups,
+                           cb_result* res, uint8_t* bits_base, uint32_t n, uint32_t smem)
+{
+  ldpc_decode4_kernel<TPC><<<n, TPC, smem, s>>>(descs, groups, res, h->d_soft.p, bits_base, h->d_crc_flags.p);
+  ++h->launches;
+  return cudaGetLastError();
+}
+
+/// Code blocks the packed decoder (ldpc_packed.cuh) accepts; `cap` = layers it would process.
+bool packed_eligible(const srsran_cuda_pusch_dec* h, const cb_desc& d, uint32_t cap)
+{
+  if (!h->use_packed || !(d.flags & FLAG_DECODE) || !(d.flags & FLAG_USE_HARQ) || d.mode == MODE_NO_CRC ||
+      d.crc_poly == 0 || d.Z < 144 || (d.Z % 16) != 0) {
+    return false;
+  }
+  return dec4_smem_layout(d.bg, d.Z, cap).total <= static_cast<uint32_t>(h->max_smem_optin);
 }
 
 template <int TPC, int CBS>
@@ -371,6 +394,8 @@ int open_context(srsran_cuda_pusch_dec* h, uint32_t min_cbs)
   CUDA_TRY(h, c.d_desc.reserve(ncb));
   CUDA_TRY(h, c.h_order.reserve(ncb));
   CUDA_TRY(h, c.d_order.reserve(ncb));
+  CUDA_TRY(h, c.h_grp.reserve(ncb));
+  CUDA_TRY(h, c.d_grp.reserve(ncb));
   CUDA_TRY(h, c.h_res.reserve(ncb));
   CUDA_TRY(h, c.d_res.reserve(ncb));
   c.open       = true;
@@ -402,19 +427,22 @@ int stage_llrs(srsran_cuda_pusch_dec* h, batch_context& c, const int8_t* src, si
       c.d_llr.release();
     }
     c.d_llr = nd;
-    pinned_buf<int8_t> nh;
-    CUDA_TRY(h, nh.reserve(ncap));
-    if (c.h_llr.p != nullptr) {
-      std::memcpy(nh.p, c.h_llr.p, off);
-      c.h_llr.release();
-    }
-    c.h_llr = nh;
   }
   if (is_pinned(src)) {
     // Caller memory is page-locked: copy straight from it at launch.
     c.copies.push_back({src, off, bytes});
   } else {
-    // Pageable caller memory: stage through the context's pinned buffer (src == nullptr), merging adjacent pieces.
+    // Pageable caller memory: stage through the context's pinned buffer (src == nullptr), merging adjacent pieces. The
+    // pinned buffer exists only on this path and follows the device buffer's capacity.
+    if (c.h_llr.cap < c.d_llr.cap) {
+      pinned_buf<int8_t> nh;
+      CUDA_TRY(h, nh.reserve(c.d_llr.cap));
+      if (c.h_llr.p != nullptr) {
+        std::memcpy(nh.p, c.h_llr.p, std::min(off, c.h_llr.cap));
+        c.h_llr.release();
+      }
+      c.h_llr = nh;
+    }
     std::memcpy(c.h_llr.p + off, src, bytes);
     if (!c.copies.empty() && c.copies.back().src == nullptr &&
         c.copies.back().dst_off + ((c.copies.back().bytes + 15) & ~size_t(15)) == off) {
@@ -529,13 +557,69 @@ int launch_context(srsran_cuda_pusch_dec* h, int ci)
     std::vector<uint32_t> idx;
   };
   std::vector<klass> classes;
-  bool               any_dematch = false;
+  uint32_t           dm_stage_bytes = 0; // largest E among the code blocks dematched through shared memory
+  bool               dm_unstaged    = false;
+  // Packed decoder: runs of consecutive code blocks with the same shape are grouped four per CTA.
+  struct pklass {
+    int      tpc;
+    uint32_t smem;
+    uint32_t first, count; // range in h_grp
+  };
+  std::vector<pklass> pclasses;
+  uint32_t            ngrp     = 0;
+  bool                grp_open = false;
+  auto same_shape = [](const cb_desc& a, const cb_desc& b) {
+    return a.bg == b.bg && a.Z == b.Z && a.mode == b.mode && a.max_it == b.max_it && a.scale_mult == b.scale_mult &&
+           a.crc_poly == b.crc_poly;
+  };
+  auto close_group = [&]() {
+    if (!grp_open) {
+      return;
+    }
+    grp_open           = false;
+    const grp_desc& g  = c.h_grp.p[ngrp];
+    const cb_desc&  d  = c.h_desc.p[g.cb[0]];
+    uint32_t        sm = (dec4_smem_layout(d.bg, d.Z, g.layer_cap).total + 1023) & ~1023U;
+    int             tp = d.Z <= 256 ? 256 : 384;
+    if (pclasses.empty() || pclasses.back().tpc != tp || pclasses.back().smem != sm) {
+      pclasses.push_back({tp, sm, ngrp, 0});
+    }
+    ++pclasses.back().count;
+    ++ngrp;
+  };
   for (uint32_t i = 0; i != ncb; ++i) {
     const cb_desc& d = c.h_desc.p[i];
-    any_dematch |= (d.flags & FLAG_DEMATCH) != 0;
+    if (d.flags & FLAG_DEMATCH) {
+      if (d.E <= DM_STAGE_CAP) {
+        dm_stage_bytes = std::max(dm_stage_bytes, d.E);
+      } else {
+        dm_unstaged = true;
+      }
+    }
     if (!(d.flags & FLAG_DECODE)) {
       continue;
     }
+    if (packed_eligible(h, d, d.layer_cap)) {
+      if (grp_open) {
+        grp_desc&      g   = c.h_grp.p[ngrp];
+        const cb_desc& f   = c.h_desc.p[g.cb[0]];
+        uint32_t       cap = std::max(g.layer_cap, d.layer_cap);
+        if (g.n < 4 && same_shape(f, d) && packed_eligible(h, d, cap)) {
+          g.cb[g.n++] = i;
+          g.layer_cap = cap;
+          continue;
+        }
+        close_group();
+      }
+      grp_desc& g = c.h_grp.p[ngrp];
+      g           = {};
+      g.cb[0]     = i;
+      g.n         = 1;
+      g.layer_cap = d.layer_cap;
+      grp_open    = true;
+      continue;
+    }
+    close_group();
     dec_smem_layout lay  = dec_layout(d.bg, d.Z, d.layer_cap);
     uint32_t        need = (lay.total + 1023) & ~1023U;
     // Buckets: 16, 24, 32, 48, 64, 96, 128, 227 KB - coarse enough for few launches, fine enough for occupancy.
@@ -565,11 +649,15 @@ int launch_context(srsran_cuda_pusch_dec* h, int ci)
     }
     found->idx.push_back(i);
   }
+  close_group();
   uint32_t pos = 0;
   for (klass& k : classes) {
     for (uint32_t i : k.idx) {
       c.h_order.p[pos++] = i;
     }
+  }
+  if (ngrp != 0) {
+    CUDA_TRY(h, cudaMemcpyAsync(c.d_grp.p, c.h_grp.p, ngrp * sizeof(grp_desc), cudaMemcpyHostToDevice, s));
   }
   CUDA_TRY(h, cudaMemcpyAsync(c.d_desc.p, c.h_desc.p, ncb * sizeof(cb_desc), cudaMemcpyHostToDevice, s));
   if (pos != 0) {
@@ -584,12 +672,25 @@ int launch_context(srsran_cuda_pusch_dec* h, int ci)
   }
   // 4. Kernels.
   CUDA_TRY(h, cudaEventRecord(c.stage[1], s));
-  if (any_dematch) {
-    rate_dematch_kernel<<<ncb, 256, 0, s>>>(c.d_desc.p, h->d_soft.p, h->combine_block);
+  if (dm_stage_bytes != 0) {
+    // + 32: the de-interleaved image is read with aligned 32-bit loads that may run a few bytes past E.
+    uint32_t smem = ((dm_stage_bytes + 15) & ~15U) + 32;
+    rate_dematch_kernel<true><<<ncb, 256, smem, s>>>(c.d_desc.p, h->d_soft.p, h->combine_block);
+    ++h->launches;
+    CUDA_TRY(h, cudaGetLastError());
+  }
+  if (dm_unstaged) {
+    rate_dematch_kernel<false><<<ncb, 256, 0, s>>>(c.d_desc.p, h->d_soft.p, h->combine_block);
     ++h->launches;
     CUDA_TRY(h, cudaGetLastError());
   }
   CUDA_TRY(h, cudaEventRecord(c.stage[2], s));
+  for (const pklass& k : pclasses) {
+    cudaError_t e = (k.tpc == 256)
+                        ? launch_decode4<256>(h, s, c.d_desc.p, c.d_grp.p + k.first, c.d_res.p, c.bits_base, k.count, k.smem)
+                        : launch_decode4<384>(h, s, c.d_desc.p, c.d_grp.p + k.first, c.d_res.p, c.bits_base, k.count, k.smem);
+    CUDA_TRY(h, e);
+  }
   pos = 0;
   for (klass& k : classes) {
     uint32_t        n   = static_cast<uint32_t>(k.idx.size());
@@ -822,6 +923,17 @@ int srsran_cuda_pusch_dec_create(int device, uint32_t max_cbs_in_flight, uint32_
     h->last_error = "cudaFuncSetAttribute(MaxDynamicSharedMemorySize) failed";
     return fail(SRSRAN_CUDA_ERR_CUDA);
   }
+  if (cudaFuncSetAttribute(ldpc_decode4_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess ||
+      cudaFuncSetAttribute(ldpc_decode4_kernel<384>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) {
+    h->last_error = "cudaFuncSetAttribute(ldpc_decode4_kernel) failed";
+    return fail(SRSRAN_CUDA_ERR_CUDA);
+  }
+  h->max_smem_optin = smem;
+  if (cudaFuncSetAttribute(rate_dematch_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           static_cast<int>(DM_STAGE_CAP + 48)) != cudaSuccess) {
+    h->last_error = "cudaFuncSetAttribute(rate_dematch_kernel) failed";
+    return fail(SRSRAN_CUDA_ERR_CUDA);
+  }
   size_t soft_bytes = (static_cast<size_t>(nof_harq_cb_slots) + 1) * SOFT_STRIDE; // + 1 scratch slot (unit-level)
   size_t bits_bytes = static_cast<size_t>(nof_harq_cb_slots) * BITS_STRIDE + 16;
   if (h->d_soft.reserve(soft_bytes) != cudaSuccess || h->d_bits.reserve(bits_bytes) != cudaSuccess ||
@@ -870,6 +982,8 @@ void srsran_cuda_pusch_dec_destroy(srsran_cuda_pusch_dec_t* h)
     c.d_desc.release();
     c.h_order.release();
     c.d_order.release();
+    c.h_grp.release();
+    c.d_grp.release();
     c.h_res.release();
     c.d_res.release();
     c.h_bits.release();
@@ -921,6 +1035,15 @@ int srsran_cuda_pusch_dec_set_combine_flavour(srsran_cuda_pusch_dec_t* h, uint32
     return SRSRAN_CUDA_ERR_INVALID;
   }
   h->combine_block = simd_block;
+  return SRSRAN_CUDA_OK;
+}
+
+int srsran_cuda_pusch_dec_set_decoder_variant(srsran_cuda_pusch_dec_t* h, uint32_t variant)
+{
+  if (h == nullptr || variant > 1) {
+    return SRSRAN_CUDA_ERR_INVALID;
+  }
+  h->use_packed = (variant == 0);
   return SRSRAN_CUDA_OK;
 }
 

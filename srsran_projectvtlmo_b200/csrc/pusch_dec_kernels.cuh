@@ -70,12 +70,20 @@ __host__ __device__ __forceinline__ uint32_t crc_push_bits(uint32_t reg, uint32_
 
 // ---------------------------------------------------------------------------------------------------------------------
 // Kernel 1: rate dematching + HARQ combining.
-// One CTA per code block. Every thread owns 16-byte chunks of the N-byte soft buffer (aligned 16-byte vector stores);
-// for every byte it derives, in closed form, the ordered list of rate-matched positions that land on it, so the
-// result is independent of scheduling and reproduces the reference's write set exactly (untouched bytes stay untouched).
+// One CTA per code block. Stage 1 streams the E rate-matched LLRs from HBM with 16-byte loads and scatters them into
+// shared memory in DE-INTERLEAVED order (d[j * E/Qm + i] = in[i * Qm + j], ldpc_rate_dematcher_impl.cpp:203-257), so
+// that stage 2 reads rate-matched position p at smem[p]. Stage 2: every thread owns aligned 16-byte chunks of the
+// soft buffer; the chunk is classified in O(1) against the break points of the reference's write set (info / filler /
+// parity / wrap / end of data / zeroed head and tail). Uniform chunks (the bulk) take a vector path; chunks that
+// contain a break point, multi-visit wraps (E > circular data length) and HARQ combining take the per-byte path, which
+// derives, in closed form, the ordered list of rate-matched positions that land on a byte. The result is independent
+// of scheduling and reproduces the reference's write set exactly (untouched bytes stay untouched).
 // ---------------------------------------------------------------------------------------------------------------------
+constexpr uint32_t DM_STAGE_CAP = 64 * 1024; ///< largest E staged through shared memory
+
 struct dm_geom {
   uint32_t N, Ncb, E, F, info, sys, D, s0, first_len, S, Qm, new_data, zero_head, tail_start, copy_at_end, blk;
+  uint32_t i_wrap, i_end; ///< break points: soft-buffer index of data slot s0, and of the first unvisited slot (E < D)
 };
 
 __device__ __forceinline__ int llr_add_scalar(int a_new, int b_old)
@@ -133,22 +141,66 @@ __device__ __forceinline__ bool dm_simd_rule(const dm_geom& g, uint32_t p)
   return (p - start) < (len / g.blk) * g.blk;
 }
 
+/// Rate-matched (de-interleaved) position p -> LLR.
+template <bool STAGED>
+__device__ __forceinline__ int dm_fetch(const dm_geom& g, const int8_t* __restrict__ in, const int8_t* sm, uint32_t p)
+{
+  if (STAGED) {
+    return sm[p];
+  }
+  if (g.Qm > 1) {
+    uint32_t q = p / g.S;
+    uint32_t r = p - q * g.S;
+    return __ldg(in + (size_t)r * g.Qm + q);
+  }
+  return __ldg(in + p);
+}
+
+/// New value of soft-buffer byte i given its old value (ldpc_rate_dematcher_impl.cpp:128-201, all passes).
+template <bool STAGED>
+__device__ __forceinline__ int dm_byte(const dm_geom& g, const int8_t* __restrict__ in, const int8_t* sm, uint32_t i, int val)
+{
+  bool     is_data = (i < g.info) || (i >= g.sys && i < g.Ncb);
+  uint32_t slot    = (i < g.info) ? i : g.info + (i - g.sys);
+  uint32_t p0      = (slot >= g.s0) ? slot - g.s0 : slot + g.D - g.s0;
+  if (g.new_data) {
+    if (i < g.zero_head || i >= g.tail_start) {
+      val = 0;
+    } else if (i >= g.info && i < g.sys) {
+      val = 127;
+    }
+  }
+  if (is_data) {
+    for (uint32_t p = p0; p < g.E; p += g.D) {
+      int x = dm_fetch<STAGED>(g, in, sm, p);
+      if (g.new_data && p < g.first_len) {
+        val = x;
+      } else {
+        val = dm_simd_rule(g, p) ? llr_add_simd(x, val) : llr_add_scalar(x, val);
+      }
+    }
+  }
+  return val;
+}
+
+template <bool STAGED>
 __global__ void __launch_bounds__(256) rate_dematch_kernel(const cb_desc* __restrict__ descs, int8_t* __restrict__ soft_base,
                                                            uint32_t combine_block)
 {
+  extern __shared__ __align__(16) int8_t dm_sm[];
   const cb_desc& d = descs[blockIdx.x];
-  if (!(d.flags & FLAG_DEMATCH)) {
+  if (!(d.flags & FLAG_DEMATCH) || ((d.E <= DM_STAGE_CAP) != STAGED)) {
     return;
   }
   dm_geom g;
-  g.N        = d.N;
-  g.Ncb      = d.Ncb;
-  g.E        = d.E;
-  g.F        = d.nof_filler;
+  g.N         = d.N;
+  g.Ncb       = d.Ncb;
+  g.E         = d.E;
+  g.F         = d.nof_filler;
   uint32_t Kb = (d.bg == 1) ? 22 : 10;
-  g.sys      = (Kb - 2) * d.Z;
-  g.info     = g.sys - g.F;
-  g.D        = g.info + (g.Ncb - g.sys);
+  g.sys       = (Kb - 2) * d.Z;
+  g.info      = g.sys - g.F;
+  g.D         = g.info + (g.Ncb - g.sys);
   uint32_t k0 = d.k0;
   g.s0        = (k0 < g.info) ? k0 : ((k0 < g.sys) ? g.info : g.info + (k0 - g.sys));
   g.first_len = g.D - g.s0;
@@ -169,120 +221,148 @@ __global__ void __launch_bounds__(256) rate_dematch_kernel(const cb_desc* __rest
       g.tail_start = g.N - (g.Ncb - idx_end);
     }
   }
+  g.i_wrap = (g.s0 < g.info) ? g.s0 : g.sys + (g.s0 - g.info);
+  {
+    uint32_t se = g.s0 + g.E; // first unvisited slot (only meaningful when E < D)
+    se          = (se >= g.D) ? se - g.D : se;
+    g.i_end     = (se < g.info) ? se : g.sys + (se - g.info);
+  }
 
   const int8_t* __restrict__ in  = d.llr;
   int8_t*                    out = soft_base + (size_t)d.slot * SOFT_STRIDE;
-  uint32_t nchunks = (g.N + 15) / 16;
 
-  for (uint32_t c = threadIdx.x; c < nchunks; c += blockDim.x) {
-    uint32_t i0 = c * 16;
-    // Pass A: classify the chunk (no memory traffic): is any byte modified, and is every byte fully determined without
-    // its old value (copied, zeroed or filler)?
-    bool any_touched = false, all_known = true;
-#pragma unroll
-    for (uint32_t b = 0; b != 16; ++b) {
-      uint32_t i = i0 + b;
-      if (i >= g.N) {
-        break;
-      }
-      bool     is_data = (i < g.info) || (i >= g.sys && i < g.Ncb);
-      uint32_t slot    = (i < g.info) ? i : g.info + (i - g.sys);
-      uint32_t p0      = (slot >= g.s0) ? slot - g.s0 : slot + g.D - g.s0;
-      bool     visited = is_data && (p0 < g.E);
-      bool     known   = g.new_data && ((visited && p0 < g.first_len) || (i < g.zero_head) ||
-                                      (i >= g.info && i < g.sys) || (i >= g.tail_start));
-      any_touched |= (visited || known);
-      all_known &= known;
-    }
-    if (!any_touched) {
-      continue;
-    }
-    uint4 oldv = make_uint4(0, 0, 0, 0);
-    bool  full = (i0 + 16 <= g.N);
-    int8_t vals[16];
-    if (!all_known) {
-      if (full) {
-        oldv = *reinterpret_cast<const uint4*>(out + i0);
+  // ---- stage 1: HBM -> shared memory, de-interleaving on the way -----------------------------------------------------
+  if (STAGED) {
+    const uint32_t mis  = (uint32_t)(reinterpret_cast<uintptr_t>(in) & 15U); // bytes before `in` in its 16-byte line
+    const uint32_t nvec = (mis + g.E + 15) / 16;
+    const int8_t*  base = in - mis;
+    for (uint32_t v = threadIdx.x; v < nvec; v += blockDim.x) {
+      int      first = (int)(v * 16) - (int)mis; // index into `in` of byte 0 of this vector
+      uint32_t lo    = first < 0 ? (uint32_t)(-first) : 0U;
+      uint32_t hi    = min(16U, (uint32_t)((int)g.E - first));
+      __align__(16) int8_t bytes[16];
+      if (lo == 0 && hi == 16) {
+        uint4 w = __ldg(reinterpret_cast<const uint4*>(base) + v);
+        *reinterpret_cast<uint4*>(bytes) = w;
       } else {
-        uint8_t* ob = reinterpret_cast<uint8_t*>(&oldv);
-        for (uint32_t b = 0; i0 + b < g.N; ++b) {
-          ob[b] = (uint8_t)out[i0 + b];
+        for (uint32_t b = lo; b < hi; ++b) {
+          bytes[b] = __ldg(in + first + (int)b);
+        }
+      }
+      if (g.Qm == 1) {
+        for (uint32_t b = lo; b < hi; ++b) {
+          dm_sm[first + (int)b] = bytes[b];
+        }
+      } else {
+        uint32_t idx = (uint32_t)(first + (int)lo);
+        uint32_t i   = idx / g.Qm;
+        uint32_t j   = idx - i * g.Qm;
+        uint32_t p   = j * g.S + i;
+#pragma unroll
+        for (uint32_t b = 0; b != 16; ++b) {
+          if (b >= lo && b < hi) {
+            dm_sm[p] = bytes[b];
+            p += g.S;
+            if (++j == g.Qm) {
+              j = 0;
+              ++i;
+              p = i;
+            }
+          }
         }
       }
     }
-    {
-      const int8_t* ob = reinterpret_cast<const int8_t*>(&oldv);
+    __syncthreads();
+  }
+
+  // ---- stage 2: soft buffer chunks -------------------------------------------------------------------------------------
+  // Only [0, Ncb) and the zeroed tail [tail_start, N) can change.
+  const uint32_t nchunks    = (g.N + 15) / 16;
+  const uint32_t head_end   = (g.Ncb + 15) / 16;          // chunks [0, head_end) cover [0, Ncb)
+  const uint32_t tail_begin = max(head_end, g.tail_start / 16); // chunks [tail_begin, nchunks) cover the zeroed tail
+  const uint32_t nwork      = head_end + (nchunks - tail_begin);
+  const bool     single     = g.E <= g.D;                 // every data byte is visited at most once
+
+  for (uint32_t w = threadIdx.x; w < nwork; w += blockDim.x) {
+    uint32_t c  = (w < head_end) ? w : tail_begin + (w - head_end);
+    uint32_t i0 = c * 16;
+    uint32_t i1 = i0 + 16;
+    bool     full = (i1 <= g.N);
+    // A chunk is uniform if no break point lies strictly inside it.
+    bool mixed = !full || !single;
+#define DM_BP(x) mixed |= ((x) > i0 && (x) < i1)
+    DM_BP(g.info);
+    DM_BP(g.sys);
+    DM_BP(g.Ncb);
+    DM_BP(g.zero_head);
+    DM_BP(g.tail_start);
+    DM_BP(g.i_wrap);
+    DM_BP(g.i_end);
+#undef DM_BP
+    if (!mixed) {
+      // Uniform chunk: byte i0 decides for all 16.
+      uint32_t i       = i0;
+      bool     is_data = (i < g.info) || (i >= g.sys && i < g.Ncb);
+      uint32_t slot    = (i < g.info) ? i : g.info + (i - g.sys);
+      uint32_t p0      = (slot >= g.s0) ? slot - g.s0 : slot + g.D - g.s0;
+      bool     visited = is_data && p0 < g.E;
+      if (visited && g.new_data && p0 < g.first_len) {
+        // plain copy of 16 consecutive rate-matched positions
+        uint4 nv;
+        if (STAGED) {
+          const uint32_t  sh = (p0 & 3U) * 8U;
+          const uint32_t* ws = reinterpret_cast<const uint32_t*>(dm_sm + (p0 & ~3U));
+          uint32_t        a0 = ws[0], a1 = ws[1], a2 = ws[2], a3 = ws[3];
+          uint32_t        a4 = sh ? ws[4] : 0U;
+          nv.x = __funnelshift_r(a0, a1, sh);
+          nv.y = __funnelshift_r(a1, a2, sh);
+          nv.z = __funnelshift_r(a2, a3, sh);
+          nv.w = __funnelshift_r(a3, a4, sh);
+        } else {
+          int8_t* nb = reinterpret_cast<int8_t*>(&nv);
 #pragma unroll
-      for (uint32_t b = 0; b != 16; ++b) {
-        vals[b] = ob[b];
+          for (uint32_t b = 0; b != 16; ++b) {
+            nb[b] = (int8_t)dm_fetch<false>(g, in, dm_sm, p0 + b);
+          }
+        }
+        *reinterpret_cast<uint4*>(out + i0) = nv;
+        continue;
+      }
+      if (!visited) {
+        if (g.new_data && (i < g.zero_head || i >= g.tail_start)) {
+          *reinterpret_cast<uint4*>(out + i0) = make_uint4(0, 0, 0, 0);
+        } else if (g.new_data && i >= g.info && i < g.sys) {
+          *reinterpret_cast<uint4*>(out + i0) = make_uint4(0x7f7f7f7fU, 0x7f7f7f7fU, 0x7f7f7f7fU, 0x7f7f7f7fU);
+        }
+        continue; // untouched otherwise
+      }
+      // visited + combine: per-byte path below
+    }
+    // Per-byte path.
+    __align__(16) int8_t vals[16];
+    if (full) {
+      *reinterpret_cast<uint4*>(vals) = *reinterpret_cast<const uint4*>(out + i0);
+    } else {
+      for (uint32_t b = 0; i0 + b < g.N; ++b) {
+        vals[b] = out[i0 + b];
       }
     }
-    // Pass B: values. (q, r) = (p / S, p % S) carried incrementally along consecutive positions.
-    uint32_t prev_p = 0xfffffffeU, q1 = 0, r1 = 0;
+    bool changed = false;
 #pragma unroll 4
     for (uint32_t b = 0; b != 16; ++b) {
       uint32_t i = i0 + b;
       if (i >= g.N) {
         break;
       }
-      bool     is_data = (i < g.info) || (i >= g.sys && i < g.Ncb);
-      uint32_t slot    = (i < g.info) ? i : g.info + (i - g.sys);
-      uint32_t p0      = (slot >= g.s0) ? slot - g.s0 : slot + g.D - g.s0;
-      bool     visited = is_data && (p0 < g.E);
-      int      val     = vals[b];
-      if (g.new_data) {
-        if (i < g.zero_head || i >= g.tail_start) {
-          val = 0;
-        } else if (i >= g.info && i < g.sys) {
-          val = 127;
-        }
-      }
-      if (visited) {
-        uint32_t p = p0;
-        bool     first = true;
-        for (; p < g.E; p += g.D) {
-          int x;
-          if (g.Qm > 1) {
-            uint32_t q, r;
-            if (first) {
-              if (p == prev_p + 1) {
-                if (++r1 == g.S) {
-                  r1 = 0;
-                  ++q1;
-                }
-              } else {
-                q1 = p / g.S;
-                r1 = p - q1 * g.S;
-              }
-              prev_p = p;
-              q      = q1;
-              r      = r1;
-            } else {
-              q = p / g.S;
-              r = p - q * g.S;
-            }
-            x = __ldg(in + (size_t)r * g.Qm + q);
-          } else {
-            x = __ldg(in + p);
-          }
-          if (g.new_data && p < g.first_len) {
-            val = x;
-          } else {
-            val = dm_simd_rule(g, p) ? llr_add_simd(x, val) : llr_add_scalar(x, val);
-          }
-          first = false;
-        }
-      }
-      vals[b] = (int8_t)val;
+      int nv  = dm_byte<STAGED>(g, in, dm_sm, i, vals[b]);
+      changed |= (nv != vals[b]);
+      vals[b] = (int8_t)nv;
+    }
+    if (!changed) {
+      continue;
     }
     if (full) {
-      uint4 nv;
-      int8_t* nb = reinterpret_cast<int8_t*>(&nv);
-#pragma unroll
-      for (uint32_t b = 0; b != 16; ++b) {
-        nb[b] = vals[b];
-      }
-      *reinterpret_cast<uint4*>(out + i0) = nv;
+      *reinterpret_cast<uint4*>(out + i0) = *reinterpret_cast<const uint4*>(vals);
     } else {
       for (uint32_t b = 0; i0 + b < g.N; ++b) {
         out[i0 + b] = vals[b];
@@ -435,7 +515,8 @@ __device__ __forceinline__ uint32_t hard_decision_crc(const int8_t* soft,
                                                       int           poly,
                                                       uint32_t*     misc,
                                                       int           t,
-                                                      int           group)
+                                                      int           group,
+                                                      bool          check_zero = true)
 {
   const int      lane   = t & 31;
   const int      warp   = t >> 5;
@@ -500,7 +581,7 @@ __device__ __forceinline__ uint32_t hard_decision_crc(const int8_t* soft,
       // total * x^rem + partial bits: continue the division over the last `rem` bits.
       total = crc_push_bits(total, misc[2], rem, gen, order);
     }
-    ok = (total == 0 && misc[1] == 0) ? 1U : 0U;
+    ok = (total == 0 && (!check_zero || misc[1] == 0)) ? 1U : 0U;
   }
   group_sync<TPC>(group);
   return ok;
@@ -632,7 +713,7 @@ __global__ void __launch_bounds__(TPC* CBS, (TPC * CBS >= 256) ? 2 : 4) ldpc_dec
         soft[i] = -1;
       }
       group_sync<TPC>(group);
-      crc_ok = hard_decision_crc<TPC>(soft, bits_slot, K, nb, (mode == MODE_CRC_AT_END) ? poly : 0, misc, t, group);
+      crc_ok = hard_decision_crc<TPC>(soft, bits_slot, K, nb, (mode == MODE_CRC_AT_END) ? poly : 0, misc, t, group, false);
       if (mode == MODE_CRC_AT_END && crc_ok) {
         iters = d.max_it;
       }
@@ -706,7 +787,7 @@ __global__ void __launch_bounds__(TPC* CBS, (TPC * CBS >= 256) ? 2 : 4) ldpc_dec
       }
     }
     if (status == 0 && mode != MODE_EARLY_STOP) {
-      crc_ok = hard_decision_crc<TPC>(soft, bits_slot, K, nb, (mode == MODE_CRC_AT_END) ? poly : 0, misc, t, group);
+      crc_ok = hard_decision_crc<TPC>(soft, bits_slot, K, nb, (mode == MODE_CRC_AT_END) ? poly : 0, misc, t, group, false);
       if (mode == MODE_CRC_AT_END && crc_ok) {
         iters = d.max_it;
       }

@@ -83,6 +83,9 @@ class Accelerator:
         self._check(self._lib.srsran_cuda_pusch_dec_read_cb_crc(self.h, absolute_cb_id, C.byref(v)), "read_cb_crc")
         return bool(v.value)
 
+    def set_decoder_variant(self, variant):
+        self._check(self._lib.srsran_cuda_pusch_dec_set_decoder_variant(self.h, variant), "set_decoder_variant")
+
     def set_combine_flavour(self, simd_block):
         self._check(self._lib.srsran_cuda_pusch_dec_set_combine_flavour(self.h, simd_block), "set_combine_flavour")
 

@@ -333,3 +333,85 @@ def test_hw_accelerator_call_sequence(acc):
                 assert crc_ok == bool(hb.crc[cb])
                 assert np.array_equal(bits, data_p)
         hw.free_queue()
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Packed decoder (four code blocks per CTA): groups of 1..4 same-shape code blocks, mixed shapes in one batch, both
+# decoder variants against the oracle's pusch_codeblock_decoder restatement
+# ---------------------------------------------------------------------------------------------------------------------
+def _cb_llrs(rng, bg, z, F, crc_poly, E, qm, rv, nref, mu):
+    K = ob.kb(bg) * z
+    crc_len = {1: 24, 2: 24, 3: 16}[crc_poly]
+    npay = K - F - crc_len
+    msg = np.zeros(K, np.uint8)
+    msg[:npay] = rng.integers(0, 2, npay, dtype=np.uint8)
+    c = ob.port_crc(crc_poly, np.packbits(msg[:npay]), npay)
+    msg[npay:npay + crc_len] = [(c >> (crc_len - 1 - i)) & 1 for i in range(crc_len)]
+    cw = synth.ldpc_encode(msg, bg, z)
+    return awgn_llrs(rng, synth.rate_match(cw, bg, z, F, E, rv, qm, nref), mu)
+
+
+@pytest.mark.parametrize("variant", [0, 1])
+def test_packed_decoder_groups_via_hal(acc, variant):
+    rng = np.random.default_rng(40 + variant)
+    hw = pusch.hw_accelerator_pusch_dec_cuda(acc)
+    acc.set_decoder_variant(variant)
+    try:
+        for rnd in range(6):
+            early_stop = int(rng.integers(0, 2))
+            max_it = int(rng.integers(1, 7))
+            ops = []
+            slot = 7000
+            # several runs of same-shape code blocks back to back: groups of 4 plus a remainder, shapes alternate
+            for _ in range(int(rng.integers(2, 5))):
+                bg = int(rng.integers(1, 3))
+                z = int(rng.choice([144, 160, 208, 256, 288, 320, 384]))
+                K, N = ob.kb(bg) * z, ob.ns(bg) * z
+                qm = int(rng.choice([2, 4, 6, 8]))
+                crc_poly = pusch.CRC24B
+                F = int(rng.integers(0, 5)) * 8
+                # few layers: E just above the systematic part
+                E = (int((K - 2 * z - F) * rng.uniform(1.04, 1.25)) // qm) * qm
+                nref = 0 if rng.random() < 0.5 else int(N * 0.6)
+                mu = float(rng.choice([3.0, 6.0, 12.0, 20.0]))
+                for _ in range(int(rng.integers(1, 8))):
+                    llr = _cb_llrs(rng, bg, z, F, crc_poly, E, qm, 0, nref, mu)
+                    if rng.random() < 0.1:
+                        llr[:] = 0
+                    ops.append((bg, z, qm, F, E, nref, llr, slot))
+                    slot += 1
+            hw.reserve_queue()
+            for i, (bg, z, qm, F, E, nref, llr, s) in enumerate(ops):
+                K, N = ob.kb(bg) * z, ob.ns(bg) * z
+                cfg = pusch.CbConfig(bg, qm, len(ops), 0, E, z, N, nref, K - 24 - F, F, max_it, early_stop, 1, 24,
+                                     pusch.CB_CRC24B, s)
+                hw.configure_operation(cfg, i)
+                assert hw.enqueue_operation(llr, None, i)
+            for i, (bg, z, qm, F, E, nref, llr, s) in enumerate(ops):
+                K, N = ob.kb(bg) * z, ob.ns(bg) * z
+                bits = np.full(K // 8, 0x5A, np.uint8)
+                soft = np.zeros(N, np.int8)
+                while not hw.dequeue_operation(bits, soft, i):
+                    pass
+                crc_ok, iters = hw.read_operation_outputs(i, s)
+                want_soft = np.zeros(N, np.int8)
+                want_bits = np.full(K // 8, 0x5A, np.uint8)
+                # the slots are reused round after round: start the oracle from what the slot held
+                want_soft[:] = _packed_prev.get(s, np.zeros(25344, np.int8))[:N]
+                it = ob.port().oracle_cb_decode(ob._p8(want_bits), ob._pi(want_soft), N, ob._pi(llr), E, 1, 0, qm, nref, F,
+                                                bg, z, pusch.CRC24B, early_stop, max_it)
+                full = _packed_prev.get(s, np.zeros(25344, np.int8)).copy()
+                full[:N] = want_soft
+                _packed_prev[s] = full
+                key = (variant, rnd, i, bg, z, qm, F, E, nref, early_stop, max_it)
+                assert np.array_equal(soft, want_soft), key
+                assert crc_ok == (it >= 0), key
+                assert iters == (it if it >= 0 else max_it), key
+                if not (early_stop and not llr.any()):
+                    assert np.array_equal(bits, want_bits), key
+            hw.free_queue()
+    finally:
+        acc.set_decoder_variant(0)
+
+
+_packed_prev = {}
