@@ -186,6 +186,11 @@ int srsran_cuda_pusch_dec_submit_tbs(srsran_cuda_pusch_dec_t* handle, uint32_t n
  * to, in milliseconds: [0] host->device copies, [1] rate-dematch kernel, [2] LDPC decode kernels, [3] TB assembly + CRC
  * kernel, [4] device->host copies. Waits for the batch to complete. Used by the benchmark's roofline accounting. */
 int srsran_cuda_pusch_dec_ticket_timing(srsran_cuda_pusch_dec_t* handle, int ticket, float* stage_ms);
+/* Device-side stopwatch over several batches: timer_start arms an event that is recorded on the stream of the NEXT batch
+ * launched, in front of its first copy; timer_stop records an event behind everything launched so far, waits for it and
+ * returns the elapsed milliseconds between the two (CUDA events on the streams the work runs on). */
+int srsran_cuda_pusch_dec_timer_start(srsran_cuda_pusch_dec_t* handle);
+int srsran_cuda_pusch_dec_timer_stop(srsran_cuda_pusch_dec_t* handle, float* elapsed_ms);
 /* Blocks until everything submitted on this handle has completed. */
 int srsran_cuda_pusch_dec_synchronize(srsran_cuda_pusch_dec_t* handle);
 

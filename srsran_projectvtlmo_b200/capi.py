@@ -76,6 +76,8 @@ SYMBOLS = {
     "srsran_cuda_pusch_dec_submit_tbs": (C.c_int, [C.c_void_p, C.c_uint32, C.POINTER(TbConfig),
                                                     C.POINTER(C.c_void_p), u32p, intp]),
     "srsran_cuda_pusch_dec_ticket_timing": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_float)]),
+    "srsran_cuda_pusch_dec_timer_start": (C.c_int, [C.c_void_p]),
+    "srsran_cuda_pusch_dec_timer_stop": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
     "srsran_cuda_pusch_dec_synchronize": (C.c_int, [C.c_void_p]),
     "srsran_cuda_ldpc_rate_dematch": (C.c_int, [C.c_void_p, i8p, C.c_uint32, i8p, C.c_uint32, C.c_int, C.c_uint32,
                                                  C.c_uint32, C.c_uint32, C.c_uint32]),

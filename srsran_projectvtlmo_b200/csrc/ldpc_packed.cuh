@@ -38,7 +38,7 @@ __host__ __device__ inline dec4_layout dec4_smem_layout(uint32_t bg, uint32_t Z,
   uint32_t    Kb = (bg == 1) ? 22 : 10;
   dec4_layout l;
   l.tab_off  = 0;
-  l.soft_off = (nedges * 4 + 15) & ~15U;
+  l.soft_off = (nedges * 8 + 15) & ~15U;
   l.c2v_off  = l.soft_off + (Kb + layer_cap) * Z * 8;
   l.hb_off   = l.c2v_off + nedges * Z * 4;
   l.crc_off  = l.hb_off + 4 * (Kb * Z / 32) * 4;
@@ -47,58 +47,37 @@ __host__ __device__ inline dec4_layout dec4_smem_layout(uint32_t bg, uint32_t Z,
   return l;
 }
 
+/// Soft-buffer index of edge `te` = (node base, shift) for lifted check j: base + (j + shift) mod Z, the modulo by a
+/// multiply-high so that the address arithmetic issues on the FMA pipe (the ALU pipe is the bottleneck of this kernel).
+__device__ __forceinline__ uint32_t edge_addr(uint2 te, uint32_t j, uint32_t Z, uint32_t zmagic)
+{
+  uint32_t k = j + te.y;
+  return te.x + k - __umulhi(k, zmagic) * Z;
+}
+
 template <int DEG>
-__device__ __forceinline__ void
-process_check4(uint2* __restrict__ soft, uint32_t* __restrict__ c2v_row, const uint32_t* __restrict__ tab_row, int j, int Z, uint32_t mult)
+__device__ __forceinline__ void process_check4(uint2* __restrict__       soft,
+                                               uint32_t* __restrict__    c2v_row,
+                                               const uint2* __restrict__ tab_row,
+                                               uint32_t                  j,
+                                               uint32_t                  Z,
+                                               uint32_t                  zmagic,
+                                               uint32_t                  mult)
 {
   pk::check4<DEG> ck;
-  int             addr[DEG];
   ck.begin();
 #pragma unroll
   for (int e = 0; e != DEG; ++e) {
-    uint32_t te = tab_row[e];
-    int      k  = j + (int)(te >> 16);
-    k           = (k >= Z) ? k - Z : k;
-    addr[e]     = (int)(te & 0xffffU) + k;
-    uint2 s     = soft[addr[e]];
+    uint2 s = soft[edge_addr(tab_row[e], j, Z, zmagic)];
     ck.gather(e, s.x, s.y, c2v_row[e * Z + j]);
   }
   ck.reduce(mult);
 #pragma unroll
   for (int e = 0; e != DEG; ++e) {
     uint32_t s0, s1;
-    c2v_row[e * Z + j] = ck.scatter(e, s0, s1);
-    soft[addr[e]]      = make_uint2(s0, s1);
+    c2v_row[e * Z + j]                            = ck.scatter(e, s0, s1);
+    soft[edge_addr(tab_row[e], j, Z, zmagic)] = make_uint2(s0, s1);
   }
-}
-
-/// CRC of the first nb bits of hb (MSB-first 32-bit words) by ONE warp. tabs[k][b] = (b(x) x^(8k) x^order) mod g.
-__device__ __forceinline__ uint32_t warp_crc_words(const uint32_t* hb, uint32_t nb, int poly, const uint32_t* tabs, int lane)
-{
-  const uint32_t gen = crc_gen(poly), order = crc_order(poly);
-  const uint32_t nfull = nb / 32, rem = nb % 32;
-  const uint32_t per   = (nfull + 31) / 32;
-  uint32_t       w0 = min(nfull, (uint32_t)lane * per), w1 = min(nfull, w0 + per);
-  uint32_t       acc = 0;
-  const uint32_t sh  = (32 - order) / 8; // tables that multiply a register byte by x^32
-  for (uint32_t w = w0; w < w1; ++w) {
-    uint32_t word = hb[w];
-    uint32_t r    = tabs[3 * 256 + (word >> 24)] ^ tabs[2 * 256 + ((word >> 16) & 0xff)] ^ tabs[256 + ((word >> 8) & 0xff)] ^
-                 tabs[word & 0xff];
-    uint32_t m = tabs[sh * 256 + (acc & 0xff)] ^ tabs[(sh + 1) * 256 + ((acc >> 8) & 0xff)];
-    if (order == 24) {
-      m ^= tabs[(sh + 2) * 256 + (acc >> 16)];
-    }
-    acc = m ^ r;
-  }
-  if (w1 > w0 && w1 != nfull) {
-    acc = gf2_mulmod(acc, c_xpow32[poly - 1][nfull - w1], gen, order);
-  }
-  acc = __reduce_xor_sync(0xffffffffU, acc);
-  if (rem != 0) {
-    acc = crc_push_bits(acc, hb[nfull], rem, gen, order);
-  }
-  return acc;
 }
 
 template <int TPC>
@@ -112,7 +91,8 @@ __global__ void __launch_bounds__(TPC, 1) ldpc_decode4_kernel(const cb_desc* __r
   extern __shared__ __align__(16) uint8_t smem_raw[];
   const int      t    = threadIdx.x;
   const int      lane = t & 31;
-  const int      warp = t >> 5;
+  // Broadcast from lane 0 so that the compiler knows the warp index is warp-uniform (uniform loop bounds around ballots).
+  const int      warp = __shfl_sync(0xffffffffU, t >> 5, 0);
   constexpr int  NW   = TPC / 32;
   const grp_desc g    = groups[blockIdx.x];
   const cb_desc& d0   = descs[g.cb[0]];
@@ -122,7 +102,7 @@ __global__ void __launch_bounds__(TPC, 1) ldpc_decode4_kernel(const cb_desc* __r
   const uint32_t HBW  = K / 32;
 
   const dec4_layout lay  = dec4_smem_layout(bg, Z, L);
-  uint32_t*         tab  = reinterpret_cast<uint32_t*>(smem_raw + lay.tab_off);
+  uint2*            tab  = reinterpret_cast<uint2*>(smem_raw + lay.tab_off);
   uint2*            soft = reinterpret_cast<uint2*>(smem_raw + lay.soft_off);
   uint32_t*         c2v  = reinterpret_cast<uint32_t*>(smem_raw + lay.c2v_off);
   uint32_t*         hb   = reinterpret_cast<uint32_t*>(smem_raw + lay.hb_off);
@@ -162,8 +142,7 @@ __global__ void __launch_bounds__(TPC, 1) ldpc_decode4_kernel(const cb_desc* __r
   // ---- prologue ----------------------------------------------------------------------------------------------------------
   const uint32_t nedges = c_row_ptr[bg - 1][L];
   for (uint32_t e = t; e < nedges; e += TPC) {
-    uint32_t sh = c_shift[bg - 1][d0.ils][e] % Z;
-    tab[e]      = ((uint32_t)c_col[bg - 1][e] * Z) | (sh << 16);
+    tab[e] = make_uint2((uint32_t)c_col[bg - 1][e] * Z, c_shift[bg - 1][d0.ils][e] % Z);
   }
   {
     uint4*         c4 = reinterpret_cast<uint4*>(c2v);
@@ -174,13 +153,7 @@ __global__ void __launch_bounds__(TPC, 1) ldpc_decode4_kernel(const cb_desc* __r
     }
   }
   if (poly != 0) {
-    const uint32_t gen = crc_gen(poly), order = crc_order(poly);
-    for (uint32_t i = t; i < 1024; i += TPC) {
-      // (b(x) x^(8k) x^order) mod g, k = i / 256: push the byte followed by k zero bytes.
-      uint32_t r = crc_push_bits(0, (i & 0xffU) << 24, 8, gen, order);
-      r          = crc_push_bits(r, 0, 8 * (i >> 8), gen, order);
-      tabs[i]    = r;
-    }
+    build_crc_tables(tabs, poly, t, TPC);
   }
   if (t < 32) {
     misc[t] = 0;
@@ -238,41 +211,42 @@ __global__ void __launch_bounds__(TPC, 1) ldpc_decode4_kernel(const cb_desc* __r
     // All-zero input with early stop: the reference returns before touching the output (ldpc_decoder_impl.cpp:88-94).
     done[c] = !live[c] || (allzero[c] && mode == MODE_EARLY_STOP);
   }
-  const int j = t;
+  const uint32_t j      = t;
+  const uint32_t zmagic = 0xffffffffU / Z + 1; // ceil(2^32 / Z): floor(k / Z) = umulhi(k, zmagic) for k < 2 Z
   for (uint32_t it = 0; it != max_it; ++it) {
     for (uint32_t l = 0; l != L; ++l) {
       uint32_t e0  = c_row_ptr[bg - 1][l];
       int      deg = (int)c_row_ptr[bg - 1][l + 1] - (int)e0;
-      if (j < (int)Z) {
-        uint32_t*       c2v_row = c2v + (size_t)e0 * Z;
-        const uint32_t* tab_row = tab + e0;
+      if (j < Z) {
+        uint32_t*    c2v_row = c2v + (size_t)e0 * Z;
+        const uint2* tab_row = tab + e0;
         switch (deg) {
           case 3:
-            process_check4<3>(soft, c2v_row, tab_row, j, Z, mult);
+            process_check4<3>(soft, c2v_row, tab_row, j, Z, zmagic, mult);
             break;
           case 4:
-            process_check4<4>(soft, c2v_row, tab_row, j, Z, mult);
+            process_check4<4>(soft, c2v_row, tab_row, j, Z, zmagic, mult);
             break;
           case 5:
-            process_check4<5>(soft, c2v_row, tab_row, j, Z, mult);
+            process_check4<5>(soft, c2v_row, tab_row, j, Z, zmagic, mult);
             break;
           case 6:
-            process_check4<6>(soft, c2v_row, tab_row, j, Z, mult);
+            process_check4<6>(soft, c2v_row, tab_row, j, Z, zmagic, mult);
             break;
           case 7:
-            process_check4<7>(soft, c2v_row, tab_row, j, Z, mult);
+            process_check4<7>(soft, c2v_row, tab_row, j, Z, zmagic, mult);
             break;
           case 8:
-            process_check4<8>(soft, c2v_row, tab_row, j, Z, mult);
+            process_check4<8>(soft, c2v_row, tab_row, j, Z, zmagic, mult);
             break;
           case 9:
-            process_check4<9>(soft, c2v_row, tab_row, j, Z, mult);
+            process_check4<9>(soft, c2v_row, tab_row, j, Z, zmagic, mult);
             break;
           case 10:
-            process_check4<10>(soft, c2v_row, tab_row, j, Z, mult);
+            process_check4<10>(soft, c2v_row, tab_row, j, Z, zmagic, mult);
             break;
           default:
-            process_check4<19>(soft, c2v_row, tab_row, j, Z, mult);
+            process_check4<19>(soft, c2v_row, tab_row, j, Z, zmagic, mult);
             break;
         }
       }
@@ -288,25 +262,37 @@ __global__ void __launch_bounds__(TPC, 1) ldpc_decode4_kernel(const cb_desc* __r
     }
     __syncthreads();
     {
-      uint32_t zany[4] = {0, 0, 0, 0};
+      // Lane l takes variable 32 w + 31 - l: ballot bit l is then already in MSB-first order.
+      uint32_t nz0 = 0x00010001U, nz1 = 0x00010001U; // stays 1 in the lanes that saw no zero soft bit
       for (uint32_t w = warp; w < HBW; w += NW) {
-        uint2    s    = soft[w * 32 + lane];
-        uint32_t v[4] = {s.x & 0xffffU, s.y & 0xffffU, s.x >> 16, s.y >> 16};
-#pragma unroll
-        for (int c = 0; c != 4; ++c) {
-          uint32_t b = __ballot_sync(0xffffffffU, v[c] <= pk::BS);
-          zany[c] |= __ballot_sync(0xffffffffU, v[c] == pk::BS);
-          if (lane == 0) {
-            hb[c * HBW + w] = __brev(b);
-          }
+        uint2    s  = soft[w * 32 + 31 - lane];
+        uint32_t p0 = pk::addmin_s2_relu(s.x, PK_REP2(0x10000U - pk::BS), 0x00010001U); // 1 where soft > 0
+        uint32_t p1 = pk::addmin_s2_relu(s.y, PK_REP2(0x10000U - pk::BS), 0x00010001U);
+        nz0 &= pk::minu2(s.x ^ pk::SOFT_ZERO2, 0x00010001U);
+        nz1 &= pk::minu2(s.y ^ pk::SOFT_ZERO2, 0x00010001U);
+        uint32_t b0 = __ballot_sync(0xffffffffU, (p0 & 0xffffU) == 0);
+        uint32_t b1 = __ballot_sync(0xffffffffU, (p1 & 0xffffU) == 0);
+        uint32_t b2 = __ballot_sync(0xffffffffU, (p0 >> 16) == 0);
+        uint32_t b3 = __ballot_sync(0xffffffffU, (p1 >> 16) == 0);
+        uint32_t blo = (lane & 1) ? b1 : b0, bhi = (lane & 1) ? b3 : b2;
+        if (lane < 4) {
+          hb[lane * HBW + w] = (lane & 2) ? bhi : blo;
         }
       }
-      if (lane == 0) {
-#pragma unroll
-        for (int c = 0; c != 4; ++c) {
-          if (zany[c] != 0) {
-            atomicOr(&misc[4 + c], 1U);
-          }
+      nz0 = __reduce_and_sync(0xffffffffU, nz0);
+      nz1 = __reduce_and_sync(0xffffffffU, nz1);
+      if (lane == 0 && (nz0 & nz1) != 0x00010001U) {
+        if (!(nz0 & 1U)) {
+          atomicOr(&misc[4], 1U);
+        }
+        if (!(nz1 & 1U)) {
+          atomicOr(&misc[5], 1U);
+        }
+        if (!(nz0 >> 16)) {
+          atomicOr(&misc[6], 1U);
+        }
+        if (!(nz1 >> 16)) {
+          atomicOr(&misc[7], 1U);
         }
       }
     }
@@ -316,7 +302,7 @@ __global__ void __launch_bounds__(TPC, 1) ldpc_decode4_kernel(const cb_desc* __r
 #pragma unroll
       for (int c = 0; c != 4; ++c) {
         if (c == warp && !done[c]) {
-          uint32_t crc = warp_crc_words(hb + c * HBW, nbits[c], poly, tabs, lane);
+          uint32_t crc = warp_crc_words<false>(hb + c * HBW, nbits[c], poly, tabs, lane);
           ok           = (crc == 0 && (mode != MODE_EARLY_STOP || misc[4 + c] == 0)) ? 1U : 0U;
         }
       }

@@ -166,7 +166,11 @@ struct check4 {
   /// Edge e: soft words (s0, s1) and the packed messages cw of the previous iteration.
   PK_MFN void gather(int e, uint32_t s0, uint32_t s1, uint32_t cw)
   {
+#if defined(__CUDA_ARCH__)
+    uint32_t c[2] = {cw & 0x00ff00ffU, __byte_perm(cw, 0, 0x4341)};
+#else
     uint32_t c[2] = {cw & 0x00ff00ffU, (cw >> 8) & 0x00ff00ffU};
+#endif
     uint32_t s[2] = {s0, s1};
 #pragma unroll
     for (int r = 0; r != 2; ++r) {
@@ -182,7 +186,7 @@ struct check4 {
     }
   }
 
-  uint32_t nm1[2], mp1[2], mn1[2], mp2[2], mn2[2], pm1[2], pm2[2], xp[2];
+  uint32_t nm1[2], pm1[2], pm2[2];
 
   PK_MFN void reduce(uint32_t mult)
   {
@@ -190,16 +194,12 @@ struct check4 {
     for (int r = 0; r != 2; ++r) {
       uint32_t s1 = scale2(m1[r] & 0x7fff7fffU, mult);
       uint32_t s2 = scale2(m2[r] & 0x7fff7fffU, mult);
-      mp1[r]      = 0x00800080U + s1;
-      mn1[r]      = 0x00800080U - s1;
-      mp2[r]      = 0x00800080U + s2;
-      mn2[r]      = 0x00800080U - s2;
       nm1[r]      = 0x00010000U - m1[r];
-      // bit 15 of x = parity of the non-negative v2c; the sign product is negative iff (#negative) is odd.
-      xp[r]        = (DEG & 1) ? ~x[r] : x[r];
-      uint32_t pmk = lane_mask(xp[r]);
-      pm1[r]       = sel(pmk, mn1[r], mp1[r]);
-      pm2[r]       = sel(pmk, mn2[r], mp2[r]);
+      // bit 15 of x = parity of the non-negative v2c; the sign product P is negative iff (#negative) is odd.
+      uint32_t pmk = lane_mask((DEG & 1) ? ~x[r] : x[r]);
+      // 128 + P * M for the two candidate magnitudes (min1: every edge but the minimum, min2: the minimum itself).
+      pm1[r] = sel(pmk, 0x00800080U - s1, 0x00800080U + s1);
+      pm2[r] = sel(pmk, 0x00800080U - s2, 0x00800080U + s2);
     }
   }
 
@@ -212,22 +212,21 @@ struct check4 {
       uint32_t aa = a[e][r], qq = q[e][r];
       uint32_t t    = addmin_u2(aa, nm1[r], 0x00010001U); // 1: |q| > min1 -> min1, 0: this edge is the minimum -> min2
       uint32_t mask = t * 0xffffU;
-      uint32_t mp   = sel(mask, mp1[r], mp2[r]);
-      uint32_t mn   = sel(mask, mn1[r], mn2[r]);
-      uint32_t pm   = sel(mask, pm1[r], pm2[r]);
-      uint32_t ts   = ~(xp[r] ^ qq) & 0x80008000U;        // lanes whose new message is negative
-      cn[r]         = addmax_s2(ts, mp, mn);              // 128 +- M
+      uint32_t pm   = sel(mask, pm1[r], pm2[r]);          // 128 + P * M
+      uint32_t sq   = lane_mask(qq);                      // lanes with q >= 0
+      // new message c = sign(q) * P * M (the sign product of the OTHER edges is P * sign(q)), stored as 128 + c
+      cn[r] = sel(sq, pm, 0x01000100U - pm);
       // soft = sign(q) * promote(min(|q|, 120) + P * M); infinite |q| (>= INF - 120) passes the clamp.
       uint32_t av = addmax_u2(aa, PK_REP2(0x10000U - INF_CUT), minu2(aa, PK_REP2(BQ + 120U)));
       uint32_t v  = av + pm;                               // bias BQ + 128 = BS
       uint32_t t2 = addmin_s2_relu(v, PK_REP2(0x10000U - (BS + 120U)), 0x00010001U);
       uint32_t w  = minu2(v + t2 * INF, PK_REP2(BS + INF));
       uint32_t nw = 0x01010100U - w;                       // lane-wise 2 * BS - w
-      sn[r]       = sel(lane_mask(qq), w, nw);
+      sn[r]       = sel(sq, w, nw);
     }
     s0 = sn[0];
     s1 = sn[1];
-    return cn[0] | (cn[1] << 8);
+    return cn[0] + (cn[1] << 8);
   }
 };
 

@@ -110,6 +110,9 @@ struct batch_context {
   device_buf<uint32_t>      d_order;
   pinned_buf<grp_desc>      h_grp; // packed-decoder groups (four code blocks per CTA)
   device_buf<grp_desc>      d_grp;
+  pinned_buf<uint32_t>      h_tbmap; // per code block: index of its transport block in h_tb, or 0xffffffff
+  device_buf<uint32_t>      d_tbmap;
+  device_buf<uint32_t>      d_tbshare; // per code block: its share of the TB CRC24A
   pinned_buf<cb_result>     h_res;
   device_buf<cb_result>     d_res;
   pinned_buf<uint8_t>       h_bits;
@@ -153,6 +156,9 @@ struct srsran_cuda_pusch_dec {
   uint32_t combine_block     = 64; // AVX-512 flavour of the reference's combine (32 = AVX2, 0 = generic)
   uint64_t launches          = 0;
   bool     use_packed        = true; // route eligible code blocks to the packed (4 per CTA) decoder
+  cudaEvent_t timer_begin    = nullptr;
+  cudaEvent_t timer_end      = nullptr;
+  bool        timer_armed    = false;
   int      max_smem_optin    = 0;
   std::string last_error;
 
@@ -325,6 +331,16 @@ int upload_tables(srsran_cuda_pusch_dec* h)
   CUDA_TRY(h, cudaMemcpyToSymbol(c_shift, shift, sizeof(shift)));
   CUDA_TRY(h, cudaMemcpyToSymbol(c_xpow32, xp32, sizeof(xp32)));
   CUDA_TRY(h, cudaMemcpyToSymbol(c_xpow128, xp128, sizeof(xp128)));
+  uint32_t xp2[3][32];
+  for (int poly = 1; poly <= 3; ++poly) {
+    uint32_t gen = crc_gen(poly), order = crc_order(poly);
+    uint32_t v   = 2; // x
+    for (int i = 0; i != 32; ++i) {
+      xp2[poly - 1][i] = v;
+      v                = gf2_mulmod(v, v, gen, order);
+    }
+  }
+  CUDA_TRY(h, cudaMemcpyToSymbol(c_xpow2, xp2, sizeof(xp2)));
   return SRSRAN_CUDA_OK;
 }
 
@@ -396,6 +412,9 @@ int open_context(srsran_cuda_pusch_dec* h, uint32_t min_cbs)
   CUDA_TRY(h, c.d_order.reserve(ncb));
   CUDA_TRY(h, c.h_grp.reserve(ncb));
   CUDA_TRY(h, c.d_grp.reserve(ncb));
+  CUDA_TRY(h, c.h_tbmap.reserve(ncb));
+  CUDA_TRY(h, c.d_tbmap.reserve(ncb));
+  CUDA_TRY(h, c.d_tbshare.reserve(ncb));
   CUDA_TRY(h, c.h_res.reserve(ncb));
   CUDA_TRY(h, c.d_res.reserve(ncb));
   c.open       = true;
@@ -429,8 +448,14 @@ int stage_llrs(srsran_cuda_pusch_dec* h, batch_context& c, const int8_t* src, si
     c.d_llr = nd;
   }
   if (is_pinned(src)) {
-    // Caller memory is page-locked: copy straight from it at launch.
-    c.copies.push_back({src, off, bytes});
+    // Caller memory is page-locked: copy straight from it at launch. Pieces that are adjacent on both sides (e.g. the
+    // transport blocks of one slot laid out back to back) are merged into one copy.
+    if (!c.copies.empty() && c.copies.back().src != nullptr && c.copies.back().src + c.copies.back().bytes == src &&
+        c.copies.back().dst_off + c.copies.back().bytes == off) {
+      c.copies.back().bytes += bytes;
+    } else {
+      c.copies.push_back({src, off, bytes});
+    }
   } else {
     // Pageable caller memory: stage through the context's pinned buffer (src == nullptr), merging adjacent pieces. The
     // pinned buffer exists only on this path and follows the device buffer's capacity.
@@ -527,7 +552,8 @@ int add_cb(srsran_cuda_pusch_dec* h, batch_context& c, const cb_params& p, const
     d.bits_out  = c.d_bits.p + static_cast<size_t>(idx) * BITS_STRIDE;
     c.want_bits = true;
   }
-  c.h_desc.p[idx] = d;
+  c.h_desc.p[idx]  = d;
+  c.h_tbmap.p[idx] = 0xffffffffU;
   c.cb_meta.push_back({K, p.max_it, p.slot});
   *idx_out = idx;
   return SRSRAN_CUDA_OK;
@@ -545,6 +571,10 @@ int launch_context(srsran_cuda_pusch_dec* h, int ci)
     return SRSRAN_CUDA_OK;
   }
   // 1. Host -> device: LLRs (direct from pinned caller memory when possible), descriptors.
+  if (h->timer_armed) {
+    h->timer_armed = false;
+    CUDA_TRY(h, cudaEventRecord(h->timer_begin, s));
+  }
   CUDA_TRY(h, cudaEventRecord(c.stage[0], s));
   for (const batch_context::copy_job& j : c.copies) {
     const int8_t* src = (j.src != nullptr) ? j.src : c.h_llr.p + j.dst_off;
@@ -665,6 +695,7 @@ int launch_context(srsran_cuda_pusch_dec* h, int ci)
   }
   if (ntb != 0) {
     CUDA_TRY(h, cudaMemcpyAsync(c.d_tb.p, c.h_tb.p, ntb * sizeof(tb_desc), cudaMemcpyHostToDevice, s));
+    CUDA_TRY(h, cudaMemcpyAsync(c.d_tbmap.p, c.h_tbmap.p, ncb * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
   }
   // 3. HARQ ordering: kernels of this context run after the kernels of the previously launched context.
   if (h->last_launched >= 0 && h->last_launched != ci) {
@@ -718,7 +749,11 @@ int launch_context(srsran_cuda_pusch_dec* h, int ci)
   }
   CUDA_TRY(h, cudaEventRecord(c.stage[3], s));
   if (ntb != 0) {
-    tb_assemble_crc_kernel<<<ntb, CRC_THREADS, 0, s>>>(c.d_tb.p, c.d_tbres.p, h->d_bits.p, h->d_crc_flags.p, c.d_tbout.p);
+    tb_gather_kernel<<<(ncb + TBG_WARPS - 1) / TBG_WARPS, TBG_WARPS * 32, 0, s>>>(c.d_tb.p, c.d_tbmap.p, ncb, h->d_bits.p,
+                                                                                 c.d_tbout.p, c.d_tbshare.p);
+    ++h->launches;
+    CUDA_TRY(h, cudaGetLastError());
+    tb_finalize_kernel<<<(ntb + 7) / 8, 256, 0, s>>>(c.d_tb.p, ntb, c.d_tbres.p, c.d_tbshare.p, h->d_crc_flags.p);
     ++h->launches;
     CUDA_TRY(h, cudaGetLastError());
   }
@@ -846,6 +881,9 @@ int add_tb(srsran_cuda_pusch_dec* h, batch_context& c, const srsran_cuda_pusch_d
   t.out_offset      = static_cast<uint32_t>(c.tbout_used);
   uint32_t ti       = static_cast<uint32_t>(c.tb_meta.size());
   c.h_tb.p[ti]      = t;
+  for (int i = 0; i != C; ++i) {
+    c.h_tbmap.p[first_cb + i] = ti;
+  }
   c.tb_meta.push_back({first_cb, static_cast<uint32_t>(C), cfg.tbs_bits, t.out_offset, cfg.nof_ldpc_iterations, false});
   c.tbout_used += (cfg.tbs_bits / 8 + 3 + 15) & ~size_t(15);
   return SRSRAN_CUDA_OK;
@@ -960,6 +998,10 @@ int srsran_cuda_pusch_dec_create(int device, uint32_t max_cbs_in_flight, uint32_
       return fail(SRSRAN_CUDA_ERR_CUDA);
     }
   }
+  if (cudaEventCreate(&h->timer_begin) != cudaSuccess || cudaEventCreate(&h->timer_end) != cudaSuccess) {
+    h->last_error = "event creation failed";
+    return fail(SRSRAN_CUDA_ERR_CUDA);
+  }
   if (cudaDeviceSynchronize() != cudaSuccess) {
     h->last_error = "device synchronisation failed";
     return fail(SRSRAN_CUDA_ERR_CUDA);
@@ -984,6 +1026,9 @@ void srsran_cuda_pusch_dec_destroy(srsran_cuda_pusch_dec_t* h)
     c.d_order.release();
     c.h_grp.release();
     c.d_grp.release();
+    c.h_tbmap.release();
+    c.d_tbmap.release();
+    c.d_tbshare.release();
     c.h_res.release();
     c.d_res.release();
     c.h_bits.release();
@@ -1009,6 +1054,12 @@ void srsran_cuda_pusch_dec_destroy(srsran_cuda_pusch_dec_t* h)
     if (c.stream != nullptr) {
       cudaStreamDestroy(c.stream);
     }
+  }
+  if (h->timer_begin != nullptr) {
+    cudaEventDestroy(h->timer_begin);
+  }
+  if (h->timer_end != nullptr) {
+    cudaEventDestroy(h->timer_end);
   }
   h->d_soft.release();
   h->d_bits.release();
@@ -1438,6 +1489,40 @@ int srsran_cuda_pusch_dec_ticket_timing(srsran_cuda_pusch_dec_t* h, int ticket, 
   for (int i = 0; i != 5; ++i) {
     CUDA_TRY(h, cudaEventElapsedTime(&stage_ms[i], ev[i], ev[i + 1]));
   }
+  return SRSRAN_CUDA_OK;
+}
+
+int srsran_cuda_pusch_dec_timer_start(srsran_cuda_pusch_dec_t* h)
+{
+  if (h == nullptr) {
+    return SRSRAN_CUDA_ERR_INVALID;
+  }
+  h->timer_armed = true;
+  return SRSRAN_CUDA_OK;
+}
+
+int srsran_cuda_pusch_dec_timer_stop(srsran_cuda_pusch_dec_t* h, float* elapsed_ms)
+{
+  if (h == nullptr || elapsed_ms == nullptr || h->timer_armed || h->last_launched < 0) {
+    return SRSRAN_CUDA_ERR_INVALID;
+  }
+  cudaSetDevice(h->device);
+  if (h->open_ctx >= 0) {
+    int r = fixup_and_launch(h, h->open_ctx);
+    if (r != SRSRAN_CUDA_OK) {
+      return r;
+    }
+  }
+  // Everything launched so far: the streams of all contexts in flight join the last launched one.
+  cudaStream_t s = h->ctx[h->last_launched].stream;
+  for (batch_context& c : h->ctx) {
+    if (c.in_flight && c.stream != s) {
+      CUDA_TRY(h, cudaStreamWaitEvent(s, c.done, 0));
+    }
+  }
+  CUDA_TRY(h, cudaEventRecord(h->timer_end, s));
+  CUDA_TRY(h, cudaEventSynchronize(h->timer_end));
+  CUDA_TRY(h, cudaEventElapsedTime(elapsed_ms, h->timer_begin, h->timer_end));
   return SRSRAN_CUDA_OK;
 }
 

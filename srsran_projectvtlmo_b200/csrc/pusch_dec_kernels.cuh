@@ -26,6 +26,8 @@ __constant__ uint16_t c_shift[2][8][MAX_EDGES];
 __constant__ uint32_t c_xpow32[3][272];
 /// x^(128 i) mod g, i = 0..1023.
 __constant__ uint32_t c_xpow128[3][1024];
+/// x^(2^i) mod g, i = 0..31 (square-and-multiply ladders).
+__constant__ uint32_t c_xpow2[3][32];
 
 __host__ __device__ __forceinline__ uint32_t crc_gen(int poly)
 {
@@ -896,83 +898,169 @@ __global__ void __launch_bounds__(CRC_THREADS) crc_kernel(const crc_job* __restr
   }
 }
 
-/// TB assembly (pusch_decoder_impl.cpp:384-497): concatenates the payload bits of every code block (dropping CB CRC,
-/// filler and zero padding), then checks CRC24A over TBS + 24 bits. One CTA per TB.
-__global__ void __launch_bounds__(CRC_THREADS) tb_assemble_crc_kernel(const tb_desc* __restrict__ tbs,
-                                                                      tb_result_dev* __restrict__ tb_results,
-                                                                      const uint8_t* __restrict__ bits_base,
-                                                                      uint32_t* __restrict__ crc_flags,
-                                                                      uint8_t* __restrict__ tb_out)
+// ---------------------------------------------------------------------------------------------------------------------
+// TB assembly (pusch_decoder_impl.cpp:384-497) in two small kernels so that a transport block of 152 code blocks is
+// handled by 152 warps instead of one CTA:
+//   tb_gather_kernel    one WARP per code block: copies its payload bits (dropping CB CRC, filler and zero padding)
+//                       to their bit position in the transport block, and computes its share of the TB CRC24A:
+//                       (payload(x) x^24 mod g) * x^(bits behind it) mod g  (CRCs are linear over GF(2))
+//   tb_finalize_kernel  one WARP per transport block: all code blocks ok? XOR of the shares == 0? result + CRC-flag reset
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int TBG_WARPS = 16;
+
+/// Byte tables tabs[k][b] = (b(x) x^(8k) x^order) mod g, k = 0..3, built by the whole CTA.
+__device__ __forceinline__ void build_crc_tables(uint32_t* tabs, int poly, int t, int nthreads)
 {
-  __shared__ uint32_t lut[256];
-  __shared__ uint32_t red[33];
-  __shared__ uint32_t all_ok;
-  const tb_desc       tb = tbs[blockIdx.x];
-  const int           t  = threadIdx.x;
-  if (t == 0) {
-    all_ok = 1;
+  const uint32_t gen = crc_gen(poly), order = crc_order(poly);
+  for (int i = t; i < 1024; i += nthreads) {
+    uint32_t r = crc_push_bits(0, ((uint32_t)i & 0xffU) << 24, 8, gen, order);
+    tabs[i]    = crc_push_bits(r, 0, 8 * ((uint32_t)i >> 8), gen, order);
   }
-  __syncthreads();
-  for (uint32_t i = t; i < tb.nof_cbs; i += CRC_THREADS) {
-    if (crc_flags[tb.first_slot + i] == 0) {
-      all_ok = 0;
+}
+
+/// CRC state after the first nb bits of a message held as 32-bit words, by ONE warp. BSWAP: the words are in memory
+/// byte order (MSB-first bytes, as the decoders store them), else MSB-first numeric words.
+template <bool BSWAP>
+__device__ __forceinline__ uint32_t warp_crc_words(const uint32_t* words, uint32_t nb, int poly, const uint32_t* tabs, int lane)
+{
+  const uint32_t gen = crc_gen(poly), order = crc_order(poly);
+  const uint32_t nfull = nb / 32, rem = nb % 32;
+  const uint32_t per   = (nfull + 31) / 32;
+  uint32_t       w0 = min(nfull, (uint32_t)lane * per), w1 = min(nfull, w0 + per);
+  uint32_t       acc = 0;
+  const uint32_t sh  = (32 - order) / 8; // tables that multiply a register byte by x^32
+  for (uint32_t w = w0; w < w1; ++w) {
+    uint32_t word = BSWAP ? __byte_perm(words[w], 0, 0x0123) : words[w];
+    uint32_t r    = tabs[3 * 256 + (word >> 24)] ^ tabs[2 * 256 + ((word >> 16) & 0xff)] ^ tabs[256 + ((word >> 8) & 0xff)] ^
+                 tabs[word & 0xff];
+    uint32_t m = tabs[sh * 256 + (acc & 0xff)] ^ tabs[(sh + 1) * 256 + ((acc >> 8) & 0xff)];
+    if (order == 24) {
+      m ^= tabs[(sh + 2) * 256 + (acc >> 16)];
     }
+    acc = m ^ r;
   }
+  if (w1 > w0 && w1 != nfull) {
+    acc = gf2_mulmod(acc, c_xpow32[poly - 1][nfull - w1], gen, order);
+  }
+  acc = __reduce_xor_sync(0xffffffffU, acc);
+  if (rem != 0) {
+    uint32_t last = BSWAP ? __byte_perm(words[nfull], 0, 0x0123) : words[nfull];
+    acc           = crc_push_bits(acc, last, rem, gen, order);
+  }
+  return acc;
+}
+
+/// x^e mod g, by one warp: lane i contributes x^(2^i) if bit i of e is set, the factors are multiplied in a butterfly.
+__device__ __forceinline__ uint32_t warp_xpow(uint32_t e, int poly, int lane)
+{
+  const uint32_t gen = crc_gen(poly), order = crc_order(poly);
+  uint32_t       f   = ((e >> lane) & 1U) ? c_xpow2[poly - 1][lane] : 1U;
+#pragma unroll
+  for (int d = 16; d >= 1; d >>= 1) {
+    f = gf2_mulmod(f, __shfl_xor_sync(0xffffffffU, f, d), gen, order);
+  }
+  return f;
+}
+
+__global__ void __launch_bounds__(TBG_WARPS * 32) tb_gather_kernel(const tb_desc* __restrict__ tbs,
+                                                                   const uint32_t* __restrict__ tb_of_cb,
+                                                                   uint32_t nof_cbs,
+                                                                   const uint8_t* __restrict__ bits_base,
+                                                                   uint8_t* __restrict__ tb_out,
+                                                                   uint32_t* __restrict__ crc_share)
+{
+  __shared__ uint32_t tabs[1024];
+  const int           t = threadIdx.x, lane = t & 31;
+  const int           warp = __shfl_sync(0xffffffffU, t >> 5, 0);
+  build_crc_tables(tabs, 1, t, TBG_WARPS * 32);
   __syncthreads();
-  uint8_t*       out       = tb_out + tb.out_offset;
-  const uint32_t tb_bytes  = tb.tbs_bits / 8;
+  const uint32_t cb = blockIdx.x * TBG_WARPS + warp;
+  if (cb >= nof_cbs) {
+    return;
+  }
+  const uint32_t tbi = tb_of_cb[cb];
+  if (tbi == 0xffffffffU) {
+    return;
+  }
+  const tb_desc   tb   = tbs[tbi];
+  const uint32_t  r    = cb - tb.first_cb;
+  const uint32_t* src  = reinterpret_cast<const uint32_t*>(bits_base + (size_t)(tb.first_slot + r) * BITS_STRIDE);
+  uint32_t*       out  = reinterpret_cast<uint32_t*>(tb_out + tb.out_offset);
   if (tb.nof_cbs == 1) {
-    // The code-block CRC is the TB CRC; copy the payload only if it is ok.
-    if (all_ok) {
-      const uint8_t* src = bits_base + (size_t)tb.first_slot * BITS_STRIDE;
-      for (uint32_t i = t; i < tb_bytes; i += CRC_THREADS) {
-        out[i] = src[i];
-      }
+    // The code-block CRC is the TB CRC: the payload is the first TBS bits.
+    const uint32_t nw = (tb.tbs_bits / 8 + 3) / 4;
+    for (uint32_t i = lane; i < nw; i += 32) {
+      out[i] = src[i];
     }
-    if (t == 0) {
-      tb_results[blockIdx.x] = {all_ok, all_ok};
+    if (lane == 0) {
+      crc_share[cb] = 0;
     }
     return;
   }
-  if (!all_ok) {
-    if (t == 0) {
-      tb_results[blockIdx.x] = {0U, 0U};
+  const uint32_t Lp = tb.cb_data_bits;
+  // (1) share of the TB CRC
+  uint32_t crc = warp_crc_words<true>(src, Lp, 1, tabs, lane);
+  uint32_t pw  = warp_xpow(Lp * (tb.nof_cbs - 1 - r), 1, lane);
+  if (lane == 0) {
+    crc_share[cb] = gf2_mulmod(crc, pw, crc_gen(1), crc_order(1));
+  }
+  // (2) payload bits [0, Lp) -> TB bits [o, o + Lp). A 32-bit output word belongs to the code block holding its first bit.
+  const uint32_t  o     = r * Lp;
+  const uint32_t  m0    = (o + 31) / 32;
+  const uint32_t  m1    = (o + Lp + 31) / 32;
+  const bool      last  = (r + 1 == tb.nof_cbs);
+  const uint32_t* nxt   = reinterpret_cast<const uint32_t*>(bits_base + (size_t)(tb.first_slot + r + 1) * BITS_STRIDE);
+  for (uint32_t m = m0 + lane; m < m1; m += 32) {
+    uint32_t w  = 32 * m - o;
+    uint32_t sw = w >> 5, sh = w & 31;
+    uint32_t A  = __byte_perm(src[sw], 0, 0x0123);
+    uint32_t v  = A;
+    if (sh != 0) {
+      uint32_t B = __byte_perm(src[sw + 1], 0, 0x0123);
+      v          = (A << sh) | (B >> (32 - sh));
+    }
+    uint32_t avail = Lp - w;
+    if (avail < 32) {
+      uint32_t tail = last ? 0U : (__byte_perm(nxt[0], 0, 0x0123) >> avail);
+      v             = (v & (0xffffffffU << (32 - avail))) | tail;
+    }
+    out[m] = __byte_perm(v, 0, 0x0123);
+  }
+}
+
+__global__ void __launch_bounds__(256) tb_finalize_kernel(const tb_desc* __restrict__ tbs,
+                                                          uint32_t nof_tbs,
+                                                          tb_result_dev* __restrict__ tb_results,
+                                                          const uint32_t* __restrict__ crc_share,
+                                                          uint32_t* __restrict__ crc_flags)
+{
+  const int      lane = threadIdx.x & 31;
+  const uint32_t tbi  = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (tbi >= nof_tbs) {
+    return;
+  }
+  const tb_desc tb  = tbs[tbi];
+  bool          ok  = true;
+  uint32_t      crc = 0;
+  for (uint32_t i = lane; i < tb.nof_cbs; i += 32) {
+    ok = ok && (crc_flags[tb.first_slot + i] != 0);
+    crc ^= crc_share[tb.first_cb + i];
+  }
+  const uint32_t all_ok = __all_sync(0xffffffffU, ok) ? 1U : 0U;
+  crc                   = __reduce_xor_sync(0xffffffffU, crc);
+  if (tb.nof_cbs == 1 || !all_ok) {
+    // Single code block: its CRC is the TB CRC. Otherwise the TB CRC is only checked when every code block is ok.
+    if (lane == 0) {
+      tb_results[tbi] = {all_ok, all_ok};
     }
     return;
   }
-  // Gather TBS + 24 bits. Output byte b holds TB bits [8b, 8b+8): bit o lives in code block o / Lp at offset o % Lp.
-  const uint32_t Lp     = tb.cb_data_bits;
-  const uint32_t nbytes = tb_bytes + 3;
-  for (uint32_t b = t; b < nbytes; b += CRC_THREADS) {
-    uint32_t o    = 8 * b;
-    uint32_t cb   = o / Lp;
-    uint32_t w    = o - cb * Lp;
-    uint32_t byte = 0;
-    uint32_t got  = 0;
-    while (got < 8) {
-      const uint8_t* src  = bits_base + (size_t)(tb.first_slot + cb) * BITS_STRIDE;
-      uint32_t       take = min(8 - got, Lp - w);
-      // `take` bits starting at bit w of src.
-      uint32_t two = ((uint32_t)src[w >> 3] << 8) | (uint32_t)src[(w >> 3) + 1];
-      uint32_t v   = (two >> (16 - (w & 7) - take)) & ((1U << take) - 1);
-      byte |= v << (8 - got - take);
-      got += take;
-      w += take;
-      if (w == Lp) {
-        w = 0;
-        ++cb;
-      }
-    }
-    out[b] = (uint8_t)byte;
-  }
-  __syncthreads();
-  uint32_t crc = block_crc_bytes(out, nbytes, 1, lut, red);
-  if (t == 0) {
-    tb_results[blockIdx.x] = {crc == 0 ? 1U : 0U, 1U};
+  if (lane == 0) {
+    tb_results[tbi] = {crc == 0 ? 1U : 0U, 1U};
   }
   if (crc != 0) {
     // At least one code block is a false positive: reset them all (pusch_decoder_impl.cpp:425-428).
-    for (uint32_t i = t; i < tb.nof_cbs; i += CRC_THREADS) {
+    for (uint32_t i = lane; i < tb.nof_cbs; i += 32) {
       crc_flags[tb.first_slot + i] = 0;
     }
   }

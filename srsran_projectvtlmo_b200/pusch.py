@@ -67,6 +67,14 @@ class Accelerator:
     def synchronize(self):
         self._check(self._lib.srsran_cuda_pusch_dec_synchronize(self.h), "synchronize")
 
+    def timer_start(self):
+        self._check(self._lib.srsran_cuda_pusch_dec_timer_start(self.h), "timer_start")
+
+    def timer_stop(self):
+        ms = C.c_float(0)
+        self._check(self._lib.srsran_cuda_pusch_dec_timer_stop(self.h, C.byref(ms)), "timer_stop")
+        return float(ms.value)
+
     def read_softbuffer(self, absolute_cb_id, n):
         out = np.zeros(n, np.int8)
         self._check(self._lib.srsran_cuda_pusch_dec_read_softbuffer(self.h, absolute_cb_id,
