@@ -1,0 +1,276 @@
+// TEST INFRASTRUCTURE - drop-in proof on the reference's own classes.
+//
+// Builds (oracle/Makefile, target hwacc) into oracle/_ref/hwacc_parity from the UNMODIFIED reference sources where they
+// lie under /root/reference plus the repo's C++ host adapters (srsran_projectvtlmo_b200/host/):
+//
+//   reference pusch_decoder_hw_impl  +  OUR hal::hw_accelerator_pusch_dec (CUDA, B200)      <- device under test
+//   reference pusch_decoder_impl     +  reference AVX-512/AVX2 ldpc_decoder / rate dematcher <- the oracle
+//
+// Both decode the same transport blocks (reference pdsch_encoder_impl as the transmitter, AWGN, int8 LLRs) over the HARQ
+// sequence rv 0,2,3,1 like pusch_decoder_vectortest.cpp:261-397 and must agree on TB CRC, TB bytes, number of code blocks
+// and LDPC iteration statistics. Exit code 0 = parity, 1 = mismatch, 2 = no CUDA device.
+#include "hw_accelerator_factories_cuda.h"
+#include "channel_coding_factories_cuda.h"
+#include "pdsch_encoder_impl.h"
+#include "pusch_decoder_hw_impl.h"
+#include "pusch_decoder_impl.h"
+#include "srsran/phy/upper/channel_coding/channel_coding_factories.h"
+#include "srsran/phy/upper/channel_processors/pusch/pusch_decoder_notifier.h"
+#include "srsran/phy/upper/channel_processors/pusch/pusch_decoder_result.h"
+#include "srsran/phy/upper/unique_rx_buffer.h"
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <random>
+#include <vector>
+
+using namespace srsran;
+
+namespace {
+
+class harness_rx_buffer : public unique_rx_buffer::callback
+{
+public:
+  harness_rx_buffer(unsigned nof_cbs_, unsigned first_absolute_id_) :
+    nof_cbs(nof_cbs_), first_absolute_id(first_absolute_id_), crcs(new bool[nof_cbs_]()), soft(nof_cbs_), data(nof_cbs_)
+  {
+    for (unsigned i = 0; i != nof_cbs; ++i) {
+      soft[i].assign(ldpc::MAX_CODEBLOCK_SIZE, log_likelihood_ratio(0));
+      data[i].assign(ldpc::MAX_CODEBLOCK_SIZE / 8 + 8, 0);
+    }
+  }
+  unsigned   get_nof_codeblocks() const override { return nof_cbs; }
+  void       reset_codeblocks_crc() override { std::fill(crcs.get(), crcs.get() + nof_cbs, false); }
+  span<bool> get_codeblocks_crc() override { return span<bool>(crcs.get(), nof_cbs); }
+  unsigned   get_absolute_codeblock_id(unsigned codeblock_id) const override { return first_absolute_id + codeblock_id; }
+  span<log_likelihood_ratio> get_codeblock_soft_bits(unsigned codeblock_id, unsigned codeblock_size) override
+  {
+    return span<log_likelihood_ratio>(soft[codeblock_id]).first(codeblock_size);
+  }
+  bit_buffer get_codeblock_data_bits(unsigned codeblock_id, unsigned data_size) override
+  {
+    return bit_buffer::from_bytes(span<uint8_t>(data[codeblock_id])).first(data_size);
+  }
+  void lock() override {}
+  void unlock() override {}
+  void release() override {}
+
+  unsigned                                       nof_cbs, first_absolute_id;
+  std::unique_ptr<bool[]>                        crcs;
+  std::vector<std::vector<log_likelihood_ratio>> soft;
+  std::vector<std::vector<uint8_t>>              data;
+};
+
+class notifier_t : public pusch_decoder_notifier
+{
+public:
+  void on_sch_data(const pusch_decoder_result& result) override
+  {
+    res  = result;
+    done = true;
+  }
+  pusch_decoder_result res;
+  bool                 done = false;
+};
+
+struct tb_case {
+  const char* name;
+  unsigned    tbs_bits, bg, Qm, nof_layers, nof_llrs, Nref;
+  double      mu;
+  bool        early_stop;
+  unsigned    max_it;
+};
+
+pusch_decoder_result run(pusch_decoder&                decoder,
+                         harness_rx_buffer&            buffer,
+                         std::vector<uint8_t>&         tb_out,
+                         const std::vector<int8_t>&    llrs,
+                         const tb_case&                c,
+                         unsigned                      rv,
+                         bool                          new_data)
+{
+  if (new_data) {
+    buffer.reset_codeblocks_crc(); // rx_buffer_pool_impl::reserve does this for new data
+  }
+  pusch_decoder::configuration cfg;
+  cfg.base_graph          = (c.bg == 1) ? ldpc_base_graph_type::BG1 : ldpc_base_graph_type::BG2;
+  cfg.rv                  = rv;
+  cfg.mod                 = static_cast<modulation_scheme>(c.Qm);
+  cfg.Nref                = c.Nref;
+  cfg.nof_layers          = c.nof_layers;
+  cfg.nof_ldpc_iterations = c.max_it;
+  cfg.use_early_stop      = c.early_stop;
+  cfg.new_data            = new_data;
+  notifier_t            notifier;
+  pusch_decoder_buffer& buf = decoder.new_data(span<uint8_t>(tb_out), unique_rx_buffer(buffer), notifier, cfg);
+  buf.on_new_softbits(span<const log_likelihood_ratio>(reinterpret_cast<const log_likelihood_ratio*>(llrs.data()), llrs.size()));
+  buf.on_end_softbits();
+  return notifier.res;
+}
+
+} // namespace
+
+int main()
+{
+  // ---- device under test: reference pusch_decoder_hw_impl over the CUDA accelerator ------------------------------------
+  hal::cuda_hwacc_pusch_dec_configuration acc_cfg;
+  acc_cfg.device            = 0;
+  acc_cfg.max_cbs_in_flight = 256;
+  acc_cfg.nof_harq_cb_slots = 4096;
+  auto hw_factory           = hal::create_cuda_pusch_dec_acc_factory(acc_cfg);
+  if (!hw_factory) {
+    std::printf("hwacc_parity: no usable CUDA device (%s)\n", srsran_cuda_pusch_dec_last_error(nullptr));
+    return 2;
+  }
+  auto crc_factory = create_crc_calculator_factory_sw("auto");
+  auto seg_factory = create_ldpc_segmenter_rx_factory_sw();
+
+  pusch_decoder_hw_impl::sch_crc hw_crcs = {crc_factory->create(crc_generator_poly::CRC16),
+                                            crc_factory->create(crc_generator_poly::CRC24A),
+                                            crc_factory->create(crc_generator_poly::CRC24B)};
+  pusch_decoder_hw_impl          hw_decoder(seg_factory->create(), hw_crcs, hw_factory->create());
+
+  // ---- oracle: reference software decoder ---------------------------------------------------------------------------------
+  auto dec_factory = create_ldpc_decoder_factory_sw("auto");
+  auto dem_factory = create_ldpc_rate_dematcher_factory_sw("auto");
+  std::vector<std::unique_ptr<pusch_codeblock_decoder>> cb_decoders(1);
+  {
+    pusch_codeblock_decoder::sch_crc crcs;
+    crcs.crc16     = crc_factory->create(crc_generator_poly::CRC16);
+    crcs.crc24A    = crc_factory->create(crc_generator_poly::CRC24A);
+    crcs.crc24B    = crc_factory->create(crc_generator_poly::CRC24B);
+    cb_decoders[0] = std::make_unique<pusch_codeblock_decoder>(dem_factory->create(), dec_factory->create(), crcs);
+  }
+  auto pool = std::make_shared<pusch_decoder_impl::codeblock_decoder_pool>(std::move(cb_decoders));
+  pusch_decoder_impl::sch_crc sw_crcs;
+  sw_crcs.crc16  = crc_factory->create(crc_generator_poly::CRC16);
+  sw_crcs.crc24A = crc_factory->create(crc_generator_poly::CRC24A);
+  sw_crcs.crc24B = crc_factory->create(crc_generator_poly::CRC24B);
+  pusch_decoder_impl sw_decoder(seg_factory->create(), pool, std::move(sw_crcs), nullptr, MAX_RB, 4);
+
+  // ---- transmitter --------------------------------------------------------------------------------------------------------
+  auto               seg_tx = create_ldpc_segmenter_tx_factory_sw(crc_factory);
+  auto               enc_f  = create_ldpc_encoder_factory_sw("auto");
+  auto               rm_f   = create_ldpc_rate_matcher_factory_sw();
+  pdsch_encoder_impl encoder(seg_tx->create(), enc_f->create(), rm_f->create());
+
+  // TBS / number of LLRs of SURVEY.md section 8 (156 RE per PRB): name, TBS, BG, Qm, layers, LLRs, Nref, mu, early stop, its
+  const tb_case cases[] = {
+      {"52prb_16qam_r658", 21000, 1, 4, 1, 32448, 25344, 1.15, true, 6},
+      {"52prb_qpsk_r120_bg2", 1928, 2, 2, 1, 16224, 25344, 0.35, true, 6},
+      {"25prb_qpsk_r120_bg2", 928, 2, 2, 1, 7800, 25344, 0.5, true, 6},
+      {"52prb_16qam_r378_noearlystop", 12040, 1, 4, 1, 32448, 25344, 0.8, false, 3},
+      {"273prb_256qam_r948_2layer", 638984, 1, 8, 2, 681408, 25223, 9.0, true, 6},
+      {"273prb_256qam_r948_2layer_highsnr", 638984, 1, 8, 2, 681408, 25223, 18.0, true, 6},
+  };
+  std::mt19937 rgen(2026);
+  int          failures = 0;
+  unsigned     next_abs = 0;
+  for (const tb_case& c : cases) {
+    unsigned nof_cbs = ldpc::compute_nof_codeblocks(units::bits(c.tbs_bits),
+                                                    (c.bg == 1) ? ldpc_base_graph_type::BG1 : ldpc_base_graph_type::BG2);
+    harness_rx_buffer sw_buffer(nof_cbs, 0), hw_buffer(nof_cbs, next_abs);
+    next_abs += nof_cbs;
+    std::vector<uint8_t> tb(c.tbs_bits / 8), tb_sw(tb.size()), tb_hw(tb.size()), cw(c.nof_llrs);
+    for (uint8_t& b : tb) {
+      b = static_cast<uint8_t>(rgen());
+    }
+    std::vector<int8_t>              llrs(c.nof_llrs);
+    std::normal_distribution<double> noise(0.0, std::sqrt(2.0 * c.mu));
+    const unsigned                   rvs[4] = {0, 2, 3, 1};
+    for (unsigned i = 0; i != 4; ++i) {
+      pdsch_encoder::configuration ecfg;
+      ecfg.base_graph     = (c.bg == 1) ? ldpc_base_graph_type::BG1 : ldpc_base_graph_type::BG2;
+      ecfg.rv             = rvs[i];
+      ecfg.mod            = static_cast<modulation_scheme>(c.Qm);
+      ecfg.Nref           = c.Nref;
+      ecfg.nof_layers     = c.nof_layers;
+      ecfg.nof_ch_symbols = c.nof_llrs / c.Qm;
+      encoder.encode(span<uint8_t>(cw), span<const uint8_t>(tb), ecfg);
+      for (unsigned k = 0; k != c.nof_llrs; ++k) {
+        double x = (cw[k] ? -c.mu : c.mu) + noise(rgen);
+        llrs[k]  = static_cast<int8_t>(std::max(-120.0, std::min(120.0, std::round(4.0 * x))));
+      }
+      pusch_decoder_result r_sw = run(sw_decoder, sw_buffer, tb_sw, llrs, c, rvs[i], i == 0);
+      pusch_decoder_result r_hw = run(hw_decoder, hw_buffer, tb_hw, llrs, c, rvs[i], i == 0);
+      bool same = (r_sw.tb_crc_ok == r_hw.tb_crc_ok) && (r_sw.nof_codeblocks_total == r_hw.nof_codeblocks_total) &&
+                  (r_sw.ldpc_decoder_stats.get_nof_observations() == r_hw.ldpc_decoder_stats.get_nof_observations());
+      if (same && r_sw.ldpc_decoder_stats.get_nof_observations() != 0) {
+        same = (r_sw.ldpc_decoder_stats.get_min() == r_hw.ldpc_decoder_stats.get_min()) &&
+               (r_sw.ldpc_decoder_stats.get_max() == r_hw.ldpc_decoder_stats.get_max()) &&
+               (std::abs(r_sw.ldpc_decoder_stats.get_mean() - r_hw.ldpc_decoder_stats.get_mean()) < 1e-4);
+      }
+      if (same && r_sw.tb_crc_ok) {
+        same = (tb_sw == tb_hw) && (tb_hw == tb);
+      }
+      // Code-block CRC flags as the two rx buffers hold them.
+      for (unsigned cb = 0; same && cb != nof_cbs; ++cb) {
+        same = (sw_buffer.crcs[cb] == hw_buffer.crcs[cb]);
+      }
+      std::printf("%-36s rv%u: cbs=%u crc sw/hw=%d/%d obs=%u/%u it[min,max]=[%u,%u]/[%u,%u] -> %s\n", c.name, rvs[i], nof_cbs,
+                  r_sw.tb_crc_ok, r_hw.tb_crc_ok, (unsigned)r_sw.ldpc_decoder_stats.get_nof_observations(),
+                  (unsigned)r_hw.ldpc_decoder_stats.get_nof_observations(),
+                  r_sw.ldpc_decoder_stats.get_nof_observations() ? r_sw.ldpc_decoder_stats.get_min() : 0,
+                  r_sw.ldpc_decoder_stats.get_nof_observations() ? r_sw.ldpc_decoder_stats.get_max() : 0,
+                  r_hw.ldpc_decoder_stats.get_nof_observations() ? r_hw.ldpc_decoder_stats.get_min() : 0,
+                  r_hw.ldpc_decoder_stats.get_nof_observations() ? r_hw.ldpc_decoder_stats.get_max() : 0, same ? "ok" : "MISMATCH");
+      failures += same ? 0 : 1;
+      if (r_sw.tb_crc_ok) {
+        break;
+      }
+    }
+  }
+
+  // ---- unit-level factories: "cuda" ldpc_decoder / rate dematcher / crc_calculator against the reference's "auto" ---------
+  {
+    auto device  = std::make_shared<hal::cuda_pusch_dec_device>(acc_cfg);
+    auto crc_gpu = create_crc_calculator_factory_cuda(device);
+    auto dem_gpu = create_ldpc_rate_dematcher_factory_cuda(device)->create();
+    auto dec_gpu = create_ldpc_decoder_factory_cuda(device)->create();
+    auto dem_cpu = dem_factory->create();
+    auto dec_cpu = dec_factory->create();
+    std::uniform_int_distribution<int> llr_dist(-120, 120);
+    for (crc_generator_poly poly : {crc_generator_poly::CRC24A, crc_generator_poly::CRC24B, crc_generator_poly::CRC16}) {
+      std::vector<uint8_t> msg(997);
+      for (uint8_t& b : msg) {
+        b = static_cast<uint8_t>(rgen());
+      }
+      bool same = crc_gpu->create(poly)->calculate_byte(msg) == crc_factory->create(poly)->calculate_byte(msg);
+      std::printf("crc_calculator cuda vs auto, poly %d: %s\n", (int)poly, same ? "ok" : "MISMATCH");
+      failures += same ? 0 : 1;
+    }
+    // One BG1 Z=384 code block: dematch (rv 0 then rv 2 combining) and decode with CRC24B early stop.
+    codeblock_metadata meta;
+    meta.tb_common.base_graph        = ldpc_base_graph_type::BG1;
+    meta.tb_common.lifting_size      = ldpc::LS384;
+    meta.tb_common.mod               = modulation_scheme::QAM256;
+    meta.tb_common.Nref              = 12611;
+    meta.cb_specific.nof_filler_bits = 16;
+    meta.cb_specific.nof_crc_bits    = 24;
+    std::vector<log_likelihood_ratio> soft_cpu(25344, 0), soft_gpu(25344, 0), in(8960);
+    bool                              same = true;
+    for (unsigned rv : {0U, 2U}) {
+      meta.tb_common.rv = rv;
+      for (auto& v : in) {
+        v = llr_dist(rgen);
+      }
+      dem_cpu->rate_dematch(soft_cpu, in, rv == 0, meta);
+      dem_gpu->rate_dematch(soft_gpu, in, rv == 0, meta);
+      same = same && std::equal(soft_cpu.begin(), soft_cpu.end(), soft_gpu.begin());
+    }
+    std::printf("ldpc_rate_dematcher cuda vs auto: %s\n", same ? "ok" : "MISMATCH");
+    failures += same ? 0 : 1;
+    std::vector<uint8_t>    out_cpu(1056, 0), out_gpu(1056, 0);
+    bit_buffer              bb_cpu = bit_buffer::from_bytes(out_cpu), bb_gpu = bit_buffer::from_bytes(out_gpu);
+    ldpc_decoder::configuration dcfg;
+    dcfg.block_conf = meta;
+    auto crc24b     = crc_factory->create(crc_generator_poly::CRC24B);
+    auto it_cpu     = dec_cpu->decode(bb_cpu, soft_cpu, crc24b.get(), dcfg);
+    auto it_gpu     = dec_gpu->decode(bb_gpu, soft_gpu, crc24b.get(), dcfg);
+    same            = (it_cpu == it_gpu) && (out_cpu == out_gpu);
+    std::printf("ldpc_decoder cuda vs auto: %s\n", same ? "ok" : "MISMATCH");
+    failures += same ? 0 : 1;
+  }
+  std::printf("hwacc_parity: %s (%d mismatches)\n", failures ? "FAILED" : "PASSED", failures);
+  return failures ? 1 : 0;
+}

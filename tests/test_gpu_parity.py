@@ -415,3 +415,20 @@ def test_packed_decoder_groups_via_hal(acc, variant):
 
 
 _packed_prev = {}
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Drop-in proof: the reference's own pusch_decoder_hw_impl driving this repo's C++ hal accelerator (CUDA), compared with
+# the reference's software pusch_decoder_impl on the same transport blocks (oracle/hwacc_harness.cpp)
+# ---------------------------------------------------------------------------------------------------------------------
+def test_reference_hw_decoder_over_cuda_accelerator():
+    import subprocess
+    from pathlib import Path
+
+    exe = Path(__file__).resolve().parent.parent / "oracle" / "_ref" / "hwacc_parity"
+    if not exe.exists():
+        pytest.skip("oracle/_ref/hwacc_parity not built (needs /root/reference at build time)")
+    r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=600)
+    print(r.stdout)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+    assert "PASSED" in r.stdout
