@@ -205,6 +205,7 @@ def main():
     ap.add_argument("--ref-seconds", type=float, default=20.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--latency-reps", type=int, default=200)
+    ap.add_argument("--decoder-variant", type=int, default=0, help="0 auto (packed, 4 lanes per thread), 1 one code block per thread group, 2 packed with 2 threads per check")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
 
@@ -233,6 +234,7 @@ def main():
     tbs, nllr, payloads, sets = make_inputs(B, 2, args.mu, 1000 + rank)
     ncb = 152
     acc = pusch.Accelerator(device=local_rank, max_cbs_in_flight=B * ncb, nof_harq_cb_slots=B * ncb)
+    acc.set_decoder_variant(args.decoder_variant)
     cfgs = [capi.TbConfig(tbs, w["bg"], 0, w["qm"], w["nref"], w["layers"], w["max_it"], w["early_stop"], 1, i * ncb)
             for i in range(B)]
 
@@ -371,7 +373,7 @@ def main():
             "scaling": "weak", "vs_baseline": None, "dtype": "int8", "data": "synthetic",
             "config": {"workload": w["name"], "tbs_bits": tbs, "codeblocks_per_tb": ncb, "tbs_per_step_per_gpu": B,
                        "lifting_size": 384, "base_graph": 1, "max_iterations": w["max_it"], "early_stop": True,
-                       "mu": args.mu, "mean_iterations": mean_it, "tb_crc_ok_fraction": ok_tbs / (B * args.steps),
+                       "mu": args.mu, "decoder_variant": args.decoder_variant, "mean_iterations": mean_it, "tb_crc_ok_fraction": ok_tbs / (B * args.steps),
                        "timing": "device stopwatch (CUDA events on the library streams) over all steps, <= 3 batches in flight; "
                                  "inputs alternate between two sets larger than L2 (no flush needed)"},
             "e2e": {"value": e2e, "unit": "Gbit/s", "h2d_bytes_per_step": B * nllr,

@@ -359,4 +359,302 @@ __global__ void __launch_bounds__(TPC, 1) ldpc_decode4_kernel(const cb_desc* __r
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Kernel 2c: same four-code-block group per CTA, but TWO threads per lifted check (2 x TPC threads): thread (h, j) owns
+// code blocks h and h + 2 (one register of two 16-bit lanes). Twice the warps per scheduler (6 instead of 3) and half the
+// registers per thread hide the fixed ALU / shared-memory latencies the 4-lanes-per-thread kernel stalls on; the price is
+// one extra address computation and narrower shared-memory accesses per edge. Shared memory holds two planes of soft
+// values (4 bytes per variable lift each) and two planes of messages (2 bytes per lifted edge each).
+// ---------------------------------------------------------------------------------------------------------------------
+template <int DEG>
+__device__ __forceinline__ void process_check2(uint32_t* __restrict__    soft,
+                                               uint16_t* __restrict__    c2v_row,
+                                               const uint2* __restrict__ tab_row,
+                                               uint32_t                  j,
+                                               uint32_t                  Z,
+                                               uint32_t                  zmagic,
+                                               uint32_t                  mult)
+{
+  pk::check2<DEG> ck;
+  ck.begin();
+#pragma unroll
+  for (int e = 0; e != DEG; ++e) {
+    ck.gather(e, soft[edge_addr(tab_row[e], j, Z, zmagic)], c2v_row[e * Z + j]);
+  }
+  ck.reduce(mult);
+#pragma unroll
+  for (int e = 0; e != DEG; ++e) {
+    uint32_t s0;
+    c2v_row[e * Z + j]                        = (uint16_t)ck.scatter(e, s0);
+    soft[edge_addr(tab_row[e], j, Z, zmagic)] = s0;
+  }
+}
+
+template <int TPC>
+__global__ void __launch_bounds__(2 * TPC, 1) ldpc_decode4h_kernel(const cb_desc* __restrict__ descs,
+                                                                    const grp_desc* __restrict__ groups,
+                                                                    cb_result* __restrict__ results,
+                                                                    const int8_t* __restrict__ soft_base,
+                                                                    uint8_t* __restrict__ bits_base,
+                                                                    uint32_t* __restrict__ crc_flags)
+{
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  constexpr int  NT   = 2 * TPC;
+  constexpr int  NW   = NT / 32;
+  const int      t    = threadIdx.x;
+  const int      lane = t & 31;
+  const int      warp = __shfl_sync(0xffffffffU, t >> 5, 0);
+  const int      h    = warp / (NW / 2); // plane: code blocks h and h + 2
+  const grp_desc g    = groups[blockIdx.x];
+  const cb_desc& d0   = descs[g.cb[0]];
+  const uint32_t Z = d0.Z, bg = d0.bg, Kb = (bg == 1) ? 22 : 10, K = Kb * Z, L = g.layer_cap;
+  const uint32_t mode = d0.mode, max_it = d0.max_it, mult = d0.scale_mult;
+  const int      poly = d0.crc_poly;
+  const uint32_t HBW  = K / 32;
+  const uint32_t nvar = (Kb + L) * Z;
+
+  const dec4_layout lay    = dec4_smem_layout(bg, Z, L);
+  uint2*            tab    = reinterpret_cast<uint2*>(smem_raw + lay.tab_off);
+  uint32_t*         soft   = reinterpret_cast<uint32_t*>(smem_raw + lay.soft_off) + (size_t)h * nvar;
+  const uint32_t    nedges = c_row_ptr[bg - 1][L];
+  uint16_t*         c2v    = reinterpret_cast<uint16_t*>(smem_raw + lay.c2v_off) + (size_t)h * nedges * Z;
+  uint32_t*         hb     = reinterpret_cast<uint32_t*>(smem_raw + lay.hb_off);
+  uint32_t*         tabs   = reinterpret_cast<uint32_t*>(smem_raw + lay.crc_off);
+  uint32_t*         misc   = reinterpret_cast<uint32_t*>(smem_raw + lay.misc_off);
+
+  // ---- per-lane (code block) setup: uniform across the CTA ---------------------------------------------------------------
+  const int8_t* src[4];
+  uint32_t      n_load[4], nbits[4], cbi[4];
+  bool          live[4];
+  const uint32_t cap_in = (Kb + L) * Z - 2 * Z;
+#pragma unroll
+  for (int c = 0; c != 4; ++c) {
+    cbi[c]  = g.cb[c < (int)g.n ? c : 0];
+    live[c] = c < (int)g.n;
+    const cb_desc& d = descs[cbi[c]];
+    src[c]    = soft_base + (size_t)d.slot * SOFT_STRIDE;
+    n_load[c] = live[c] ? min(min(d.n_in, d.scan_len), cap_in) : 0U;
+    nbits[c]  = K - d.nof_filler;
+    if (live[c] && (d.flags & FLAG_TRACK_CRC) && !d.new_data && crc_flags[d.slot] != 0) {
+      live[c]   = false;
+      n_load[c] = 0;
+      if (t == 0) {
+        results[cbi[c]] = {0, 1U, 0U, 2U};
+      }
+      if (d.bits_out != nullptr) {
+        const uint32_t* from = reinterpret_cast<const uint32_t*>(bits_base + (size_t)d.slot * BITS_STRIDE);
+        for (uint32_t i = t; i < HBW; i += NT) {
+          reinterpret_cast<uint32_t*>(d.bits_out)[i] = from[i];
+        }
+      }
+    }
+  }
+
+  // ---- prologue ----------------------------------------------------------------------------------------------------------
+  for (uint32_t e = t; e < nedges; e += NT) {
+    tab[e] = make_uint2((uint32_t)c_col[bg - 1][e] * Z, c_shift[bg - 1][d0.ils][e] % Z);
+  }
+  {
+    uint4*         c4 = reinterpret_cast<uint4*>(smem_raw + lay.c2v_off);
+    const uint32_t n4 = nedges * Z / 4; // both planes: nedges * Z * 4 bytes
+    const uint4    zz = make_uint4(pk::C2V_ZERO4, pk::C2V_ZERO4, pk::C2V_ZERO4, pk::C2V_ZERO4);
+    for (uint32_t i = t; i < n4; i += NT) {
+      c4[i] = zz;
+    }
+  }
+  if (poly != 0) {
+    build_crc_tables(tabs, poly, t, NT);
+  }
+  if (t < 32) {
+    misc[t] = 0;
+  }
+  __syncthreads();
+  {
+    const uint32_t nq    = nvar / 4; // quads of variable nodes
+    const uint32_t punct = 2 * Z / 4;
+    uint32_t       nz0 = 0, nz1 = 0;
+    const int      tl = t - h * TPC; // index within the plane's threads
+    for (uint32_t v = tl; v < nq; v += TPC) {
+      uint32_t w0 = 0, w1 = 0;
+      if (v >= punct) {
+        uint32_t p = (v - punct) * 4;
+        if (p < n_load[h]) {
+          w0 = __ldg(reinterpret_cast<const uint32_t*>(src[h] + p));
+        }
+        if (p < n_load[h + 2]) {
+          w1 = __ldg(reinterpret_cast<const uint32_t*>(src[h + 2] + p));
+        }
+        nz0 |= w0;
+        nz1 |= w1;
+      }
+      w0 ^= 0x80808080U;
+      w1 ^= 0x80808080U;
+      uint4 o;
+      o.x = pk::soft_from_biased_bytes(__byte_perm(w0, w1, 0x4400) & 0x00ff00ffU);
+      o.y = pk::soft_from_biased_bytes(__byte_perm(w0, w1, 0x5511) & 0x00ff00ffU);
+      o.z = pk::soft_from_biased_bytes(__byte_perm(w0, w1, 0x6622) & 0x00ff00ffU);
+      o.w = pk::soft_from_biased_bytes(__byte_perm(w0, w1, 0x7733) & 0x00ff00ffU);
+      reinterpret_cast<uint4*>(soft)[v] = o;
+    }
+    nz0 = __reduce_or_sync(0xffffffffU, nz0);
+    nz1 = __reduce_or_sync(0xffffffffU, nz1);
+    if (lane == 0) {
+      if (nz0 != 0) {
+        atomicOr(&misc[h], 1U);
+      }
+      if (nz1 != 0) {
+        atomicOr(&misc[h + 2], 1U);
+      }
+    }
+  }
+  __syncthreads();
+  bool allzero[4];
+#pragma unroll
+  for (int c = 0; c != 4; ++c) {
+    allzero[c] = (misc[c] == 0);
+  }
+
+  // ---- iterations --------------------------------------------------------------------------------------------------------
+  int      iters[4]  = {-1, -1, -1, -1};
+  uint32_t crc_ok[4] = {0, 0, 0, 0};
+  bool     done[4];
+#pragma unroll
+  for (int c = 0; c != 4; ++c) {
+    done[c] = !live[c] || (allzero[c] && mode == MODE_EARLY_STOP);
+  }
+  const uint32_t j      = t - h * TPC;
+  const uint32_t zmagic = 0xffffffffU / Z + 1;
+  for (uint32_t it = 0; it != max_it; ++it) {
+    for (uint32_t l = 0; l != L; ++l) {
+      uint32_t e0  = c_row_ptr[bg - 1][l];
+      int      deg = (int)c_row_ptr[bg - 1][l + 1] - (int)e0;
+      if (j < Z) {
+        uint16_t*    c2v_row = c2v + (size_t)e0 * Z;
+        const uint2* tab_row = tab + e0;
+        switch (deg) {
+          case 3:
+            process_check2<3>(soft, c2v_row, tab_row, j, Z, zmagic, mult);
+            break;
+          case 4:
+            process_check2<4>(soft, c2v_row, tab_row, j, Z, zmagic, mult);
+            break;
+          case 5:
+            process_check2<5>(soft, c2v_row, tab_row, j, Z, zmagic, mult);
+            break;
+          case 6:
+            process_check2<6>(soft, c2v_row, tab_row, j, Z, zmagic, mult);
+            break;
+          case 7:
+            process_check2<7>(soft, c2v_row, tab_row, j, Z, zmagic, mult);
+            break;
+          case 8:
+            process_check2<8>(soft, c2v_row, tab_row, j, Z, zmagic, mult);
+            break;
+          case 9:
+            process_check2<9>(soft, c2v_row, tab_row, j, Z, zmagic, mult);
+            break;
+          case 10:
+            process_check2<10>(soft, c2v_row, tab_row, j, Z, zmagic, mult);
+            break;
+          default:
+            process_check2<19>(soft, c2v_row, tab_row, j, Z, zmagic, mult);
+            break;
+        }
+      }
+      __syncthreads();
+    }
+    const bool last_it = (it + 1 == max_it);
+    if (mode != MODE_EARLY_STOP && !last_it) {
+      continue;
+    }
+    if (t < 8) {
+      misc[4 + t] = 0;
+    }
+    __syncthreads();
+    {
+      // Plane h by its own warps; lane l takes variable 32 w + 31 - l: ballot bit l is already in MSB-first order.
+      uint32_t nz = 0x00010001U;
+      for (uint32_t w = warp - h * (NW / 2); w < HBW; w += NW / 2) {
+        uint32_t s  = soft[w * 32 + 31 - lane];
+        uint32_t p  = pk::addmin_s2_relu(s, PK_REP2(0x10000U - pk::BS), 0x00010001U); // 1 where soft > 0
+        nz &= pk::minu2(s ^ pk::SOFT_ZERO2, 0x00010001U);
+        uint32_t blo = __ballot_sync(0xffffffffU, (p & 0xffffU) == 0);
+        uint32_t bhi = __ballot_sync(0xffffffffU, (p >> 16) == 0);
+        if (lane < 2) {
+          hb[(h + 2 * lane) * HBW + w] = lane ? bhi : blo;
+        }
+      }
+      nz = __reduce_and_sync(0xffffffffU, nz);
+      if (lane == 0) {
+        if (!(nz & 1U)) {
+          atomicOr(&misc[4 + h], 1U);
+        }
+        if (!(nz >> 16)) {
+          atomicOr(&misc[6 + h], 1U);
+        }
+      }
+    }
+    __syncthreads();
+    if (warp < 4) {
+      uint32_t ok = 0;
+#pragma unroll
+      for (int c = 0; c != 4; ++c) {
+        if (c == warp && !done[c]) {
+          uint32_t crc = warp_crc_words<false>(hb + c * HBW, nbits[c], poly, tabs, lane);
+          ok           = (crc == 0 && (mode != MODE_EARLY_STOP || misc[4 + c] == 0)) ? 1U : 0U;
+        }
+      }
+      if (lane == 0) {
+        misc[8 + warp] = ok;
+      }
+    }
+    __syncthreads();
+    bool all_done = true;
+#pragma unroll
+    for (int c = 0; c != 4; ++c) {
+      if (done[c]) {
+        continue;
+      }
+      bool ok = misc[8 + c] != 0;
+      if (ok || last_it) {
+        const cb_desc& d    = descs[cbi[c]];
+        uint32_t*      slot = reinterpret_cast<uint32_t*>(bits_base + (size_t)d.slot * BITS_STRIDE);
+        for (uint32_t i = t; i < HBW; i += NT) {
+          uint32_t wd = __byte_perm(hb[c * HBW + i], 0, 0x0123);
+          slot[i]     = wd;
+          if (d.bits_out != nullptr) {
+            reinterpret_cast<uint32_t*>(d.bits_out)[i] = wd;
+          }
+        }
+      }
+      if (ok) {
+        done[c]   = true;
+        crc_ok[c] = 1;
+        iters[c]  = (mode == MODE_EARLY_STOP) ? (int)it + 1 : (int)max_it;
+      } else {
+        all_done = false;
+      }
+    }
+    __syncthreads();
+    if (all_done) {
+      break;
+    }
+  }
+
+  if (t == 0) {
+#pragma unroll
+    for (int c = 0; c != 4; ++c) {
+      if (!live[c]) {
+        continue;
+      }
+      const cb_desc& d = descs[cbi[c]];
+      results[cbi[c]]  = {iters[c], crc_ok[c], L, 0U};
+      if (d.flags & FLAG_TRACK_CRC) {
+        crc_flags[d.slot] = crc_ok[c];
+      }
+    }
+  }
+}
+
 } // namespace pusch_dec

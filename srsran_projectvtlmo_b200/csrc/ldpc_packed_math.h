@@ -150,35 +150,36 @@ PK_FN uint32_t soft_from_biased_bytes(uint32_t ub2)
   return lane + tp * (INF - 127U) - tn * (INF - 127U);
 }
 
-/// State of one lifted check for four code blocks while a layer is processed.
-template <int DEG>
-struct check4 {
-  uint32_t q[DEG][2]; ///< v2c + BQ
-  uint32_t a[DEG][2]; ///< |v2c| + BQ
-  uint32_t m1[2], m2[2], x[2];
+/// State of one lifted check while a layer is processed, for 2 * NR code blocks (NR registers of two 16-bit lanes).
+/// KEEP_A: keep |v2c| of every edge in registers between the two passes (else it is recomputed: 2 instructions).
+template <int DEG, int NR, bool KEEP_A = true>
+struct check_lanes {
+  uint32_t q[DEG][NR];                  ///< v2c + BQ
+  uint32_t a[KEEP_A ? DEG : 1][NR];     ///< |v2c| + BQ
+  uint32_t m1[NR], m2[NR], x[NR];
+  uint32_t nm1[NR], pm1[NR], pm2[NR];
 
   PK_MFN void begin()
   {
-    m1[0] = m1[1] = m2[0] = m2[1] = PK_REP2(BQ + 120U);
-    x[0] = x[1] = 0;
+#pragma unroll
+    for (int r = 0; r != NR; ++r) {
+      m1[r] = m2[r] = PK_REP2(BQ + 120U);
+      x[r]          = 0;
+    }
   }
 
-  /// Edge e: soft words (s0, s1) and the packed messages cw of the previous iteration.
-  PK_MFN void gather(int e, uint32_t s0, uint32_t s1, uint32_t cw)
+  /// Edge e: soft words s[r] (S + BS per lane) and messages of the previous iteration c[r] (c + 128 per lane).
+  PK_MFN void gather(int e, const uint32_t* s, const uint32_t* c)
   {
-#if defined(__CUDA_ARCH__)
-    uint32_t c[2] = {cw & 0x00ff00ffU, __byte_perm(cw, 0, 0x4341)};
-#else
-    uint32_t c[2] = {cw & 0x00ff00ffU, (cw >> 8) & 0x00ff00ffU};
-#endif
-    uint32_t s[2] = {s0, s1};
 #pragma unroll
-    for (int r = 0; r != 2; ++r) {
+    for (int r = 0; r != NR; ++r) {
       uint32_t qq = s[r] - c[r];          // lanes never borrow: S + BS > c + 128
       uint32_t nq = 0x00010000U - qq;     // lane-wise 0x10000 - q
       uint32_t aa = maxu2(qq, nq);
       q[e][r]     = qq;
-      a[e][r]     = aa;
+      if (KEEP_A) {
+        a[e][r] = aa;
+      }
       x[r] ^= qq;
       uint32_t t = maxu2(m1[r], aa);
       m2[r]      = minu2(m2[r], t);
@@ -186,12 +187,10 @@ struct check4 {
     }
   }
 
-  uint32_t nm1[2], pm1[2], pm2[2];
-
   PK_MFN void reduce(uint32_t mult)
   {
 #pragma unroll
-    for (int r = 0; r != 2; ++r) {
+    for (int r = 0; r != NR; ++r) {
       uint32_t s1 = scale2(m1[r] & 0x7fff7fffU, mult);
       uint32_t s2 = scale2(m2[r] & 0x7fff7fffU, mult);
       nm1[r]      = 0x00010000U - m1[r];
@@ -203,13 +202,13 @@ struct check4 {
     }
   }
 
-  /// New packed messages (returned) and new soft words of edge e.
-  PK_MFN uint32_t scatter(int e, uint32_t& s0, uint32_t& s1)
+  /// New soft words sn[r] and new messages cn[r] (128 + c per lane) of edge e.
+  PK_MFN void scatter(int e, uint32_t* sn, uint32_t* cn)
   {
-    uint32_t cn[2], sn[2];
 #pragma unroll
-    for (int r = 0; r != 2; ++r) {
-      uint32_t aa = a[e][r], qq = q[e][r];
+    for (int r = 0; r != NR; ++r) {
+      uint32_t qq = q[e][r];
+      uint32_t aa = KEEP_A ? a[e][r] : maxu2(qq, 0x00010000U - qq);
       uint32_t t    = addmin_u2(aa, nm1[r], 0x00010001U); // 1: |q| > min1 -> min1, 0: this edge is the minimum -> min2
       uint32_t mask = t * 0xffffU;
       uint32_t pm   = sel(mask, pm1[r], pm2[r]);          // 128 + P * M
@@ -224,9 +223,50 @@ struct check4 {
       uint32_t nw = 0x01010100U - w;                       // lane-wise 2 * BS - w
       sn[r]       = sel(sq, w, nw);
     }
+  }
+};
+
+/// Four code blocks per thread, messages of one lifted edge packed in one 32-bit word (byte c = code block c): register 0
+/// holds code blocks 0 and 2, register 1 code blocks 1 and 3.
+template <int DEG>
+struct check4 : check_lanes<DEG, 2> {
+  PK_MFN void gather(int e, uint32_t s0, uint32_t s1, uint32_t cw)
+  {
+#if defined(__CUDA_ARCH__)
+    uint32_t c[2] = {cw & 0x00ff00ffU, __byte_perm(cw, 0, 0x4341)};
+#else
+    uint32_t c[2] = {cw & 0x00ff00ffU, (cw >> 8) & 0x00ff00ffU};
+#endif
+    uint32_t s[2] = {s0, s1};
+    check_lanes<DEG, 2>::gather(e, s, c);
+  }
+
+  /// New packed messages (returned) and new soft words of edge e.
+  PK_MFN uint32_t scatter(int e, uint32_t& s0, uint32_t& s1)
+  {
+    uint32_t cn[2], sn[2];
+    check_lanes<DEG, 2>::scatter(e, sn, cn);
     s0 = sn[0];
     s1 = sn[1];
     return cn[0] + (cn[1] << 8);
+  }
+};
+
+/// Two code blocks per thread (one register), messages of one lifted edge in one 16-bit word (low byte = lane 0).
+template <int DEG>
+struct check2 : check_lanes<DEG, 1, false> {
+  PK_MFN void gather(int e, uint32_t s0, uint32_t cw16)
+  {
+    uint32_t c = (cw16 & 0xffU) | ((cw16 & 0xff00U) << 8);
+    check_lanes<DEG, 1, false>::gather(e, &s0, &c);
+  }
+
+  PK_MFN uint32_t scatter(int e, uint32_t& s0)
+  {
+    uint32_t cn, sn;
+    check_lanes<DEG, 1, false>::scatter(e, &sn, &cn);
+    s0 = sn;
+    return (cn & 0xffU) | (cn >> 8); // bits 0-7 and 16-23 -> one 16-bit word
   }
 };
 

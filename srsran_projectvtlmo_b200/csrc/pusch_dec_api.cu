@@ -156,6 +156,7 @@ struct srsran_cuda_pusch_dec {
   uint32_t combine_block     = 64; // AVX-512 flavour of the reference's combine (32 = AVX2, 0 = generic)
   uint64_t launches          = 0;
   bool     use_packed        = true; // route eligible code blocks to the packed (4 per CTA) decoder
+  bool     packed_half       = false; // packed decoder with two threads per lifted check (measured slower: A/B only)
   cudaEvent_t timer_begin    = nullptr;
   cudaEvent_t timer_end      = nullptr;
   bool        timer_armed    = false;
@@ -274,6 +275,15 @@ cudaError_t launch_decode4(srsran_cuda_pusch_dec* h, cudaStream_t s, const cb_de
                            cb_result* res, uint8_t* bits_base, uint32_t n, uint32_t smem)
 {
   ldpc_decode4_kernel<TPC><<<n, TPC, smem, s>>>(descs, groups, res, h->d_soft.p, bits_base, h->d_crc_flags.p);
+  ++h->launches;
+  return cudaGetLastError();
+}
+
+template <int TPC>
+cudaError_t launch_decode4h(srsran_cuda_pusch_dec* h, cudaStream_t s, const cb_desc* descs, const grp_desc* groups,
+                            cb_result* res, uint8_t* bits_base, uint32_t n, uint32_t smem)
+{
+  ldpc_decode4h_kernel<TPC><<<n, 2 * TPC, smem, s>>>(descs, groups, res, h->d_soft.p, bits_base, h->d_crc_flags.p);
   ++h->launches;
   return cudaGetLastError();
 }
@@ -717,9 +727,15 @@ int launch_context(srsran_cuda_pusch_dec* h, int ci)
   }
   CUDA_TRY(h, cudaEventRecord(c.stage[2], s));
   for (const pklass& k : pclasses) {
-    cudaError_t e = (k.tpc == 256)
-                        ? launch_decode4<256>(h, s, c.d_desc.p, c.d_grp.p + k.first, c.d_res.p, c.bits_base, k.count, k.smem)
-                        : launch_decode4<384>(h, s, c.d_desc.p, c.d_grp.p + k.first, c.d_res.p, c.bits_base, k.count, k.smem);
+    const grp_desc* grp = c.d_grp.p + k.first;
+    cudaError_t     e;
+    if (h->packed_half) {
+      e = (k.tpc == 256) ? launch_decode4h<256>(h, s, c.d_desc.p, grp, c.d_res.p, c.bits_base, k.count, k.smem)
+                         : launch_decode4h<384>(h, s, c.d_desc.p, grp, c.d_res.p, c.bits_base, k.count, k.smem);
+    } else {
+      e = (k.tpc == 256) ? launch_decode4<256>(h, s, c.d_desc.p, grp, c.d_res.p, c.bits_base, k.count, k.smem)
+                         : launch_decode4<384>(h, s, c.d_desc.p, grp, c.d_res.p, c.bits_base, k.count, k.smem);
+    }
     CUDA_TRY(h, e);
   }
   pos = 0;
@@ -962,7 +978,9 @@ int srsran_cuda_pusch_dec_create(int device, uint32_t max_cbs_in_flight, uint32_
     return fail(SRSRAN_CUDA_ERR_CUDA);
   }
   if (cudaFuncSetAttribute(ldpc_decode4_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess ||
-      cudaFuncSetAttribute(ldpc_decode4_kernel<384>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) {
+      cudaFuncSetAttribute(ldpc_decode4_kernel<384>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess ||
+      cudaFuncSetAttribute(ldpc_decode4h_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess ||
+      cudaFuncSetAttribute(ldpc_decode4h_kernel<384>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) {
     h->last_error = "cudaFuncSetAttribute(ldpc_decode4_kernel) failed";
     return fail(SRSRAN_CUDA_ERR_CUDA);
   }
@@ -1091,10 +1109,11 @@ int srsran_cuda_pusch_dec_set_combine_flavour(srsran_cuda_pusch_dec_t* h, uint32
 
 int srsran_cuda_pusch_dec_set_decoder_variant(srsran_cuda_pusch_dec_t* h, uint32_t variant)
 {
-  if (h == nullptr || variant > 1) {
+  if (h == nullptr || variant > 2) {
     return SRSRAN_CUDA_ERR_INVALID;
   }
-  h->use_packed = (variant == 0);
+  h->use_packed  = (variant != 1);
+  h->packed_half = (variant == 2);
   return SRSRAN_CUDA_OK;
 }
 

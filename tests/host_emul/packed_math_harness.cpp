@@ -59,9 +59,46 @@ void run_check(uint32_t* soft, uint32_t* c2v_row, const uint32_t* tab_row, int j
   }
 }
 
+/// Same check with the two-code-blocks-per-thread variant (check2): two "threads" (r = 0, 1) share the lifted check.
+template <int DEG>
+void run_check_halves(uint32_t* soft, uint32_t* c2v_row, const uint32_t* tab_row, int j, int Z, uint32_t mult)
+{
+  for (int r = 0; r != 2; ++r) {
+    check2<DEG> ck;
+    int         addr[DEG];
+    ck.begin();
+    for (int e = 0; e != DEG; ++e) {
+      uint32_t te = tab_row[e];
+      int      k  = j + (int)(te >> 16);
+      k           = (k >= Z) ? k - Z : k;
+      addr[e]     = (int)(te & 0xffffU) + k;
+      uint32_t cw = c2v_row[e * Z + j];
+      uint32_t c16 = ((cw >> (8 * r)) & 0xffU) | (((cw >> (16 + 8 * r)) & 0xffU) << 8);
+      ck.gather(e, soft[2 * addr[e] + r], c16);
+    }
+    ck.reduce(mult);
+    for (int e = 0; e != DEG; ++e) {
+      uint32_t s0;
+      uint32_t c16 = ck.scatter(e, s0);
+      uint32_t cw  = c2v_row[e * Z + j];
+      cw &= ~((0xffU << (8 * r)) | (0xffU << (16 + 8 * r)));
+      cw |= ((c16 & 0xffU) << (8 * r)) | ((c16 >> 8) << (16 + 8 * r));
+      c2v_row[e * Z + j]    = cw;
+      soft[2 * addr[e] + r] = s0;
+    }
+  }
+}
+
 } // namespace
 
 extern "C" {
+
+static int g_lanes_per_thread = 4;
+/// Selects the per-thread packing the emulation runs: 4 (check4) or 2 (check2).
+void pk_host_set_lanes_per_thread(int n)
+{
+  g_lanes_per_thread = n;
+}
 
 /// Decodes up to four code blocks (lanes) packed together. llrs[c]: n_in[c] int8 LLRs (decoder input, natural order).
 /// mode 1: early stop with CRC after every iteration; mode 2: CRC after max_it iterations. bits_out[c]: K/8 bytes,
@@ -132,7 +169,11 @@ int pk_host_decode_group(uint8_t* const* bits_out, const int8_t* const* llrs, co
         switch (deg) {
 #define CASE(D)                                                                                                        \
   case D:                                                                                                              \
-    run_check<D>(soft.data(), cr, tab.data() + e0, j, (int)Z, mult);                                                   \
+    if (g_lanes_per_thread == 4) {                                                                                     \
+      run_check<D>(soft.data(), cr, tab.data() + e0, j, (int)Z, mult);                                                 \
+    } else {                                                                                                           \
+      run_check_halves<D>(soft.data(), cr, tab.data() + e0, j, (int)Z, mult);                                          \
+    }                                                                                                                  \
     break;
           CASE(3) CASE(4) CASE(5) CASE(6) CASE(7) CASE(8) CASE(9) CASE(10) CASE(19)
 #undef CASE

@@ -62,8 +62,10 @@ def ref_layers(llr, bg, z):
     return cbl // z - ob.kb(bg)
 
 
+@pytest.mark.parametrize("lanes_per_thread", [4, 2])
 @pytest.mark.parametrize("bg", [1, 2])
-def test_packed_math_matches_oracle(emu, bg):
+def test_packed_math_matches_oracle(emu, bg, lanes_per_thread):
+    emu.pk_host_set_lanes_per_thread(lanes_per_thread)
     rng = np.random.default_rng(100 + bg)
     zs = [2, 3, 5, 7, 9, 11, 13, 15, 16, 24, 36, 52, 80, 104, 144, 208, 288, 384]
     for z in zs:
@@ -105,6 +107,7 @@ def test_packed_math_matches_oracle(emu, bg):
 
 
 def test_packed_math_saturating_inputs(emu):
+    emu.pk_host_set_lanes_per_thread(4)
     """High-SNR inputs drive many soft values to +-infinity (promotion), low-SNR random +-120 inputs never converge."""
     rng = np.random.default_rng(7)
     for (bg, z) in [(1, 96), (2, 120), (1, 384)]:
