@@ -1,0 +1,130 @@
+#!/usr/bin/env python3
+"""Supplementary measurements for the BASELINE.json configurations other than the headline one (bench.py measures
+config 2). One JSON line per configuration on stdout; results are kept under profiles/. GPU box only.
+
+  c1        ldpc_decoder benchmark input: BG1, Z=384, rate 1/3 (46 layers), 6 iterations, no CRC, random +-10 LLRs
+  c2_worst  config 2 with random +-10 LLRs (never converges: 6 iterations x 4 layers x 152 code blocks)
+  c3        52-PRB QPSK / 16QAM transport blocks on BG2 / BG1 with mixed lifting sizes, 64 UEs per slot
+  c4        HARQ rv0 -> rv2 -> rv3 with HBM-resident soft combining, 64 UEs per slot (config-2 sized TBs)
+"""
+import json
+import sys
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+
+import torch  # noqa: E402
+
+from srsran_projectvtlmo_b200 import capi, pusch, synth  # noqa: E402
+
+
+def awgn(rng, bits, mu):
+    return synth.awgn_llrs(rng, bits, mu)
+
+
+def run_tbs(acc, cfgs, dev_llrs, nllrs, reps=5):
+    """Device-resident submit of one batch, `reps` times; returns mean stage times and results of the last run."""
+    stage = np.zeros(5)
+    res = None
+    for _ in range(reps):
+        tk = pusch.submit_tbs(acc, cfgs, [(d.data_ptr(), n) for d, n in zip(dev_llrs, nllrs)], device_resident=True)
+        stage += np.array(pusch.ticket_timing(acc, tk[0]))
+        res = [pusch.poll_tb(acc, t, None) for t in tk]
+    return stage / reps, res
+
+
+def c1(acc):
+    mt = np.random.RandomState(0)
+    n = 592
+    llr = ((mt.randint(0, 2 ** 32, (n, 25344), dtype=np.uint64) & 1) * 20 - 10).astype(np.int8)
+    dec = pusch.ldpc_decoder_cuda(acc)
+    bits = np.zeros((n, 1056), np.uint8)
+    lib = acc._lib
+    its = (np.zeros(n, np.int32))
+    import ctypes as C
+
+    def go():
+        st = lib.srsran_cuda_ldpc_decode_batch(acc.h, bits.ctypes.data_as(capi.u8p), llr.ctypes.data_as(capi.i8p), n, 25344,
+                                               1, 384, 0, 0, 6, C.c_float(0.8), its.ctypes.data_as(capi.intp))
+        assert st == 0
+    go()
+    t0 = time.perf_counter()
+    for _ in range(3):
+        go()
+    dt = (time.perf_counter() - t0) / 3
+    return {"config": "c1_bg1_z384_rate13_6it_nocrc", "codeblocks": n, "wall_ms_host_buffers": dt * 1e3,
+            "info_gbit_per_s": n * 8448 / dt / 1e9, "coded_gbit_per_s": n * 25344 / dt / 1e9,
+            "note": "unit-level ldpc_decoder interface, host buffers in and out (H2D of 15 MB inside the time)"}
+
+
+def c2_worst(acc):
+    rng = np.random.default_rng(1)
+    B, ncb = 64, 152
+    tbs, nllr = 1277992, 1362816
+    llr = torch.from_numpy((rng.integers(0, 2, (B, nllr)) * 20 - 10).astype(np.int8)).cuda()
+    cfgs = [capi.TbConfig(tbs, 1, 0, 8, 12611, 4, 6, 1, 1, i * ncb) for i in range(B)]
+    stage, res = run_tbs(acc, cfgs, [llr[i] for i in range(B)], [nllr] * B)
+    kern = stage[1] + stage[2] + stage[3]
+    return {"config": "c2_worst_random_llrs_6it", "tbs": B, "stage_ms": stage.tolist(),
+            "info_gbit_per_s_kernels": B * tbs / (kern * 1e-3) / 1e9, "tb_crc_ok": sum(r.tb_crc_ok for r in res),
+            "iter_mean": float(np.mean([r.iter_mean for r in res]))}
+
+
+def c3(acc):
+    rng = np.random.default_rng(2)
+    cases = [(52, 2, 120, 1, 2, 0.9), (52, 2, 449, 1, 1, 2.0), (52, 4, 378, 1, 1, 3.0), (52, 4, 658, 1, 1, 6.0),
+             (25, 2, 120, 1, 2, 0.9), (10, 4, 490, 1, 2, 4.0), (4, 2, 308, 1, 2, 1.5), (1, 2, 120, 1, 2, 0.9)]
+    cfgs, llrs, nllrs, bits = [], [], [], 0
+    slot = 0
+    for ue in range(64):
+        prb, qm, R, nl, bg, mu = cases[ue % len(cases)]
+        tbs = synth.tbs_for(prb, qm, R, nl)
+        nllr = prb * 156 * qm * nl
+        tb = rng.integers(0, 256, tbs // 8, dtype=np.uint8)
+        l = awgn(rng, synth.encode_tb(tb, bg, 0, qm, 25344, nl, nllr), mu)
+        nseg = len(pusch.segment(tbs, bg, qm, nl, nllr))
+        cfgs.append(capi.TbConfig(tbs, bg, 0, qm, 25344, nl, 6, 1, 1, slot))
+        slot += nseg
+        llrs.append(torch.from_numpy(l).cuda())
+        nllrs.append(nllr)
+        bits += tbs
+    stage, res = run_tbs(acc, cfgs, llrs, nllrs)
+    kern = stage[1] + stage[2] + stage[3]
+    return {"config": "c3_20MHz_mixed_small_tbs_64ues", "tbs": 64, "info_bits": bits, "stage_ms": stage.tolist(),
+            "info_gbit_per_s_kernels": bits / (kern * 1e-3) / 1e9, "tb_crc_ok": sum(r.tb_crc_ok for r in res),
+            "slot_kernels_us": kern * 1e3}
+
+
+def c4(acc):
+    rng = np.random.default_rng(3)
+    B, ncb = 64, 152
+    tbs, nllr = 1277992, 1362816
+    tb = rng.integers(0, 256, tbs // 8, dtype=np.uint8)
+    out = []
+    for i, rv in enumerate([0, 2, 3]):
+        cw = synth.encode_tb(tb, 1, rv, 8, 12611, 4, nllr)
+        llr = torch.from_numpy(np.stack([awgn(rng, cw, 9.0) for _ in range(4)])).cuda()
+        cfgs = [capi.TbConfig(tbs, 1, rv, 8, 12611, 4, 6, 1, int(i == 0), k * ncb) for k in range(B)]
+        stage, res = run_tbs(acc, cfgs, [llr[k % 4] for k in range(B)], [nllr] * B, reps=1)
+        kern = stage[1] + stage[2] + stage[3]
+        out.append({"rv": rv, "stage_ms": stage.tolist(), "tb_crc_ok": sum(r.tb_crc_ok for r in res),
+                    "observations": sum(r.nof_observations for r in res),
+                    "info_gbit_per_s_kernels": B * tbs / (kern * 1e-3) / 1e9})
+    return {"config": "c4_harq_rv0_rv2_rv3_64ues_config2_tbs", "transmissions": out}
+
+
+def main():
+    which = sys.argv[1:] or ["c1", "c2_worst", "c3", "c4"]
+    acc = pusch.Accelerator(device=0, max_cbs_in_flight=64 * 152, nof_harq_cb_slots=64 * 152)
+    for name in which:
+        r = {"c1": c1, "c2_worst": c2_worst, "c3": c3, "c4": c4}[name](acc)
+        print(json.dumps(r), flush=True)
+    acc.close()
+
+
+if __name__ == "__main__":
+    main()
