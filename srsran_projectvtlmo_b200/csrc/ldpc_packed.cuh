@@ -28,7 +28,8 @@ struct dec4_layout {
   uint32_t tab_off, soft_off, c2v_off, hb_off, crc_off, misc_off, total;
 };
 
-__host__ __device__ inline dec4_layout dec4_smem_layout(uint32_t bg, uint32_t Z, uint32_t layer_cap)
+/// `lanes` = code blocks per CTA (4, or 2 for the single-plane variant of ldpc_decode4h_kernel).
+__host__ __device__ inline dec4_layout dec4_smem_layout(uint32_t bg, uint32_t Z, uint32_t layer_cap, uint32_t lanes = 4)
 {
 #ifdef __CUDA_ARCH__
   uint32_t nedges = c_row_ptr[bg - 1][layer_cap];
@@ -39,8 +40,8 @@ __host__ __device__ inline dec4_layout dec4_smem_layout(uint32_t bg, uint32_t Z,
   dec4_layout l;
   l.tab_off  = 0;
   l.soft_off = (nedges * 8 + 15) & ~15U;
-  l.c2v_off  = l.soft_off + (Kb + layer_cap) * Z * 8;
-  l.hb_off   = l.c2v_off + nedges * Z * 4;
+  l.c2v_off  = l.soft_off + (Kb + layer_cap) * Z * 2 * lanes;
+  l.hb_off   = l.c2v_off + nedges * Z * lanes;
   l.crc_off  = l.hb_off + 4 * (Kb * Z / 32) * 4;
   l.misc_off = l.crc_off + 4 * 256 * 4;
   l.total    = l.misc_off + 128;
@@ -137,6 +138,10 @@ __global__ void __launch_bounds__(TPC, 1) ldpc_decode4_kernel(const cb_desc* __r
         }
       }
     }
+  }
+
+  if (!(live[0] || live[1] || live[2] || live[3])) {
+    return; // every code block of the group was already decoded (retransmission of an acknowledged TB)
   }
 
   // ---- prologue ----------------------------------------------------------------------------------------------------------
@@ -391,8 +396,10 @@ __device__ __forceinline__ void process_check2(uint32_t* __restrict__    soft,
   }
 }
 
-template <int TPC>
-__global__ void __launch_bounds__(2 * TPC, 1) ldpc_decode4h_kernel(const cb_desc* __restrict__ descs,
+/// NP = number of planes: 2 -> four code blocks per CTA on 2 x TPC threads, 1 -> two code blocks per CTA on TPC threads
+/// (half the shared memory: groups whose state does not fit four code blocks, e.g. HARQ retransmissions with many layers).
+template <int TPC, int NP>
+__global__ void __launch_bounds__(NP * TPC, 1) ldpc_decode4h_kernel(const cb_desc* __restrict__ descs,
                                                                     const grp_desc* __restrict__ groups,
                                                                     cb_result* __restrict__ results,
                                                                     const int8_t* __restrict__ soft_base,
@@ -400,12 +407,13 @@ __global__ void __launch_bounds__(2 * TPC, 1) ldpc_decode4h_kernel(const cb_desc
                                                                     uint32_t* __restrict__ crc_flags)
 {
   extern __shared__ __align__(16) uint8_t smem_raw[];
-  constexpr int  NT   = 2 * TPC;
+  constexpr int  NT   = NP * TPC;
+  constexpr int  NC   = 2 * NP; // code blocks per CTA
   constexpr int  NW   = NT / 32;
   const int      t    = threadIdx.x;
   const int      lane = t & 31;
   const int      warp = __shfl_sync(0xffffffffU, t >> 5, 0);
-  const int      h    = warp / (NW / 2); // plane: code blocks h and h + 2
+  const int      h    = warp / (NW / NP); // plane: code blocks h and h + NP
   const grp_desc g    = groups[blockIdx.x];
   const cb_desc& d0   = descs[g.cb[0]];
   const uint32_t Z = d0.Z, bg = d0.bg, Kb = (bg == 1) ? 22 : 10, K = Kb * Z, L = g.layer_cap;
@@ -414,7 +422,7 @@ __global__ void __launch_bounds__(2 * TPC, 1) ldpc_decode4h_kernel(const cb_desc
   const uint32_t HBW  = K / 32;
   const uint32_t nvar = (Kb + L) * Z;
 
-  const dec4_layout lay    = dec4_smem_layout(bg, Z, L);
+  const dec4_layout lay    = dec4_smem_layout(bg, Z, L, NC);
   uint2*            tab    = reinterpret_cast<uint2*>(smem_raw + lay.tab_off);
   uint32_t*         soft   = reinterpret_cast<uint32_t*>(smem_raw + lay.soft_off) + (size_t)h * nvar;
   const uint32_t    nedges = c_row_ptr[bg - 1][L];
@@ -430,8 +438,8 @@ __global__ void __launch_bounds__(2 * TPC, 1) ldpc_decode4h_kernel(const cb_desc
   const uint32_t cap_in = (Kb + L) * Z - 2 * Z;
 #pragma unroll
   for (int c = 0; c != 4; ++c) {
-    cbi[c]  = g.cb[c < (int)g.n ? c : 0];
-    live[c] = c < (int)g.n;
+    cbi[c]  = g.cb[(c < (int)g.n && c < NC) ? c : 0];
+    live[c] = c < (int)g.n && c < NC;
     const cb_desc& d = descs[cbi[c]];
     src[c]    = soft_base + (size_t)d.slot * SOFT_STRIDE;
     n_load[c] = live[c] ? min(min(d.n_in, d.scan_len), cap_in) : 0U;
@@ -451,13 +459,17 @@ __global__ void __launch_bounds__(2 * TPC, 1) ldpc_decode4h_kernel(const cb_desc
     }
   }
 
+  if (!(live[0] || live[1] || live[2] || live[3])) {
+    return; // every code block of the group was already decoded (retransmission of an acknowledged TB)
+  }
+
   // ---- prologue ----------------------------------------------------------------------------------------------------------
   for (uint32_t e = t; e < nedges; e += NT) {
     tab[e] = make_uint2((uint32_t)c_col[bg - 1][e] * Z, c_shift[bg - 1][d0.ils][e] % Z);
   }
   {
     uint4*         c4 = reinterpret_cast<uint4*>(smem_raw + lay.c2v_off);
-    const uint32_t n4 = nedges * Z / 4; // both planes: nedges * Z * 4 bytes
+    const uint32_t n4 = nedges * Z * NC / 16; // all planes: nedges * Z * NC bytes
     const uint4    zz = make_uint4(pk::C2V_ZERO4, pk::C2V_ZERO4, pk::C2V_ZERO4, pk::C2V_ZERO4);
     for (uint32_t i = t; i < n4; i += NT) {
       c4[i] = zz;
@@ -482,8 +494,8 @@ __global__ void __launch_bounds__(2 * TPC, 1) ldpc_decode4h_kernel(const cb_desc
         if (p < n_load[h]) {
           w0 = __ldg(reinterpret_cast<const uint32_t*>(src[h] + p));
         }
-        if (p < n_load[h + 2]) {
-          w1 = __ldg(reinterpret_cast<const uint32_t*>(src[h + 2] + p));
+        if (p < n_load[h + NP]) {
+          w1 = __ldg(reinterpret_cast<const uint32_t*>(src[h + NP] + p));
         }
         nz0 |= w0;
         nz1 |= w1;
@@ -504,7 +516,7 @@ __global__ void __launch_bounds__(2 * TPC, 1) ldpc_decode4h_kernel(const cb_desc
         atomicOr(&misc[h], 1U);
       }
       if (nz1 != 0) {
-        atomicOr(&misc[h + 2], 1U);
+        atomicOr(&misc[h + NP], 1U);
       }
     }
   }
@@ -575,14 +587,14 @@ __global__ void __launch_bounds__(2 * TPC, 1) ldpc_decode4h_kernel(const cb_desc
     {
       // Plane h by its own warps; lane l takes variable 32 w + 31 - l: ballot bit l is already in MSB-first order.
       uint32_t nz = 0x00010001U;
-      for (uint32_t w = warp - h * (NW / 2); w < HBW; w += NW / 2) {
+      for (uint32_t w = warp - h * (NW / NP); w < HBW; w += NW / NP) {
         uint32_t s  = soft[w * 32 + 31 - lane];
         uint32_t p  = pk::addmin_s2_relu(s, PK_REP2(0x10000U - pk::BS), 0x00010001U); // 1 where soft > 0
         nz &= pk::minu2(s ^ pk::SOFT_ZERO2, 0x00010001U);
         uint32_t blo = __ballot_sync(0xffffffffU, (p & 0xffffU) == 0);
         uint32_t bhi = __ballot_sync(0xffffffffU, (p >> 16) == 0);
         if (lane < 2) {
-          hb[(h + 2 * lane) * HBW + w] = lane ? bhi : blo;
+          hb[(h + NP * lane) * HBW + w] = lane ? bhi : blo;
         }
       }
       nz = __reduce_and_sync(0xffffffffU, nz);
@@ -591,7 +603,7 @@ __global__ void __launch_bounds__(2 * TPC, 1) ldpc_decode4h_kernel(const cb_desc
           atomicOr(&misc[4 + h], 1U);
         }
         if (!(nz >> 16)) {
-          atomicOr(&misc[6 + h], 1U);
+          atomicOr(&misc[4 + NP + h], 1U);
         }
       }
     }

@@ -97,6 +97,11 @@ struct batch_context {
   cudaEvent_t  done       = nullptr; // everything (incl. D2H) complete
   cudaEvent_t  kernels    = nullptr; // kernels complete (HARQ ordering between contexts)
   cudaEvent_t  stage[4]   = {nullptr, nullptr, nullptr, nullptr}; // begin, copies in, dematch done, decode done
+  // Decode launch classes (different lifting-size / shared-memory shapes) run concurrently on side streams.
+  static constexpr int NOF_SIDE = 7;
+  cudaStream_t side[NOF_SIDE]  = {};
+  cudaEvent_t  fork            = nullptr;
+  cudaEvent_t  join[NOF_SIDE]  = {};
   bool         open       = false;   // accepting operations, not launched
   bool         in_flight  = false;   // launched, results not yet consumed
   uint32_t     generation = 0;
@@ -217,6 +222,10 @@ uint32_t compute_k0(uint32_t bg, uint32_t rv, uint32_t Ncb, uint32_t N, uint32_t
 uint32_t extent_after_dematch(uint32_t prev, uint32_t N, uint32_t Ncb, uint32_t k0, uint32_t E, uint32_t info,
                               uint32_t sys, bool new_data)
 {
+  if (prev > N) {
+    // The slot still holds LLRs of an earlier, longer code block beyond this one's N bytes: nothing here clears them.
+    return prev;
+  }
   uint32_t D         = info + (Ncb - sys);
   uint32_t s0        = (k0 < info) ? k0 : ((k0 < sys) ? info : info + (k0 - sys));
   uint32_t first_len = D - s0;
@@ -279,23 +288,23 @@ cudaError_t launch_decode4(srsran_cuda_pusch_dec* h, cudaStream_t s, const cb_de
   return cudaGetLastError();
 }
 
-template <int TPC>
+template <int TPC, int NP>
 cudaError_t launch_decode4h(srsran_cuda_pusch_dec* h, cudaStream_t s, const cb_desc* descs, const grp_desc* groups,
                             cb_result* res, uint8_t* bits_base, uint32_t n, uint32_t smem)
 {
-  ldpc_decode4h_kernel<TPC><<<n, 2 * TPC, smem, s>>>(descs, groups, res, h->d_soft.p, bits_base, h->d_crc_flags.p);
+  ldpc_decode4h_kernel<TPC, NP><<<n, NP * TPC, smem, s>>>(descs, groups, res, h->d_soft.p, bits_base, h->d_crc_flags.p);
   ++h->launches;
   return cudaGetLastError();
 }
 
 /// Code blocks the packed decoder (ldpc_packed.cuh) accepts; `cap` = layers it would process.
-bool packed_eligible(const srsran_cuda_pusch_dec* h, const cb_desc& d, uint32_t cap)
+bool packed_eligible(const srsran_cuda_pusch_dec* h, const cb_desc& d, uint32_t cap, uint32_t lanes)
 {
   if (!h->use_packed || !(d.flags & FLAG_DECODE) || !(d.flags & FLAG_USE_HARQ) || d.mode == MODE_NO_CRC ||
       d.crc_poly == 0 || d.Z < 144 || (d.Z % 16) != 0) {
     return false;
   }
-  return dec4_smem_layout(d.bg, d.Z, cap).total <= static_cast<uint32_t>(h->max_smem_optin);
+  return dec4_smem_layout(d.bg, d.Z, cap, lanes).total <= static_cast<uint32_t>(h->max_smem_optin);
 }
 
 template <int TPC, int CBS>
@@ -602,9 +611,11 @@ int launch_context(srsran_cuda_pusch_dec* h, int ci)
   // Packed decoder: runs of consecutive code blocks with the same shape are grouped four per CTA.
   struct pklass {
     int      tpc;
+    uint32_t lanes; // code blocks per CTA: 4, or 2 when the state of four does not fit in shared memory
     uint32_t smem;
     uint32_t first, count; // range in h_grp
   };
+  uint32_t grp_lanes = 4;
   std::vector<pklass> pclasses;
   uint32_t            ngrp     = 0;
   bool                grp_open = false;
@@ -612,17 +623,53 @@ int launch_context(srsran_cuda_pusch_dec* h, int ci)
     return a.bg == b.bg && a.Z == b.Z && a.mode == b.mode && a.max_it == b.max_it && a.scale_mult == b.scale_mult &&
            a.crc_poly == b.crc_poly;
   };
+  // One code block per thread group (ldpc_decode_kernel): launch classes by threads per code block x shared-memory bucket.
+  auto add_single = [&](uint32_t i) {
+    const cb_desc&  d    = c.h_desc.p[i];
+    dec_smem_layout lay  = dec_layout(d.bg, d.Z, d.layer_cap);
+    uint32_t        need = (lay.total + 1023) & ~1023U;
+    // Buckets: coarse enough for few launches, fine enough for occupancy.
+    static const uint32_t buckets[] = {16, 24, 32, 40, 48, 64, 80, 96, 112, 128, 160, 192, 227};
+    uint32_t              bsz       = 227 * 1024;
+    for (uint32_t b : buckets) {
+      if (need <= b * 1024) {
+        bsz = b * 1024;
+        break;
+      }
+    }
+    if (need > 227 * 1024) {
+      return false;
+    }
+    int    tc    = tpc_class(d.Z);
+    klass* found = nullptr;
+    for (klass& k : classes) {
+      if (k.tpc == tc && k.smem == bsz) {
+        found = &k;
+        break;
+      }
+    }
+    if (found == nullptr) {
+      classes.push_back({tc, bsz, {}});
+      found = &classes.back();
+    }
+    found->idx.push_back(i);
+    return true;
+  };
   auto close_group = [&]() {
     if (!grp_open) {
       return;
     }
     grp_open           = false;
     const grp_desc& g  = c.h_grp.p[ngrp];
+    if (g.n == 1 && add_single(g.cb[0])) {
+      // A lone code block gains nothing from the packed kernels (they occupy a whole SM): general kernel.
+      return;
+    }
     const cb_desc&  d  = c.h_desc.p[g.cb[0]];
-    uint32_t        sm = (dec4_smem_layout(d.bg, d.Z, g.layer_cap).total + 1023) & ~1023U;
+    uint32_t        sm = (dec4_smem_layout(d.bg, d.Z, g.layer_cap, grp_lanes).total + 1023) & ~1023U;
     int             tp = d.Z <= 256 ? 256 : 384;
-    if (pclasses.empty() || pclasses.back().tpc != tp || pclasses.back().smem != sm) {
-      pclasses.push_back({tp, sm, ngrp, 0});
+    if (pclasses.empty() || pclasses.back().tpc != tp || pclasses.back().smem != sm || pclasses.back().lanes != grp_lanes) {
+      pclasses.push_back({tp, grp_lanes, sm, ngrp, 0});
     }
     ++pclasses.back().count;
     ++ngrp;
@@ -639,12 +686,13 @@ int launch_context(srsran_cuda_pusch_dec* h, int ci)
     if (!(d.flags & FLAG_DECODE)) {
       continue;
     }
-    if (packed_eligible(h, d, d.layer_cap)) {
+    const uint32_t lanes_fit = packed_eligible(h, d, d.layer_cap, 4) ? 4U : (packed_eligible(h, d, d.layer_cap, 2) ? 2U : 0U);
+    if (lanes_fit != 0) {
       if (grp_open) {
         grp_desc&      g   = c.h_grp.p[ngrp];
         const cb_desc& f   = c.h_desc.p[g.cb[0]];
         uint32_t       cap = std::max(g.layer_cap, d.layer_cap);
-        if (g.n < 4 && same_shape(f, d) && packed_eligible(h, d, cap)) {
+        if (g.n < grp_lanes && same_shape(f, d) && packed_eligible(h, d, cap, grp_lanes)) {
           g.cb[g.n++] = i;
           g.layer_cap = cap;
           continue;
@@ -656,38 +704,15 @@ int launch_context(srsran_cuda_pusch_dec* h, int ci)
       g.cb[0]     = i;
       g.n         = 1;
       g.layer_cap = d.layer_cap;
+      grp_lanes   = lanes_fit;
       grp_open    = true;
       continue;
     }
     close_group();
-    dec_smem_layout lay  = dec_layout(d.bg, d.Z, d.layer_cap);
-    uint32_t        need = (lay.total + 1023) & ~1023U;
-    // Buckets: 16, 24, 32, 48, 64, 96, 128, 227 KB - coarse enough for few launches, fine enough for occupancy.
-    static const uint32_t buckets[] = {16, 24, 32, 40, 48, 64, 80, 96, 112, 128, 160, 192, 227};
-    uint32_t              bsz       = 227 * 1024;
-    for (uint32_t b : buckets) {
-      if (need <= b * 1024) {
-        bsz = b * 1024;
-        break;
-      }
-    }
-    if (need > 227 * 1024) {
+    if (!add_single(i)) {
       h->last_error = "code block does not fit in shared memory";
       return SRSRAN_CUDA_ERR_INVALID;
     }
-    int    tc    = tpc_class(d.Z);
-    klass* found = nullptr;
-    for (klass& k : classes) {
-      if (k.tpc == tc && k.smem == bsz) {
-        found = &k;
-        break;
-      }
-    }
-    if (found == nullptr) {
-      classes.push_back({tc, bsz, {}});
-      found = &classes.back();
-    }
-    found->idx.push_back(i);
   }
   close_group();
   uint32_t pos = 0;
@@ -726,15 +751,40 @@ int launch_context(srsran_cuda_pusch_dec* h, int ci)
     CUDA_TRY(h, cudaGetLastError());
   }
   CUDA_TRY(h, cudaEventRecord(c.stage[2], s));
+  // Launch classes are independent (disjoint code blocks): class 0 stays on the batch stream, the others fork onto side
+  // streams and join before the TB assembly, so a slot of mixed small transport blocks costs its slowest class, not the sum.
+  const size_t nof_classes = pclasses.size() + classes.size();
+  uint32_t     side_used   = 0;
+  size_t       class_no    = 0;
+  if (nof_classes > 1) {
+    CUDA_TRY(h, cudaEventRecord(c.fork, s));
+  }
+  auto class_stream = [&]() -> cudaStream_t {
+    size_t k = class_no++;
+    if (k == 0) {
+      return s;
+    }
+    int          si = static_cast<int>((k - 1) % batch_context::NOF_SIDE);
+    cudaStream_t st = c.side[si];
+    if (!(side_used & (1U << si))) {
+      side_used |= 1U << si;
+      cudaStreamWaitEvent(st, c.fork, 0);
+    }
+    return st;
+  };
   for (const pklass& k : pclasses) {
     const grp_desc* grp = c.d_grp.p + k.first;
+    cudaStream_t    st  = class_stream();
     cudaError_t     e;
-    if (h->packed_half) {
-      e = (k.tpc == 256) ? launch_decode4h<256>(h, s, c.d_desc.p, grp, c.d_res.p, c.bits_base, k.count, k.smem)
-                         : launch_decode4h<384>(h, s, c.d_desc.p, grp, c.d_res.p, c.bits_base, k.count, k.smem);
+    if (k.lanes == 2) {
+      e = (k.tpc == 256) ? launch_decode4h<256, 1>(h, st, c.d_desc.p, grp, c.d_res.p, c.bits_base, k.count, k.smem)
+                         : launch_decode4h<384, 1>(h, st, c.d_desc.p, grp, c.d_res.p, c.bits_base, k.count, k.smem);
+    } else if (h->packed_half) {
+      e = (k.tpc == 256) ? launch_decode4h<256, 2>(h, st, c.d_desc.p, grp, c.d_res.p, c.bits_base, k.count, k.smem)
+                         : launch_decode4h<384, 2>(h, st, c.d_desc.p, grp, c.d_res.p, c.bits_base, k.count, k.smem);
     } else {
-      e = (k.tpc == 256) ? launch_decode4<256>(h, s, c.d_desc.p, grp, c.d_res.p, c.bits_base, k.count, k.smem)
-                         : launch_decode4<384>(h, s, c.d_desc.p, grp, c.d_res.p, c.bits_base, k.count, k.smem);
+      e = (k.tpc == 256) ? launch_decode4<256>(h, st, c.d_desc.p, grp, c.d_res.p, c.bits_base, k.count, k.smem)
+                         : launch_decode4<384>(h, st, c.d_desc.p, grp, c.d_res.p, c.bits_base, k.count, k.smem);
     }
     CUDA_TRY(h, e);
   }
@@ -742,26 +792,33 @@ int launch_context(srsran_cuda_pusch_dec* h, int ci)
   for (klass& k : classes) {
     uint32_t        n   = static_cast<uint32_t>(k.idx.size());
     const uint32_t* ord = c.d_order.p + pos;
+    cudaStream_t    st  = class_stream();
     cudaError_t     e   = cudaSuccess;
     switch (k.tpc) {
       case 0:
-        e = launch_decode<32, 4>(h, s, c.d_desc.p, ord, c.d_res.p, c.bits_base, n, k.smem);
+        e = launch_decode<32, 4>(h, st, c.d_desc.p, ord, c.d_res.p, c.bits_base, n, k.smem);
         break;
       case 1:
-        e = launch_decode<64, 2>(h, s, c.d_desc.p, ord, c.d_res.p, c.bits_base, n, k.smem);
+        e = launch_decode<64, 2>(h, st, c.d_desc.p, ord, c.d_res.p, c.bits_base, n, k.smem);
         break;
       case 2:
-        e = launch_decode<128, 1>(h, s, c.d_desc.p, ord, c.d_res.p, c.bits_base, n, k.smem);
+        e = launch_decode<128, 1>(h, st, c.d_desc.p, ord, c.d_res.p, c.bits_base, n, k.smem);
         break;
       case 3:
-        e = launch_decode<256, 1>(h, s, c.d_desc.p, ord, c.d_res.p, c.bits_base, n, k.smem);
+        e = launch_decode<256, 1>(h, st, c.d_desc.p, ord, c.d_res.p, c.bits_base, n, k.smem);
         break;
       default:
-        e = launch_decode<384, 1>(h, s, c.d_desc.p, ord, c.d_res.p, c.bits_base, n, k.smem);
+        e = launch_decode<384, 1>(h, st, c.d_desc.p, ord, c.d_res.p, c.bits_base, n, k.smem);
         break;
     }
     CUDA_TRY(h, e);
     pos += n;
+  }
+  for (int si = 0; si != batch_context::NOF_SIDE; ++si) {
+    if (side_used & (1U << si)) {
+      CUDA_TRY(h, cudaEventRecord(c.join[si], c.side[si]));
+      CUDA_TRY(h, cudaStreamWaitEvent(s, c.join[si], 0));
+    }
   }
   CUDA_TRY(h, cudaEventRecord(c.stage[3], s));
   if (ntb != 0) {
@@ -979,8 +1036,10 @@ int srsran_cuda_pusch_dec_create(int device, uint32_t max_cbs_in_flight, uint32_
   }
   if (cudaFuncSetAttribute(ldpc_decode4_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess ||
       cudaFuncSetAttribute(ldpc_decode4_kernel<384>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess ||
-      cudaFuncSetAttribute(ldpc_decode4h_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess ||
-      cudaFuncSetAttribute(ldpc_decode4h_kernel<384>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) {
+      cudaFuncSetAttribute(ldpc_decode4h_kernel<256, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess ||
+      cudaFuncSetAttribute(ldpc_decode4h_kernel<384, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess ||
+      cudaFuncSetAttribute(ldpc_decode4h_kernel<256, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess ||
+      cudaFuncSetAttribute(ldpc_decode4h_kernel<384, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) {
     h->last_error = "cudaFuncSetAttribute(ldpc_decode4_kernel) failed";
     return fail(SRSRAN_CUDA_ERR_CUDA);
   }
@@ -1010,6 +1069,11 @@ int srsran_cuda_pusch_dec_create(int device, uint32_t max_cbs_in_flight, uint32_
               cudaEventCreate(&c.done) == cudaSuccess && cudaEventCreate(&c.kernels) == cudaSuccess;
     for (cudaEvent_t& e : c.stage) {
       ok = ok && cudaEventCreate(&e) == cudaSuccess;
+    }
+    ok = ok && cudaEventCreateWithFlags(&c.fork, cudaEventDisableTiming) == cudaSuccess;
+    for (int k = 0; k != batch_context::NOF_SIDE; ++k) {
+      ok = ok && cudaStreamCreateWithFlags(&c.side[k], cudaStreamNonBlocking) == cudaSuccess &&
+           cudaEventCreateWithFlags(&c.join[k], cudaEventDisableTiming) == cudaSuccess;
     }
     if (!ok) {
       h->last_error = "stream / event creation failed";
@@ -1067,6 +1131,17 @@ void srsran_cuda_pusch_dec_destroy(srsran_cuda_pusch_dec_t* h)
     for (cudaEvent_t e : c.stage) {
       if (e != nullptr) {
         cudaEventDestroy(e);
+      }
+    }
+    if (c.fork != nullptr) {
+      cudaEventDestroy(c.fork);
+    }
+    for (int k = 0; k != batch_context::NOF_SIDE; ++k) {
+      if (c.join[k] != nullptr) {
+        cudaEventDestroy(c.join[k]);
+      }
+      if (c.side[k] != nullptr) {
+        cudaStreamDestroy(c.side[k]);
       }
     }
     if (c.stream != nullptr) {
@@ -1675,9 +1750,10 @@ int srsran_cuda_ldpc_decode_batch(srsran_cuda_pusch_dec_t* h, uint8_t* bits, con
       if (r != SRSRAN_CUDA_OK) {
         return r;
       }
-      CUDA_TRY(h, cudaMemcpy(c.d_unit_bits.p + static_cast<size_t>(i) * BITS_STRIDE,
-                             bits + static_cast<size_t>(done + i) * nbytes, nbytes, cudaMemcpyHostToDevice));
     }
+    // One strided copy seeds all the scratch data-bit slots (ordered before the kernels on the batch stream).
+    CUDA_TRY(h, cudaMemcpy2DAsync(c.d_unit_bits.p, BITS_STRIDE, bits + static_cast<size_t>(done) * nbytes, nbytes, nbytes, n,
+                                  cudaMemcpyHostToDevice, c.stream));
     for (uint32_t i = 0; i != n; ++i) {
       cb_params p = {};
       p.bg        = base_graph;

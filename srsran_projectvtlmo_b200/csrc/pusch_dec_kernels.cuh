@@ -330,6 +330,23 @@ __global__ void __launch_bounds__(256) rate_dematch_kernel(const cb_desc* __rest
         *reinterpret_cast<uint4*>(out + i0) = nv;
         continue;
       }
+      if (STAGED && visited && dm_simd_rule(g, p0 + 15)) {
+        // HARQ combining of 16 consecutive positions inside the SIMD body of one combine_softbits call
+        // (ldpc_rate_dematcher_avx512_impl.cpp:29-64): clamp(adds_epi8(new, old), +-120), four bytes per instruction group.
+        const uint32_t  sh = (p0 & 3U) * 8U;
+        const uint32_t* ws = reinterpret_cast<const uint32_t*>(dm_sm + (p0 & ~3U));
+        uint32_t        a0 = ws[0], a1 = ws[1], a2 = ws[2], a3 = ws[3];
+        uint32_t        a4 = sh ? ws[4] : 0U;
+        uint4           nw = make_uint4(__funnelshift_r(a0, a1, sh), __funnelshift_r(a1, a2, sh), __funnelshift_r(a2, a3, sh),
+                              __funnelshift_r(a3, a4, sh));
+        // A new transmission zeroes the head of the buffer before its wrapped part is combined onto it.
+        uint4 ov = (g.new_data && i < g.zero_head) ? make_uint4(0, 0, 0, 0) : *reinterpret_cast<const uint4*>(out + i0);
+        auto  comb = [](uint32_t x, uint32_t y) {
+          return __vmins4(__vmaxs4(__vaddss4(x, y), 0x88888888U), 0x78787878U);
+        };
+        *reinterpret_cast<uint4*>(out + i0) = make_uint4(comb(nw.x, ov.x), comb(nw.y, ov.y), comb(nw.z, ov.z), comb(nw.w, ov.w));
+        continue;
+      }
       if (!visited) {
         if (g.new_data && (i < g.zero_head || i >= g.tail_start)) {
           *reinterpret_cast<uint4*>(out + i0) = make_uint4(0, 0, 0, 0);

@@ -371,7 +371,7 @@ def test_packed_decoder_groups_via_hal(acc, variant):
                 crc_poly = pusch.CRC24B
                 F = int(rng.integers(0, 5)) * 8
                 # few layers: E just above the systematic part
-                E = (int((K - 2 * z - F) * rng.uniform(1.04, 1.25)) // qm) * qm
+                E = (int((K - 2 * z - F) * rng.uniform(1.04, 1.9 if rng.random() < 0.4 else 1.25)) // qm) * qm
                 nref = 0 if rng.random() < 0.5 else int(N * 0.6)
                 mu = float(rng.choice([3.0, 6.0, 12.0, 20.0]))
                 for _ in range(int(rng.integers(1, 8))):

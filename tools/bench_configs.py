@@ -51,11 +51,12 @@ def c1(acc):
         st = lib.srsran_cuda_ldpc_decode_batch(acc.h, bits.ctypes.data_as(capi.u8p), llr.ctypes.data_as(capi.i8p), n, 25344,
                                                1, 384, 0, 0, 6, C.c_float(0.8), its.ctypes.data_as(capi.intp))
         assert st == 0
-    go()
-    t0 = time.perf_counter()
-    for _ in range(3):
+    for _ in range(5):  # every batch context of the handle allocates its staging on first use
         go()
-    dt = (time.perf_counter() - t0) / 3
+    t0 = time.perf_counter()
+    for _ in range(4):
+        go()
+    dt = (time.perf_counter() - t0) / 4
     return {"config": "c1_bg1_z384_rate13_6it_nocrc", "codeblocks": n, "wall_ms_host_buffers": dt * 1e3,
             "info_gbit_per_s": n * 8448 / dt / 1e9, "coded_gbit_per_s": n * 25344 / dt / 1e9,
             "note": "unit-level ldpc_decoder interface, host buffers in and out (H2D of 15 MB inside the time)"}
