@@ -242,28 +242,33 @@ __global__ void __launch_bounds__(256) rate_dematch_kernel(const cb_desc* __rest
       int      first = (int)(v * 16) - (int)mis; // index into `in` of byte 0 of this vector
       uint32_t lo    = first < 0 ? (uint32_t)(-first) : 0U;
       uint32_t hi    = min(16U, (uint32_t)((int)g.E - first));
-      __align__(16) int8_t bytes[16];
       if (lo == 0 && hi == 16) {
-        uint4 w = __ldg(reinterpret_cast<const uint4*>(base) + v);
-        *reinterpret_cast<uint4*>(bytes) = w;
-      } else {
-        for (uint32_t b = lo; b < hi; ++b) {
-          bytes[b] = __ldg(in + first + (int)b);
-        }
-      }
-      if (g.Qm == 1) {
-        for (uint32_t b = lo; b < hi; ++b) {
-          dm_sm[first + (int)b] = bytes[b];
-        }
-      } else {
-        uint32_t idx = (uint32_t)(first + (int)lo);
-        uint32_t i   = idx / g.Qm;
-        uint32_t j   = idx - i * g.Qm;
-        uint32_t p   = j * g.S + i;
+        // Whole vector inside the code block (all but the first / last one).
+        const uint4    w   = __ldg(reinterpret_cast<const uint4*>(base) + v);
+        const uint32_t idx = (uint32_t)first;
+        if (g.Qm == 8 && (idx & 15U) == 0 && (g.S & 1U) == 0) {
+          // Two modulation symbols (rows i, i + 1; i even) x 8 bits: bit j of both rows lands on d[j S + i], d[j S + i + 1].
+          const uint32_t i = idx >> 3;
+          uint16_t*      d = reinterpret_cast<uint16_t*>(dm_sm + i);
+          const uint32_t h = g.S >> 1; // stride between columns in 16-bit units
+          d[0 * h] = (uint16_t)__byte_perm(w.x, w.z, 0x0040);
+          d[1 * h] = (uint16_t)__byte_perm(w.x, w.z, 0x0051);
+          d[2 * h] = (uint16_t)__byte_perm(w.x, w.z, 0x0062);
+          d[3 * h] = (uint16_t)__byte_perm(w.x, w.z, 0x0073);
+          d[4 * h] = (uint16_t)__byte_perm(w.y, w.w, 0x0040);
+          d[5 * h] = (uint16_t)__byte_perm(w.y, w.w, 0x0051);
+          d[6 * h] = (uint16_t)__byte_perm(w.y, w.w, 0x0062);
+          d[7 * h] = (uint16_t)__byte_perm(w.y, w.w, 0x0073);
+        } else if (g.Qm == 1 && (idx & 15U) == 0) {
+          *reinterpret_cast<uint4*>(dm_sm + idx) = w;
+        } else {
+          const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
+          uint32_t       i     = idx / g.Qm;
+          uint32_t       j     = idx - i * g.Qm;
+          uint32_t       p     = (g.Qm > 1) ? j * g.S + i : idx;
 #pragma unroll
-        for (uint32_t b = 0; b != 16; ++b) {
-          if (b >= lo && b < hi) {
-            dm_sm[p] = bytes[b];
+          for (uint32_t b = 0; b != 16; ++b) {
+            dm_sm[p] = (int8_t)(ww[b >> 2] >> (8 * (b & 3)));
             p += g.S;
             if (++j == g.Qm) {
               j = 0;
@@ -272,6 +277,17 @@ __global__ void __launch_bounds__(256) rate_dematch_kernel(const cb_desc* __rest
             }
           }
         }
+        continue;
+      }
+      // Partial vector at either end of the code block: byte by byte.
+      for (uint32_t b = lo; b < hi; ++b) {
+        uint32_t idx = (uint32_t)(first + (int)b);
+        uint32_t p   = idx;
+        if (g.Qm > 1) {
+          uint32_t i = idx / g.Qm;
+          p          = (idx - i * g.Qm) * g.S + i;
+        }
+        dm_sm[p] = __ldg(in + idx);
       }
     }
     __syncthreads();
