@@ -44,7 +44,7 @@ __host__ __device__ inline dec4_layout dec4_smem_layout(uint32_t bg, uint32_t Z,
   l.hb_off   = l.c2v_off + nedges * Z * lanes;
   l.crc_off  = l.hb_off + 4 * (Kb * Z / 32) * 4;
   l.misc_off = l.crc_off + 4 * 256 * 4;
-  l.total    = l.misc_off + 128;
+  l.total    = l.misc_off + 64 + 4 * 64; // 16 flag words + four lane_state records
   return l;
 }
 
@@ -81,6 +81,17 @@ __device__ __forceinline__ void process_check4(uint2* __restrict__       soft,
   }
 }
 
+/// Per code block state of a packed group, kept in shared memory so that it does not occupy registers in the layer loop.
+struct lane_state {
+  const int8_t* src;       ///< decoder input (HARQ slot)
+  uint8_t*      bits_out;  ///< batch output copy (may be null)
+  uint32_t*     slot_bits; ///< data bits of the HARQ slot
+  uint32_t      n_load, nbits, cbi, slot, flags;
+  int32_t       iters;
+  uint32_t      crc_ok, live, done;
+};
+static_assert(sizeof(lane_state) == 64, "lane_state is 64 bytes");
+
 template <int TPC>
 __global__ void __launch_bounds__(TPC, 1) ldpc_decode4_kernel(const cb_desc* __restrict__ descs,
                                                                const grp_desc* __restrict__ groups,
@@ -90,17 +101,17 @@ __global__ void __launch_bounds__(TPC, 1) ldpc_decode4_kernel(const cb_desc* __r
                                                                uint32_t* __restrict__ crc_flags)
 {
   extern __shared__ __align__(16) uint8_t smem_raw[];
-  const int      t    = threadIdx.x;
-  const int      lane = t & 31;
+  const int       t    = threadIdx.x;
+  const int       lane = t & 31;
   // Broadcast from lane 0 so that the compiler knows the warp index is warp-uniform (uniform loop bounds around ballots).
-  const int      warp = __shfl_sync(0xffffffffU, t >> 5, 0);
-  constexpr int  NW   = TPC / 32;
-  const grp_desc g    = groups[blockIdx.x];
-  const cb_desc& d0   = descs[g.cb[0]];
-  const uint32_t Z = d0.Z, bg = d0.bg, Kb = (bg == 1) ? 22 : 10, K = Kb * Z, L = g.layer_cap;
-  const uint32_t mode = d0.mode, max_it = d0.max_it, mult = d0.scale_mult;
-  const int      poly = d0.crc_poly;
-  const uint32_t HBW  = K / 32;
+  const int       warp = __shfl_sync(0xffffffffU, t >> 5, 0);
+  constexpr int   NW   = TPC / 32;
+  const grp_desc& g    = groups[blockIdx.x];
+  const cb_desc&  d0   = descs[g.cb[0]];
+  const uint32_t  Z = d0.Z, bg = d0.bg, Kb = (bg == 1) ? 22 : 10, K = Kb * Z, L = g.layer_cap;
+  const uint32_t  mode = d0.mode, max_it = d0.max_it, mult = d0.scale_mult;
+  const int       poly = d0.crc_poly;
+  const uint32_t  HBW  = K / 32;
 
   const dec4_layout lay  = dec4_smem_layout(bg, Z, L);
   uint2*            tab  = reinterpret_cast<uint2*>(smem_raw + lay.tab_off);
@@ -109,39 +120,55 @@ __global__ void __launch_bounds__(TPC, 1) ldpc_decode4_kernel(const cb_desc* __r
   uint32_t*         hb   = reinterpret_cast<uint32_t*>(smem_raw + lay.hb_off);
   uint32_t*         tabs = reinterpret_cast<uint32_t*>(smem_raw + lay.crc_off);
   uint32_t*         misc = reinterpret_cast<uint32_t*>(smem_raw + lay.misc_off);
+  lane_state*       st   = reinterpret_cast<lane_state*>(smem_raw + lay.misc_off + 64);
   // misc: [0..3] any non-zero input, [4..7] any zero soft bit, [8..11] crc ok of this round
 
-  // ---- per-lane (code block) setup: uniform across the CTA ---------------------------------------------------------------
-  const int8_t* src[4];
-  uint32_t      n_load[4], nbits[4], cbi[4];
-  bool          live[4]; // takes part in decoding (valid, not skipped)
-  const uint32_t cap_in = (Kb + L) * Z - 2 * Z;
-#pragma unroll
-  for (int c = 0; c != 4; ++c) {
-    cbi[c]  = g.cb[c < (int)g.n ? c : 0];
-    live[c] = c < (int)g.n;
-    const cb_desc& d = descs[cbi[c]];
-    src[c]    = soft_base + (size_t)d.slot * SOFT_STRIDE;
-    n_load[c] = live[c] ? min(min(d.n_in, d.scan_len), cap_in) : 0U;
-    nbits[c]  = K - d.nof_filler;
-    if (live[c] && (d.flags & FLAG_TRACK_CRC) && !d.new_data && crc_flags[d.slot] != 0) {
+  // ---- per code block setup (one thread each; the state lives in shared memory, not in registers) ---------------------------
+  if (t < 16) {
+    misc[t] = 0;
+  }
+  if (t < 4) {
+    const int      c      = t;
+    const bool     valid  = c < (int)g.n;
+    const cb_desc& d      = descs[g.cb[valid ? c : 0]];
+    const uint32_t cap_in = (Kb + L) * Z - 2 * Z;
+    lane_state     ls;
+    ls.src       = soft_base + (size_t)d.slot * SOFT_STRIDE;
+    ls.bits_out  = d.bits_out;
+    ls.slot_bits = reinterpret_cast<uint32_t*>(bits_base + (size_t)d.slot * BITS_STRIDE);
+    ls.n_load    = valid ? min(min(d.n_in, d.scan_len), cap_in) : 0U;
+    ls.nbits     = K - d.nof_filler;
+    ls.cbi       = g.cb[valid ? c : 0];
+    ls.slot      = d.slot;
+    ls.flags     = d.flags;
+    ls.iters     = -1;
+    ls.crc_ok    = 0;
+    ls.live      = valid ? 1U : 0U;
+    ls.done      = 0; // 2 = skipped: decoded in an earlier transmission
+    if (valid && (d.flags & FLAG_TRACK_CRC) && !d.new_data && crc_flags[d.slot] != 0) {
       // Already decoded in an earlier transmission: only dematched (pusch_decoder_impl.cpp:335-345).
-      live[c]   = false;
-      n_load[c] = 0;
-      if (t == 0) {
-        results[cbi[c]] = {0, 1U, 0U, 2U};
-      }
-      if (d.bits_out != nullptr) {
-        const uint32_t* from = reinterpret_cast<const uint32_t*>(bits_base + (size_t)d.slot * BITS_STRIDE);
+      ls.live         = 0;
+      ls.n_load       = 0;
+      ls.done         = 2;
+      results[ls.cbi] = {0, 1U, 0U, 2U};
+    }
+    st[c] = ls;
+  }
+  __syncthreads();
+  {
+    uint32_t any_live = 0;
+#pragma unroll
+    for (int c = 0; c != 4; ++c) {
+      any_live |= st[c].live;
+      if (st[c].done == 2 && st[c].bits_out != nullptr) {
         for (uint32_t i = t; i < HBW; i += TPC) {
-          reinterpret_cast<uint32_t*>(d.bits_out)[i] = from[i];
+          reinterpret_cast<uint32_t*>(st[c].bits_out)[i] = st[c].slot_bits[i];
         }
       }
     }
-  }
-
-  if (!(live[0] || live[1] || live[2] || live[3])) {
-    return; // every code block of the group was already decoded (retransmission of an acknowledged TB)
+    if (any_live == 0) {
+      return; // every code block of the group was already decoded (retransmission of an acknowledged TB)
+    }
   }
 
   // ---- prologue ----------------------------------------------------------------------------------------------------------
@@ -160,14 +187,17 @@ __global__ void __launch_bounds__(TPC, 1) ldpc_decode4_kernel(const cb_desc* __r
   if (poly != 0) {
     build_crc_tables(tabs, poly, t, TPC);
   }
-  if (t < 32) {
-    misc[t] = 0;
-  }
-  __syncthreads();
   {
     const uint32_t nq    = (Kb + L) * Z / 4; // quads of variable nodes
     const uint32_t punct = 2 * Z / 4;
     uint32_t       nz[4] = {0, 0, 0, 0};
+    const int8_t*  src[4];
+    uint32_t       n_load[4];
+#pragma unroll
+    for (int c = 0; c != 4; ++c) {
+      src[c]    = st[c].src;
+      n_load[c] = st[c].n_load;
+    }
     for (uint32_t v = t; v < nq; v += TPC) {
       uint32_t w[4] = {0, 0, 0, 0};
       if (v >= punct) {
@@ -201,21 +231,15 @@ __global__ void __launch_bounds__(TPC, 1) ldpc_decode4_kernel(const cb_desc* __r
     }
   }
   __syncthreads();
-  bool allzero[4];
-#pragma unroll
-  for (int c = 0; c != 4; ++c) {
-    allzero[c] = (misc[c] == 0);
+  if (t < 4) {
+    // All-zero input with early stop: the reference returns before touching the output (ldpc_decoder_impl.cpp:88-94).
+    if (!st[t].live || (misc[t] == 0 && mode == MODE_EARLY_STOP)) {
+      st[t].done = max(st[t].done, 1U);
+    }
   }
+  __syncthreads();
 
   // ---- iterations --------------------------------------------------------------------------------------------------------
-  int      iters[4]  = {-1, -1, -1, -1};
-  uint32_t crc_ok[4] = {0, 0, 0, 0};
-  bool     done[4];
-#pragma unroll
-  for (int c = 0; c != 4; ++c) {
-    // All-zero input with early stop: the reference returns before touching the output (ldpc_decoder_impl.cpp:88-94).
-    done[c] = !live[c] || (allzero[c] && mode == MODE_EARLY_STOP);
-  }
   const uint32_t j      = t;
   const uint32_t zmagic = 0xffffffffU / Z + 1; // ceil(2^32 / Z): floor(k / Z) = umulhi(k, zmagic) for k < 2 Z
   for (uint32_t it = 0; it != max_it; ++it) {
@@ -262,10 +286,6 @@ __global__ void __launch_bounds__(TPC, 1) ldpc_decode4_kernel(const cb_desc* __r
       continue;
     }
     // Hard decision of the first K soft bits of every code block: bit = (llr <= 0), MSB first; "any zero" flags.
-    if (t < 8) {
-      misc[4 + t] = 0;
-    }
-    __syncthreads();
     {
       // Lane l takes variable 32 w + 31 - l: ballot bit l is then already in MSB-first order.
       uint32_t nz0 = 0x00010001U, nz1 = 0x00010001U; // stays 1 in the lanes that saw no zero soft bit
@@ -304,66 +324,52 @@ __global__ void __launch_bounds__(TPC, 1) ldpc_decode4_kernel(const cb_desc* __r
     __syncthreads();
     if (warp < 4) {
       uint32_t ok = 0;
-#pragma unroll
-      for (int c = 0; c != 4; ++c) {
-        if (c == warp && !done[c]) {
-          uint32_t crc = warp_crc_words<false>(hb + c * HBW, nbits[c], poly, tabs, lane);
-          ok           = (crc == 0 && (mode != MODE_EARLY_STOP || misc[4 + c] == 0)) ? 1U : 0U;
-        }
+      if (!st[warp].done) {
+        uint32_t crc = warp_crc_words<false>(hb + warp * HBW, st[warp].nbits, poly, tabs, lane);
+        ok           = (crc == 0 && (mode != MODE_EARLY_STOP || misc[4 + warp] == 0)) ? 1U : 0U;
       }
       if (lane == 0) {
         misc[8 + warp] = ok;
       }
     }
     __syncthreads();
-    bool all_done = true;
 #pragma unroll
     for (int c = 0; c != 4; ++c) {
-      if (done[c]) {
-        continue;
-      }
-      bool ok = misc[8 + c] != 0;
-      if (ok || last_it) {
+      if (!st[c].done && (misc[8 + c] != 0 || last_it)) {
         // The output holds the hard decision of the last iteration run (ldpc_decoder_impl.cpp:126-146).
-        const cb_desc& d    = descs[cbi[c]];
-        uint32_t*      slot = reinterpret_cast<uint32_t*>(bits_base + (size_t)d.slot * BITS_STRIDE);
+        uint32_t* slot = st[c].slot_bits;
+        uint32_t* out  = reinterpret_cast<uint32_t*>(st[c].bits_out);
         for (uint32_t i = t; i < HBW; i += TPC) {
           uint32_t wd = __byte_perm(hb[c * HBW + i], 0, 0x0123);
           slot[i]     = wd;
-          if (d.bits_out != nullptr) {
-            reinterpret_cast<uint32_t*>(d.bits_out)[i] = wd;
+          if (out != nullptr) {
+            out[i] = wd;
           }
         }
       }
-      if (ok) {
-        done[c]   = true;
-        crc_ok[c] = 1;
-        iters[c]  = (mode == MODE_EARLY_STOP) ? (int)it + 1 : (int)max_it;
-      } else {
-        all_done = false;
-      }
     }
-    __syncthreads(); // hb and misc are rewritten by the next round
-    if (all_done) {
+    __syncthreads();
+    if (t < 4) {
+      if (!st[t].done && misc[8 + t] != 0) {
+        st[t].done   = 1;
+        st[t].crc_ok = 1;
+        st[t].iters  = (mode == MODE_EARLY_STOP) ? (int)it + 1 : (int)max_it;
+      }
+      misc[4 + t] = 0; // "any zero" flags of the next round
+    }
+    __syncthreads();
+    if (st[0].done && st[1].done && st[2].done && st[3].done) {
       break;
     }
   }
 
-  if (t == 0) {
-#pragma unroll
-    for (int c = 0; c != 4; ++c) {
-      if (!live[c]) {
-        continue;
-      }
-      const cb_desc& d = descs[cbi[c]];
-      results[cbi[c]]  = {iters[c], crc_ok[c], L, 0U};
-      if (d.flags & FLAG_TRACK_CRC) {
-        crc_flags[d.slot] = crc_ok[c];
-      }
+  if (t < 4 && st[t].live) {
+    results[st[t].cbi] = {st[t].iters, st[t].crc_ok, L, 0U};
+    if (st[t].flags & FLAG_TRACK_CRC) {
+      crc_flags[st[t].slot] = st[t].crc_ok;
     }
   }
 }
-
 
 // ---------------------------------------------------------------------------------------------------------------------
 // Kernel 2c: same four-code-block group per CTA, but TWO threads per lifted check (2 x TPC threads): thread (h, j) owns
@@ -400,11 +406,11 @@ __device__ __forceinline__ void process_check2(uint32_t* __restrict__    soft,
 /// (half the shared memory: groups whose state does not fit four code blocks, e.g. HARQ retransmissions with many layers).
 template <int TPC, int NP>
 __global__ void __launch_bounds__(NP * TPC, 1) ldpc_decode4h_kernel(const cb_desc* __restrict__ descs,
-                                                                    const grp_desc* __restrict__ groups,
-                                                                    cb_result* __restrict__ results,
-                                                                    const int8_t* __restrict__ soft_base,
-                                                                    uint8_t* __restrict__ bits_base,
-                                                                    uint32_t* __restrict__ crc_flags)
+                                                                     const grp_desc* __restrict__ groups,
+                                                                     cb_result* __restrict__ results,
+                                                                     const int8_t* __restrict__ soft_base,
+                                                                     uint8_t* __restrict__ bits_base,
+                                                                     uint32_t* __restrict__ crc_flags)
 {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   constexpr int  NT   = NP * TPC;
@@ -414,7 +420,7 @@ __global__ void __launch_bounds__(NP * TPC, 1) ldpc_decode4h_kernel(const cb_des
   const int      lane = t & 31;
   const int      warp = __shfl_sync(0xffffffffU, t >> 5, 0);
   const int      h    = warp / (NW / NP); // plane: code blocks h and h + NP
-  const grp_desc g    = groups[blockIdx.x];
+  const grp_desc& g   = groups[blockIdx.x];
   const cb_desc& d0   = descs[g.cb[0]];
   const uint32_t Z = d0.Z, bg = d0.bg, Kb = (bg == 1) ? 22 : 10, K = Kb * Z, L = g.layer_cap;
   const uint32_t mode = d0.mode, max_it = d0.max_it, mult = d0.scale_mult;
@@ -430,37 +436,55 @@ __global__ void __launch_bounds__(NP * TPC, 1) ldpc_decode4h_kernel(const cb_des
   uint32_t*         hb     = reinterpret_cast<uint32_t*>(smem_raw + lay.hb_off);
   uint32_t*         tabs   = reinterpret_cast<uint32_t*>(smem_raw + lay.crc_off);
   uint32_t*         misc   = reinterpret_cast<uint32_t*>(smem_raw + lay.misc_off);
+  lane_state*       st     = reinterpret_cast<lane_state*>(smem_raw + lay.misc_off + 64);
+  // misc: [0..3] any non-zero input, [4..7] any zero soft bit, [8..11] crc ok of this round, [12] nothing left to decode
 
-  // ---- per-lane (code block) setup: uniform across the CTA ---------------------------------------------------------------
-  const int8_t* src[4];
-  uint32_t      n_load[4], nbits[4], cbi[4];
-  bool          live[4];
-  const uint32_t cap_in = (Kb + L) * Z - 2 * Z;
+  // ---- per code block setup (one thread each) ------------------------------------------------------------------------------
+  if (t < 16) {
+    misc[t] = 0;
+  }
+  if (t < 4) {
+    const int      c      = t;
+    const bool     valid  = c < (int)g.n && c < NC;
+    const cb_desc& d      = descs[g.cb[valid ? c : 0]];
+    const uint32_t cap_in = (Kb + L) * Z - 2 * Z;
+    lane_state     ls;
+    ls.src       = soft_base + (size_t)d.slot * SOFT_STRIDE;
+    ls.bits_out  = d.bits_out;
+    ls.slot_bits = reinterpret_cast<uint32_t*>(bits_base + (size_t)d.slot * BITS_STRIDE);
+    ls.n_load    = valid ? min(min(d.n_in, d.scan_len), cap_in) : 0U;
+    ls.nbits     = K - d.nof_filler;
+    ls.cbi       = g.cb[valid ? c : 0];
+    ls.slot      = d.slot;
+    ls.flags     = d.flags;
+    ls.iters     = -1;
+    ls.crc_ok    = 0;
+    ls.live      = valid ? 1U : 0U;
+    ls.done      = 0; // 2 = skipped: decoded in an earlier transmission
+    if (valid && (d.flags & FLAG_TRACK_CRC) && !d.new_data && crc_flags[d.slot] != 0) {
+      // Already decoded in an earlier transmission: only dematched (pusch_decoder_impl.cpp:335-345).
+      ls.live           = 0;
+      ls.n_load         = 0;
+      ls.done           = 2;
+      results[ls.cbi] = {0, 1U, 0U, 2U};
+    }
+    st[c] = ls;
+  }
+  __syncthreads();
+  {
+    uint32_t any_live = 0;
 #pragma unroll
-  for (int c = 0; c != 4; ++c) {
-    cbi[c]  = g.cb[(c < (int)g.n && c < NC) ? c : 0];
-    live[c] = c < (int)g.n && c < NC;
-    const cb_desc& d = descs[cbi[c]];
-    src[c]    = soft_base + (size_t)d.slot * SOFT_STRIDE;
-    n_load[c] = live[c] ? min(min(d.n_in, d.scan_len), cap_in) : 0U;
-    nbits[c]  = K - d.nof_filler;
-    if (live[c] && (d.flags & FLAG_TRACK_CRC) && !d.new_data && crc_flags[d.slot] != 0) {
-      live[c]   = false;
-      n_load[c] = 0;
-      if (t == 0) {
-        results[cbi[c]] = {0, 1U, 0U, 2U};
-      }
-      if (d.bits_out != nullptr) {
-        const uint32_t* from = reinterpret_cast<const uint32_t*>(bits_base + (size_t)d.slot * BITS_STRIDE);
+    for (int c = 0; c != 4; ++c) {
+      any_live |= st[c].live;
+      if (st[c].done == 2 && st[c].bits_out != nullptr) {
         for (uint32_t i = t; i < HBW; i += NT) {
-          reinterpret_cast<uint32_t*>(d.bits_out)[i] = from[i];
+          reinterpret_cast<uint32_t*>(st[c].bits_out)[i] = st[c].slot_bits[i];
         }
       }
     }
-  }
-
-  if (!(live[0] || live[1] || live[2] || live[3])) {
-    return; // every code block of the group was already decoded (retransmission of an acknowledged TB)
+    if (any_live == 0) {
+      return; // every code block of the group was already decoded (retransmission of an acknowledged TB)
+    }
   }
 
   // ---- prologue ----------------------------------------------------------------------------------------------------------
@@ -478,24 +502,23 @@ __global__ void __launch_bounds__(NP * TPC, 1) ldpc_decode4h_kernel(const cb_des
   if (poly != 0) {
     build_crc_tables(tabs, poly, t, NT);
   }
-  if (t < 32) {
-    misc[t] = 0;
-  }
-  __syncthreads();
   {
     const uint32_t nq    = nvar / 4; // quads of variable nodes
     const uint32_t punct = 2 * Z / 4;
     uint32_t       nz0 = 0, nz1 = 0;
     const int      tl = t - h * TPC; // index within the plane's threads
+    const int8_t*  s0 = st[h].src;
+    const int8_t*  s1 = st[h + NP].src;
+    const uint32_t l0 = st[h].n_load, l1 = st[h + NP].n_load;
     for (uint32_t v = tl; v < nq; v += TPC) {
       uint32_t w0 = 0, w1 = 0;
       if (v >= punct) {
         uint32_t p = (v - punct) * 4;
-        if (p < n_load[h]) {
-          w0 = __ldg(reinterpret_cast<const uint32_t*>(src[h] + p));
+        if (p < l0) {
+          w0 = __ldg(reinterpret_cast<const uint32_t*>(s0 + p));
         }
-        if (p < n_load[h + NP]) {
-          w1 = __ldg(reinterpret_cast<const uint32_t*>(src[h + NP] + p));
+        if (p < l1) {
+          w1 = __ldg(reinterpret_cast<const uint32_t*>(s1 + p));
         }
         nz0 |= w0;
         nz1 |= w1;
@@ -521,20 +544,15 @@ __global__ void __launch_bounds__(NP * TPC, 1) ldpc_decode4h_kernel(const cb_des
     }
   }
   __syncthreads();
-  bool allzero[4];
-#pragma unroll
-  for (int c = 0; c != 4; ++c) {
-    allzero[c] = (misc[c] == 0);
+  if (t < 4) {
+    // All-zero input with early stop: the reference returns before touching the output (ldpc_decoder_impl.cpp:88-94).
+    if (!st[t].live || (misc[t] == 0 && mode == MODE_EARLY_STOP)) {
+      st[t].done = max(st[t].done, 1U);
+    }
   }
+  __syncthreads();
 
   // ---- iterations --------------------------------------------------------------------------------------------------------
-  int      iters[4]  = {-1, -1, -1, -1};
-  uint32_t crc_ok[4] = {0, 0, 0, 0};
-  bool     done[4];
-#pragma unroll
-  for (int c = 0; c != 4; ++c) {
-    done[c] = !live[c] || (allzero[c] && mode == MODE_EARLY_STOP);
-  }
   const uint32_t j      = t - h * TPC;
   const uint32_t zmagic = 0xffffffffU / Z + 1;
   for (uint32_t it = 0; it != max_it; ++it) {
@@ -580,10 +598,6 @@ __global__ void __launch_bounds__(NP * TPC, 1) ldpc_decode4h_kernel(const cb_des
     if (mode != MODE_EARLY_STOP && !last_it) {
       continue;
     }
-    if (t < 8) {
-      misc[4 + t] = 0;
-    }
-    __syncthreads();
     {
       // Plane h by its own warps; lane l takes variable 32 w + 31 - l: ballot bit l is already in MSB-first order.
       uint32_t nz = 0x00010001U;
@@ -610,61 +624,49 @@ __global__ void __launch_bounds__(NP * TPC, 1) ldpc_decode4h_kernel(const cb_des
     __syncthreads();
     if (warp < 4) {
       uint32_t ok = 0;
-#pragma unroll
-      for (int c = 0; c != 4; ++c) {
-        if (c == warp && !done[c]) {
-          uint32_t crc = warp_crc_words<false>(hb + c * HBW, nbits[c], poly, tabs, lane);
-          ok           = (crc == 0 && (mode != MODE_EARLY_STOP || misc[4 + c] == 0)) ? 1U : 0U;
-        }
+      if (!st[warp].done) {
+        uint32_t crc = warp_crc_words<false>(hb + warp * HBW, st[warp].nbits, poly, tabs, lane);
+        ok           = (crc == 0 && (mode != MODE_EARLY_STOP || misc[4 + warp] == 0)) ? 1U : 0U;
       }
       if (lane == 0) {
         misc[8 + warp] = ok;
       }
     }
     __syncthreads();
-    bool all_done = true;
 #pragma unroll
     for (int c = 0; c != 4; ++c) {
-      if (done[c]) {
-        continue;
-      }
-      bool ok = misc[8 + c] != 0;
-      if (ok || last_it) {
-        const cb_desc& d    = descs[cbi[c]];
-        uint32_t*      slot = reinterpret_cast<uint32_t*>(bits_base + (size_t)d.slot * BITS_STRIDE);
+      if (!st[c].done && (misc[8 + c] != 0 || last_it)) {
+        // The output holds the hard decision of the last iteration run (ldpc_decoder_impl.cpp:126-146).
+        uint32_t* slot = st[c].slot_bits;
+        uint32_t* out  = reinterpret_cast<uint32_t*>(st[c].bits_out);
         for (uint32_t i = t; i < HBW; i += NT) {
           uint32_t wd = __byte_perm(hb[c * HBW + i], 0, 0x0123);
           slot[i]     = wd;
-          if (d.bits_out != nullptr) {
-            reinterpret_cast<uint32_t*>(d.bits_out)[i] = wd;
+          if (out != nullptr) {
+            out[i] = wd;
           }
         }
       }
-      if (ok) {
-        done[c]   = true;
-        crc_ok[c] = 1;
-        iters[c]  = (mode == MODE_EARLY_STOP) ? (int)it + 1 : (int)max_it;
-      } else {
-        all_done = false;
-      }
     }
     __syncthreads();
-    if (all_done) {
+    if (t < 4) {
+      if (!st[t].done && misc[8 + t] != 0) {
+        st[t].done   = 1;
+        st[t].crc_ok = 1;
+        st[t].iters  = (mode == MODE_EARLY_STOP) ? (int)it + 1 : (int)max_it;
+      }
+      misc[4 + t] = 0; // "any zero" flags of the next round
+    }
+    __syncthreads();
+    if (st[0].done && st[1].done && st[2].done && st[3].done) {
       break;
     }
   }
 
-  if (t == 0) {
-#pragma unroll
-    for (int c = 0; c != 4; ++c) {
-      if (!live[c]) {
-        continue;
-      }
-      const cb_desc& d = descs[cbi[c]];
-      results[cbi[c]]  = {iters[c], crc_ok[c], L, 0U};
-      if (d.flags & FLAG_TRACK_CRC) {
-        crc_flags[d.slot] = crc_ok[c];
-      }
+  if (t < 4 && st[t].live) {
+    results[st[t].cbi] = {st[t].iters, st[t].crc_ok, L, 0U};
+    if (st[t].flags & FLAG_TRACK_CRC) {
+      crc_flags[st[t].slot] = st[t].crc_ok;
     }
   }
 }

@@ -360,6 +360,15 @@ int upload_tables(srsran_cuda_pusch_dec* h)
     }
   }
   CUDA_TRY(h, cudaMemcpyToSymbol(c_xpow2, xp2, sizeof(xp2)));
+  static uint32_t tabs[3][1024];
+  for (int poly = 1; poly <= 3; ++poly) {
+    uint32_t gen = crc_gen(poly), order = crc_order(poly);
+    for (uint32_t i = 0; i != 1024; ++i) {
+      uint32_t r        = crc_push_bits(0, (i & 0xffU) << 24, 8, gen, order);
+      tabs[poly - 1][i] = crc_push_bits(r, 0, 8 * (i >> 8), gen, order);
+    }
+  }
+  CUDA_TRY(h, cudaMemcpyToSymbol(g_crc_tabs, tabs, sizeof(tabs)));
   return SRSRAN_CUDA_OK;
 }
 

@@ -28,6 +28,8 @@ __constant__ uint32_t c_xpow32[3][272];
 __constant__ uint32_t c_xpow128[3][1024];
 /// x^(2^i) mod g, i = 0..31 (square-and-multiply ladders).
 __constant__ uint32_t c_xpow2[3][32];
+/// Byte tables of the three CRCs: g_crc_tabs[poly - 1][k * 256 + b] = (b(x) x^(8k) x^order) mod g, k = 0..3.
+__device__ uint32_t g_crc_tabs[3][1024];
 
 __host__ __device__ __forceinline__ uint32_t crc_gen(int poly)
 {
@@ -941,13 +943,12 @@ __global__ void __launch_bounds__(CRC_THREADS) crc_kernel(const crc_job* __restr
 // ---------------------------------------------------------------------------------------------------------------------
 constexpr int TBG_WARPS = 16;
 
-/// Byte tables tabs[k][b] = (b(x) x^(8k) x^order) mod g, k = 0..3, built by the whole CTA.
+/// Byte tables tabs[k][b] = (b(x) x^(8k) x^order) mod g, k = 0..3: copied from the precomputed global tables (4 KB).
 __device__ __forceinline__ void build_crc_tables(uint32_t* tabs, int poly, int t, int nthreads)
 {
-  const uint32_t gen = crc_gen(poly), order = crc_order(poly);
+  const uint32_t* src = g_crc_tabs[poly - 1];
   for (int i = t; i < 1024; i += nthreads) {
-    uint32_t r = crc_push_bits(0, ((uint32_t)i & 0xffU) << 24, 8, gen, order);
-    tabs[i]    = crc_push_bits(r, 0, 8 * ((uint32_t)i >> 8), gen, order);
+    tabs[i] = src[i];
   }
 }
 
