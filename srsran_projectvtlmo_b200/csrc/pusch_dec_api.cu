@@ -166,6 +166,7 @@ struct srsran_cuda_pusch_dec {
   cudaEvent_t timer_end      = nullptr;
   bool        timer_armed    = false;
   int      max_smem_optin    = 0;
+  int      nof_sms           = 148;
   std::string last_error;
 
   device_buf<int8_t>   d_soft;
@@ -683,6 +684,14 @@ int launch_context(srsran_cuda_pusch_dec* h, int ci)
     ++pclasses.back().count;
     ++ngrp;
   };
+  // Latency mode: when four-per-CTA groups would leave more than half of the SMs idle (a single transport block), two
+  // code blocks per CTA spread the batch over twice as many SMs and halve the work per thread.
+  uint32_t nof_packable = 0;
+  for (uint32_t i = 0; i != ncb; ++i) {
+    const cb_desc& d = c.h_desc.p[i];
+    nof_packable += ((d.flags & FLAG_DECODE) && packed_eligible(h, d, d.layer_cap, 2)) ? 1U : 0U;
+  }
+  const bool small_batch = (nof_packable + 3) / 4 <= static_cast<uint32_t>(h->nof_sms) / 2;
   for (uint32_t i = 0; i != ncb; ++i) {
     const cb_desc& d = c.h_desc.p[i];
     if (d.flags & FLAG_DEMATCH) {
@@ -695,7 +704,9 @@ int launch_context(srsran_cuda_pusch_dec* h, int ci)
     if (!(d.flags & FLAG_DECODE)) {
       continue;
     }
-    const uint32_t lanes_fit = packed_eligible(h, d, d.layer_cap, 4) ? 4U : (packed_eligible(h, d, d.layer_cap, 2) ? 2U : 0U);
+    const uint32_t lanes_fit = (!small_batch && packed_eligible(h, d, d.layer_cap, 4))
+                                   ? 4U
+                                   : (packed_eligible(h, d, d.layer_cap, 2) ? 2U : 0U);
     if (lanes_fit != 0) {
       if (grp_open) {
         grp_desc&      g   = c.h_grp.p[ngrp];
@@ -1033,6 +1044,7 @@ int srsran_cuda_pusch_dec_create(int device, uint32_t max_cbs_in_flight, uint32_
     return code;
   };
   cudaDeviceGetAttribute(&h->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
+  cudaDeviceGetAttribute(&h->nof_sms, cudaDevAttrMultiProcessorCount, device);
   if (upload_tables(h) != SRSRAN_CUDA_OK) {
     return fail(SRSRAN_CUDA_ERR_CUDA);
   }
