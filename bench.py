@@ -205,7 +205,7 @@ def main():
     ap.add_argument("--ref-seconds", type=float, default=20.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--latency-reps", type=int, default=200)
-    ap.add_argument("--decoder-variant", type=int, default=0, help="0 auto (packed, 4 lanes per thread), 1 one code block per thread group, 2 packed with 2 threads per check")
+    ap.add_argument("--decoder-variant", type=int, default=0, help="0 auto, 1 general kernel only, 2 packed groups with 2 threads per check, 3 one code block per CTA packed kernel everywhere")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
 

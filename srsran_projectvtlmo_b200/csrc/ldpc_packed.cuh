@@ -234,10 +234,18 @@ __global__ void __launch_bounds__(TPC, 1) ldpc_decode4_kernel(const cb_desc* __r
   if (t < 4) {
     // All-zero input with early stop: the reference returns before touching the output (ldpc_decoder_impl.cpp:88-94).
     if (!st[t].live || (misc[t] == 0 && mode == MODE_EARLY_STOP)) {
-      st[t].done = max(st[t].done, 1U);
+      st[t].done = max(st[t].done, st[t].live ? 3U : 1U);
     }
   }
   __syncthreads();
+#pragma unroll
+  for (int c = 0; c != 4; ++c) {
+    if (st[c].done == 3 && st[c].bits_out != nullptr) {
+      for (uint32_t i = t; i < HBW; i += blockDim.x) {
+        reinterpret_cast<uint32_t*>(st[c].bits_out)[i] = st[c].slot_bits[i]; // untouched output
+      }
+    }
+  }
 
   // ---- iterations --------------------------------------------------------------------------------------------------------
   const uint32_t j      = t;
@@ -547,10 +555,18 @@ __global__ void __launch_bounds__(NP * TPC, 1) ldpc_decode4h_kernel(const cb_des
   if (t < 4) {
     // All-zero input with early stop: the reference returns before touching the output (ldpc_decoder_impl.cpp:88-94).
     if (!st[t].live || (misc[t] == 0 && mode == MODE_EARLY_STOP)) {
-      st[t].done = max(st[t].done, 1U);
+      st[t].done = max(st[t].done, st[t].live ? 3U : 1U);
     }
   }
   __syncthreads();
+#pragma unroll
+  for (int c = 0; c != 4; ++c) {
+    if (st[c].done == 3 && st[c].bits_out != nullptr) {
+      for (uint32_t i = t; i < HBW; i += blockDim.x) {
+        reinterpret_cast<uint32_t*>(st[c].bits_out)[i] = st[c].slot_bits[i]; // untouched output
+      }
+    }
+  }
 
   // ---- iterations --------------------------------------------------------------------------------------------------------
   const uint32_t j      = t - h * TPC;
@@ -667,6 +683,335 @@ __global__ void __launch_bounds__(NP * TPC, 1) ldpc_decode4h_kernel(const cb_des
     results[st[t].cbi] = {st[t].iters, st[t].crc_ok, L, 0U};
     if (st[t].flags & FLAG_TRACK_CRC) {
       crc_flags[st[t].slot] = st[t].crc_ok;
+    }
+  }
+}
+
+} // namespace pusch_dec
+
+namespace pusch_dec {
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Kernel 2d: ONE code block per CTA on the packed arithmetic - the four 16-bit lanes hold four lifted checks of the same
+// code block (j, j + Z/4, j + Z/2, j + 3Z/4; see "intra-code-block packing" in ldpc_packed_math.h), Z/4 threads per
+// code block. No grouping constraint: ragged batches (any mix of base graph, lifting size with Z % 4 == 0, layers,
+// modes), every code block early-stops on its own, and up to four CTAs share an SM so the serial phases of one (input
+// load, CRC) overlap the layer sweeps of the others. Shared memory per code block: 2 bytes per variable lift + 1 byte per
+// lifted edge (BASELINE config 2: 51 KB; config 1, 46 layers: 173 KB).
+// ---------------------------------------------------------------------------------------------------------------------
+struct decq_layout {
+  uint32_t tab_off, soft_off, c2v_off, hb_off, crc_off, misc_off, total;
+};
+
+__host__ __device__ inline decq_layout decq_smem_layout(uint32_t bg, uint32_t Z, uint32_t layer_cap)
+{
+#ifdef __CUDA_ARCH__
+  uint32_t nedges = c_row_ptr[bg - 1][layer_cap];
+#else
+  uint32_t nedges = ((bg == 1) ? NR_BG1_ROW_PTR : NR_BG2_ROW_PTR)[layer_cap];
+#endif
+  uint32_t    Kb = (bg == 1) ? 22 : 10;
+  decq_layout l;
+  l.tab_off  = 0;
+  l.soft_off = (nedges * 8 + 15) & ~15U;
+  l.c2v_off  = l.soft_off + (((Kb + layer_cap) * Z * 2 + 15) & ~15U);
+  l.hb_off   = l.c2v_off + ((nedges * Z + 15) & ~15U);
+  l.crc_off  = l.hb_off + (((Kb * Z + 31) / 32 * 4 + 4 + 15) & ~15U);
+  l.misc_off = l.crc_off + 4 * 256 * 4;
+  l.total    = l.misc_off + 128;
+  return l;
+}
+
+/// Selector pairs for pk::rot4 by q quarter turns (entries 0..3) and back (entries 4..7 = rotation by (4 - q) mod 4).
+__constant__ uint2 c_rot4[8] = {{0x3210U, 0x7654U}, {0x7654U, 0x1032U}, {0x1032U, 0x5476U}, {0x5476U, 0x3210U},
+                                {0x3210U, 0x7654U}, {0x5476U, 0x3210U}, {0x1032U, 0x5476U}, {0x7654U, 0x1032U}};
+
+template <int DEG>
+__device__ __forceinline__ void process_check_q4(uint2* __restrict__       soft,
+                                                 uint32_t* __restrict__    c2v_row,
+                                                 const uint2* __restrict__ tab_row,
+                                                 const uint2* __restrict__ rot,
+                                                 uint32_t                  j,
+                                                 uint32_t                  Z,
+                                                 uint32_t                  Z4,
+                                                 uint32_t                  zmagic,
+                                                 uint32_t                  z4magic,
+                                                 uint32_t                  mult)
+{
+  pk::check4<DEG> ck;
+  ck.begin();
+#pragma unroll
+  for (int e = 0; e != DEG; ++e) {
+    const uint2 te = tab_row[e];            // (column * Z/4, shift)
+    uint32_t    k  = j + te.y;
+    k -= __umulhi(k, zmagic) * Z;
+    const uint32_t q = __umulhi(k, z4magic); // quarter of the column the first check lands in
+    const uint2    s = soft[te.x + k - q * Z4];
+    const uint2    r = rot[q];
+    ck.gather(e, __byte_perm(s.x, s.y, r.x), __byte_perm(s.x, s.y, r.y), c2v_row[e * Z4 + j]);
+  }
+  ck.reduce(mult);
+#pragma unroll
+  for (int e = 0; e != DEG; ++e) {
+    const uint2 te = tab_row[e];
+    uint32_t    k  = j + te.y;
+    k -= __umulhi(k, zmagic) * Z;
+    const uint32_t q = __umulhi(k, z4magic);
+    uint32_t       s0, s1;
+    c2v_row[e * Z4 + j] = ck.scatter(e, s0, s1);
+    const uint2 r       = rot[4 + q];
+    soft[te.x + k - q * Z4] = make_uint2(__byte_perm(s0, s1, r.x), __byte_perm(s0, s1, r.y));
+  }
+}
+
+template <int TPB>
+__global__ void __launch_bounds__(TPB, (TPB == 96) ? 4 : 6) ldpc_decode_q4_kernel(const cb_desc* __restrict__ descs,
+                                                                                   const uint32_t* __restrict__ order,
+                                                                                   cb_result* __restrict__ results,
+                                                                                   const int8_t* __restrict__ soft_base,
+                                                                                   uint8_t* __restrict__ bits_base,
+                                                                                   uint32_t* __restrict__ crc_flags)
+{
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  constexpr int  NW   = TPB / 32;
+  const int      t    = threadIdx.x;
+  const int      lane = t & 31;
+  const int      warp = __shfl_sync(0xffffffffU, t >> 5, 0);
+  const uint32_t cb   = order[blockIdx.x];
+  const cb_desc& d    = descs[cb];
+  const uint32_t Z = d.Z, bg = d.bg, Kb = (bg == 1) ? 22 : 10, K = Kb * Z, Z4 = Z / 4;
+  const uint32_t HBW  = (K + 31) / 32;
+  uint32_t*      slot_bits = reinterpret_cast<uint32_t*>(bits_base + (size_t)d.slot * BITS_STRIDE);
+
+  // Code blocks whose CRC is already ok are only dematched (pusch_decoder_impl.cpp:335-345).
+  if ((d.flags & FLAG_TRACK_CRC) && !d.new_data && crc_flags[d.slot] != 0) {
+    if (t == 0) {
+      results[cb] = {0, 1U, 0U, 2U};
+    }
+    if (d.bits_out != nullptr) {
+      for (uint32_t i = t; i < HBW; i += TPB) {
+        reinterpret_cast<uint32_t*>(d.bits_out)[i] = slot_bits[i];
+      }
+    }
+    return;
+  }
+
+  const uint32_t    Lcap = d.layer_cap;
+  const decq_layout lay  = decq_smem_layout(bg, Z, Lcap);
+  uint2*            tab  = reinterpret_cast<uint2*>(smem_raw + lay.tab_off);
+  uint2*            soft = reinterpret_cast<uint2*>(smem_raw + lay.soft_off);
+  uint32_t*         c2v  = reinterpret_cast<uint32_t*>(smem_raw + lay.c2v_off);
+  uint32_t*         hb   = reinterpret_cast<uint32_t*>(smem_raw + lay.hb_off);
+  uint32_t*         tabs = reinterpret_cast<uint32_t*>(smem_raw + lay.crc_off);
+  uint32_t*         misc = reinterpret_cast<uint32_t*>(smem_raw + lay.misc_off);
+  uint2*            rot  = reinterpret_cast<uint2*>(smem_raw + lay.misc_off + 64);
+  // misc: [0] index after the last non-zero input LLR, [1] any zero soft bit, [2] crc ok
+
+  const uint32_t mode = d.mode, max_it = d.max_it, mult = d.scale_mult;
+  const int      poly = (mode == MODE_NO_CRC) ? 0 : (int)d.crc_poly;
+  const uint32_t nb   = K - d.nof_filler;
+  const uint32_t zmagic = 0xffffffffU / Z + 1, z4magic = 0xffffffffU / Z4 + 1;
+
+  // ---- prologue ----------------------------------------------------------------------------------------------------------
+  if (t < 8) {
+    rot[t] = c_rot4[t];
+  }
+  if (t < 16) {
+    misc[t] = 0;
+  }
+  const uint32_t nedges_cap = c_row_ptr[bg - 1][Lcap];
+  for (uint32_t e = t; e < nedges_cap; e += TPB) {
+    tab[e] = make_uint2((uint32_t)c_col[bg - 1][e] * Z4, c_shift[bg - 1][d.ils][e] % Z);
+  }
+  for (uint32_t i = t; i < nedges_cap * Z4; i += TPB) {
+    c2v[i] = pk::C2V_ZERO4;
+  }
+  if (poly != 0) {
+    build_crc_tables(tabs, poly, t, TPB);
+  }
+  __syncthreads();
+  {
+    const int8_t*  src    = (d.flags & FLAG_USE_HARQ) ? soft_base + (size_t)d.slot * SOFT_STRIDE : d.llr;
+    const uint32_t cap_in = (Kb + Lcap) * Z - 2 * Z;
+    const uint32_t n_load = min(min(d.n_in, d.scan_len), cap_in);
+    const uint32_t ncols  = Kb + Lcap;
+    uint32_t       last   = 0;
+    uint32_t       c = 0, b = t; // word (c, b), b < Z4
+    while (b >= Z4) {
+      b -= Z4;
+      ++c;
+    }
+    while (c < ncols) {
+      uint32_t ub[4];
+#pragma unroll
+      for (uint32_t m = 0; m != 4; ++m) {
+        uint32_t i = c * Z + b + m * Z4; // variable index; decoder input index is i - 2 Z
+        int      x = 0;
+        if (i >= 2 * Z && i - 2 * Z < n_load) {
+          x = __ldg(src + (i - 2 * Z));
+          if (x != 0) {
+            last = max(last, i - 2 * Z + 1);
+          }
+        }
+        ub[m] = (uint32_t)(uint8_t)(x ^ 0x80);
+      }
+      soft[c * Z4 + b] = make_uint2(pk::soft_from_biased_bytes(ub[0] | (ub[2] << 16)), pk::soft_from_biased_bytes(ub[1] | (ub[3] << 16)));
+      b += TPB;
+      while (b >= Z4) {
+        b -= Z4;
+        ++c;
+      }
+    }
+    last = __reduce_max_sync(0xffffffffU, last);
+    if (lane == 0 && last != 0) {
+      atomicMax(&misc[0], last);
+    }
+  }
+  __syncthreads();
+  const uint32_t last = misc[0];
+  // Layers actually processed (ldpc_decoder_impl.cpp:86-114); never more than the host's bound.
+  uint32_t L = 0;
+  if (last != 0) {
+    uint32_t cbl = max(last + 2 * Z, K + 4 * Z);
+    L            = min((cbl + Z - 1) / Z - Kb, Lcap);
+  }
+
+  int      iters  = -1;
+  uint32_t crc_ok = 0;
+  // All-zero input (ldpc_decoder_impl.cpp:88-94): with a CRC calculator the reference returns before touching the output;
+  // without one the output becomes all ones (the hard decision of the untouched zero soft bits).
+  const bool skip_all = (last == 0 && mode == MODE_EARLY_STOP);
+  if (skip_all && d.bits_out != nullptr) {
+    for (uint32_t i = t; i < HBW; i += TPB) {
+      reinterpret_cast<uint32_t*>(d.bits_out)[i] = slot_bits[i]; // untouched output
+    }
+  }
+  const uint32_t j = t;
+  for (uint32_t it = 0; it != max_it && !skip_all; ++it) {
+    for (uint32_t l = 0; l != L; ++l) {
+      uint32_t e0  = c_row_ptr[bg - 1][l];
+      int      deg = (int)c_row_ptr[bg - 1][l + 1] - (int)e0;
+      if (j < Z4) {
+        uint32_t*    c2v_row = c2v + (size_t)e0 * Z4;
+        const uint2* tab_row = tab + e0;
+        switch (deg) {
+          case 3:
+            process_check_q4<3>(soft, c2v_row, tab_row, rot, j, Z, Z4, zmagic, z4magic, mult);
+            break;
+          case 4:
+            process_check_q4<4>(soft, c2v_row, tab_row, rot, j, Z, Z4, zmagic, z4magic, mult);
+            break;
+          case 5:
+            process_check_q4<5>(soft, c2v_row, tab_row, rot, j, Z, Z4, zmagic, z4magic, mult);
+            break;
+          case 6:
+            process_check_q4<6>(soft, c2v_row, tab_row, rot, j, Z, Z4, zmagic, z4magic, mult);
+            break;
+          case 7:
+            process_check_q4<7>(soft, c2v_row, tab_row, rot, j, Z, Z4, zmagic, z4magic, mult);
+            break;
+          case 8:
+            process_check_q4<8>(soft, c2v_row, tab_row, rot, j, Z, Z4, zmagic, z4magic, mult);
+            break;
+          case 9:
+            process_check_q4<9>(soft, c2v_row, tab_row, rot, j, Z, Z4, zmagic, z4magic, mult);
+            break;
+          case 10:
+            process_check_q4<10>(soft, c2v_row, tab_row, rot, j, Z, Z4, zmagic, z4magic, mult);
+            break;
+          default:
+            process_check_q4<19>(soft, c2v_row, tab_row, rot, j, Z, Z4, zmagic, z4magic, mult);
+            break;
+        }
+      }
+      __syncthreads();
+    }
+    const bool last_it = (it + 1 == max_it);
+    if (mode != MODE_EARLY_STOP && !last_it) {
+      continue;
+    }
+    // Hard decision of the first K soft bits: bit = (llr <= 0), MSB first. A warp takes 32 consecutive bases of one
+    // column: four ballots give four runs of 32 bits (one per quarter of the column), OR-ed into the packed words.
+    for (uint32_t i = t; i < HBW + 1; i += TPB) {
+      hb[i] = 0;
+    }
+    __syncthreads();
+    {
+      const uint32_t rpc   = (Z4 + 31) / 32; // runs per column and quarter
+      const uint32_t nrows = Kb * rpc;
+      uint32_t       nz0 = 0x00010001U, nz1 = 0x00010001U;
+      for (uint32_t r = warp; r < nrows; r += NW) {
+        const uint32_t c  = r / rpc;
+        const uint32_t b0 = (r - c * rpc) * 32;
+        const uint32_t b  = b0 + 31 - lane; // ballot bit l <-> base b0 + 31 - l: the run is MSB-first
+        uint2          s  = make_uint2(pk::SOFT_ZERO2 + 0x00010001U, pk::SOFT_ZERO2 + 0x00010001U); // positive
+        if (b < Z4) {
+          s = soft[c * Z4 + b];
+        }
+        uint32_t p0 = pk::addmin_s2_relu(s.x, PK_REP2(0x10000U - pk::BS), 0x00010001U); // 1 where soft > 0
+        uint32_t p1 = pk::addmin_s2_relu(s.y, PK_REP2(0x10000U - pk::BS), 0x00010001U);
+        nz0 &= pk::minu2(s.x ^ pk::SOFT_ZERO2, 0x00010001U);
+        nz1 &= pk::minu2(s.y ^ pk::SOFT_ZERO2, 0x00010001U);
+        const bool in = b < Z4;
+        uint32_t   run[4];
+        run[0] = __ballot_sync(0xffffffffU, in && (p0 & 0xffffU) == 0); // quarter 0: k = b
+        run[1] = __ballot_sync(0xffffffffU, in && (p1 & 0xffffU) == 0); // quarter 1: k = b + Z/4
+        run[2] = __ballot_sync(0xffffffffU, in && (p0 >> 16) == 0);     // quarter 2
+        run[3] = __ballot_sync(0xffffffffU, in && (p1 >> 16) == 0);     // quarter 3
+        if (lane < 4) {
+          const uint32_t mine = (lane & 2) ? ((lane & 1) ? run[3] : run[2]) : ((lane & 1) ? run[1] : run[0]);
+          const uint32_t o    = c * Z + lane * Z4 + b0; // bit offset of the first variable of this run
+          const uint32_t sh   = o & 31;
+          if (mine != 0) {
+            atomicOr(&hb[o >> 5], mine >> sh);
+            if (sh != 0) {
+              atomicOr(&hb[(o >> 5) + 1], mine << (32 - sh));
+            }
+          }
+        }
+      }
+      nz0 = __reduce_and_sync(0xffffffffU, nz0);
+      nz1 = __reduce_and_sync(0xffffffffU, nz1);
+      if (lane == 0 && (nz0 & nz1) != 0x00010001U) {
+        atomicOr(&misc[1], 1U);
+      }
+    }
+    __syncthreads();
+    if (warp == 0) {
+      uint32_t ok = 0;
+      if (poly != 0) {
+        uint32_t crc = warp_crc_words<false>(hb, nb, poly, tabs, lane);
+        ok           = (crc == 0 && (mode != MODE_EARLY_STOP || misc[1] == 0)) ? 1U : 0U;
+      }
+      if (lane == 0) {
+        misc[2] = ok;
+        misc[1] = 0;
+      }
+    }
+    __syncthreads();
+    const bool ok = misc[2] != 0;
+    if (ok || last_it) {
+      // The output holds the hard decision of the last iteration run (ldpc_decoder_impl.cpp:126-146).
+      for (uint32_t i = t; i < HBW; i += TPB) {
+        uint32_t wd  = __byte_perm(hb[i], 0, 0x0123); // bits beyond K are zero; the host merges a partial last byte
+        slot_bits[i] = wd;
+        if (d.bits_out != nullptr) {
+          reinterpret_cast<uint32_t*>(d.bits_out)[i] = wd;
+        }
+      }
+    }
+    if (ok) {
+      crc_ok = 1;
+      iters  = (mode == MODE_EARLY_STOP) ? (int)it + 1 : (int)max_it;
+      break;
+    }
+    __syncthreads();
+  }
+
+  if (t == 0) {
+    results[cb] = {iters, crc_ok, L, 0U};
+    if (d.flags & FLAG_TRACK_CRC) {
+      crc_flags[d.slot] = crc_ok;
     }
   }
 }

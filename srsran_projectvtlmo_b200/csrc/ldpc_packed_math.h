@@ -270,5 +270,50 @@ struct check2 : check_lanes<DEG, 1, false> {
   }
 };
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Intra-code-block packing: the four lanes hold four lifted checks of the SAME code block, j, j + Z/4, j + Z/2 and
+// j + 3Z/4 (Z % 4 == 0), so a single code block of any shape runs on the packed arithmetic with Z/4 threads.
+// Soft values are stored per "base" index b in [0, Z/4): word(col, b) = { r0 = (S[b], S[b + Z/2]), r1 = (S[b + Z/4],
+// S[b + 3Z/4]) } (lanes L0..L3 = quarters 0..3 of the column: r0 = (L0, L2), r1 = (L1, L3)). For an edge with circulant
+// shift s, check j + m Z/4 reads S[(j + m Z/4 + s) mod Z]: with k = (j + s) mod Z = q Z/4 + b these are the lanes
+// (q + m) mod 4 of word(col, b) - a rotation of the four lanes by q quarter turns, done with two PRMTs.
+// ---------------------------------------------------------------------------------------------------------------------
+
+/// Byte-permute selectors (for prmt(r0, r1, sel)) that rotate the lanes (L0, L1, L2, L3) left by q: .x gives the new r0 =
+/// (L[q], L[q+2]), .y the new r1 = (L[q+1], L[q+3]).
+PK_FN void rot4_selectors(uint32_t q, uint32_t& sel0, uint32_t& sel1)
+{
+  // q = 0: r0, r1 | 1: r1, swap(r0) | 2: swap(r0), swap(r1) | 3: swap(r1), r0
+  const uint32_t t0[4] = {0x3210U, 0x7654U, 0x1032U, 0x5476U};
+  const uint32_t t1[4] = {0x7654U, 0x1032U, 0x5476U, 0x3210U};
+  sel0 = t0[q & 3U];
+  sel1 = t1[q & 3U];
+}
+
+PK_FN uint32_t prmt2(uint32_t a, uint32_t b, uint32_t sel)
+{
+#if defined(__CUDA_ARCH__)
+  return __byte_perm(a, b, sel);
+#else
+  uint64_t all = ((uint64_t)b << 32) | a;
+  uint32_t r   = 0;
+  for (int i = 0; i != 4; ++i) {
+    r |= (uint32_t)((all >> (8 * ((sel >> (4 * i)) & 7U))) & 0xffU) << (8 * i);
+  }
+  return r;
+#endif
+}
+
+/// Rotates the four lanes of (r0, r1) left by q quarter turns (see above).
+PK_FN void rot4(uint32_t& r0, uint32_t& r1, uint32_t q)
+{
+  uint32_t s0, s1;
+  rot4_selectors(q, s0, s1);
+  uint32_t n0 = prmt2(r0, r1, s0);
+  uint32_t n1 = prmt2(r0, r1, s1);
+  r0          = n0;
+  r1          = n1;
+}
+
 } // namespace pk
 } // namespace pusch_dec

@@ -162,6 +162,7 @@ struct srsran_cuda_pusch_dec {
   uint64_t launches          = 0;
   bool     use_packed        = true; // route eligible code blocks to the packed (4 per CTA) decoder
   bool     packed_half       = false; // packed decoder with two threads per lifted check (measured slower: A/B only)
+  bool     prefer_q4         = false; // one code block per CTA on the packed arithmetic also where groups of four would fit
   cudaEvent_t timer_begin    = nullptr;
   cudaEvent_t timer_end      = nullptr;
   bool        timer_armed    = false;
@@ -296,6 +297,24 @@ cudaError_t launch_decode4h(srsran_cuda_pusch_dec* h, cudaStream_t s, const cb_d
   ldpc_decode4h_kernel<TPC, NP><<<n, NP * TPC, smem, s>>>(descs, groups, res, h->d_soft.p, bits_base, h->d_crc_flags.p);
   ++h->launches;
   return cudaGetLastError();
+}
+
+template <int TPB>
+cudaError_t launch_decode_q4(srsran_cuda_pusch_dec* h, cudaStream_t s, const cb_desc* descs, const uint32_t* order,
+                             cb_result* res, uint8_t* bits_base, uint32_t n, uint32_t smem)
+{
+  ldpc_decode_q4_kernel<TPB><<<n, TPB, smem, s>>>(descs, order, res, h->d_soft.p, bits_base, h->d_crc_flags.p);
+  ++h->launches;
+  return cudaGetLastError();
+}
+
+/// Code blocks the one-code-block packed kernel (ldpc_decode_q4_kernel) accepts.
+bool q4_eligible(const srsran_cuda_pusch_dec* h, const cb_desc& d)
+{
+  if (!h->use_packed || !(d.flags & FLAG_DECODE) || d.Z < 16 || (d.Z % 4) != 0) {
+    return false;
+  }
+  return decq_smem_layout(d.bg, d.Z, d.layer_cap).total <= static_cast<uint32_t>(h->max_smem_optin);
 }
 
 /// Code blocks the packed decoder (ldpc_packed.cuh) accepts; `cap` = layers it would process.
@@ -633,9 +652,31 @@ int launch_context(srsran_cuda_pusch_dec* h, int ci)
     return a.bg == b.bg && a.Z == b.Z && a.mode == b.mode && a.max_it == b.max_it && a.scale_mult == b.scale_mult &&
            a.crc_poly == b.crc_poly;
   };
-  // One code block per thread group (ldpc_decode_kernel): launch classes by threads per code block x shared-memory bucket.
+  std::vector<klass> qclasses; // ldpc_decode_q4_kernel: tpc = threads per CTA (32 / 64 / 96)
+  // One code block per thread group: the packed single-code-block kernel where it applies, else ldpc_decode_kernel;
+  // launch classes by threads per code block x shared-memory bucket.
   auto add_single = [&](uint32_t i) {
     const cb_desc&  d    = c.h_desc.p[i];
+    if (q4_eligible(h, d)) {
+      uint32_t need = (decq_smem_layout(d.bg, d.Z, d.layer_cap).total + 1023) & ~1023U;
+      // Buckets keep the number of launches small; a finer grid for the small sizes, where occupancy matters.
+      // 2 KB steps up to 64 KB (the sizes where one more CTA per SM is at stake), coarser above.
+      uint32_t bsz = (need <= 64 * 1024) ? ((need + 2047) & ~2047U) : std::min<uint32_t>((need + 16383) & ~16383U, 227 * 1024);
+      int    tp    = d.Z <= 128 ? 32 : (d.Z <= 256 ? 64 : 96);
+      klass* found = nullptr;
+      for (klass& k : qclasses) {
+        if (k.tpc == tp && k.smem == bsz) {
+          found = &k;
+          break;
+        }
+      }
+      if (found == nullptr) {
+        qclasses.push_back({tp, bsz, {}});
+        found = &qclasses.back();
+      }
+      found->idx.push_back(i);
+      return true;
+    }
     dec_smem_layout lay  = dec_layout(d.bg, d.Z, d.layer_cap);
     uint32_t        need = (lay.total + 1023) & ~1023U;
     // Buckets: coarse enough for few launches, fine enough for occupancy.
@@ -704,7 +745,8 @@ int launch_context(srsran_cuda_pusch_dec* h, int ci)
     if (!(d.flags & FLAG_DECODE)) {
       continue;
     }
-    const uint32_t lanes_fit = (!small_batch && packed_eligible(h, d, d.layer_cap, 4))
+    const bool     inter_cb  = !(h->prefer_q4 && q4_eligible(h, d));
+    const uint32_t lanes_fit = !inter_cb ? 0U : (!small_batch && packed_eligible(h, d, d.layer_cap, 4))
                                    ? 4U
                                    : (packed_eligible(h, d, d.layer_cap, 2) ? 2U : 0U);
     if (lanes_fit != 0) {
@@ -741,6 +783,11 @@ int launch_context(srsran_cuda_pusch_dec* h, int ci)
       c.h_order.p[pos++] = i;
     }
   }
+  for (klass& k : qclasses) {
+    for (uint32_t i : k.idx) {
+      c.h_order.p[pos++] = i;
+    }
+  }
   if (ngrp != 0) {
     CUDA_TRY(h, cudaMemcpyAsync(c.d_grp.p, c.h_grp.p, ngrp * sizeof(grp_desc), cudaMemcpyHostToDevice, s));
   }
@@ -773,7 +820,7 @@ int launch_context(srsran_cuda_pusch_dec* h, int ci)
   CUDA_TRY(h, cudaEventRecord(c.stage[2], s));
   // Launch classes are independent (disjoint code blocks): class 0 stays on the batch stream, the others fork onto side
   // streams and join before the TB assembly, so a slot of mixed small transport blocks costs its slowest class, not the sum.
-  const size_t nof_classes = pclasses.size() + classes.size();
+  const size_t nof_classes = pclasses.size() + classes.size() + qclasses.size();
   uint32_t     side_used   = 0;
   size_t       class_no    = 0;
   if (nof_classes > 1) {
@@ -831,6 +878,16 @@ int launch_context(srsran_cuda_pusch_dec* h, int ci)
         e = launch_decode<384, 1>(h, st, c.d_desc.p, ord, c.d_res.p, c.bits_base, n, k.smem);
         break;
     }
+    CUDA_TRY(h, e);
+    pos += n;
+  }
+  for (klass& k : qclasses) {
+    uint32_t        n   = static_cast<uint32_t>(k.idx.size());
+    const uint32_t* ord = c.d_order.p + pos;
+    cudaStream_t    st  = class_stream();
+    cudaError_t     e   = (k.tpc == 32) ? launch_decode_q4<32>(h, st, c.d_desc.p, ord, c.d_res.p, c.bits_base, n, k.smem)
+                          : (k.tpc == 64) ? launch_decode_q4<64>(h, st, c.d_desc.p, ord, c.d_res.p, c.bits_base, n, k.smem)
+                                          : launch_decode_q4<96>(h, st, c.d_desc.p, ord, c.d_res.p, c.bits_base, n, k.smem);
     CUDA_TRY(h, e);
     pos += n;
   }
@@ -1059,6 +1116,9 @@ int srsran_cuda_pusch_dec_create(int device, uint32_t max_cbs_in_flight, uint32_
       cudaFuncSetAttribute(ldpc_decode4_kernel<384>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess ||
       cudaFuncSetAttribute(ldpc_decode4h_kernel<256, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess ||
       cudaFuncSetAttribute(ldpc_decode4h_kernel<384, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess ||
+      cudaFuncSetAttribute(ldpc_decode_q4_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess ||
+      cudaFuncSetAttribute(ldpc_decode_q4_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess ||
+      cudaFuncSetAttribute(ldpc_decode_q4_kernel<96>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess ||
       cudaFuncSetAttribute(ldpc_decode4h_kernel<256, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess ||
       cudaFuncSetAttribute(ldpc_decode4h_kernel<384, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) {
     h->last_error = "cudaFuncSetAttribute(ldpc_decode4_kernel) failed";
@@ -1205,11 +1265,12 @@ int srsran_cuda_pusch_dec_set_combine_flavour(srsran_cuda_pusch_dec_t* h, uint32
 
 int srsran_cuda_pusch_dec_set_decoder_variant(srsran_cuda_pusch_dec_t* h, uint32_t variant)
 {
-  if (h == nullptr || variant > 2) {
+  if (h == nullptr || variant > 3) {
     return SRSRAN_CUDA_ERR_INVALID;
   }
   h->use_packed  = (variant != 1);
   h->packed_half = (variant == 2);
+  h->prefer_q4   = (variant == 3);
   return SRSRAN_CUDA_OK;
 }
 

@@ -351,7 +351,7 @@ def _cb_llrs(rng, bg, z, F, crc_poly, E, qm, rv, nref, mu):
     return awgn_llrs(rng, synth.rate_match(cw, bg, z, F, E, rv, qm, nref), mu)
 
 
-@pytest.mark.parametrize("variant", [0, 1, 2])
+@pytest.mark.parametrize("variant", [0, 1, 2, 3])
 def test_packed_decoder_groups_via_hal(acc, variant):
     rng = np.random.default_rng(40 + variant)
     hw = pusch.hw_accelerator_pusch_dec_cuda(acc)

@@ -141,3 +141,38 @@ def test_packed_math_no_scaling(emu):
         want = np.full((K + 7) // 8, 0x5A, np.uint8)
         it, want, _ = ob.port_decode(llr, bg, z, F, 3, 5, want, scaling=1.0)
         assert iters[c] == it and np.array_equal(outs[c], want), c
+
+
+@pytest.mark.parametrize("bg", [1, 2])
+def test_intra_codeblock_packing_matches_oracle(emu, bg):
+    """Four lifted checks of ONE code block per thread (lane rotation by quarter turns): every Z divisible by 4."""
+    rng = np.random.default_rng(300 + bg)
+    for z in [4, 8, 12, 16, 20, 24, 28, 32, 36, 40, 44, 48, 52, 56, 60, 64, 72, 80, 88, 96, 104, 112, 120, 128, 144,
+              160, 176, 192, 208, 224, 240, 256, 288, 320, 352, 384]:
+        K, N = ob.kb(bg) * z, ob.ns(bg) * z
+        crc_poly = int(rng.choice([1, 2, 3])) if K >= 64 else 3
+        mu = float(rng.choice([2, 3, 4, 6, 8, 20]))
+        nlen = int(rng.integers(K + 2 * z, N + 1)) if rng.random() < 0.8 else N
+        if z >= 208:
+            nlen = min(nlen, K + 12 * z)
+        llr, F = make_lane(rng, bg, z, crc_poly, mu)
+        llr = llr[:nlen].copy()
+        if rng.random() < 0.3:
+            llr[int(rng.integers(K, nlen)):] = 0
+        max_it = int(rng.integers(1, 9))
+        layers = min(ref_layers(llr, bg, z) + int(rng.integers(0, 2)), 46 if bg == 1 else 42)
+        for mode in (1, 2):
+            out = np.full((K + 7) // 8, 0x5A, np.uint8)
+            it = C.c_int(0)
+            keep = np.ascontiguousarray(llr)
+            r = emu.pk_host_decode_q4(out.ctypes.data_as(C.c_void_p), keep.ctypes.data_as(C.c_void_p), keep.size, bg, z, F,
+                                      crc_poly, max_it, mode, MULT, layers, C.byref(it))
+            assert r == 0
+            want = np.full((K + 7) // 8, 0x5A, np.uint8)
+            if mode == 1:
+                wit, want, _ = ob.port_decode(llr, bg, z, F, crc_poly, max_it, want)
+            else:
+                _, want, _ = ob.port_decode(llr, bg, z, F, ob.CRC_NONE, max_it, want)
+                wit = max_it if ob.port_crc(crc_poly, want, K - F) == 0 else -1
+            assert it.value == wit, (bg, z, mode, F, crc_poly, max_it, layers)
+            assert np.array_equal(out, want), (bg, z, mode, F, crc_poly, max_it, layers)
