@@ -836,30 +836,68 @@ __global__ void __launch_bounds__(TPB, (TPB == 96) ? 4 : 6) ldpc_decode_q4_kerne
     const uint32_t n_load = min(min(d.n_in, d.scan_len), cap_in);
     const uint32_t ncols  = Kb + Lcap;
     uint32_t       last   = 0;
-    uint32_t       c = 0, b = t; // word (c, b), b < Z4
-    while (b >= Z4) {
-      b -= Z4;
-      ++c;
-    }
-    while (c < ncols) {
-      uint32_t ub[4];
+    if ((Z4 & 3U) == 0 && (reinterpret_cast<uintptr_t>(src) & 3U) == 0) {
+      // Four consecutive bases per thread: one 32-bit load per quarter of the column, transposed in registers.
+      const uint32_t qpc   = Z4 / 4; // quads per column
+      const uint32_t nquad = ncols * qpc;
+      const uint32_t qmag  = 0xffffffffU / qpc + 1;
+      for (uint32_t qi = t; qi < nquad; qi += TPB) {
+        const uint32_t c  = (qpc == 1) ? qi : __umulhi(qi, qmag); // (the magic constant overflows for a divisor of 1)
+        const uint32_t b  = (qi - c * qpc) * 4;
+        uint32_t       w[4];
 #pragma unroll
-      for (uint32_t m = 0; m != 4; ++m) {
-        uint32_t i = c * Z + b + m * Z4; // variable index; decoder input index is i - 2 Z
-        int      x = 0;
-        if (i >= 2 * Z && i - 2 * Z < n_load) {
-          x = __ldg(src + (i - 2 * Z));
-          if (x != 0) {
-            last = max(last, i - 2 * Z + 1);
+        for (uint32_t m = 0; m != 4; ++m) {
+          const int idx = (int)(c * Z + m * Z4 + b) - (int)(2 * Z); // index into the decoder input
+          w[m]          = 0;
+          if (idx >= 0 && (uint32_t)idx < n_load) {
+            w[m] = __ldg(reinterpret_cast<const uint32_t*>(src + idx));
+            if ((uint32_t)idx + 4 > n_load) {
+              w[m] &= 0xffffffffU >> (8 * ((uint32_t)idx + 4 - n_load)); // input ends inside this word
+            }
+            if (w[m] != 0) {
+              last = max(last, (uint32_t)idx + 4 - (__clz(w[m]) >> 3));
+            }
           }
+          w[m] ^= 0x80808080U;
         }
-        ub[m] = (uint32_t)(uint8_t)(x ^ 0x80);
+        uint4* dst = reinterpret_cast<uint4*>(soft + c * Z4 + b);
+        uint2  o[4];
+#pragma unroll
+        for (int bb = 0; bb != 4; ++bb) {
+          uint32_t selb = (uint32_t)bb * 0x11U + 0x4400U + (uint32_t)bb * 0x1100U; // byte bb of x -> byte 0, of y -> byte 2
+          o[bb] = make_uint2(pk::soft_from_biased_bytes(__byte_perm(w[0], w[2], selb) & 0x00ff00ffU),
+                             pk::soft_from_biased_bytes(__byte_perm(w[1], w[3], selb) & 0x00ff00ffU));
+        }
+        dst[0] = make_uint4(o[0].x, o[0].y, o[1].x, o[1].y);
+        dst[1] = make_uint4(o[2].x, o[2].y, o[3].x, o[3].y);
       }
-      soft[c * Z4 + b] = make_uint2(pk::soft_from_biased_bytes(ub[0] | (ub[2] << 16)), pk::soft_from_biased_bytes(ub[1] | (ub[3] << 16)));
-      b += TPB;
+    } else {
+      uint32_t c = 0, b = t; // word (c, b), b < Z4
       while (b >= Z4) {
         b -= Z4;
         ++c;
+      }
+      while (c < ncols) {
+        uint32_t ub[4];
+#pragma unroll
+        for (uint32_t m = 0; m != 4; ++m) {
+          uint32_t i = c * Z + b + m * Z4; // variable index; decoder input index is i - 2 Z
+          int      x = 0;
+          if (i >= 2 * Z && i - 2 * Z < n_load) {
+            x = __ldg(src + (i - 2 * Z));
+            if (x != 0) {
+              last = max(last, i - 2 * Z + 1);
+            }
+          }
+          ub[m] = (uint32_t)(uint8_t)(x ^ 0x80);
+        }
+        soft[c * Z4 + b] =
+            make_uint2(pk::soft_from_biased_bytes(ub[0] | (ub[2] << 16)), pk::soft_from_biased_bytes(ub[1] | (ub[3] << 16)));
+        b += TPB;
+        while (b >= Z4) {
+          b -= Z4;
+          ++c;
+        }
       }
     }
     last = __reduce_max_sync(0xffffffffU, last);
@@ -937,32 +975,32 @@ __global__ void __launch_bounds__(TPB, (TPB == 96) ? 4 : 6) ldpc_decode_q4_kerne
     }
     __syncthreads();
     {
-      const uint32_t rpc   = (Z4 + 31) / 32; // runs per column and quarter
-      const uint32_t nrows = Kb * rpc;
+      // The CTA has ceil(Z4 / 32) warps, one per run of 32 bases: warp w owns bases [32 w, 32 w + 32) of every column.
+      const uint32_t b0 = 32 * warp;
+      const uint32_t b  = b0 + 31 - lane; // ballot bit l <-> base b0 + 31 - l: the run is MSB-first
+      const bool     in = b < Z4;
       uint32_t       nz0 = 0x00010001U, nz1 = 0x00010001U;
-      for (uint32_t r = warp; r < nrows; r += NW) {
-        const uint32_t c  = r / rpc;
-        const uint32_t b0 = (r - c * rpc) * 32;
-        const uint32_t b  = b0 + 31 - lane; // ballot bit l <-> base b0 + 31 - l: the run is MSB-first
-        uint2          s  = make_uint2(pk::SOFT_ZERO2 + 0x00010001U, pk::SOFT_ZERO2 + 0x00010001U); // positive
-        if (b < Z4) {
+      for (uint32_t c = 0; c != Kb; ++c) {
+        uint2 s = make_uint2(pk::SOFT_ZERO2 + 0x00010001U, pk::SOFT_ZERO2 + 0x00010001U); // positive, non-zero
+        if (in) {
           s = soft[c * Z4 + b];
         }
         uint32_t p0 = pk::addmin_s2_relu(s.x, PK_REP2(0x10000U - pk::BS), 0x00010001U); // 1 where soft > 0
         uint32_t p1 = pk::addmin_s2_relu(s.y, PK_REP2(0x10000U - pk::BS), 0x00010001U);
         nz0 &= pk::minu2(s.x ^ pk::SOFT_ZERO2, 0x00010001U);
         nz1 &= pk::minu2(s.y ^ pk::SOFT_ZERO2, 0x00010001U);
-        const bool in = b < Z4;
-        uint32_t   run[4];
-        run[0] = __ballot_sync(0xffffffffU, in && (p0 & 0xffffU) == 0); // quarter 0: k = b
-        run[1] = __ballot_sync(0xffffffffU, in && (p1 & 0xffffU) == 0); // quarter 1: k = b + Z/4
-        run[2] = __ballot_sync(0xffffffffU, in && (p0 >> 16) == 0);     // quarter 2
-        run[3] = __ballot_sync(0xffffffffU, in && (p1 >> 16) == 0);     // quarter 3
+        uint32_t r0 = __ballot_sync(0xffffffffU, (p0 & 0xffffU) == 0); // quarter 0: k = b
+        uint32_t r1 = __ballot_sync(0xffffffffU, (p1 & 0xffffU) == 0); // quarter 1: k = b + Z/4
+        uint32_t r2 = __ballot_sync(0xffffffffU, (p0 >> 16) == 0);     // quarter 2
+        uint32_t r3 = __ballot_sync(0xffffffffU, (p1 >> 16) == 0);     // quarter 3
+        uint32_t rlo = (lane & 1) ? r1 : r0, rhi = (lane & 1) ? r3 : r2;
         if (lane < 4) {
-          const uint32_t mine = (lane & 2) ? ((lane & 1) ? run[3] : run[2]) : ((lane & 1) ? run[1] : run[0]);
+          const uint32_t mine = (lane & 2) ? rhi : rlo;
           const uint32_t o    = c * Z + lane * Z4 + b0; // bit offset of the first variable of this run
           const uint32_t sh   = o & 31;
-          if (mine != 0) {
+          if (sh == 0 && (Z4 & 31U) == 0) {
+            hb[o >> 5] = mine; // aligned runs (Z = 128, 256, 384): every word has exactly one writer
+          } else if (mine != 0) {
             atomicOr(&hb[o >> 5], mine >> sh);
             if (sh != 0) {
               atomicOr(&hb[(o >> 5) + 1], mine << (32 - sh));
