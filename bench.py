@@ -393,13 +393,13 @@ def main():
                          "share_of_step": stage_ms[2] / sum(stage_ms) if sum(stage_ms) else None},
             # The decoder is bound by INT-ALU issue, not by shared-memory bandwidth: 37.9 ALU-pipe instructions per
             # (thread, edge) for four code blocks = 9.49 per code-block edge update (SASS of the layer body, counted from
-            # profiles/r1_v3_packed_decode_ncu_summary.txt); the ALU pipe retires 16 lanes/clk per SM sub-partition.
+            # profiles/r1_v4_packed_decode_ncu_summary.txt); the ALU pipe retires 16 lanes/clk per SM sub-partition.
             "roofline_alu": {"kernel": "ldpc_decode4_kernel", "bound": "int-alu-issue",
                              "achieved": 9.49 * U / dec_s / 1e12 if dec_s > 0 else 0.0,
                              "peak": 148 * 4 * 16 * sm_clk / 1e12, "unit": "T thread-instr/s",
                              "frac": (9.49 * U / dec_s) / (148 * 4 * 16 * sm_clk) if dec_s > 0 else None,
                              "algorithmic": "9.49 ALU instructions per edge update x U (mean iterations, not executed ones)",
-                             "ncu_alu_pipe_busy": 0.61},
+                             "ncu_alu_pipe_busy": 0.66},
             "roofline_dematch": {"kernel": "rate_dematch_kernel", "bound": "hbm", "achieved": hbm_ach,
                                  "peak": peaks.get("hbm_gbs"), "unit": "GB/s",
                                  "frac": hbm_ach / peaks["hbm_gbs"] if peaks.get("hbm_gbs") else None, "traffic": None,
