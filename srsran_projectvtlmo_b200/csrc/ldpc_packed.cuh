@@ -739,28 +739,27 @@ __device__ __forceinline__ void process_check_q4(uint2* __restrict__       soft,
                                                  uint32_t                  mult)
 {
   pk::check4<DEG> ck;
+  uint32_t        aq[DEG]; // soft-buffer index << 2 | quarter turns, kept for the write-back
   ck.begin();
 #pragma unroll
   for (int e = 0; e != DEG; ++e) {
     const uint2 te = tab_row[e];            // (column * Z/4, shift)
     uint32_t    k  = j + te.y;
     k -= __umulhi(k, zmagic) * Z;
-    const uint32_t q = __umulhi(k, z4magic); // quarter of the column the first check lands in
-    const uint2    s = soft[te.x + k - q * Z4];
-    const uint2    r = rot[q];
+    const uint32_t q  = __umulhi(k, z4magic); // quarter of the column the first check lands in
+    const uint32_t ad = te.x + k - q * Z4;
+    aq[e]             = (ad << 2) | q;
+    const uint2 s     = soft[ad];
+    const uint2 r     = rot[q];
     ck.gather(e, __byte_perm(s.x, s.y, r.x), __byte_perm(s.x, s.y, r.y), c2v_row[e * Z4 + j]);
   }
   ck.reduce(mult);
 #pragma unroll
   for (int e = 0; e != DEG; ++e) {
-    const uint2 te = tab_row[e];
-    uint32_t    k  = j + te.y;
-    k -= __umulhi(k, zmagic) * Z;
-    const uint32_t q = __umulhi(k, z4magic);
-    uint32_t       s0, s1;
+    uint32_t s0, s1;
     c2v_row[e * Z4 + j] = ck.scatter(e, s0, s1);
-    const uint2 r       = rot[4 + q];
-    soft[te.x + k - q * Z4] = make_uint2(__byte_perm(s0, s1, r.x), __byte_perm(s0, s1, r.y));
+    const uint2 r       = rot[4 + (aq[e] & 3U)];
+    soft[aq[e] >> 2]    = make_uint2(__byte_perm(s0, s1, r.x), __byte_perm(s0, s1, r.y));
   }
 }
 

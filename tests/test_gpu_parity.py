@@ -432,3 +432,51 @@ def test_reference_hw_decoder_over_cuda_accelerator():
     print(r.stdout)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
     assert "PASSED" in r.stdout
+
+
+def test_hw_accelerator_queue_full_retry():
+    """enqueue_operation returns False when the queue is full; the caller dequeues what it has and retries, exactly like
+    pusch_decoder_hw_impl::on_end_softbits (pusch_decoder_hw_impl.cpp:189-338). A 3-code-block TB through a queue of 2."""
+    rng = np.random.default_rng(9)
+    small = pusch.Accelerator(device=0, max_cbs_in_flight=2, nof_harq_cb_slots=16)
+    try:
+        hw = pusch.hw_accelerator_pusch_dec_cuda(small)
+        prb, qm, R, nl, bg, nref = 52, 4, 658, 1, 1, 25344
+        tbs = synth.tbs_for(prb, qm, R, nl)
+        nllr = prb * 156 * qm * nl
+        tb = rng.integers(0, 256, tbs // 8, dtype=np.uint8)
+        llr = awgn_llrs(rng, synth.encode_tb(tb, bg, 0, qm, nref, nl, nllr), 6.0)
+        metas = pusch.segment(tbs, bg, qm, nl, nllr)
+        assert len(metas) == 3
+        port = ob.PortPusch()
+        tb_p, res_p = port.decode(0, tbs // 8, llr, bg, 0, qm, nref, nl, 6, True, True)
+        assert res_p.tb_crc_ok
+        hw.reserve_queue()
+        enq = deq = 0
+        got = {}
+        while deq != len(metas):
+            while enq != len(metas):
+                m = metas[enq]
+                K = m.full_length // 3
+                hw.configure_operation(pusch.CbConfig(bg, qm, len(metas), 0, m.rm_length, m.lifting_size, m.full_length, nref,
+                                                      K - m.nof_crc_bits - m.nof_filler_bits, m.nof_filler_bits, 6, 1, 1, 24,
+                                                      pusch.CB_CRC24B, enq), enq)
+                if not hw.enqueue_operation(llr[m.cw_offset:m.cw_offset + m.rm_length], None, enq):
+                    break  # queue full
+                enq += 1
+            assert enq > deq
+            while deq != enq:
+                K = metas[deq].full_length // 3
+                bits = np.zeros(K // 8, np.uint8)
+                while not hw.dequeue_operation(bits, None, deq):
+                    pass
+                got[deq] = (bits, hw.read_operation_outputs(deq, deq))
+                deq += 1
+        hw.free_queue()
+        assert enq == 3 and all(got[i][1][0] for i in range(3))
+        # the payload bits of the three code blocks concatenate to the TB (+ 24 CRC bits)
+        payload = np.concatenate([np.unpackbits(got[i][0])[:metas[i].full_length // 3 - 24 - metas[i].nof_filler_bits]
+                                  for i in range(3)])[:tbs]
+        assert np.array_equal(np.packbits(payload), tb)
+    finally:
+        small.close()
