@@ -480,3 +480,41 @@ def test_hw_accelerator_queue_full_retry():
         assert np.array_equal(np.packbits(payload), tb)
     finally:
         small.close()
+
+
+def test_pusch_ragged_batch_mixed_shapes(acc):
+    """One submit of transport blocks with different base graphs, lifting sizes, code-block counts and code rates (BASELINE
+    config 3 + a multi-code-block TB): every decoder kernel runs in the same batch, on concurrent streams."""
+    rng = np.random.default_rng(10)
+    cases = [(52, 2, 120, 1, 2, 0.9), (52, 2, 449, 1, 1, 2.0), (52, 4, 378, 1, 1, 3.0), (52, 4, 658, 1, 1, 6.0),
+             (25, 2, 120, 1, 2, 0.4), (10, 4, 490, 1, 2, 4.0), (4, 2, 308, 1, 2, 1.5), (1, 2, 120, 1, 2, 0.9),
+             (106, 8, 948, 2, 1, 18.0), (30, 6, 567, 1, 1, 6.0), (52, 4, 658, 1, 1, 2.0)]
+    cfgs, llrs, ref = [], [], []
+    slot = 5000
+    for k in range(22):
+        prb, qm, R, nl, bg, mu = cases[k % len(cases)]
+        tbs = synth.tbs_for(prb, qm, R, nl)
+        nllr = prb * 156 * qm * nl
+        nref = 25344 if k % 3 else 12611
+        tb = rng.integers(0, 256, tbs // 8, dtype=np.uint8)
+        llr = awgn_llrs(rng, synth.encode_tb(tb, bg, 0, qm, nref, nl, nllr), mu)
+        nseg = len(pusch.segment(tbs, bg, qm, nl, nllr))
+        es = int(k % 4 != 3)
+        cfgs.append(pusch.TbConfig(tbs, bg, 0, qm, nref, nl, 5, es, 1, slot))
+        slot += nseg
+        llrs.append(llr)
+        port = ob.PortPusch()
+        ref.append((tb, port.decode(0, tbs // 8, llr, bg, 0, qm, nref, nl, 5, bool(es), True)))
+    tickets = pusch.submit_tbs(acc, cfgs, llrs)
+    nok = 0
+    for k, t in enumerate(tickets):
+        out = np.zeros(cfgs[k].tbs_bits // 8, np.uint8)
+        res = pusch.poll_tb(acc, t, out)
+        tb, (tb_p, res_p) = ref[k]
+        assert res.tb_crc_ok == res_p.tb_crc_ok, k
+        assert (res.nof_codeblocks_total, res.nof_observations, res.iter_min, res.iter_max) == \
+               (res_p.nof_codeblocks, res_p.nof_observations, res_p.iter_min, res_p.iter_max), k
+        if res_p.tb_crc_ok:
+            nok += 1
+            assert np.array_equal(out, tb), k
+    assert 5 <= nok <= 22
