@@ -173,6 +173,11 @@ int srsran_cuda_pusch_dec_submit_tb(srsran_cuda_pusch_dec_t* handle, const srsra
 int srsran_cuda_pusch_dec_poll_tb(srsran_cuda_pusch_dec_t* handle, int ticket, int block, uint8_t* tb,
                                   srsran_cuda_pusch_dec_tb_result* result);
 
+/* Zero-copy access to the bytes of a completed TB: `*data` points into the batch's page-locked result buffer (tbs_bits / 8
+ * bytes, valid until the ticket's batch context is reused, i.e. for at least the next two submissions); NULL if the
+ * reference would not have written the TB (a code-block CRC failed). The ticket must have completed (poll_tb returned 1). */
+int srsran_cuda_pusch_dec_tb_data(srsran_cuda_pusch_dec_t* handle, int ticket, const uint8_t** data);
+
 /* Same as submit_tb for a batch of TBs whose LLRs are ALREADY RESIDENT in device memory (`llrs_dev[i]` points to
  * `nof_llrs[i]` int8 LLRs in HBM); used when the demodulator runs on the device, and by the benchmark's device-resident
  * leg. One ticket per TB is written to `tickets`. `stream` is a cudaStream_t (NULL = the handle's own stream). */

@@ -96,6 +96,7 @@ struct batch_context {
   cudaStream_t stream     = nullptr;
   cudaEvent_t  done       = nullptr; // everything (incl. D2H) complete
   cudaEvent_t  kernels    = nullptr; // kernels complete (HARQ ordering between contexts)
+  cudaEvent_t  copied     = nullptr; // host -> device copies complete (copies of consecutive batches go one after the other)
   cudaEvent_t  stage[4]   = {nullptr, nullptr, nullptr, nullptr}; // begin, copies in, dematch done, decode done
   // Decode launch classes (different lifting-size / shared-memory shapes) run concurrently on side streams.
   static constexpr int NOF_SIDE = 7;
@@ -624,6 +625,11 @@ int launch_context(srsran_cuda_pusch_dec* h, int ci)
     CUDA_TRY(h, cudaEventRecord(h->timer_begin, s));
   }
   CUDA_TRY(h, cudaEventRecord(c.stage[0], s));
+  // The copies of this batch start when those of the previous batch are through: they share one PCIe link, and taking
+  // turns lets the previous batch's kernels start (and overlap this batch's copies) as early as possible.
+  if (h->last_launched >= 0 && h->last_launched != ci && !c.copies.empty()) {
+    CUDA_TRY(h, cudaStreamWaitEvent(s, h->ctx[h->last_launched].copied, 0));
+  }
   for (const batch_context::copy_job& j : c.copies) {
     const int8_t* src = (j.src != nullptr) ? j.src : c.h_llr.p + j.dst_off;
     CUDA_TRY(h, cudaMemcpyAsync(c.d_llr.p + j.dst_off, src, j.bytes, cudaMemcpyHostToDevice, s));
@@ -799,6 +805,7 @@ int launch_context(srsran_cuda_pusch_dec* h, int ci)
     CUDA_TRY(h, cudaMemcpyAsync(c.d_tb.p, c.h_tb.p, ntb * sizeof(tb_desc), cudaMemcpyHostToDevice, s));
     CUDA_TRY(h, cudaMemcpyAsync(c.d_tbmap.p, c.h_tbmap.p, ncb * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
   }
+  CUDA_TRY(h, cudaEventRecord(c.copied, s));
   // 3. HARQ ordering: kernels of this context run after the kernels of the previously launched context.
   if (h->last_launched >= 0 && h->last_launched != ci) {
     CUDA_TRY(h, cudaStreamWaitEvent(s, h->ctx[h->last_launched].kernels, 0));
@@ -1147,7 +1154,8 @@ int srsran_cuda_pusch_dec_create(int device, uint32_t max_cbs_in_flight, uint32_
   h->extent.assign(nof_harq_cb_slots + 1, 0);
   for (batch_context& c : h->ctx) {
     bool ok = cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking) == cudaSuccess &&
-              cudaEventCreate(&c.done) == cudaSuccess && cudaEventCreate(&c.kernels) == cudaSuccess;
+              cudaEventCreate(&c.done) == cudaSuccess && cudaEventCreate(&c.kernels) == cudaSuccess &&
+              cudaEventCreateWithFlags(&c.copied, cudaEventDisableTiming) == cudaSuccess;
     for (cudaEvent_t& e : c.stage) {
       ok = ok && cudaEventCreate(&e) == cudaSuccess;
     }
@@ -1208,6 +1216,9 @@ void srsran_cuda_pusch_dec_destroy(srsran_cuda_pusch_dec_t* h)
     }
     if (c.kernels != nullptr) {
       cudaEventDestroy(c.kernels);
+    }
+    if (c.copied != nullptr) {
+      cudaEventDestroy(c.copied);
     }
     for (cudaEvent_t e : c.stage) {
       if (e != nullptr) {
@@ -1645,6 +1656,26 @@ int srsran_cuda_pusch_dec_poll_tb(srsran_cuda_pusch_dec_t* h, int ticket, int bl
   }
   m.polled = true;
   return 1;
+}
+
+int srsran_cuda_pusch_dec_tb_data(srsran_cuda_pusch_dec_t* h, int ticket, const uint8_t** data)
+{
+  if (h == nullptr || ticket < 0 || data == nullptr) {
+    return SRSRAN_CUDA_ERR_INVALID;
+  }
+  int      ci  = (ticket >> 16) & 0xf;
+  uint32_t ti  = static_cast<uint32_t>(ticket) & 0xffff;
+  uint32_t gen = (static_cast<uint32_t>(ticket) >> 20) & 0x3ff;
+  if (ci >= NOF_CONTEXTS) {
+    return SRSRAN_CUDA_ERR_INVALID;
+  }
+  batch_context& c = h->ctx[ci];
+  if ((c.generation & 0x3ff) != gen || ti >= c.tb_meta.size() || !c.in_flight || cudaEventQuery(c.done) != cudaSuccess) {
+    h->last_error = "stale, unknown or unfinished ticket";
+    return SRSRAN_CUDA_ERR_STATE;
+  }
+  *data = c.h_tbres.p[ti].written ? c.h_tbout.p + c.tb_meta[ti].out_offset : nullptr;
+  return SRSRAN_CUDA_OK;
 }
 
 int srsran_cuda_pusch_dec_ticket_timing(srsran_cuda_pusch_dec_t* h, int ticket, float* stage_ms)

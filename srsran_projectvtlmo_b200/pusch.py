@@ -303,6 +303,15 @@ def poll_tb(acc: Accelerator, ticket, tb_out=None, block=True):
     return (res if st == 1 else None)
 
 
+def tb_data(acc: Accelerator, ticket, nbytes):
+    """Zero-copy view (numpy, read-only use) of a completed TB in the batch's page-locked result buffer, or None."""
+    p = capi.u8p()
+    acc._check(acc._lib.srsran_cuda_pusch_dec_tb_data(acc.h, ticket, C.byref(p)), "tb_data")
+    if not p:
+        return None
+    return np.ctypeslib.as_array(p, shape=(nbytes,))
+
+
 def ticket_timing(acc: Accelerator, ticket):
     """Device-side stage durations [h2d, dematch, decode, tb_crc, d2h] in ms of the batch `ticket` belongs to."""
     ms = (C.c_float * 5)()
