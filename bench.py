@@ -233,10 +233,13 @@ def main():
     B = args.tbs_per_step
     tbs, nllr, payloads, sets = make_inputs(B, 2, args.mu, 1000 + rank)
     ncb = 152
-    acc = pusch.Accelerator(device=local_rank, max_cbs_in_flight=B * ncb, nof_harq_cb_slots=B * ncb)
+    # Two sets of HARQ slots used in turn, like HARQ processes rotating from one slot (TTI) to the next: consecutive batches
+    # then share no soft-buffer state and the library lets them overlap on the GPU.
+    acc = pusch.Accelerator(device=local_rank, max_cbs_in_flight=B * ncb, nof_harq_cb_slots=2 * B * ncb)
     acc.set_decoder_variant(args.decoder_variant)
-    cfgs = [capi.TbConfig(tbs, w["bg"], 0, w["qm"], w["nref"], w["layers"], w["max_it"], w["early_stop"], 1, i * ncb)
-            for i in range(B)]
+    cfg_sets = [[capi.TbConfig(tbs, w["bg"], 0, w["qm"], w["nref"], w["layers"], w["max_it"], w["early_stop"], 1,
+                               (s * B + i) * ncb) for i in range(B)] for s in range(2)]
+    cfgs = cfg_sets[0]
 
     # Device-resident inputs (value leg) and page-locked host inputs (e2e leg).
     dev_sets = [torch.from_numpy(s).cuda() for s in sets]
@@ -253,11 +256,11 @@ def main():
     def step_device(i):
         d = dev_sets[i % 2]
         lst = [(d[k].data_ptr(), nllr) for k in range(B)]
-        return pusch.submit_tbs(acc, cfgs, lst, device_resident=True)
+        return pusch.submit_tbs(acc, cfg_sets[i % 2], lst, device_resident=True)
 
     def step_host(i):
         buf = host_sets[i % 2][1]
-        return pusch.submit_tbs(acc, cfgs, [buf[k] for k in range(B)])
+        return pusch.submit_tbs(acc, cfg_sets[i % 2], [buf[k] for k in range(B)])
 
     tb_out = np.zeros(tbs // 8, np.uint8)
 

@@ -97,12 +97,16 @@ struct batch_context {
   cudaEvent_t  done       = nullptr; // everything (incl. D2H) complete
   cudaEvent_t  kernels    = nullptr; // kernels complete (HARQ ordering between contexts)
   cudaEvent_t  copied     = nullptr; // host -> device copies complete (copies of consecutive batches go one after the other)
+  cudaStream_t tail       = nullptr; // high-priority stream of the small end-of-batch kernels and the result copies
+  cudaEvent_t  decoded    = nullptr; // decode kernels complete (fork point of `tail`)
   cudaEvent_t  stage[4]   = {nullptr, nullptr, nullptr, nullptr}; // begin, copies in, dematch done, decode done
   // Decode launch classes (different lifting-size / shared-memory shapes) run concurrently on side streams.
   static constexpr int NOF_SIDE = 7;
   cudaStream_t side[NOF_SIDE]  = {};
   cudaEvent_t  fork            = nullptr;
   cudaEvent_t  join[NOF_SIDE]  = {};
+  uint32_t     slot_lo    = 0xffffffffU; // range of HARQ slots this batch touches (ordering between batches)
+  uint32_t     slot_hi    = 0;
   bool         open       = false;   // accepting operations, not launched
   bool         in_flight  = false;   // launched, results not yet consumed
   uint32_t     generation = 0;
@@ -467,6 +471,8 @@ int open_context(srsran_cuda_pusch_dec* h, uint32_t min_cbs)
   CUDA_TRY(h, c.h_res.reserve(ncb));
   CUDA_TRY(h, c.d_res.reserve(ncb));
   c.open       = true;
+  c.slot_lo    = 0xffffffffU;
+  c.slot_hi    = 0;
   c.llr_used   = 0;
   c.tbout_used = 0;
   c.want_bits  = false;
@@ -603,6 +609,12 @@ int add_cb(srsran_cuda_pusch_dec* h, batch_context& c, const cb_params& p, const
   }
   c.h_desc.p[idx]  = d;
   c.h_tbmap.p[idx] = 0xffffffffU;
+  if (p.flags & (FLAG_DEMATCH | FLAG_USE_HARQ | FLAG_TRACK_CRC)) {
+    c.slot_lo = std::min(c.slot_lo, p.slot);
+    c.slot_hi = std::max(c.slot_hi, p.slot);
+  } else {
+    // unit-level decode: scratch data-bit slots of this context only, no HARQ state
+  }
   c.cb_meta.push_back({K, p.max_it, p.slot});
   *idx_out = idx;
   return SRSRAN_CUDA_OK;
@@ -807,8 +819,16 @@ int launch_context(srsran_cuda_pusch_dec* h, int ci)
   }
   CUDA_TRY(h, cudaEventRecord(c.copied, s));
   // 3. HARQ ordering: kernels of this context run after the kernels of the previously launched context.
-  if (h->last_launched >= 0 && h->last_launched != ci) {
-    CUDA_TRY(h, cudaStreamWaitEvent(s, h->ctx[h->last_launched].kernels, 0));
+  //    Batches whose HARQ slot ranges are disjoint share no state (soft bits, data bits, CRC flags are per slot; every other
+  //    buffer is per context), so they may overlap: the next batch's dematching fills the tail of this batch's decoding.
+  for (int k = 0; k != NOF_CONTEXTS; ++k) {
+    const batch_context& o = h->ctx[k];
+    if (k == ci || !o.in_flight || o.slot_lo > o.slot_hi) {
+      continue;
+    }
+    if (c.slot_lo <= o.slot_hi && o.slot_lo <= c.slot_hi) {
+      CUDA_TRY(h, cudaStreamWaitEvent(s, o.kernels, 0));
+    }
   }
   // 4. Kernels.
   CUDA_TRY(h, cudaEventRecord(c.stage[1], s));
@@ -905,26 +925,33 @@ int launch_context(srsran_cuda_pusch_dec* h, int ci)
     }
   }
   CUDA_TRY(h, cudaEventRecord(c.stage[3], s));
+  // The small end-of-batch kernels and the result copies go to a high-priority stream: when the next batch overlaps this
+  // one, its decode CTAs must not keep these few CTAs (and with them the completion of this batch) waiting.
+  cudaStream_t ts = c.tail;
+  CUDA_TRY(h, cudaEventRecord(c.decoded, s));
+  CUDA_TRY(h, cudaStreamWaitEvent(ts, c.decoded, 0));
   if (ntb != 0) {
-    tb_gather_kernel<<<(ncb + TBG_WARPS - 1) / TBG_WARPS, TBG_WARPS * 32, 0, s>>>(c.d_tb.p, c.d_tbmap.p, ncb, h->d_bits.p,
-                                                                                 c.d_tbout.p, c.d_tbshare.p);
+    tb_gather_kernel<<<(ncb + TBG_WARPS - 1) / TBG_WARPS, TBG_WARPS * 32, 0, ts>>>(c.d_tb.p, c.d_tbmap.p, ncb, h->d_bits.p,
+                                                                                  c.d_tbout.p, c.d_tbshare.p);
     ++h->launches;
     CUDA_TRY(h, cudaGetLastError());
-    tb_finalize_kernel<<<(ntb + 7) / 8, 256, 0, s>>>(c.d_tb.p, ntb, c.d_tbres.p, c.d_tbshare.p, h->d_crc_flags.p);
+    tb_finalize_kernel<<<(ntb + 7) / 8, 256, 0, ts>>>(c.d_tb.p, ntb, c.d_tbres.p, c.d_tbshare.p, h->d_crc_flags.p);
     ++h->launches;
     CUDA_TRY(h, cudaGetLastError());
   }
-  CUDA_TRY(h, cudaEventRecord(c.kernels, s));
+  CUDA_TRY(h, cudaEventRecord(c.kernels, ts));
   // 5. Device -> host.
-  CUDA_TRY(h, cudaMemcpyAsync(c.h_res.p, c.d_res.p, ncb * sizeof(cb_result), cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(h, cudaMemcpyAsync(c.h_res.p, c.d_res.p, ncb * sizeof(cb_result), cudaMemcpyDeviceToHost, ts));
   if (c.want_bits) {
-    CUDA_TRY(h, cudaMemcpyAsync(c.h_bits.p, c.d_bits.p, static_cast<size_t>(ncb) * BITS_STRIDE, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(h, cudaMemcpyAsync(c.h_bits.p, c.d_bits.p, static_cast<size_t>(ncb) * BITS_STRIDE, cudaMemcpyDeviceToHost, ts));
   }
   if (ntb != 0) {
-    CUDA_TRY(h, cudaMemcpyAsync(c.h_tbres.p, c.d_tbres.p, ntb * sizeof(tb_result_dev), cudaMemcpyDeviceToHost, s));
-    CUDA_TRY(h, cudaMemcpyAsync(c.h_tbout.p, c.d_tbout.p, c.tbout_used, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(h, cudaMemcpyAsync(c.h_tbres.p, c.d_tbres.p, ntb * sizeof(tb_result_dev), cudaMemcpyDeviceToHost, ts));
+    CUDA_TRY(h, cudaMemcpyAsync(c.h_tbout.p, c.d_tbout.p, c.tbout_used, cudaMemcpyDeviceToHost, ts));
   }
-  CUDA_TRY(h, cudaEventRecord(c.done, s));
+  CUDA_TRY(h, cudaEventRecord(c.done, ts));
+  // The batch stream joins the tail so that the next use of this context (and stream-ordered waits on it) see it complete.
+  CUDA_TRY(h, cudaStreamWaitEvent(s, c.done, 0));
   c.in_flight      = true;
   h->last_launched = ci;
   return SRSRAN_CUDA_OK;
@@ -1152,10 +1179,14 @@ int srsran_cuda_pusch_dec_create(int device, uint32_t max_cbs_in_flight, uint32_
     return fail(SRSRAN_CUDA_ERR_CUDA);
   }
   h->extent.assign(nof_harq_cb_slots + 1, 0);
+  int prio_low = 0, prio_high = 0;
+  cudaDeviceGetStreamPriorityRange(&prio_low, &prio_high);
   for (batch_context& c : h->ctx) {
     bool ok = cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking) == cudaSuccess &&
               cudaEventCreate(&c.done) == cudaSuccess && cudaEventCreate(&c.kernels) == cudaSuccess &&
-              cudaEventCreateWithFlags(&c.copied, cudaEventDisableTiming) == cudaSuccess;
+              cudaEventCreateWithFlags(&c.copied, cudaEventDisableTiming) == cudaSuccess &&
+              cudaEventCreateWithFlags(&c.decoded, cudaEventDisableTiming) == cudaSuccess &&
+              cudaStreamCreateWithPriority(&c.tail, cudaStreamNonBlocking, prio_high) == cudaSuccess;
     for (cudaEvent_t& e : c.stage) {
       ok = ok && cudaEventCreate(&e) == cudaSuccess;
     }
@@ -1219,6 +1250,12 @@ void srsran_cuda_pusch_dec_destroy(srsran_cuda_pusch_dec_t* h)
     }
     if (c.copied != nullptr) {
       cudaEventDestroy(c.copied);
+    }
+    if (c.decoded != nullptr) {
+      cudaEventDestroy(c.decoded);
+    }
+    if (c.tail != nullptr) {
+      cudaStreamDestroy(c.tail);
     }
     for (cudaEvent_t e : c.stage) {
       if (e != nullptr) {
