@@ -299,8 +299,8 @@ __global__ void __launch_bounds__(TPC, 1) ldpc_decode4_kernel(const cb_desc* __r
       uint32_t nz0 = 0x00010001U, nz1 = 0x00010001U; // stays 1 in the lanes that saw no zero soft bit
       for (uint32_t w = warp; w < HBW; w += NW) {
         uint2    s  = soft[w * 32 + 31 - lane];
-        uint32_t p0 = pk::addmin_s2_relu(s.x, PK_REP2(0x10000U - pk::BS), 0x00010001U); // 1 where soft > 0
-        uint32_t p1 = pk::addmin_s2_relu(s.y, PK_REP2(0x10000U - pk::BS), 0x00010001U);
+        uint32_t p0 = pk::positive_lanes(s.x); // 1 where soft > 0
+        uint32_t p1 = pk::positive_lanes(s.y);
         nz0 &= pk::minu2(s.x ^ pk::SOFT_ZERO2, 0x00010001U);
         nz1 &= pk::minu2(s.y ^ pk::SOFT_ZERO2, 0x00010001U);
         uint32_t b0 = __ballot_sync(0xffffffffU, (p0 & 0xffffU) == 0);
@@ -619,7 +619,7 @@ __global__ void __launch_bounds__(NP * TPC, 1) ldpc_decode4h_kernel(const cb_des
       uint32_t nz = 0x00010001U;
       for (uint32_t w = warp - h * (NW / NP); w < HBW; w += NW / NP) {
         uint32_t s  = soft[w * 32 + 31 - lane];
-        uint32_t p  = pk::addmin_s2_relu(s, PK_REP2(0x10000U - pk::BS), 0x00010001U); // 1 where soft > 0
+        uint32_t p  = pk::positive_lanes(s); // 1 where soft > 0
         nz &= pk::minu2(s ^ pk::SOFT_ZERO2, 0x00010001U);
         uint32_t blo = __ballot_sync(0xffffffffU, (p & 0xffffU) == 0);
         uint32_t bhi = __ballot_sync(0xffffffffU, (p >> 16) == 0);
@@ -984,8 +984,8 @@ __global__ void __launch_bounds__(TPB, (TPB == 96) ? 4 : 6) ldpc_decode_q4_kerne
         if (in) {
           s = soft[c * Z4 + b];
         }
-        uint32_t p0 = pk::addmin_s2_relu(s.x, PK_REP2(0x10000U - pk::BS), 0x00010001U); // 1 where soft > 0
-        uint32_t p1 = pk::addmin_s2_relu(s.y, PK_REP2(0x10000U - pk::BS), 0x00010001U);
+        uint32_t p0 = pk::positive_lanes(s.x); // 1 where soft > 0
+        uint32_t p1 = pk::positive_lanes(s.y);
         nz0 &= pk::minu2(s.x ^ pk::SOFT_ZERO2, 0x00010001U);
         nz1 &= pk::minu2(s.y ^ pk::SOFT_ZERO2, 0x00010001U);
         uint32_t r0 = __ballot_sync(0xffffffffU, (p0 & 0xffffU) == 0); // quarter 0: k = b

@@ -1,18 +1,21 @@
 // Packed (four code blocks per thread) arithmetic of the layered normalized min-sum LDPC decoder.
 //
 // Four code blocks with the same base graph and lifting size are decoded together: thread j owns lifted check j of
-// every layer for all four, in 2 x u16x2 registers (register 0 = code blocks 0 and 2, register 1 = code blocks 1 and 3).
-// All quantities are kept as BIASED UNSIGNED 16-bit lanes so that negation and subtraction are plain 32-bit integer
-// operations (no inter-lane borrow; they can issue on the FMA pipe as IMAD) and only min / max / select / permute
-// use the ALU pipe (VIMNMX.U16x2, VIADDMNMX.[US]16x2, LOP3, PRMT - all single SASS instructions on sm_100a):
+// every layer for all four, in 2 registers of two 16-bit lanes (register 0 = code blocks 0 and 2, register 1 = code
+// blocks 1 and 3). The lanes are IEEE binary16 numbers and the per-edge arithmetic is done with half2 instructions:
+// every finite quantity of the decoder is an integer of magnitude <= 1392 (exact in binary16), so the results are the
+// reference's integers bit for bit, while most of the work issues on the FMA pipe (HFMA2 / HADD2 with free |x|, -x and
+// saturate-to-[0,1] modifiers) instead of the ALU pipe that bounds an integer formulation (measured on sm_100a,
+// tools/ubench/pipes.cu: HFMA2 runs beside VIMNMX / LOP3 / PRMT; HMNMX2 and HSET2 share the ALU pipe):
 //
-//   soft value  S in [-120, 120] or +-INF(8192)   stored as S + BS,  BS = 0x8080   (shared memory, 2 bytes per lane)
-//   c2v message c in [-120, 120]                  stored as c + 128                 (shared memory, 1 byte per lane)
-//   v2c         q = S - c                         held as   q + 0x8000  => bit 15 set <=> q >= 0
-//   |q|                                           held as |q| + 0x8000
+//   soft value  S in [-120, 120] or "infinite"   stored as the half S + 1152           (shared memory, 2 bytes per lane)
+//   c2v message c in [-120, 120]                 stored as the byte c + 128            (shared memory, 1 byte per lane)
+//   a message byte b becomes the half 1024 + b = c + 1152 by placing 0x64 above it (one PRMT), so
+//   v2c         q = S - c  =  half(S + 1152) - half(c + 1152)                          (exact, |q| <= 248)
 //
-// "Infinite" soft values (+-127 in the reference: fillers and promoted sums) are held as +-8192 so that they survive
-// the subtraction of any message, never win a minimum (minima start at 120) and stay infinite under the update.
+// "Infinite" soft values (+-127 in the reference: fillers and promoted sums) are halves of magnitude >= 5800 (up to and
+// including the IEEE infinities): they survive the subtraction of any message, never win a minimum (minima start at
+// 120) and stay infinite under the update. No operation below can produce a NaN (no inf - inf, no 0 x inf).
 //
 // Reference arithmetic reproduced bit for bit (AVX2 / AVX-512 flavour):
 //   v2c   : ldpc_decoder_avx512.cpp:81-121    clamp(soft - c2v, +-120), +-127 sticky
@@ -20,10 +23,16 @@
 //   c2v   : ldpc_decoder_avx512.cpp:167-216   (min-excluding-self * 52428) >> 16 with sign
 //   soft  : ldpc_decoder_avx512.cpp:218-259   promotion sum: |sum| > 120 -> +-127, +-127 sticky
 //
-// This header is plain C++ (host emulation of the few intrinsics) unless compiled for the device, so that the same
-// code is exercised on the CPU against the oracle (tests/test_packed_math_cpu.py via tools/packed_math_harness.cpp).
+// This header is plain C++ (host emulation of the few intrinsics, halves through _Float16) unless compiled for the
+// device, so that the same code is exercised on the CPU against the oracle (tests/test_packed_math_cpu.py via
+// tests/host_emul/packed_math_harness.cpp).
 #pragma once
 #include <stdint.h>
+#if defined(__CUDACC__)
+#include <cuda_fp16.h>
+#else
+#include <string.h>
+#endif
 
 #if defined(__CUDACC__)
 #define PK_FN __host__ __device__ __forceinline__
@@ -39,23 +48,25 @@ namespace pk {
 /// The same 16-bit value in both lanes.
 #define PK_REP2(v) ((((uint32_t)(v)) & 0xffffU) | (((uint32_t)(v)) << 16))
 
-constexpr uint32_t BS      = 0x8080U; ///< bias of stored soft values
-constexpr uint32_t BQ      = 0x8000U; ///< bias of v2c values and magnitudes
-constexpr uint32_t INF     = 8192U;   ///< magnitude standing for the reference's +-127
-constexpr uint32_t INF_CUT = 4096U;
-constexpr uint32_t SOFT_ZERO2 = PK_REP2(0x8080U);
+// binary16 constants (bit patterns).
+constexpr uint32_t H_ONE     = 0x3c00U; ///< 1
+constexpr uint32_t H_120     = 0x5780U; ///< 120
+constexpr uint32_t H_128     = 0x5800U; ///< 128
+constexpr uint32_t H_1024    = 0x6400U; ///< 1024
+constexpr uint32_t H_1152    = 0x6480U; ///< 1152 = 1024 + 128
+constexpr uint32_t H_8192    = 0x7000U; ///< 8192
+constexpr uint32_t H_INV128  = 0x2000U; ///< 1 / 128
+constexpr uint32_t H_M15_16  = 0xbb80U; ///< -120 / 128
+constexpr uint32_t H_POS_INF = 0x7090U; ///< +9344: soft value of a +127 input
+constexpr uint32_t H_NEG_INF = 0xeee0U; ///< -7040: soft value of a -127 input
+
+constexpr uint32_t BS         = H_1152; ///< bit pattern of a zero soft value (patterns compare like SIGNED 16-bit integers)
+constexpr uint32_t SOFT_ZERO2 = PK_REP2(H_1152);
 constexpr uint32_t C2V_ZERO4  = 0x80808080U;
 
 #define PK_LANES(expr_lo, expr_hi) ((uint32_t)(uint16_t)(expr_lo) | ((uint32_t)(uint16_t)(expr_hi) << 16))
-PK_FN uint32_t maxu2(uint32_t a, uint32_t b)
-{
-#if defined(__CUDA_ARCH__)
-  return __vmaxu2(a, b);
-#else
-  uint16_t al = a, ah = a >> 16, bl = b, bh = b >> 16;
-  return PK_LANES(al > bl ? al : bl, ah > bh ? ah : bh);
-#endif
-}
+
+// ---- integer helpers (loader, hard decision) -----------------------------------------------------------------------------
 PK_FN uint32_t minu2(uint32_t a, uint32_t b)
 {
 #if defined(__CUDA_ARCH__)
@@ -69,35 +80,7 @@ PK_FN uint32_t add2(uint32_t a, uint32_t b)
 {
   return PK_LANES((uint16_t)a + (uint16_t)b, (uint16_t)(a >> 16) + (uint16_t)(b >> 16));
 }
-/// min(a + b, c) on unsigned lanes, the sum wrapping modulo 2^16 (add.u16x2 + min.u16x2 = VIADDMNMX.U16x2).
-PK_FN uint32_t addmin_u2(uint32_t a, uint32_t b, uint32_t c)
-{
-#if defined(__CUDA_ARCH__)
-  return __viaddmin_u16x2(a, b, c);
-#else
-  return minu2(add2(a, b), c);
-#endif
-}
-PK_FN uint32_t addmax_u2(uint32_t a, uint32_t b, uint32_t c)
-{
-#if defined(__CUDA_ARCH__)
-  return __viaddmax_u16x2(a, b, c);
-#else
-  return maxu2(add2(a, b), c);
-#endif
-}
-PK_FN uint32_t addmax_s2(uint32_t a, uint32_t b, uint32_t c)
-{
-#if defined(__CUDA_ARCH__)
-  return __viaddmax_s16x2(a, b, c);
-#else
-  uint32_t s  = add2(a, b);
-  int16_t  sl = (int16_t)(uint16_t)s, sh = (int16_t)(uint16_t)(s >> 16), cl = (int16_t)(uint16_t)c,
-          ch = (int16_t)(uint16_t)(c >> 16);
-  return PK_LANES(sl > cl ? sl : cl, sh > ch ? sh : ch);
-#endif
-}
-/// max(min(a + b, c), 0) on signed lanes.
+/// max(min(a + b, c), 0) on signed 16-bit lanes (VIADDMNMX.S16x2.RELU).
 PK_FN uint32_t addmin_s2_relu(uint32_t a, uint32_t b, uint32_t c)
 {
 #if defined(__CUDA_ARCH__)
@@ -110,25 +93,33 @@ PK_FN uint32_t addmin_s2_relu(uint32_t a, uint32_t b, uint32_t c)
   return PK_LANES(rl < 0 ? 0 : rl, rh < 0 ? 0 : rh);
 #endif
 }
-/// 0xffff in every lane whose bit 15 is set.
-PK_FN uint32_t lane_mask(uint32_t a)
+/// 1 in every lane whose soft value is > 0.
+PK_FN uint32_t positive_lanes(uint32_t s)
+{
+  return addmin_s2_relu(s, PK_REP2(0x10000U - BS), 0x00010001U);
+}
+/// Hard decision of one 16-bit soft pattern: the bit is 1 for soft <= 0 (log_likelihood_ratio.cpp:226-252).
+PK_FN bool lane_hard_bit(uint32_t lane16)
+{
+  return (int16_t)(uint16_t)lane16 <= (int16_t)BS;
+}
+
+PK_FN uint32_t prmt2(uint32_t a, uint32_t b, uint32_t sel)
 {
 #if defined(__CUDA_ARCH__)
-  // prmt's sign-replicate mode (selector nibble bit 3). NOT __byte_perm: that intrinsic ignores bit 3 of the nibbles.
-  uint32_t r;
-  asm("prmt.b32 %0, %1, 0, 0xbb99;" : "=r"(r) : "r"(a));
-  return r;
+  return __byte_perm(a, b, sel);
 #else
-  return ((a & 0x8000U) ? 0xffffU : 0U) | ((a & 0x80000000U) ? 0xffff0000U : 0U);
+  uint64_t all = ((uint64_t)b << 32) | a;
+  uint32_t r   = 0;
+  for (int i = 0; i != 4; ++i) {
+    r |= (uint32_t)((all >> (8 * ((sel >> (4 * i)) & 7U))) & 0xffU) << (8 * i);
+  }
+  return r;
 #endif
 }
 
-PK_FN uint32_t sel(uint32_t mask, uint32_t a, uint32_t b)
-{
-  return (a & mask) | (b & ~mask);
-}
-
-/// Lane-wise (m * mult) >> 16 on true magnitudes m <= 120 (mm512::scale_epi8, avx512_support.h:65-107); mult == 0: identity.
+/// Lane-wise (m * mult) >> 16 on integer magnitudes m <= 120 (mm512::scale_epi8, avx512_support.h:65-107); mult == 0:
+/// identity.
 PK_FN uint32_t scale2(uint32_t m, uint32_t mult)
 {
   if (mult == 0) {
@@ -139,51 +130,176 @@ PK_FN uint32_t scale2(uint32_t m, uint32_t mult)
   return lo | hi;
 }
 
-/// Packed soft value (two lanes) of two int8 LLRs x0 (low lane) and x1 (high lane) given as biased bytes ub = x ^ 0x80
-/// in bits 0-7 and 16-23 of `ub2`: +-127 become +-INF.
-PK_FN uint32_t soft_from_biased_bytes(uint32_t ub2)
+// ---- half2 helpers: device = one SASS instruction each (modifiers folded), host = _Float16 emulation ----------------------
+#if !defined(__CUDA_ARCH__)
+namespace host {
+inline double h2d(uint32_t bits16)
 {
-  uint32_t lane = ub2 | 0x80008000U;                                            // x + 0x8080 (x + 128 + 0x8000)
-  uint32_t tp   = addmin_s2_relu(lane, PK_REP2(0x10000U - 0x80feU), 0x00010001U);  // 1 where ub == 255 (x == 127)
-  uint32_t nl   = 0x01010100U - lane;                                           // 2 * 0x8080 - lane, lane-wise
-  uint32_t tn   = addmin_s2_relu(nl, PK_REP2(0x10000U - 0x80feU), 0x00010001U);    // 1 where x == -127
-  return lane + tp * (INF - 127U) - tn * (INF - 127U);
+  uint16_t  u = (uint16_t)bits16;
+  _Float16 f;
+  memcpy(&f, &u, 2);
+  return (double)f;
+}
+inline uint32_t d2h(double d)
+{
+  _Float16 f = (_Float16)d; // one rounding to nearest even; overflow gives an infinity
+  uint16_t u;
+  memcpy(&u, &f, 2);
+  return u;
+}
+inline double sat01(double d)
+{
+  return d != d ? 0.0 : (d < 0.0 ? 0.0 : (d > 1.0 ? 1.0 : d));
+}
+inline double dabs(double d)
+{
+  return d < 0 ? -d : d;
+}
+template <typename F>
+inline uint32_t lanes2(uint32_t a, uint32_t b, uint32_t c, F f)
+{
+  return PK_LANES(d2h(f(h2d(a), h2d(b), h2d(c))), d2h(f(h2d(a >> 16), h2d(b >> 16), h2d(c >> 16))));
+}
+} // namespace host
+#else
+__device__ __forceinline__ __half2 pk_h(uint32_t u)
+{
+  return *reinterpret_cast<__half2*>(&u);
+}
+__device__ __forceinline__ uint32_t pk_u(__half2 h)
+{
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+#endif
+
+/// a - b
+PK_FN uint32_t hsub2(uint32_t a, uint32_t b)
+{
+#if defined(__CUDA_ARCH__)
+  return pk_u(__hsub2(pk_h(a), pk_h(b)));
+#else
+  return host::lanes2(a, b, 0, [](double x, double y, double) { return x - y; });
+#endif
+}
+/// a + b
+PK_FN uint32_t hadd2(uint32_t a, uint32_t b)
+{
+#if defined(__CUDA_ARCH__)
+  return pk_u(__hadd2(pk_h(a), pk_h(b)));
+#else
+  return host::lanes2(a, b, 0, [](double x, double y, double) { return x + y; });
+#endif
+}
+/// a * b + c
+PK_FN uint32_t hfma2(uint32_t a, uint32_t b, uint32_t c)
+{
+#if defined(__CUDA_ARCH__)
+  return pk_u(__hfma2(pk_h(a), pk_h(b), pk_h(c)));
+#else
+  return host::lanes2(a, b, c, [](double x, double y, double z) { return x * y + z; });
+#endif
+}
+/// min(a, b)
+PK_FN uint32_t hmin2(uint32_t a, uint32_t b)
+{
+#if defined(__CUDA_ARCH__)
+  return pk_u(__hmin2(pk_h(a), pk_h(b)));
+#else
+  return host::lanes2(a, b, 0, [](double x, double y, double) { return x < y ? x : y; });
+#endif
+}
+/// min(|q|, m)
+PK_FN uint32_t hmin2_abs(uint32_t q, uint32_t m)
+{
+#if defined(__CUDA_ARCH__)
+  return pk_u(__hmin2(__habs2(pk_h(q)), pk_h(m)));
+#else
+  return host::lanes2(q, m, 0, [](double x, double y, double) { return host::dabs(x) < y ? host::dabs(x) : y; });
+#endif
+}
+/// max(|q|, m)
+PK_FN uint32_t hmax2_abs(uint32_t q, uint32_t m)
+{
+#if defined(__CUDA_ARCH__)
+  return pk_u(__hmax2(__habs2(pk_h(q)), pk_h(m)));
+#else
+  return host::lanes2(q, m, 0, [](double x, double y, double) { return host::dabs(x) > y ? host::dabs(x) : y; });
+#endif
+}
+/// saturate(|q| - m): for integers, 1 where |q| > m and 0 elsewhere.
+PK_FN uint32_t habs_gt(uint32_t q, uint32_t m)
+{
+#if defined(__CUDA_ARCH__)
+  return pk_u(__hadd2_sat(__habs2(pk_h(q)), __hneg2(pk_h(m))));
+#else
+  return host::lanes2(q, m, 0, [](double x, double y, double) { return host::sat01(host::dabs(x) - y); });
+#endif
+}
+/// saturate(a + b)
+PK_FN uint32_t hadd2_sat(uint32_t a, uint32_t b)
+{
+#if defined(__CUDA_ARCH__)
+  return pk_u(__hadd2_sat(pk_h(a), pk_h(b)));
+#else
+  return host::lanes2(a, b, 0, [](double x, double y, double) { return host::sat01(x + y); });
+#endif
+}
+/// saturate(|q| * b + c)
+PK_FN uint32_t habs_fma_sat(uint32_t q, uint32_t b, uint32_t c)
+{
+#if defined(__CUDA_ARCH__)
+  return pk_u(__hfma2_sat(__habs2(pk_h(q)), pk_h(b), pk_h(c)));
+#else
+  return host::lanes2(q, b, c, [](double x, double y, double z) { return host::sat01(host::dabs(x) * y + z); });
+#endif
+}
+/// a * b + |q|
+PK_FN uint32_t hfma2_abs_c(uint32_t a, uint32_t b, uint32_t q)
+{
+#if defined(__CUDA_ARCH__)
+  return pk_u(__hfma2(pk_h(a), pk_h(b), __habs2(pk_h(q))));
+#else
+  return host::lanes2(a, b, q, [](double x, double y, double z) { return x * y + host::dabs(z); });
+#endif
 }
 
-/// State of one lifted check while a layer is processed, for 2 * NR code blocks (NR registers of two 16-bit lanes).
-/// KEEP_A: keep |v2c| of every edge in registers between the two passes (else it is recomputed: 2 instructions).
-template <int DEG, int NR, bool KEEP_A = true>
+/// Packed soft value (two lanes) of two int8 LLRs x0 (low lane) and x1 (high lane) given as biased bytes ub = x ^ 0x80
+/// in bits 0-7 and 16-23 of `ub2`: the half x + 1152 = 0x6400 | ub; +-127 become infinite.
+PK_FN uint32_t soft_from_biased_bytes(uint32_t ub2)
+{
+  uint32_t lane = ub2 | PK_REP2(H_1024);
+  uint32_t tp   = addmin_s2_relu(lane, PK_REP2(0x10000U - 0x64feU), 0x00010001U); // 1 where ub == 255 (x == 127)
+  uint32_t tn   = addmin_s2_relu(~lane, PK_REP2(0x6403U), 0x00010001U);           // 1 where ub <= 1   (x <= -127)
+  return lane + tp * (H_POS_INF - 0x64ffU) + tn * (H_NEG_INF - 0x6401U);           // no carry between the lanes
+}
+
+/// State of one lifted check while a layer is processed, for 2 * NR code blocks (NR registers of two binary16 lanes).
+template <int DEG, int NR>
 struct check_lanes {
-  uint32_t q[DEG][NR];                  ///< v2c + BQ
-  uint32_t a[KEEP_A ? DEG : 1][NR];     ///< |v2c| + BQ
+  uint32_t q[DEG][NR]; ///< v2c
   uint32_t m1[NR], m2[NR], x[NR];
-  uint32_t nm1[NR], pm1[NR], pm2[NR];
+  uint32_t pm2[NR], dpm[NR];
 
   PK_MFN void begin()
   {
 #pragma unroll
     for (int r = 0; r != NR; ++r) {
-      m1[r] = m2[r] = PK_REP2(BQ + 120U);
+      m1[r] = m2[r] = PK_REP2(H_120);
       x[r]          = 0;
     }
   }
 
-  /// Edge e: soft words s[r] (S + BS per lane) and messages of the previous iteration c[r] (c + 128 per lane).
+  /// Edge e: soft words s[r] (half S + 1152 per lane) and messages of the previous iteration c[r] (half c + 1152 per lane).
   PK_MFN void gather(int e, const uint32_t* s, const uint32_t* c)
   {
 #pragma unroll
     for (int r = 0; r != NR; ++r) {
-      uint32_t qq = s[r] - c[r];          // lanes never borrow: S + BS > c + 128
-      uint32_t nq = 0x00010000U - qq;     // lane-wise 0x10000 - q
-      uint32_t aa = maxu2(qq, nq);
+      uint32_t qq = hsub2(s[r], c[r]);
       q[e][r]     = qq;
-      if (KEEP_A) {
-        a[e][r] = aa;
-      }
-      x[r] ^= qq;
-      uint32_t t = maxu2(m1[r], aa);
-      m2[r]      = minu2(m2[r], t);
-      m1[r]      = minu2(m1[r], aa);
+      x[r] ^= qq; // bit 15 of every lane: parity of the negative v2c (a zero v2c is +0: it counts as positive)
+      uint32_t t = hmax2_abs(qq, m1[r]);
+      m2[r]      = hmin2(m2[r], t);
+      m1[r]      = hmin2_abs(qq, m1[r]);
     }
   }
 
@@ -191,37 +307,39 @@ struct check_lanes {
   {
 #pragma unroll
     for (int r = 0; r != NR; ++r) {
-      uint32_t s1 = scale2(m1[r] & 0x7fff7fffU, mult);
-      uint32_t s2 = scale2(m2[r] & 0x7fff7fffU, mult);
-      nm1[r]      = 0x00010000U - m1[r];
-      // bit 15 of x = parity of the non-negative v2c; the sign product P is negative iff (#negative) is odd.
-      uint32_t pmk = lane_mask((DEG & 1) ? ~x[r] : x[r]);
-      // 128 + P * M for the two candidate magnitudes (min1: every edge but the minimum, min2: the minimum itself).
-      pm1[r] = sel(pmk, 0x00800080U - s1, 0x00800080U + s1);
-      pm2[r] = sel(pmk, 0x00800080U - s2, 0x00800080U + s2);
+      // The two minima are integers in [0, 120]: the half 1024 + m has m in its low mantissa bits, and back.
+      uint32_t i1  = hadd2(m1[r], PK_REP2(H_1024)) & 0x00ff00ffU;
+      uint32_t i2  = hadd2(m2[r], PK_REP2(H_1024)) & 0x00ff00ffU;
+      uint32_t s1  = hsub2(scale2(i1, mult) | PK_REP2(H_1024), PK_REP2(H_1024));
+      uint32_t s2  = hsub2(scale2(i2, mult) | PK_REP2(H_1024), PK_REP2(H_1024));
+      uint32_t sgn = x[r] & 0x80008000U; // the sign product P of all edges
+      // P * M for the two candidate magnitudes (min1: every edge but the minimum, min2: the minimum itself).
+      uint32_t pm1 = s1 ^ sgn;
+      pm2[r]       = s2 ^ sgn;
+      dpm[r]       = hsub2(pm1, pm2[r]);
     }
   }
 
-  /// New soft words sn[r] and new messages cn[r] (128 + c per lane) of edge e.
+  /// New soft words sn[r] (half S + 1152) and new messages cn[r] (half c + 1152: the message byte is the low byte of
+  /// every lane) of edge e.
   PK_MFN void scatter(int e, uint32_t* sn, uint32_t* cn)
   {
 #pragma unroll
     for (int r = 0; r != NR; ++r) {
       uint32_t qq = q[e][r];
-      uint32_t aa = KEEP_A ? a[e][r] : maxu2(qq, 0x00010000U - qq);
-      uint32_t t    = addmin_u2(aa, nm1[r], 0x00010001U); // 1: |q| > min1 -> min1, 0: this edge is the minimum -> min2
-      uint32_t mask = t * 0xffffU;
-      uint32_t pm   = sel(mask, pm1[r], pm2[r]);          // 128 + P * M
-      uint32_t sq   = lane_mask(qq);                      // lanes with q >= 0
-      // new message c = sign(q) * P * M (the sign product of the OTHER edges is P * sign(q)), stored as 128 + c
-      cn[r] = sel(sq, pm, 0x01000100U - pm);
-      // soft = sign(q) * promote(min(|q|, 120) + P * M); infinite |q| (>= INF - 120) passes the clamp.
-      uint32_t av = addmax_u2(aa, PK_REP2(0x10000U - INF_CUT), minu2(aa, PK_REP2(BQ + 120U)));
-      uint32_t v  = av + pm;                               // bias BQ + 128 = BS
-      uint32_t t2 = addmin_s2_relu(v, PK_REP2(0x10000U - (BS + 120U)), 0x00010001U);
-      uint32_t w  = minu2(v + t2 * INF, PK_REP2(BS + INF));
-      uint32_t nw = 0x01010100U - w;                       // lane-wise 2 * BS - w
-      sn[r]       = sel(sq, w, nw);
+      uint32_t t  = habs_gt(qq, m1[r]);                       // 1: |q| > min1 -> min1, 0: this edge is the minimum -> min2
+      uint32_t pm = hfma2(t, dpm[r], pm2[r]);                 // P * M
+      uint32_t sq = (qq & 0x80008000U) | PK_REP2(H_ONE);      // sign(q) as +-1
+      // new message c = sign(q) * P * M (the sign product of the OTHER edges is P * sign(q))
+      cn[r] = hfma2(sq, pm, PK_REP2(H_1152));
+      // soft = sign(q) * promote(min(|q|, 120) + P * M); an infinite |q| stays infinite:
+      // u = saturate((|q| - 120) / 128) is exact for |q| <= 248, so |q| - 128 u = min(|q|, 120) for every finite |q|.
+      uint32_t u  = habs_fma_sat(qq, PK_REP2(H_INV128), PK_REP2(H_M15_16));
+      uint32_t av = hfma2_abs_c(u, PK_REP2(H_128 | 0x8000U), qq);
+      uint32_t v  = hadd2(av, pm);
+      uint32_t t2 = hadd2_sat(v, PK_REP2(H_120 | 0x8000U));   // 1 where v > 120 (v is an integer or infinite)
+      uint32_t w  = hfma2(t2, PK_REP2(H_8192), v);
+      sn[r]       = hfma2(sq, w, PK_REP2(H_1152));
     }
   }
 };
@@ -232,11 +350,7 @@ template <int DEG>
 struct check4 : check_lanes<DEG, 2> {
   PK_MFN void gather(int e, uint32_t s0, uint32_t s1, uint32_t cw)
   {
-#if defined(__CUDA_ARCH__)
-    uint32_t c[2] = {cw & 0x00ff00ffU, __byte_perm(cw, 0, 0x4341)};
-#else
-    uint32_t c[2] = {cw & 0x00ff00ffU, (cw >> 8) & 0x00ff00ffU};
-#endif
+    uint32_t c[2] = {prmt2(cw, 0x64646464U, 0x4240U), prmt2(cw, 0x64646464U, 0x4341U)};
     uint32_t s[2] = {s0, s1};
     check_lanes<DEG, 2>::gather(e, s, c);
   }
@@ -248,25 +362,25 @@ struct check4 : check_lanes<DEG, 2> {
     check_lanes<DEG, 2>::scatter(e, sn, cn);
     s0 = sn[0];
     s1 = sn[1];
-    return cn[0] + (cn[1] << 8);
+    return prmt2(cn[0], cn[1], 0x6240U);
   }
 };
 
 /// Two code blocks per thread (one register), messages of one lifted edge in one 16-bit word (low byte = lane 0).
 template <int DEG>
-struct check2 : check_lanes<DEG, 1, false> {
+struct check2 : check_lanes<DEG, 1> {
   PK_MFN void gather(int e, uint32_t s0, uint32_t cw16)
   {
-    uint32_t c = (cw16 & 0xffU) | ((cw16 & 0xff00U) << 8);
-    check_lanes<DEG, 1, false>::gather(e, &s0, &c);
+    uint32_t c = prmt2(cw16, 0x64646464U, 0x4140U);
+    check_lanes<DEG, 1>::gather(e, &s0, &c);
   }
 
   PK_MFN uint32_t scatter(int e, uint32_t& s0)
   {
     uint32_t cn, sn;
-    check_lanes<DEG, 1, false>::scatter(e, &sn, &cn);
+    check_lanes<DEG, 1>::scatter(e, &sn, &cn);
     s0 = sn;
-    return (cn & 0xffU) | (cn >> 8); // bits 0-7 and 16-23 -> one 16-bit word
+    return prmt2(cn, 0U, 0x4420U); // low bytes of the two lanes -> one 16-bit word
   }
 };
 
@@ -288,20 +402,6 @@ PK_FN void rot4_selectors(uint32_t q, uint32_t& sel0, uint32_t& sel1)
   const uint32_t t1[4] = {0x7654U, 0x1032U, 0x5476U, 0x3210U};
   sel0 = t0[q & 3U];
   sel1 = t1[q & 3U];
-}
-
-PK_FN uint32_t prmt2(uint32_t a, uint32_t b, uint32_t sel)
-{
-#if defined(__CUDA_ARCH__)
-  return __byte_perm(a, b, sel);
-#else
-  uint64_t all = ((uint64_t)b << 32) | a;
-  uint32_t r   = 0;
-  for (int i = 0; i != 4; ++i) {
-    r |= (uint32_t)((all >> (8 * ((sel >> (4 * i)) & 7U))) & 0xffU) << (8 * i);
-  }
-  return r;
-#endif
 }
 
 /// Rotates the four lanes of (r0, r1) left by q quarter turns (see above).

@@ -185,7 +185,7 @@ int pk_host_decode_q4(uint8_t* bits_out, const int8_t* llrs, uint32_t n_in, uint
         uint32_t c = i / Z, k = i % Z, m = k / Z4, b = k % Z4;
         uint32_t w    = soft[2 * (c * Z4 + b) + (m & 1)];
         uint32_t lane = (m & 2) ? (w >> 16) : (w & 0xffffU);
-        if (lane <= BS) {
+        if (lane_hard_bit(lane)) {
           hb[i >> 3] |= (uint8_t)(0x80U >> (i & 7));
         }
         any_zero |= (lane == BS);
@@ -265,7 +265,7 @@ int pk_host_decode_group(uint8_t* const* bits_out, const int8_t* const* llrs, co
     for (uint32_t i = 0; i != K; ++i) {
       uint32_t w    = soft[2 * i + (c & 1)];
       uint32_t lane = (c & 2) ? (w >> 16) : (w & 0xffffU);
-      if (lane <= BS) {
+      if (lane_hard_bit(lane)) {
         hb[i >> 3] |= (uint8_t)(0x80U >> (i & 7));
       }
       any_zero |= (lane == BS);
