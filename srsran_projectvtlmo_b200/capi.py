@@ -8,8 +8,11 @@ import ctypes as C
 import subprocess
 from pathlib import Path
 
+import os
+
 HERE = Path(__file__).resolve().parent
-LIB_PATH = HERE / "libsrsran_cuda_pusch_dec.so"
+# SRSRAN_CUDA_PUSCH_DEC_LIB: another build of the same library (kernel A/B measurements); never a different implementation.
+LIB_PATH = Path(os.environ.get("SRSRAN_CUDA_PUSCH_DEC_LIB", HERE / "libsrsran_cuda_pusch_dec.so"))
 
 OK, ERR_NO_DEVICE, ERR_INVALID, ERR_NO_MEMORY, ERR_CUDA, ERR_STATE = 0, -1, -2, -3, -4, -5
 CRC_NONE, CRC24A, CRC24B, CRC16 = 0, 1, 2, 3

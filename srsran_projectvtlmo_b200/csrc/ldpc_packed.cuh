@@ -44,7 +44,7 @@ __host__ __device__ inline dec4_layout dec4_smem_layout(uint32_t bg, uint32_t Z,
   l.hb_off   = l.c2v_off + nedges * Z * lanes;
   l.crc_off  = l.hb_off + 4 * (Kb * Z / 32) * 4;
   l.misc_off = l.crc_off + 4 * 256 * 4;
-  l.total    = l.misc_off + 64 + 4 * 64; // 16 flag words + four lane_state records
+  l.total    = l.misc_off + 128 + 4 * 64; // 32 flag / scratch words + four lane_state records
   return l;
 }
 
@@ -56,9 +56,12 @@ __device__ __forceinline__ uint32_t edge_addr(uint2 te, uint32_t j, uint32_t Z, 
   return te.x + k - __umulhi(k, zmagic) * Z;
 }
 
+/// One lifted check (thread j) of a layer of degree DEG for the four code blocks of the group. `tab_row[e]` = (byte offset
+/// of the edge's variable node in the soft array, circulant shift); the soft addresses are computed once and kept for
+/// the write-back (the modulo by a multiply-high: the address arithmetic issues on the FMA pipe).
 template <int DEG>
-__device__ __forceinline__ void process_check4(uint2* __restrict__       soft,
-                                               uint32_t* __restrict__    c2v_row,
+__device__ __forceinline__ void process_check4(uint8_t* __restrict__     soft_bytes,
+                                               uint32_t* __restrict__    c2v_j,
                                                const uint2* __restrict__ tab_row,
                                                uint32_t                  j,
                                                uint32_t                  Z,
@@ -66,18 +69,23 @@ __device__ __forceinline__ void process_check4(uint2* __restrict__       soft,
                                                uint32_t                  mult)
 {
   pk::check4<DEG> ck;
+  uint32_t        addr[DEG];
   ck.begin();
 #pragma unroll
   for (int e = 0; e != DEG; ++e) {
-    uint2 s = soft[edge_addr(tab_row[e], j, Z, zmagic)];
-    ck.gather(e, s.x, s.y, c2v_row[e * Z + j]);
+    const uint2 te = tab_row[e];
+    uint32_t    k  = j + te.y;
+    k -= __umulhi(k, zmagic) * Z;
+    addr[e]       = te.x + k * 8;
+    const uint2 s = *reinterpret_cast<const uint2*>(soft_bytes + addr[e]);
+    ck.gather(e, s.x, s.y, c2v_j[e * Z]);
   }
   ck.reduce(mult);
 #pragma unroll
   for (int e = 0; e != DEG; ++e) {
     uint32_t s0, s1;
-    c2v_row[e * Z + j]                            = ck.scatter(e, s0, s1);
-    soft[edge_addr(tab_row[e], j, Z, zmagic)] = make_uint2(s0, s1);
+    c2v_j[e * Z]                                       = ck.scatter(e, s0, s1);
+    *reinterpret_cast<uint2*>(soft_bytes + addr[e]) = make_uint2(s0, s1);
   }
 }
 
@@ -120,11 +128,11 @@ __global__ void __launch_bounds__(TPC, 1) ldpc_decode4_kernel(const cb_desc* __r
   uint32_t*         hb   = reinterpret_cast<uint32_t*>(smem_raw + lay.hb_off);
   uint32_t*         tabs = reinterpret_cast<uint32_t*>(smem_raw + lay.crc_off);
   uint32_t*         misc = reinterpret_cast<uint32_t*>(smem_raw + lay.misc_off);
-  lane_state*       st   = reinterpret_cast<lane_state*>(smem_raw + lay.misc_off + 64);
-  // misc: [0..3] any non-zero input, [4..7] any zero soft bit, [8..11] crc ok of this round
+  lane_state*       st   = reinterpret_cast<lane_state*>(smem_raw + lay.misc_off + 128);
+  // misc: [0..3] any non-zero input, [4..7] / [8..11] any zero soft bit (even / odd check rounds), [16..16+NW) CRC shares
 
   // ---- per code block setup (one thread each; the state lives in shared memory, not in registers) ---------------------------
-  if (t < 16) {
+  if (t < 32) {
     misc[t] = 0;
   }
   if (t < 4) {
@@ -174,22 +182,13 @@ __global__ void __launch_bounds__(TPC, 1) ldpc_decode4_kernel(const cb_desc* __r
   // ---- prologue ----------------------------------------------------------------------------------------------------------
   const uint32_t nedges = c_row_ptr[bg - 1][L];
   for (uint32_t e = t; e < nedges; e += TPC) {
-    tab[e] = make_uint2((uint32_t)c_col[bg - 1][e] * Z, c_shift[bg - 1][d0.ils][e] % Z);
+    tab[e] = make_uint2((uint32_t)c_col[bg - 1][e] * Z * 8, c_shift[bg - 1][d0.ils][e] % Z);
   }
   {
-    uint4*         c4 = reinterpret_cast<uint4*>(c2v);
-    const uint32_t n4 = nedges * Z / 4;
-    const uint4    zz = make_uint4(pk::C2V_ZERO4, pk::C2V_ZERO4, pk::C2V_ZERO4, pk::C2V_ZERO4);
-    for (uint32_t i = t; i < n4; i += TPC) {
-      c4[i] = zz;
-    }
-  }
-  if (poly != 0) {
-    build_crc_tables(tabs, poly, t, TPC);
-  }
-  {
-    const uint32_t nq    = (Kb + L) * Z / 4; // quads of variable nodes
-    const uint32_t punct = 2 * Z / 4;
+    // Input of the four code blocks, 16 variable nodes per code block and step (Z % 16 == 0): the 128-bit loads of a
+    // step are all in flight together, the messages are cleared while they travel.
+    const uint32_t n16   = (Kb + L) * Z / 16;
+    const uint32_t punct = 2 * Z / 16;
     uint32_t       nz[4] = {0, 0, 0, 0};
     const int8_t*  src[4];
     uint32_t       n_load[4];
@@ -198,28 +197,65 @@ __global__ void __launch_bounds__(TPC, 1) ldpc_decode4_kernel(const cb_desc* __r
       src[c]    = st[c].src;
       n_load[c] = st[c].n_load;
     }
-    for (uint32_t v = t; v < nq; v += TPC) {
-      uint32_t w[4] = {0, 0, 0, 0};
-      if (v >= punct) {
-        uint32_t p = (v - punct) * 4;
-#pragma unroll
-        for (int c = 0; c != 4; ++c) {
-          if (p < n_load[c]) {
-            w[c] = __ldg(reinterpret_cast<const uint32_t*>(src[c] + p));
-          }
-          nz[c] |= w[c];
-        }
-      }
+    auto fetch = [&](uint32_t v, uint4* w) {
 #pragma unroll
       for (int c = 0; c != 4; ++c) {
-        w[c] ^= 0x80808080U;
+        w[c] = make_uint4(0, 0, 0, 0);
       }
+      if (v >= punct && v < n16) {
+        const uint32_t p = (v - punct) * 16;
 #pragma unroll
-      for (int b = 0; b != 4; ++b) {
-        uint32_t selb = (uint32_t)b * 0x11U + 0x4400U + (uint32_t)b * 0x1100U; // byte b of x -> bytes 0,1; of y -> 2,3
-        uint32_t r0   = __byte_perm(w[0], w[2], selb) & 0x00ff00ffU;
-        uint32_t r1   = __byte_perm(w[1], w[3], selb) & 0x00ff00ffU;
-        soft[v * 4 + b] = make_uint2(pk::soft_from_biased_bytes(r0), pk::soft_from_biased_bytes(r1));
+        for (int c = 0; c != 4; ++c) {
+          if (p + 16 <= n_load[c]) {
+            w[c] = __ldg(reinterpret_cast<const uint4*>(src[c] + p));
+          } else if (p < n_load[c]) {
+            // last, partial step: 4-byte granules (the bytes of the slot beyond the input are zero, see cb_desc::scan_len)
+            const uint32_t* q = reinterpret_cast<const uint32_t*>(src[c] + p);
+            w[c].x = __ldg(q);
+            w[c].y = (p + 4 < n_load[c]) ? __ldg(q + 1) : 0U;
+            w[c].z = (p + 8 < n_load[c]) ? __ldg(q + 2) : 0U;
+            w[c].w = (p + 12 < n_load[c]) ? __ldg(q + 3) : 0U;
+          }
+        }
+      }
+    };
+    uint4 w[4];
+    fetch(t, w);
+    {
+      uint4*         c4 = reinterpret_cast<uint4*>(c2v);
+      const uint32_t n4 = nedges * Z / 4;
+      const uint4    zz = make_uint4(pk::C2V_ZERO4, pk::C2V_ZERO4, pk::C2V_ZERO4, pk::C2V_ZERO4);
+      for (uint32_t i = t; i < n4; i += TPC) {
+        c4[i] = zz;
+      }
+    }
+    if (poly != 0) {
+      build_crc_tables(tabs, poly, t, TPC);
+    }
+    for (uint32_t v = t; v < n16; v += TPC) {
+      uint32_t ww[4][4];
+#pragma unroll
+      for (int c = 0; c != 4; ++c) {
+        nz[c] |= w[c].x | w[c].y | w[c].z | w[c].w;
+        ww[c][0] = w[c].x ^ 0x80808080U;
+        ww[c][1] = w[c].y ^ 0x80808080U;
+        ww[c][2] = w[c].z ^ 0x80808080U;
+        ww[c][3] = w[c].w ^ 0x80808080U;
+      }
+      fetch(v + TPC, w); // next step's loads travel while this one is converted
+#pragma unroll
+      for (int i = 0; i != 4; ++i) {
+#pragma unroll
+        for (int b = 0; b != 4; b += 2) {
+          uint32_t sel0 = (uint32_t)b * 0x11U + 0x4400U + (uint32_t)b * 0x1100U; // byte b of x -> bytes 0,1; of y -> 2,3
+          uint32_t sel1 = sel0 + 0x1111U;
+          uint4    o;
+          o.x = pk::soft_from_biased_bytes(__byte_perm(ww[0][i], ww[2][i], sel0) & 0x00ff00ffU);
+          o.y = pk::soft_from_biased_bytes(__byte_perm(ww[1][i], ww[3][i], sel0) & 0x00ff00ffU);
+          o.z = pk::soft_from_biased_bytes(__byte_perm(ww[0][i], ww[2][i], sel1) & 0x00ff00ffU);
+          o.w = pk::soft_from_biased_bytes(__byte_perm(ww[1][i], ww[3][i], sel1) & 0x00ff00ffU);
+          *reinterpret_cast<uint4*>(&soft[v * 16 + i * 4 + b]) = o;
+        }
       }
     }
 #pragma unroll
@@ -231,59 +267,62 @@ __global__ void __launch_bounds__(TPC, 1) ldpc_decode4_kernel(const cb_desc* __r
     }
   }
   __syncthreads();
-  if (t < 4) {
-    // All-zero input with early stop: the reference returns before touching the output (ldpc_decoder_impl.cpp:88-94).
-    if (!st[t].live || (misc[t] == 0 && mode == MODE_EARLY_STOP)) {
-      st[t].done = max(st[t].done, st[t].live ? 3U : 1U);
-    }
-  }
-  __syncthreads();
+  // Code blocks that are not decoded: not live, or all-zero input with early stop (the reference returns before touching
+  // the output, ldpc_decoder_impl.cpp:88-94). Every thread keeps the same mask of finished code blocks.
+  uint32_t done_mask = 0;
 #pragma unroll
   for (int c = 0; c != 4; ++c) {
-    if (st[c].done == 3 && st[c].bits_out != nullptr) {
-      for (uint32_t i = t; i < HBW; i += blockDim.x) {
+    const bool zero_in = st[c].live && misc[c] == 0 && mode == MODE_EARLY_STOP;
+    if (!st[c].live || zero_in) {
+      done_mask |= 1U << c;
+    }
+    if (zero_in && st[c].bits_out != nullptr) {
+      for (uint32_t i = t; i < HBW; i += TPC) {
         reinterpret_cast<uint32_t*>(st[c].bits_out)[i] = st[c].slot_bits[i]; // untouched output
       }
     }
   }
 
   // ---- iterations --------------------------------------------------------------------------------------------------------
+  constexpr int  WPC    = NW / 4; // warps per code block in the CRC step
   const uint32_t j      = t;
   const uint32_t zmagic = 0xffffffffU / Z + 1; // ceil(2^32 / Z): floor(k / Z) = umulhi(k, zmagic) for k < 2 Z
-  for (uint32_t it = 0; it != max_it; ++it) {
+  uint32_t       checks = 0;                   // hard-decision rounds so far (parity selects the "any zero" flag set)
+  for (uint32_t it = 0; it != max_it && done_mask != 0xfU; ++it) {
     for (uint32_t l = 0; l != L; ++l) {
       uint32_t e0  = c_row_ptr[bg - 1][l];
       int      deg = (int)c_row_ptr[bg - 1][l + 1] - (int)e0;
       if (j < Z) {
-        uint32_t*    c2v_row = c2v + (size_t)e0 * Z;
+        uint32_t*    c2v_row = c2v + (size_t)e0 * Z + j;
         const uint2* tab_row = tab + e0;
+        uint8_t*     sb      = reinterpret_cast<uint8_t*>(soft);
         switch (deg) {
           case 3:
-            process_check4<3>(soft, c2v_row, tab_row, j, Z, zmagic, mult);
+            process_check4<3>(sb, c2v_row, tab_row, j, Z, zmagic, mult);
             break;
           case 4:
-            process_check4<4>(soft, c2v_row, tab_row, j, Z, zmagic, mult);
+            process_check4<4>(sb, c2v_row, tab_row, j, Z, zmagic, mult);
             break;
           case 5:
-            process_check4<5>(soft, c2v_row, tab_row, j, Z, zmagic, mult);
+            process_check4<5>(sb, c2v_row, tab_row, j, Z, zmagic, mult);
             break;
           case 6:
-            process_check4<6>(soft, c2v_row, tab_row, j, Z, zmagic, mult);
+            process_check4<6>(sb, c2v_row, tab_row, j, Z, zmagic, mult);
             break;
           case 7:
-            process_check4<7>(soft, c2v_row, tab_row, j, Z, zmagic, mult);
+            process_check4<7>(sb, c2v_row, tab_row, j, Z, zmagic, mult);
             break;
           case 8:
-            process_check4<8>(soft, c2v_row, tab_row, j, Z, zmagic, mult);
+            process_check4<8>(sb, c2v_row, tab_row, j, Z, zmagic, mult);
             break;
           case 9:
-            process_check4<9>(soft, c2v_row, tab_row, j, Z, zmagic, mult);
+            process_check4<9>(sb, c2v_row, tab_row, j, Z, zmagic, mult);
             break;
           case 10:
-            process_check4<10>(soft, c2v_row, tab_row, j, Z, zmagic, mult);
+            process_check4<10>(sb, c2v_row, tab_row, j, Z, zmagic, mult);
             break;
           default:
-            process_check4<19>(soft, c2v_row, tab_row, j, Z, zmagic, mult);
+            process_check4<19>(sb, c2v_row, tab_row, j, Z, zmagic, mult);
             break;
         }
       }
@@ -294,56 +333,77 @@ __global__ void __launch_bounds__(TPC, 1) ldpc_decode4_kernel(const cb_desc* __r
       continue;
     }
     // Hard decision of the first K soft bits of every code block: bit = (llr <= 0), MSB first; "any zero" flags.
+    uint32_t* zflag = misc + 4 + 4 * (checks & 1U);
     {
-      // Lane l takes variable 32 w + 31 - l: ballot bit l is then already in MSB-first order.
-      uint32_t nz0 = 0x00010001U, nz1 = 0x00010001U; // stays 1 in the lanes that saw no zero soft bit
+      // Lane l takes variable 32 w + 31 - l: ballot bit l is then already in MSB-first order. The half (soft + 1152) - 1153
+      // is negative exactly for soft <= 0; a running unsigned minimum of pattern ^ pattern(0) finds zero soft values.
+      uint32_t z0 = 0xffffffffU, z1 = 0xffffffffU;
       for (uint32_t w = warp; w < HBW; w += NW) {
-        uint2    s  = soft[w * 32 + 31 - lane];
-        uint32_t p0 = pk::positive_lanes(s.x); // 1 where soft > 0
-        uint32_t p1 = pk::positive_lanes(s.y);
-        nz0 &= pk::minu2(s.x ^ pk::SOFT_ZERO2, 0x00010001U);
-        nz1 &= pk::minu2(s.y ^ pk::SOFT_ZERO2, 0x00010001U);
-        uint32_t b0 = __ballot_sync(0xffffffffU, (p0 & 0xffffU) == 0);
-        uint32_t b1 = __ballot_sync(0xffffffffU, (p1 & 0xffffU) == 0);
-        uint32_t b2 = __ballot_sync(0xffffffffU, (p0 >> 16) == 0);
-        uint32_t b3 = __ballot_sync(0xffffffffU, (p1 >> 16) == 0);
-        uint32_t blo = (lane & 1) ? b1 : b0, bhi = (lane & 1) ? b3 : b2;
+        const uint2    s  = soft[w * 32 + 31 - lane];
+        const uint32_t d0 = pk::hadd2(s.x, PK_REP2(0xe481U)), d1 = pk::hadd2(s.y, PK_REP2(0xe481U));
+        z0 = pk::minu2(z0, s.x ^ pk::SOFT_ZERO2);
+        z1 = pk::minu2(z1, s.y ^ pk::SOFT_ZERO2);
+        const uint32_t b0 = __ballot_sync(0xffffffffU, (d0 & 0x8000U) != 0);
+        const uint32_t b1 = __ballot_sync(0xffffffffU, (d1 & 0x8000U) != 0);
+        const uint32_t b2 = __ballot_sync(0xffffffffU, (int32_t)d0 < 0);
+        const uint32_t b3 = __ballot_sync(0xffffffffU, (int32_t)d1 < 0);
         if (lane < 4) {
+          const uint32_t blo = (lane & 1) ? b1 : b0, bhi = (lane & 1) ? b3 : b2;
           hb[lane * HBW + w] = (lane & 2) ? bhi : blo;
         }
       }
-      nz0 = __reduce_and_sync(0xffffffffU, nz0);
-      nz1 = __reduce_and_sync(0xffffffffU, nz1);
-      if (lane == 0 && (nz0 & nz1) != 0x00010001U) {
-        if (!(nz0 & 1U)) {
-          atomicOr(&misc[4], 1U);
-        }
-        if (!(nz1 & 1U)) {
-          atomicOr(&misc[5], 1U);
-        }
-        if (!(nz0 >> 16)) {
-          atomicOr(&misc[6], 1U);
-        }
-        if (!(nz1 >> 16)) {
-          atomicOr(&misc[7], 1U);
-        }
-      }
-    }
-    __syncthreads();
-    if (warp < 4) {
-      uint32_t ok = 0;
-      if (!st[warp].done) {
-        uint32_t crc = warp_crc_words<false>(hb + warp * HBW, st[warp].nbits, poly, tabs, lane);
-        ok           = (crc == 0 && (mode != MODE_EARLY_STOP || misc[4 + warp] == 0)) ? 1U : 0U;
-      }
+      z0 = pk::minu2(z0, __shfl_xor_sync(0xffffffffU, z0, 16));
+      z1 = pk::minu2(z1, __shfl_xor_sync(0xffffffffU, z1, 16));
+      z0 = pk::minu2(z0, __shfl_xor_sync(0xffffffffU, z0, 8));
+      z1 = pk::minu2(z1, __shfl_xor_sync(0xffffffffU, z1, 8));
+      z0 = pk::minu2(z0, __shfl_xor_sync(0xffffffffU, z0, 4));
+      z1 = pk::minu2(z1, __shfl_xor_sync(0xffffffffU, z1, 4));
+      z0 = pk::minu2(z0, __shfl_xor_sync(0xffffffffU, z0, 2));
+      z1 = pk::minu2(z1, __shfl_xor_sync(0xffffffffU, z1, 2));
+      z0 = pk::minu2(z0, __shfl_xor_sync(0xffffffffU, z0, 1));
+      z1 = pk::minu2(z1, __shfl_xor_sync(0xffffffffU, z1, 1));
       if (lane == 0) {
-        misc[8 + warp] = ok;
+        if ((z0 & 0xffffU) == 0) {
+          atomicOr(&zflag[0], 1U);
+        }
+        if ((z1 & 0xffffU) == 0) {
+          atomicOr(&zflag[1], 1U);
+        }
+        if ((z0 >> 16) == 0) {
+          atomicOr(&zflag[2], 1U);
+        }
+        if ((z1 >> 16) == 0) {
+          atomicOr(&zflag[3], 1U);
+        }
       }
     }
     __syncthreads();
+    {
+      // CRC of every unfinished code block by WPC warps; the shares are combined by every thread after the barrier.
+      const int c     = warp / WPC;
+      uint32_t  share = 0;
+      if (poly != 0 && !((done_mask >> c) & 1U)) {
+        share = crc_share_words(hb + c * HBW, st[c].nbits, poly, tabs, (uint32_t)(warp % WPC) * 32 + lane, WPC * 32);
+      }
+      share = __reduce_xor_sync(0xffffffffU, share);
+      if (lane == 0) {
+        misc[16 + warp] = share;
+      }
+    }
+    __syncthreads();
+    uint32_t newly = 0;
 #pragma unroll
     for (int c = 0; c != 4; ++c) {
-      if (!st[c].done && (misc[8 + c] != 0 || last_it)) {
+      if ((done_mask >> c) & 1U) {
+        continue;
+      }
+      uint32_t crc = 0;
+#pragma unroll
+      for (int k = 0; k != WPC; ++k) {
+        crc ^= misc[16 + c * WPC + k];
+      }
+      const bool ok = poly != 0 && crc == 0 && (mode != MODE_EARLY_STOP || zflag[c] == 0);
+      if (ok || last_it) {
         // The output holds the hard decision of the last iteration run (ldpc_decoder_impl.cpp:126-146).
         uint32_t* slot = st[c].slot_bits;
         uint32_t* out  = reinterpret_cast<uint32_t*>(st[c].bits_out);
@@ -355,20 +415,19 @@ __global__ void __launch_bounds__(TPC, 1) ldpc_decode4_kernel(const cb_desc* __r
           }
         }
       }
+      if (ok) {
+        newly |= 1U << c;
+      }
     }
-    __syncthreads();
     if (t < 4) {
-      if (!st[t].done && misc[8 + t] != 0) {
-        st[t].done   = 1;
+      if ((newly >> t) & 1U) {
         st[t].crc_ok = 1;
         st[t].iters  = (mode == MODE_EARLY_STOP) ? (int)it + 1 : (int)max_it;
       }
-      misc[4 + t] = 0; // "any zero" flags of the next round
+      misc[4 + 4 * ((checks + 1) & 1U) + t] = 0; // "any zero" flags of the next round (last read two barriers ago)
     }
-    __syncthreads();
-    if (st[0].done && st[1].done && st[2].done && st[3].done) {
-      break;
-    }
+    done_mask |= newly;
+    ++checks;
   }
 
   if (t < 4 && st[t].live) {
@@ -413,7 +472,7 @@ __device__ __forceinline__ void process_check2(uint32_t* __restrict__    soft,
 /// NP = number of planes: 2 -> four code blocks per CTA on 2 x TPC threads, 1 -> two code blocks per CTA on TPC threads
 /// (half the shared memory: groups whose state does not fit four code blocks, e.g. HARQ retransmissions with many layers).
 template <int TPC, int NP>
-__global__ void __launch_bounds__(NP * TPC, 1) ldpc_decode4h_kernel(const cb_desc* __restrict__ descs,
+__global__ void __launch_bounds__(NP * TPC, (NP == 1) ? 2 : 1) ldpc_decode4h_kernel(const cb_desc* __restrict__ descs,
                                                                      const grp_desc* __restrict__ groups,
                                                                      cb_result* __restrict__ results,
                                                                      const int8_t* __restrict__ soft_base,

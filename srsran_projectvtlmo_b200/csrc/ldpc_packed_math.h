@@ -263,6 +263,82 @@ PK_FN uint32_t hfma2_abs_c(uint32_t a, uint32_t b, uint32_t q)
 #endif
 }
 
+/// max(m - |q|, 0)
+PK_FN uint32_t habs_rsub_relu(uint32_t q, uint32_t m)
+{
+#if defined(__CUDA_ARCH__)
+  return pk_u(__hfma2_relu(__habs2(pk_h(q)), pk_h(PK_REP2(H_ONE | 0x8000U)), pk_h(m)));
+#else
+  return host::lanes2(q, m, 0, [](double x, double y, double) { return y - host::dabs(x) > 0 ? y - host::dabs(x) : 0.0; });
+#endif
+}
+/// |q| + b
+PK_FN uint32_t habs_add(uint32_t q, uint32_t b)
+{
+#if defined(__CUDA_ARCH__)
+  return pk_u(__hadd2(__habs2(pk_h(q)), pk_h(b)));
+#else
+  return host::lanes2(q, b, 0, [](double x, double y, double) { return host::dabs(x) + y; });
+#endif
+}
+/// 1.0 where |q| > m, else 0.0 (HSET2.BF.GT: ALU pipe)
+PK_FN uint32_t habs_gt_set(uint32_t q, uint32_t m)
+{
+#if defined(__CUDA_ARCH__)
+  return pk_u(__hgt2(__habs2(pk_h(q)), pk_h(m)));
+#else
+  return host::lanes2(q, m, 0, [](double x, double y, double) { return host::dabs(x) > y ? 1.0 : 0.0; });
+#endif
+}
+/// 1.0 where a > b, else 0.0
+PK_FN uint32_t hgt_set(uint32_t a, uint32_t b)
+{
+#if defined(__CUDA_ARCH__)
+  return pk_u(__hgt2(pk_h(a), pk_h(b)));
+#else
+  return host::lanes2(a, b, 0, [](double x, double y, double) { return x > y ? 1.0 : 0.0; });
+#endif
+}
+/// max(a, b)
+PK_FN uint32_t hmax2(uint32_t a, uint32_t b)
+{
+#if defined(__CUDA_ARCH__)
+  return pk_u(__hmax2(pk_h(a), pk_h(b)));
+#else
+  return host::lanes2(a, b, 0, [](double x, double y, double) { return x > y ? x : y; });
+#endif
+}
+
+// Which pipe the interchangeable steps use (all variants compute the same values; the split balances the ALU and FMA pipes
+// inside each phase of a layer, because the warps of a CTA run the phases in lockstep between the layer barriers).
+#ifndef PK_GATHER_FMA_REGS
+#define PK_GATHER_FMA_REGS 1 ///< registers (of NR) whose min1 / min2 update runs on the FMA pipe (3 HFMA2/HADD2 for 2 HMNMX2)
+#endif
+#ifndef PK_SCATTER_T_ALU
+#define PK_SCATTER_T_ALU 1 ///< |q| > min1 by HSET2 (ALU) instead of a saturating HADD2 (FMA)
+#endif
+#ifndef PK_SCATTER_T2_ALU
+#define PK_SCATTER_T2_ALU 1 ///< v > 120 by HSET2 (ALU) instead of a saturating HADD2 (FMA)
+#endif
+#ifndef PK_SCATTER_CLAMP_ALU
+#define PK_SCATTER_CLAMP_ALU 0 ///< min(|q|, 120) with infinite pass-through by 2 HMNMX2 + HADD2 instead of 2 HFMA2
+#endif
+
+#if defined(__CUDACC__)
+/// Sign mask and 1.0 of both lanes, read from constant memory so that they stay register / constant-bank operands: as
+/// immediates the and-or below needs two LOP3 (one immediate per instruction).
+__constant__ uint32_t c_pk_sign_one[2] = {0x80008000U, PK_REP2(H_ONE)};
+#endif
+/// sign(q) as +-1 in both lanes (+1 for a zero).
+PK_FN uint32_t sign_one(uint32_t q)
+{
+#if defined(__CUDA_ARCH__)
+  return (q & c_pk_sign_one[0]) | c_pk_sign_one[1];
+#else
+  return (q & 0x80008000U) | PK_REP2(H_ONE);
+#endif
+}
+
 /// Packed soft value (two lanes) of two int8 LLRs x0 (low lane) and x1 (high lane) given as biased bytes ub = x ^ 0x80
 /// in bits 0-7 and 16-23 of `ub2`: the half x + 1152 = 0x6400 | ub; +-127 become infinite.
 PK_FN uint32_t soft_from_biased_bytes(uint32_t ub2)
@@ -297,9 +373,16 @@ struct check_lanes {
       uint32_t qq = hsub2(s[r], c[r]);
       q[e][r]     = qq;
       x[r] ^= qq; // bit 15 of every lane: parity of the negative v2c (a zero v2c is +0: it counts as positive)
-      uint32_t t = hmax2_abs(qq, m1[r]);
-      m2[r]      = hmin2(m2[r], t);
-      m1[r]      = hmin2_abs(qq, m1[r]);
+      if (r < PK_GATHER_FMA_REGS) {
+        uint32_t d = habs_rsub_relu(qq, m1[r]); // max(min1 - |q|, 0): exact, 0 for an infinite |q|
+        uint32_t t = habs_add(qq, d);            // max(min1, |q|)
+        m1[r]      = hsub2(m1[r], d);            // min(min1, |q|)
+        m2[r]      = hmin2(m2[r], t);
+      } else {
+        uint32_t t = hmax2_abs(qq, m1[r]);
+        m2[r]      = hmin2(m2[r], t);
+        m1[r]      = hmin2_abs(qq, m1[r]);
+      }
     }
   }
 
@@ -327,17 +410,24 @@ struct check_lanes {
 #pragma unroll
     for (int r = 0; r != NR; ++r) {
       uint32_t qq = q[e][r];
-      uint32_t t  = habs_gt(qq, m1[r]);                       // 1: |q| > min1 -> min1, 0: this edge is the minimum -> min2
+      // 1: |q| > min1 -> min1, 0: this edge is the minimum -> min2
+      uint32_t t  = PK_SCATTER_T_ALU ? habs_gt_set(qq, m1[r]) : habs_gt(qq, m1[r]);
       uint32_t pm = hfma2(t, dpm[r], pm2[r]);                 // P * M
-      uint32_t sq = (qq & 0x80008000U) | PK_REP2(H_ONE);      // sign(q) as +-1
+      uint32_t sq = sign_one(qq);
       // new message c = sign(q) * P * M (the sign product of the OTHER edges is P * sign(q))
       cn[r] = hfma2(sq, pm, PK_REP2(H_1152));
-      // soft = sign(q) * promote(min(|q|, 120) + P * M); an infinite |q| stays infinite:
-      // u = saturate((|q| - 120) / 128) is exact for |q| <= 248, so |q| - 128 u = min(|q|, 120) for every finite |q|.
-      uint32_t u  = habs_fma_sat(qq, PK_REP2(H_INV128), PK_REP2(H_M15_16));
-      uint32_t av = hfma2_abs_c(u, PK_REP2(H_128 | 0x8000U), qq);
+      // soft = sign(q) * promote(min(|q|, 120) + P * M); an infinite |q| stays infinite.
+      uint32_t av;
+      if (PK_SCATTER_CLAMP_ALU) {
+        av = hmax2(hmin2_abs(qq, PK_REP2(H_120)), habs_add(qq, PK_REP2(0xec00U))); // max(min(|q|, 120), |q| - 4096)
+      } else {
+        // u = saturate((|q| - 120) / 128) is exact for |q| <= 248, so |q| - 128 u = min(|q|, 120) for every finite |q|.
+        uint32_t u = habs_fma_sat(qq, PK_REP2(H_INV128), PK_REP2(H_M15_16));
+        av         = hfma2_abs_c(u, PK_REP2(H_128 | 0x8000U), qq);
+      }
       uint32_t v  = hadd2(av, pm);
-      uint32_t t2 = hadd2_sat(v, PK_REP2(H_120 | 0x8000U));   // 1 where v > 120 (v is an integer or infinite)
+      // 1 where v > 120 (v is an integer or infinite)
+      uint32_t t2 = PK_SCATTER_T2_ALU ? hgt_set(v, PK_REP2(H_120)) : hadd2_sat(v, PK_REP2(H_120 | 0x8000U));
       uint32_t w  = hfma2(t2, PK_REP2(H_8192), v);
       sn[r]       = hfma2(sq, w, PK_REP2(H_1152));
     }

@@ -167,6 +167,7 @@ struct srsran_cuda_pusch_dec {
   uint64_t launches          = 0;
   bool     use_packed        = true; // route eligible code blocks to the packed (4 per CTA) decoder
   bool     packed_half       = false; // packed decoder with two threads per lifted check (measured slower: A/B only)
+  bool     force_pairs       = false; // groups of two code blocks per CTA (two CTAs per SM) also for large batches
   bool     prefer_q4         = false; // one code block per CTA on the packed arithmetic also where groups of four would fit
   cudaEvent_t timer_begin    = nullptr;
   cudaEvent_t timer_end      = nullptr;
@@ -750,7 +751,7 @@ int launch_context(srsran_cuda_pusch_dec* h, int ci)
     const cb_desc& d = c.h_desc.p[i];
     nof_packable += ((d.flags & FLAG_DECODE) && packed_eligible(h, d, d.layer_cap, 2)) ? 1U : 0U;
   }
-  const bool small_batch = (nof_packable + 3) / 4 <= static_cast<uint32_t>(h->nof_sms) / 2;
+  const bool small_batch = h->force_pairs || (nof_packable + 3) / 4 <= static_cast<uint32_t>(h->nof_sms) / 2;
   for (uint32_t i = 0; i != ncb; ++i) {
     const cb_desc& d = c.h_desc.p[i];
     if (d.flags & FLAG_DEMATCH) {
@@ -1313,12 +1314,13 @@ int srsran_cuda_pusch_dec_set_combine_flavour(srsran_cuda_pusch_dec_t* h, uint32
 
 int srsran_cuda_pusch_dec_set_decoder_variant(srsran_cuda_pusch_dec_t* h, uint32_t variant)
 {
-  if (h == nullptr || variant > 3) {
+  if (h == nullptr || variant > 4) {
     return SRSRAN_CUDA_ERR_INVALID;
   }
   h->use_packed  = (variant != 1);
   h->packed_half = (variant == 2);
   h->prefer_q4   = (variant == 3);
+  h->force_pairs = (variant == 4);
   return SRSRAN_CUDA_OK;
 }
 

@@ -984,6 +984,38 @@ __device__ __forceinline__ uint32_t warp_crc_words(const uint32_t* words, uint32
   return acc;
 }
 
+/// Share of thread `tid` (of `nthreads`) in the CRC state after the first nb bits of a message held as MSB-first numeric
+/// 32-bit words: the XOR of all shares is the CRC. The bit string is taken right-aligned in ceil(nb / 32) words - leading
+/// zero bits do not change a zero-initialised CRC - so that every share covers whole words and no serial tail is left.
+__device__ __forceinline__ uint32_t crc_share_words(const uint32_t* words, uint32_t nb, int poly, const uint32_t* tabs,
+                                                    uint32_t tid, uint32_t nthreads)
+{
+  const uint32_t gen = crc_gen(poly), order = crc_order(poly);
+  const uint32_t nw  = (nb + 31) / 32;
+  const uint32_t rs  = (32 - nb % 32) % 32; // right shift of the whole string
+  const uint32_t per = (nw + nthreads - 1) / nthreads;
+  const uint32_t w0 = min(nw, tid * per), w1 = min(nw, w0 + per);
+  const uint32_t sh  = (32 - order) / 8; // tables that multiply a register byte by x^32
+  uint32_t       acc = 0;
+  uint32_t       prev = (w0 != 0 && w0 < nw) ? words[w0 - 1] : 0U;
+  for (uint32_t w = w0; w < w1; ++w) {
+    const uint32_t cur  = words[w];
+    const uint32_t word = __funnelshift_r(cur, prev, rs); // (prev:cur) >> rs; rs == 0 gives cur
+    prev                = cur;
+    uint32_t r = tabs[3 * 256 + (word >> 24)] ^ tabs[2 * 256 + ((word >> 16) & 0xff)] ^ tabs[256 + ((word >> 8) & 0xff)] ^
+                 tabs[word & 0xff];
+    uint32_t m = tabs[sh * 256 + (acc & 0xff)] ^ tabs[(sh + 1) * 256 + ((acc >> 8) & 0xff)];
+    if (order == 24) {
+      m ^= tabs[(sh + 2) * 256 + (acc >> 16)];
+    }
+    acc = m ^ r;
+  }
+  if (w1 > w0 && w1 != nw) {
+    acc = gf2_mulmod(acc, c_xpow32[poly - 1][nw - w1], gen, order);
+  }
+  return acc;
+}
+
 /// x^e mod g, by one warp: lane i contributes x^(2^i) if bit i of e is set, the factors are multiplied in a butterfly.
 __device__ __forceinline__ uint32_t warp_xpow(uint32_t e, int poly, int lane)
 {
