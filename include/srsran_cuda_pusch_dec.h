@@ -117,9 +117,11 @@ uint64_t srsran_cuda_pusch_dec_launch_count(const srsran_cuda_pusch_dec_t* handl
  * (ldpc_rate_dematcher_avx2_impl.cpp), 0 = generic (ldpc_rate_dematcher_impl.cpp:116-126). */
 int srsran_cuda_pusch_dec_set_combine_flavour(srsran_cuda_pusch_dec_t* handle, uint32_t simd_block);
 /* Selects the LDPC decoder kernel: 0 (default) = automatic - groups of four same-shape code blocks with few layers
- * (high-rate PUSCH, Z >= 144) run on the packed kernel (four code blocks per CTA in 16-bit SIMD lanes, one thread per
- * lifted check), the rest on the one-code-block-per-thread-group kernel; 1 = one-code-block kernel only; 2 = packed
- * kernel with TWO threads per lifted check (more warps, measured slower on B200 - kept for A/B measurements).
+ * (high-rate PUSCH, Z >= 144) run on the packed kernel (four code blocks per CTA in the two binary16 lanes of two
+ * registers, one thread per lifted check), single code blocks on the intra-code-block packed kernel (four lifted checks
+ * of one code block per thread), the rest on the general kernel; 1 = general kernel only; 2 = packed groups with TWO
+ * threads per lifted check; 3 = intra-code-block packed kernel wherever it fits; 4 = packed groups of TWO code blocks
+ * per CTA, two CTAs per SM (what a small batch uses anyway). 2-4 exist for A/B measurements.
  * Results are identical: all variants are bit-exact to the reference (ldpc_decoder_avx512.cpp). */
 int srsran_cuda_pusch_dec_set_decoder_variant(srsran_cuda_pusch_dec_t* handle, uint32_t variant);
 /* Page-locked host memory for LLR buffers (what pusch_decoder_buffer::get_next_block_view hands to the demodulator,
