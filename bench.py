@@ -45,53 +45,69 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock and throttle reasons of ONE GPU sampled through NVML from a thread of this process while the timed region
+    runs (the nvidia-smi fields of the B200_PROFILING.md recipe, read in-process: a query takes < 0.1 ms, so a 20 ms
+    region yields samples, and N ranks do not start N nvidia-smi processes)."""
 
     def __init__(self, index):
         self.index = index
         self.rows = []
-        self.proc = None
+        self.run = False
+        self.h = None
+        try:
+            import pynvml
+            self.nv = pynvml
+            pynvml.nvmlInit()
+            uuid = None
+            try:
+                uuid = "GPU-" + str(torch_uuid(index))
+                self.h = pynvml.nvmlDeviceGetHandleByUUID(uuid.encode() if bytes is str else uuid)
+            except Exception:
+                self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        except Exception:
+            self.h = None
+
+    def _loop(self):
+        nv = self.nv
+        while self.run:
+            try:
+                sm = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+                rs = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                self.rows.append((sm, rs))
+            except Exception:
+                pass
+            time.sleep(0.0005)
 
     def start(self):
-        try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
-                                         stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=self._read, daemon=True)
-            self.t.start()
-        except Exception:
-            self.proc = None
-
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+        if self.h is None:
+            return
+        self.run = True
+        self.t = threading.Thread(target=self._loop, daemon=True)
+        self.t.start()
 
     def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
+        if self.h is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml unavailable"], "samples": 0}
+        self.run = False
+        self.t.join(timeout=1)
+        nv = self.nv
         try:
-            self.proc.wait(timeout=2)
+            smax = float(nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM))
         except Exception:
-            self.proc.kill()
-        sm, smax, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
-            if len(r) < 7:
-                continue
-            try:
-                sm.append(float(r[0]))
-                smax.append(float(r[1]))
-            except ValueError:
-                continue
-            for n, v in zip(names, r[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(n)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+            smax = None
+        names = {"hw_slowdown": nv.nvmlClocksThrottleReasonHwSlowdown,
+                 "hw_thermal_slowdown": nv.nvmlClocksThrottleReasonHwThermalSlowdown,
+                 "sw_thermal_slowdown": nv.nvmlClocksThrottleReasonSwThermalSlowdown,
+                 "sw_power_cap": nv.nvmlClocksThrottleReasonSwPowerCap}
+        reasons = sorted(n for n, bit in names.items() if any(r & bit for _, r in self.rows))
+        sm = [float(c) for c, _ in self.rows]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": smax, "reasons": reasons,
+                "samples": len(sm), "source": "NVML, sampled back to back inside the timed value region"}
+
+
+def torch_uuid(index):
+    import torch
+    return torch.cuda.get_device_properties(index).uuid
 
 
 def make_inputs(tbs_per_step, nsets, mu, seed):
@@ -258,20 +274,22 @@ def main():
     dev_lists = [[(d[k].data_ptr(), nllr) for k in range(B)] for d in dev_sets]
     host_lists = [[buf[k] for k in range(B)] for _, buf in host_sets]
 
+    dev_args = [pusch.SubmitArgs(cfg_sets[s], dev_lists[s], device_resident=True) for s in range(2)]
+    host_args = [pusch.SubmitArgs(cfg_sets[s], host_lists[s]) for s in range(2)]
+
     def step_device(i):
-        return pusch.submit_tbs(acc, cfg_sets[i % 2], dev_lists[i % 2], device_resident=True)
+        return pusch.submit_tbs(acc, dev_args[i % 2])
 
     def step_host(i):
-        return pusch.submit_tbs(acc, cfg_sets[i % 2], host_lists[i % 2])
+        return pusch.submit_tbs(acc, host_args[i % 2])
 
     tb_out = np.zeros(tbs // 8, np.uint8)
 
-    def drain(tickets, check=False):
-        ok = 0
-        for t in tickets:
-            r = pusch.poll_tb(acc, t, tb_out)
-            ok += r.tb_crc_ok
-        return ok
+    tb_outs = [np.zeros(tbs // 8, np.uint8) for _ in range(B)]
+
+    def drain(tickets):
+        """Completion of one batch through the host API: TB bytes copied out, results read."""
+        return sum(r.tb_crc_ok for r in pusch.poll_tbs(acc, tickets, tb_outs))
 
     def barrier():
         if world > 1:
@@ -305,9 +323,9 @@ def main():
 
     def settle(tk):
         nonlocal ok_tbs, stage
+        res = pusch.poll_tbs(acc, tk)
         stage += np.array(pusch.ticket_timing(acc, tk[0]))
-        for t in tk:
-            r = pusch.poll_tb(acc, t, None)
+        for r in res:
             ok_tbs += r.tb_crc_ok
             iters.append(r.iter_mean)
 
@@ -332,8 +350,7 @@ def main():
     niso = min(args.steps, 6)
     for i in range(niso):
         tk = step_device(i)
-        for t in tk:
-            pusch.poll_tb(acc, t, None)
+        pusch.poll_tbs(acc, tk)
         iso += np.array(pusch.ticket_timing(acc, tk[0]))
     iso_ms = (iso / niso).tolist()
 

@@ -175,6 +175,12 @@ int srsran_cuda_pusch_dec_submit_tb(srsran_cuda_pusch_dec_t* handle, const srsra
 int srsran_cuda_pusch_dec_poll_tb(srsran_cuda_pusch_dec_t* handle, int ticket, int block, uint8_t* tb,
                                   srsran_cuda_pusch_dec_tb_result* result);
 
+/* The same for `nof_tickets` tickets in one call (a slot's worth of TBs): `tbs` may be NULL or hold NULL entries.
+ * Returns nof_tickets when all are complete (always, with `block`), 0 if `block` is 0 and any is still in flight - in
+ * which case nothing is consumed - and < 0 on error. */
+int srsran_cuda_pusch_dec_poll_tbs(srsran_cuda_pusch_dec_t* handle, uint32_t nof_tickets, const int* tickets, int block,
+                                   uint8_t* const* tbs, srsran_cuda_pusch_dec_tb_result* results);
+
 /* Zero-copy access to the bytes of a completed TB: `*data` points into the batch's page-locked result buffer (tbs_bits / 8
  * bytes, valid until the ticket's batch context is reused, i.e. for at least the next two submissions); NULL if the
  * reference would not have written the TB (a code-block CRC failed). The ticket must have completed (poll_tb returned 1). */

@@ -74,6 +74,8 @@ SYMBOLS = {
                                                  C.POINTER(CbMeta)]),
     "srsran_cuda_pusch_dec_submit_tb": (C.c_int, [C.c_void_p, C.POINTER(TbConfig), i8p, C.c_uint32]),
     "srsran_cuda_pusch_dec_poll_tb": (C.c_int, [C.c_void_p, C.c_int, C.c_int, u8p, C.POINTER(TbResult)]),
+    "srsran_cuda_pusch_dec_poll_tbs": (C.c_int, [C.c_void_p, C.c_uint32, intp, C.c_int, C.POINTER(u8p),
+                                                  C.POINTER(TbResult)]),
     "srsran_cuda_pusch_dec_tb_data": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(u8p)]),
     "srsran_cuda_pusch_dec_submit_tbs_device": (C.c_int, [C.c_void_p, C.c_uint32, C.POINTER(TbConfig),
                                                            C.POINTER(C.c_void_p), u32p, intp]),

@@ -4,6 +4,7 @@
 #include "pusch_dec_kernels.cuh"
 #include "ldpc_packed.cuh"
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -14,6 +15,16 @@
 using namespace pusch_dec;
 
 namespace {
+#ifdef PUSCH_DEC_HOST_PROF
+static double g_prof[8];
+static long   g_prof_n;
+static inline double prof_now() { return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+#define PROF_T(var) double var = prof_now()
+#define PROF_ADD(i, a, b) g_prof[i] += (b) - (a)
+#else
+#define PROF_T(var)
+#define PROF_ADD(i, a, b)
+#endif
 
 thread_local std::string g_create_error;
 
@@ -632,6 +643,7 @@ int launch_context(srsran_cuda_pusch_dec* h, int ci)
   if (ncb == 0) {
     return SRSRAN_CUDA_OK;
   }
+  PROF_T(l0);
   // 1. Host -> device: LLRs (direct from pinned caller memory when possible), descriptors.
   if (h->timer_armed) {
     h->timer_armed = false;
@@ -647,6 +659,7 @@ int launch_context(srsran_cuda_pusch_dec* h, int ci)
     const int8_t* src = (j.src != nullptr) ? j.src : c.h_llr.p + j.dst_off;
     CUDA_TRY(h, cudaMemcpyAsync(c.d_llr.p + j.dst_off, src, j.bytes, cudaMemcpyHostToDevice, s));
   }
+  PROF_T(l1);
   // 2. Group the decode operations into launch classes (threads per code block x shared-memory bucket).
   struct klass {
     int                   tpc;
@@ -746,11 +759,26 @@ int launch_context(srsran_cuda_pusch_dec* h, int ci)
   };
   // Latency mode: when four-per-CTA groups would leave more than half of the SMs idle (a single transport block), two
   // code blocks per CTA spread the batch over twice as many SMs and halve the work per thread.
+  // Consecutive code blocks mostly repeat the previous one's shape (the code blocks of a transport block): the shape
+  // dependent decisions are kept and reused while the shape fields compare equal.
+  auto same_class = [&same_shape](const cb_desc& a, const cb_desc& b) {
+    return same_shape(a, b) && a.flags == b.flags && a.layer_cap == b.layer_cap;
+  };
   uint32_t nof_packable = 0;
-  for (uint32_t i = 0; i != ncb; ++i) {
-    const cb_desc& d = c.h_desc.p[i];
-    nof_packable += ((d.flags & FLAG_DECODE) && packed_eligible(h, d, d.layer_cap, 2)) ? 1U : 0U;
+  {
+    const cb_desc* prev = nullptr;
+    uint32_t       inc  = 0;
+    for (uint32_t i = 0; i != ncb; ++i) {
+      const cb_desc& d = c.h_desc.p[i];
+      if (prev == nullptr || !same_class(*prev, d)) {
+        inc  = ((d.flags & FLAG_DECODE) && packed_eligible(h, d, d.layer_cap, 2)) ? 1U : 0U;
+        prev = &d;
+      }
+      nof_packable += inc;
+    }
   }
+  const cb_desc* memo_desc  = nullptr;
+  uint32_t       memo_lanes = 0;
   const bool small_batch = h->force_pairs || (nof_packable + 3) / 4 <= static_cast<uint32_t>(h->nof_sms) / 2;
   for (uint32_t i = 0; i != ncb; ++i) {
     const cb_desc& d = c.h_desc.p[i];
@@ -764,16 +792,21 @@ int launch_context(srsran_cuda_pusch_dec* h, int ci)
     if (!(d.flags & FLAG_DECODE)) {
       continue;
     }
-    const bool     inter_cb  = !(h->prefer_q4 && q4_eligible(h, d));
-    const uint32_t lanes_fit = !inter_cb ? 0U : (!small_batch && packed_eligible(h, d, d.layer_cap, 4))
-                                   ? 4U
-                                   : (packed_eligible(h, d, d.layer_cap, 2) ? 2U : 0U);
+    if (memo_desc == nullptr || !same_class(*memo_desc, d)) {
+      const bool inter_cb = !(h->prefer_q4 && q4_eligible(h, d));
+      memo_lanes = !inter_cb ? 0U : (!small_batch && packed_eligible(h, d, d.layer_cap, 4))
+                                  ? 4U
+                                  : (packed_eligible(h, d, d.layer_cap, 2) ? 2U : 0U);
+      memo_desc  = &d;
+    }
+    const uint32_t lanes_fit = memo_lanes;
     if (lanes_fit != 0) {
       if (grp_open) {
         grp_desc&      g   = c.h_grp.p[ngrp];
         const cb_desc& f   = c.h_desc.p[g.cb[0]];
         uint32_t       cap = std::max(g.layer_cap, d.layer_cap);
-        if (g.n < grp_lanes && same_shape(f, d) && packed_eligible(h, d, cap, grp_lanes)) {
+        if (g.n < grp_lanes && ((same_class(f, d) && g.layer_cap == d.layer_cap) ||
+                                 (same_shape(f, d) && packed_eligible(h, d, cap, grp_lanes)))) {
           g.cb[g.n++] = i;
           g.layer_cap = cap;
           continue;
@@ -807,6 +840,7 @@ int launch_context(srsran_cuda_pusch_dec* h, int ci)
       c.h_order.p[pos++] = i;
     }
   }
+  PROF_T(l2);
   if (ngrp != 0) {
     CUDA_TRY(h, cudaMemcpyAsync(c.d_grp.p, c.h_grp.p, ngrp * sizeof(grp_desc), cudaMemcpyHostToDevice, s));
   }
@@ -831,6 +865,7 @@ int launch_context(srsran_cuda_pusch_dec* h, int ci)
       CUDA_TRY(h, cudaStreamWaitEvent(s, o.kernels, 0));
     }
   }
+  PROF_T(l3);
   // 4. Kernels.
   CUDA_TRY(h, cudaEventRecord(c.stage[1], s));
   if (dm_stage_bytes != 0) {
@@ -953,6 +988,11 @@ int launch_context(srsran_cuda_pusch_dec* h, int ci)
   CUDA_TRY(h, cudaEventRecord(c.done, ts));
   // The batch stream joins the tail so that the next use of this context (and stream-ordered waits on it) see it complete.
   CUDA_TRY(h, cudaStreamWaitEvent(s, c.done, 0));
+  PROF_T(l4);
+  PROF_ADD(2, l0, l1);
+  PROF_ADD(3, l1, l2);
+  PROF_ADD(4, l2, l3);
+  PROF_ADD(5, l3, l4);
   c.in_flight      = true;
   h->last_launched = ci;
   return SRSRAN_CUDA_OK;
@@ -1034,7 +1074,31 @@ int add_tb(srsran_cuda_pusch_dec* h, batch_context& c, const srsran_cuda_pusch_d
   // pusch_decoder_impl.cpp:35-46.
   uint32_t crc_poly = (C > 1) ? SRSRAN_CUDA_CRC24B : ((cfg.tbs_bits > 3824) ? SRSRAN_CUDA_CRC24A : SRSRAN_CUDA_CRC16);
   uint32_t first_cb = static_cast<uint32_t>(c.cb_meta.size());
+  // The code blocks of a transport block differ only in their LLRs, their HARQ slot and (two values) their length E: when
+  // E and the slot's soft-buffer extent equal those of the previous code block, its descriptor is copied and patched.
+  bool     have_prev = false;
+  uint32_t prev_E = 0, prev_F = 0, prev_ext_before = 0, prev_ext_after = 0;
   for (int i = 0; i != C; ++i) {
+    const uint32_t slot = cfg.harq_first_slot + i;
+    if (have_prev && metas[i].rm_length == prev_E && metas[i].nof_filler_bits == prev_F && slot < h->nof_slots &&
+        h->extent[slot] == prev_ext_before) {
+      const uint32_t idx = static_cast<uint32_t>(c.cb_meta.size());
+      if (idx >= c.h_desc.cap) {
+        h->last_error = "batch context full";
+        return SRSRAN_CUDA_ERR_STATE;
+      }
+      cb_desc d         = c.h_desc.p[idx - 1];
+      d.llr             = llr_dev + metas[i].cw_offset;
+      d.slot            = slot;
+      c.h_desc.p[idx]   = d;
+      h->extent[slot]   = prev_ext_after;
+      c.slot_lo         = std::min(c.slot_lo, slot);
+      c.slot_hi         = std::max(c.slot_hi, slot);
+      const cb_host_meta pm = c.cb_meta.back();
+      c.cb_meta.push_back({pm.K, pm.max_it, slot});
+      continue;
+    }
+    prev_ext_before = (slot < h->nof_slots) ? h->extent[slot] : 0;
     cb_params p = {};
     p.bg        = cfg.base_graph;
     p.Z         = metas[i].lifting_size;
@@ -1055,6 +1119,10 @@ int add_tb(srsran_cuda_pusch_dec* h, batch_context& c, const srsran_cuda_pusch_d
     if (r != SRSRAN_CUDA_OK) {
       return r;
     }
+    have_prev      = true;
+    prev_E         = p.E;
+    prev_F         = p.F;
+    prev_ext_after = h->extent[slot];
   }
   uint32_t K        = metas[0].full_length / ((cfg.base_graph == 1) ? 3 : 5);
   tb_desc  t        = {};
@@ -1215,6 +1283,12 @@ int srsran_cuda_pusch_dec_create(int device, uint32_t max_cbs_in_flight, uint32_
 
 void srsran_cuda_pusch_dec_destroy(srsran_cuda_pusch_dec_t* h)
 {
+#ifdef PUSCH_DEC_HOST_PROF
+  if (g_prof_n > 8) {
+    std::fprintf(stderr, "host profile per submit (us): build %.1f launch_context %.1f [llr copies %.1f grouping %.1f desc copies %.1f kernels+tail %.1f] n=%ld\n",
+                 g_prof[0] / (g_prof_n - 8), g_prof[1] / (g_prof_n - 8), g_prof[2] / (g_prof_n - 8), g_prof[3] / (g_prof_n - 8), g_prof[4] / (g_prof_n - 8), g_prof[5] / (g_prof_n - 8), g_prof_n);
+  }
+#endif
   if (h == nullptr) {
     return;
   }
@@ -1557,6 +1631,7 @@ static int submit_common(srsran_cuda_pusch_dec_t* h, uint32_t nof_tbs, const srs
       nof_tbs == 0 || nof_tbs > MAX_TBS_PER_CTX) {
     return SRSRAN_CUDA_ERR_INVALID;
   }
+  PROF_T(p0);
   cudaSetDevice(h->device);
   if (h->open_ctx >= 0) {
     // A HAL-style batch is still open: launch it first to keep HARQ ordering.
@@ -1606,7 +1681,19 @@ static int submit_common(srsran_cuda_pusch_dec_t* h, uint32_t nof_tbs, const srs
     }
     tickets[i] = make_ticket(ci, static_cast<uint32_t>(c.tb_meta.size() - 1), c.generation);
   }
-  return launch_context(h, ci);
+  PROF_T(p1);
+  r = launch_context(h, ci);
+  PROF_T(p2);
+  PROF_ADD(0, p0, p1);
+  PROF_ADD(1, p1, p2);
+#ifdef PUSCH_DEC_HOST_PROF
+  if (++g_prof_n == 8) { // the first uses of every context allocate their buffers
+    for (double& v : g_prof) {
+      v = 0;
+    }
+  }
+#endif
+  return r;
 }
 
 int srsran_cuda_pusch_dec_submit_tbs(srsran_cuda_pusch_dec_t* h, uint32_t nof_tbs,
@@ -1695,6 +1782,33 @@ int srsran_cuda_pusch_dec_poll_tb(srsran_cuda_pusch_dec_t* h, int ticket, int bl
   }
   m.polled = true;
   return 1;
+}
+
+int srsran_cuda_pusch_dec_poll_tbs(srsran_cuda_pusch_dec_t* h, uint32_t nof_tickets, const int* tickets, int block,
+                                   uint8_t* const* tbs, srsran_cuda_pusch_dec_tb_result* results)
+{
+  if (h == nullptr || tickets == nullptr || (nof_tickets != 0 && results == nullptr)) {
+    return SRSRAN_CUDA_ERR_INVALID;
+  }
+  // All or nothing: without `block`, nothing is consumed unless every ticket's batch has completed.
+  if (!block) {
+    for (uint32_t i = 0; i != nof_tickets; ++i) {
+      int ci = (tickets[i] >> 16) & 0xf;
+      if (tickets[i] < 0 || ci >= NOF_CONTEXTS) {
+        return SRSRAN_CUDA_ERR_INVALID;
+      }
+      if (h->ctx[ci].in_flight && cudaEventQuery(h->ctx[ci].done) == cudaErrorNotReady) {
+        return 0;
+      }
+    }
+  }
+  for (uint32_t i = 0; i != nof_tickets; ++i) {
+    int r = srsran_cuda_pusch_dec_poll_tb(h, tickets[i], 1, tbs != nullptr ? tbs[i] : nullptr, &results[i]);
+    if (r < 0) {
+      return r;
+    }
+  }
+  return static_cast<int>(nof_tickets);
 }
 
 int srsran_cuda_pusch_dec_tb_data(srsran_cuda_pusch_dec_t* h, int ticket, const uint8_t** data)

@@ -276,23 +276,34 @@ class pusch_decoder_cuda:
         return res
 
 
-def submit_tbs(acc: Accelerator, configs, llrs_list, device_resident=False):
-    """Batch submit: `llrs_list` holds numpy int8 arrays (host) or (device_ptr, n) tuples (device-resident)."""
-    n = len(configs)
-    cfg_arr = (TbConfig * n)(*configs)
-    ptrs = (C.c_void_p * n)()
-    lens = (C.c_uint32 * n)()
-    keep = []
-    for i, a in enumerate(llrs_list):
-        if device_resident:
-            ptrs[i], lens[i] = a[0], a[1]
-        else:
-            keep.append(a)
-            ptrs[i], lens[i] = a.ctypes.data, a.size
-    tickets = (C.c_int * n)()
-    fn = acc._lib.srsran_cuda_pusch_dec_submit_tbs_device if device_resident else acc._lib.srsran_cuda_pusch_dec_submit_tbs
-    acc._check(fn(acc.h, n, cfg_arr, ptrs, lens, tickets), "submit_tbs")
-    return list(tickets)
+class SubmitArgs:
+    """The marshalled arguments of one submit_tbs call (configurations, LLR addresses and lengths), reusable: a caller
+    that submits the same set of TB configurations and buffers slot after slot builds them once."""
+
+    def __init__(self, configs, llrs_list, device_resident=False):
+        n = len(configs)
+        self.n = n
+        self.device_resident = device_resident
+        self.cfg_arr = (TbConfig * n)(*configs)
+        self.ptrs = (C.c_void_p * n)()
+        self.lens = (C.c_uint32 * n)()
+        self.keep = []
+        for i, a in enumerate(llrs_list):
+            if device_resident:
+                self.ptrs[i], self.lens[i] = a[0], a[1]
+            else:
+                self.keep.append(a)
+                self.ptrs[i], self.lens[i] = a.ctypes.data, a.size
+        self.tickets = (C.c_int * n)()
+
+
+def submit_tbs(acc: Accelerator, configs, llrs_list=None, device_resident=False):
+    """Batch submit: `llrs_list` holds numpy int8 arrays (host) or (device_ptr, n) tuples (device-resident); or `configs`
+    is a prepared SubmitArgs."""
+    a = configs if isinstance(configs, SubmitArgs) else SubmitArgs(configs, llrs_list, device_resident)
+    fn = acc._lib.srsran_cuda_pusch_dec_submit_tbs_device if a.device_resident else acc._lib.srsran_cuda_pusch_dec_submit_tbs
+    acc._check(fn(acc.h, a.n, a.cfg_arr, a.ptrs, a.lens, a.tickets), "submit_tbs")
+    return list(a.tickets)
 
 
 def poll_tb(acc: Accelerator, ticket, tb_out=None, block=True):
@@ -301,6 +312,23 @@ def poll_tb(acc: Accelerator, ticket, tb_out=None, block=True):
     st = acc._lib.srsran_cuda_pusch_dec_poll_tb(acc.h, ticket, int(block), p, C.byref(res))
     acc._check(st, "poll_tb")
     return (res if st == 1 else None)
+
+
+def poll_tbs(acc: Accelerator, tickets, tb_outs=None, block=True):
+    """All tickets of a batch in one call; `tb_outs`: list of numpy uint8 arrays (or None entries) or None. Returns the
+    list of results, or None when `block` is False and some TB is still in flight."""
+    n = len(tickets)
+    tk = (C.c_int * n)(*tickets)
+    res = (TbResult * n)()
+    ptrs = None
+    if tb_outs is not None:
+        ptrs = (capi.u8p * n)()
+        for i, a in enumerate(tb_outs):
+            if a is not None:
+                ptrs[i] = a.ctypes.data_as(capi.u8p)
+    st = acc._lib.srsran_cuda_pusch_dec_poll_tbs(acc.h, n, tk, int(block), ptrs, res)
+    acc._check(st, "poll_tbs")
+    return list(res) if st == n else None
 
 
 def tb_data(acc: Accelerator, ticket, nbytes):

@@ -290,6 +290,36 @@ def test_pusch_batch_of_tbs_device_resident_and_host(acc):
             assert np.array_equal(out, tbs_bytes[i])
 
 
+def test_pusch_poll_tbs_whole_batch(acc):
+    """poll_tbs (one call per batch, all or nothing when not blocking) returns what poll_tb returns ticket by ticket; a
+    retransmission batch (rv2, same HARQ slots) exercises the descriptor fast path with a non-zero soft-buffer extent."""
+    rng = np.random.default_rng(61)
+    prb, qm, R, nl, bg, nref = 106, 6, 873, 2, 1, 0
+    tbs = synth.tbs_for(prb, qm, R, nl)
+    nllr = prb * 156 * qm * nl
+    nseg = len(pusch.segment(tbs, bg, qm, nl, nllr))
+    ntb = 5
+    payload = [rng.integers(0, 256, tbs // 8, dtype=np.uint8) for _ in range(ntb)]
+    ports = [ob.PortPusch() for _ in range(ntb)]
+    for rv, new_data, mu in ((0, 1, 1.4), (2, 0, 1.4)):
+        llrs = [awgn_llrs(rng, synth.encode_tb(payload[i], bg, rv, qm, nref, nl, nllr), mu) for i in range(ntb)]
+        cfgs = [pusch.TbConfig(tbs, bg, rv, qm, nref, nl, 6, 1, new_data, 2000 + i * nseg) for i in range(ntb)]
+        tickets = pusch.submit_tbs(acc, cfgs, llrs)
+        outs = [np.zeros(tbs // 8, np.uint8) for _ in range(ntb)]
+        res = None
+        while res is None:
+            res = pusch.poll_tbs(acc, tickets, outs, block=False)
+        assert len(res) == ntb
+        for i in range(ntb):
+            tb_p, res_p = ports[i].decode(0, tbs // 8, llrs[i], bg, rv, qm, nref, nl, 6, True, bool(new_data))
+            assert res[i].tb_crc_ok == res_p.tb_crc_ok
+            assert (res[i].iter_min, res[i].iter_max, res[i].nof_observations) == \
+                (res_p.iter_min, res_p.iter_max, res_p.nof_observations)
+            assert abs(res[i].iter_mean - res_p.iter_mean) < 1e-4
+            if res_p.tb_crc_ok:
+                assert np.array_equal(outs[i], payload[i])
+
+
 # ---------------------------------------------------------------------------------------------------------------------
 # hal::hw_accelerator_pusch_dec call sequence, as driven by pusch_decoder_hw_impl::on_end_softbits (:132-342)
 # ---------------------------------------------------------------------------------------------------------------------
