@@ -49,8 +49,9 @@ class ClockSampler:
     runs (the nvidia-smi fields of the B200_PROFILING.md recipe, read in-process: a query takes < 0.1 ms, so a 20 ms
     region yields samples, and N ranks do not start N nvidia-smi processes)."""
 
-    def __init__(self, index):
+    def __init__(self, index, period_ms=4.0):
         self.index = index
+        self.period = period_ms * 1e-3
         self.rows = []
         self.run = False
         self.h = None
@@ -76,7 +77,7 @@ class ClockSampler:
                 self.rows.append((sm, rs))
             except Exception:
                 pass
-            time.sleep(0.0005)
+            time.sleep(self.period)
 
     def start(self):
         if self.h is None:
@@ -102,7 +103,7 @@ class ClockSampler:
         reasons = sorted(n for n, bit in names.items() if any(r & bit for _, r in self.rows))
         sm = [float(c) for c, _ in self.rows]
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": smax, "reasons": reasons,
-                "samples": len(sm), "source": "NVML, sampled back to back inside the timed value region"}
+                "samples": len(sm), "source": "NVML, sampled inside the timed value region"}
 
 
 def torch_uuid(index):
@@ -222,6 +223,7 @@ def main():
     ap.add_argument("--ref-seconds", type=float, default=20.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--latency-reps", type=int, default=200)
+    ap.add_argument("--clock-period-ms", type=float, default=4.0, help="NVML clock sampling period inside the timed region")
     ap.add_argument("--decoder-variant", type=int, default=0, help="0 auto, 1 general kernel only, 2 packed groups with 2 threads per check, 3 one code block per CTA packed kernel everywhere, 4 pairs of code blocks per CTA (two CTAs per SM)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
@@ -311,7 +313,7 @@ def main():
     # ---- value: device-resident inputs, K steps back to back (<= DEPTH in flight), device stopwatch ---------------------
     # The inputs of consecutive steps alternate between two sets (2 x 87 MB of LLRs + 246 MB of soft buffers per step):
     # larger than the 126 MB L2, so no explicit flush is needed between timed steps.
-    sampler = ClockSampler(local_rank)
+    sampler = ClockSampler(local_rank, args.clock_period_ms)
     gc.collect()
     gc.disable()  # no collector pauses of the submitting thread inside the timed regions
     barrier()
