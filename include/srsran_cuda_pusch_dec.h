@@ -169,6 +169,26 @@ int srsran_cuda_pusch_dec_segment(uint32_t tbs_bits, uint32_t base_graph, uint32
  * the handle across transmissions (rx_buffer::get_codeblocks_crc). */
 int srsran_cuda_pusch_dec_submit_tb(srsran_cuda_pusch_dec_t* handle, const srsran_cuda_pusch_dec_tb_config* config,
                                     const int8_t* llrs, uint32_t nof_llrs);
+/* The same with the HARQ slot of every code block given explicitly: `absolute_cb_ids[i]` is the rx_buffer's absolute
+ * code-block id of code block i (rx_buffer::get_absolute_codeblock_id, rx_buffer.h:50-53; the pool hands out ids that
+ * are NOT consecutive), `config->harq_first_slot` is ignored. This is the call a `pusch_decoder` implementation makes
+ * from on_end_softbits (pusch_decoder_impl.cpp:238-307). */
+int srsran_cuda_pusch_dec_submit_tb_cb_ids(srsran_cuda_pusch_dec_t* handle, const srsran_cuda_pusch_dec_tb_config* config,
+                                           const int8_t* llrs, uint32_t nof_llrs, const uint32_t* absolute_cb_ids,
+                                           uint32_t nof_cb_ids);
+/* Streaming ingestion of ONE transport block, for a `pusch_decoder` whose soft bits arrive block by block
+ * (pusch_decoder_buffer::on_new_softbits, pusch_decoder_impl.cpp:159-236; pusch_decoder::set_nof_softbits announces the
+ * total): `stream_begin` reserves device space for up to `max_nof_llrs` LLRs and returns a stream id >= 0; every
+ * `stream_push` appends a block and starts its host -> device copy at once (the host memory must stay valid until the
+ * ticket completes; page-locked memory from srsran_cuda_pusch_dec_host_alloc makes the copy asynchronous);
+ * `stream_submit` closes the stream and queues dematch + decode + TB assembly behind the copies: at on_end_softbits only
+ * the last block is still in flight. `absolute_cb_ids` may be NULL (then config->harq_first_slot + i). Returns a ticket
+ * for srsran_cuda_pusch_dec_poll_tb. */
+int srsran_cuda_pusch_dec_stream_begin(srsran_cuda_pusch_dec_t* handle, uint32_t max_nof_llrs);
+int srsran_cuda_pusch_dec_stream_push(srsran_cuda_pusch_dec_t* handle, int stream, const int8_t* llrs, uint32_t nof_llrs);
+int srsran_cuda_pusch_dec_stream_submit(srsran_cuda_pusch_dec_t* handle, int stream,
+                                        const srsran_cuda_pusch_dec_tb_config* config, const uint32_t* absolute_cb_ids,
+                                        uint32_t nof_cb_ids);
 /* Completion of a ticket: returns 1 and fills `tb` (tbs_bits / 8 bytes; written only when the reference writes it) and
  * `result` when done, 0 if `block` is 0 and the TB is still in flight, < 0 on error. Replaces
  * pusch_decoder_notifier::on_sch_data (pusch_decoder_notifier.h:38). */
@@ -180,6 +200,14 @@ int srsran_cuda_pusch_dec_poll_tb(srsran_cuda_pusch_dec_t* handle, int ticket, i
  * which case nothing is consumed - and < 0 on error. */
 int srsran_cuda_pusch_dec_poll_tbs(srsran_cuda_pusch_dec_t* handle, uint32_t nof_tickets, const int* tickets, int block,
                                    uint8_t* const* tbs, srsran_cuda_pusch_dec_tb_result* results);
+
+/* Per code block outputs of a completed TB: CRC flags as the reference leaves them in rx_buffer::get_codeblocks_crc()
+ * (pusch_decoder_impl.cpp:346-356,425-428: all reset when the TB CRC fails although every code block passed) and, when
+ * `nof_iterations` is not NULL, the value the reference feeds to its LDPC statistics for that code block
+ * (pusch_decoder_impl.cpp:357-363: the iteration count on success, else the configured maximum; 0xffffffff = no
+ * observation: the code block was already ok and only dematched). Returns the number of code blocks. */
+int srsran_cuda_pusch_dec_tb_cb_outputs(srsran_cuda_pusch_dec_t* handle, int ticket, uint8_t* crc_ok,
+                                        uint32_t* nof_iterations, uint32_t nof_cbs);
 
 /* Zero-copy access to the bytes of a completed TB: `*data` points into the batch's page-locked result buffer (tbs_bits / 8
  * bytes, valid until the ticket's batch context is reused, i.e. for at least the next two submissions); NULL if the

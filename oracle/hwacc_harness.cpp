@@ -4,6 +4,7 @@
 // lie under /root/reference plus the repo's C++ host adapters (srsran_projectvtlmo_b200/host/):
 //
 //   reference pusch_decoder_hw_impl  +  OUR hal::hw_accelerator_pusch_dec (CUDA, B200)      <- device under test
+//   OUR pusch_decoder_cuda_impl (the reference's pusch_decoder interface, streamed soft bits)  <- device under test
 //   reference pusch_decoder_impl     +  reference AVX-512/AVX2 ldpc_decoder / rate dematcher <- the oracle
 //
 // Both decode the same transport blocks (reference pdsch_encoder_impl as the transmitter, AWGN, int8 LLRs) over the HARQ
@@ -12,6 +13,7 @@
 #include "hw_accelerator_factories_cuda.h"
 #include "channel_coding_factories_cuda.h"
 #include "pdsch_encoder_impl.h"
+#include "pusch_decoder_cuda_impl.h"
 #include "pusch_decoder_hw_impl.h"
 #include "pusch_decoder_impl.h"
 #include "srsran/phy/upper/channel_coding/channel_coding_factories.h"
@@ -31,8 +33,13 @@ namespace {
 class harness_rx_buffer : public unique_rx_buffer::callback
 {
 public:
-  harness_rx_buffer(unsigned nof_cbs_, unsigned first_absolute_id_) :
-    nof_cbs(nof_cbs_), first_absolute_id(first_absolute_id_), crcs(new bool[nof_cbs_]()), soft(nof_cbs_), data(nof_cbs_)
+  harness_rx_buffer(unsigned nof_cbs_, unsigned first_absolute_id_, unsigned id_stride_ = 1) :
+    nof_cbs(nof_cbs_),
+    first_absolute_id(first_absolute_id_),
+    id_stride(id_stride_),
+    crcs(new bool[nof_cbs_]()),
+    soft(nof_cbs_),
+    data(nof_cbs_)
   {
     for (unsigned i = 0; i != nof_cbs; ++i) {
       soft[i].assign(ldpc::MAX_CODEBLOCK_SIZE, log_likelihood_ratio(0));
@@ -42,7 +49,11 @@ public:
   unsigned   get_nof_codeblocks() const override { return nof_cbs; }
   void       reset_codeblocks_crc() override { std::fill(crcs.get(), crcs.get() + nof_cbs, false); }
   span<bool> get_codeblocks_crc() override { return span<bool>(crcs.get(), nof_cbs); }
-  unsigned   get_absolute_codeblock_id(unsigned codeblock_id) const override { return first_absolute_id + codeblock_id; }
+  // The pool hands out identifiers from a free list: they are not consecutive in general (id_stride > 1 mimics that).
+  unsigned get_absolute_codeblock_id(unsigned codeblock_id) const override
+  {
+    return first_absolute_id + codeblock_id * id_stride;
+  }
   span<log_likelihood_ratio> get_codeblock_soft_bits(unsigned codeblock_id, unsigned codeblock_size) override
   {
     return span<log_likelihood_ratio>(soft[codeblock_id]).first(codeblock_size);
@@ -55,7 +66,7 @@ public:
   void unlock() override {}
   void release() override {}
 
-  unsigned                                       nof_cbs, first_absolute_id;
+  unsigned                                       nof_cbs, first_absolute_id, id_stride;
   std::unique_ptr<bool[]>                        crcs;
   std::vector<std::vector<log_likelihood_ratio>> soft;
   std::vector<std::vector<uint8_t>>              data;
@@ -87,7 +98,8 @@ pusch_decoder_result run(pusch_decoder&                decoder,
                          const std::vector<int8_t>&    llrs,
                          const tb_case&                c,
                          unsigned                      rv,
-                         bool                          new_data)
+                         bool                          new_data,
+                         unsigned                      feed_mode = 0)
 {
   if (new_data) {
     buffer.reset_codeblocks_crc(); // rx_buffer_pool_impl::reserve does this for new data
@@ -103,7 +115,28 @@ pusch_decoder_result run(pusch_decoder&                decoder,
   cfg.new_data            = new_data;
   notifier_t            notifier;
   pusch_decoder_buffer& buf = decoder.new_data(span<uint8_t>(tb_out), unique_rx_buffer(buffer), notifier, cfg);
-  buf.on_new_softbits(span<const log_likelihood_ratio>(reinterpret_cast<const log_likelihood_ratio*>(llrs.data()), llrs.size()));
+  const log_likelihood_ratio* src = reinterpret_cast<const log_likelihood_ratio*>(llrs.data());
+  if (feed_mode == 0) {
+    buf.on_new_softbits(span<const log_likelihood_ratio>(src, llrs.size()));
+  } else {
+    // Block by block like the UL-SCH demultiplexer (ulsch_demultiplex_impl.cpp): alternately written through the
+    // decoder's view and passed by pointer; feed_mode 1 announces the total first (pusch_decoder::set_nof_softbits).
+    if (feed_mode == 1) {
+      decoder.set_nof_softbits(units::bits(llrs.size()));
+    }
+    const size_t block = 20000 + 17 * rv;
+    unsigned     k     = 0;
+    for (size_t off = 0; off < llrs.size(); off += block, ++k) {
+      size_t n = std::min(block, llrs.size() - off);
+      if (k % 2 == 0) {
+        span<log_likelihood_ratio> view = buf.get_next_block_view(n);
+        std::copy(src + off, src + off + n, view.begin());
+        buf.on_new_softbits(view);
+      } else {
+        buf.on_new_softbits(span<const log_likelihood_ratio>(src + off, n));
+      }
+    }
+  }
   buf.on_end_softbits();
   return notifier.res;
 }
@@ -129,6 +162,14 @@ int main()
                                             crc_factory->create(crc_generator_poly::CRC24A),
                                             crc_factory->create(crc_generator_poly::CRC24B)};
   pusch_decoder_hw_impl          hw_decoder(seg_factory->create(), hw_crcs, hw_factory->create());
+
+  // ---- device under test: the pusch_decoder interface implemented directly on the device (own device context, HARQ slot
+  //      ids with a stride of 3 so that the code blocks of a TB do not sit in consecutive slots) --------------------------------
+  hal::cuda_hwacc_pusch_dec_configuration cu_cfg = acc_cfg;
+  cu_cfg.nof_harq_cb_slots                       = 8192;
+  auto                    cu_device = std::make_shared<hal::cuda_pusch_dec_device>(cu_cfg);
+  auto                    cu_factory = create_pusch_decoder_factory_cuda(cu_device, nullptr, MAX_RB, 4);
+  std::unique_ptr<pusch_decoder> cu_decoder = cu_factory->create();
 
   // ---- oracle: reference software decoder ---------------------------------------------------------------------------------
   auto dec_factory = create_ldpc_decoder_factory_sw("auto");
@@ -169,9 +210,9 @@ int main()
   for (const tb_case& c : cases) {
     unsigned nof_cbs = ldpc::compute_nof_codeblocks(units::bits(c.tbs_bits),
                                                     (c.bg == 1) ? ldpc_base_graph_type::BG1 : ldpc_base_graph_type::BG2);
-    harness_rx_buffer sw_buffer(nof_cbs, 0), hw_buffer(nof_cbs, next_abs);
+    harness_rx_buffer sw_buffer(nof_cbs, 0), hw_buffer(nof_cbs, next_abs), cu_buffer(nof_cbs, 3 * next_abs + 1, 3);
     next_abs += nof_cbs;
-    std::vector<uint8_t> tb(c.tbs_bits / 8), tb_sw(tb.size()), tb_hw(tb.size()), cw(c.nof_llrs);
+    std::vector<uint8_t> tb(c.tbs_bits / 8), tb_sw(tb.size()), tb_hw(tb.size()), tb_cu(tb.size()), cw(c.nof_llrs);
     for (uint8_t& b : tb) {
       b = static_cast<uint8_t>(rgen());
     }
@@ -193,6 +234,24 @@ int main()
       }
       pusch_decoder_result r_sw = run(sw_decoder, sw_buffer, tb_sw, llrs, c, rvs[i], i == 0);
       pusch_decoder_result r_hw = run(hw_decoder, hw_buffer, tb_hw, llrs, c, rvs[i], i == 0);
+      pusch_decoder_result r_cu = run(*cu_decoder, cu_buffer, tb_cu, llrs, c, rvs[i], i == 0, 1 + (i % 2));
+      bool same_cu = (r_sw.tb_crc_ok == r_cu.tb_crc_ok) && (r_sw.nof_codeblocks_total == r_cu.nof_codeblocks_total) &&
+                     (r_sw.ldpc_decoder_stats.get_nof_observations() == r_cu.ldpc_decoder_stats.get_nof_observations());
+      if (same_cu && r_sw.ldpc_decoder_stats.get_nof_observations() != 0) {
+        same_cu = (r_sw.ldpc_decoder_stats.get_min() == r_cu.ldpc_decoder_stats.get_min()) &&
+                  (r_sw.ldpc_decoder_stats.get_max() == r_cu.ldpc_decoder_stats.get_max()) &&
+                  (std::abs(r_sw.ldpc_decoder_stats.get_mean() - r_cu.ldpc_decoder_stats.get_mean()) < 1e-4);
+      }
+      if (same_cu && r_sw.tb_crc_ok) {
+        same_cu = (tb_sw == tb_cu);
+      }
+      for (unsigned cb = 0; same_cu && cb != nof_cbs; ++cb) {
+        same_cu = (sw_buffer.crcs[cb] == cu_buffer.crcs[cb]);
+      }
+      std::printf("%-36s rv%u: pusch_decoder_cuda_impl (%s) crc=%d obs=%u -> %s\n", c.name, rvs[i],
+                  (i % 2 == 0) ? "streamed" : "blocks, total unknown", r_cu.tb_crc_ok,
+                  (unsigned)r_cu.ldpc_decoder_stats.get_nof_observations(), same_cu ? "ok" : "MISMATCH");
+      failures += same_cu ? 0 : 1;
       bool same = (r_sw.tb_crc_ok == r_hw.tb_crc_ok) && (r_sw.nof_codeblocks_total == r_hw.nof_codeblocks_total) &&
                   (r_sw.ldpc_decoder_stats.get_nof_observations() == r_hw.ldpc_decoder_stats.get_nof_observations());
       if (same && r_sw.ldpc_decoder_stats.get_nof_observations() != 0) {

@@ -73,6 +73,11 @@ SYMBOLS = {
     "srsran_cuda_pusch_dec_segment": (C.c_int, [C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32,
                                                  C.POINTER(CbMeta)]),
     "srsran_cuda_pusch_dec_submit_tb": (C.c_int, [C.c_void_p, C.POINTER(TbConfig), i8p, C.c_uint32]),
+    "srsran_cuda_pusch_dec_submit_tb_cb_ids": (C.c_int, [C.c_void_p, C.POINTER(TbConfig), i8p, C.c_uint32, u32p, C.c_uint32]),
+    "srsran_cuda_pusch_dec_tb_cb_outputs": (C.c_int, [C.c_void_p, C.c_int, u8p, u32p, C.c_uint32]),
+    "srsran_cuda_pusch_dec_stream_begin": (C.c_int, [C.c_void_p, C.c_uint32]),
+    "srsran_cuda_pusch_dec_stream_push": (C.c_int, [C.c_void_p, C.c_int, i8p, C.c_uint32]),
+    "srsran_cuda_pusch_dec_stream_submit": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(TbConfig), u32p, C.c_uint32]),
     "srsran_cuda_pusch_dec_poll_tb": (C.c_int, [C.c_void_p, C.c_int, C.c_int, u8p, C.POINTER(TbResult)]),
     "srsran_cuda_pusch_dec_poll_tbs": (C.c_int, [C.c_void_p, C.c_uint32, intp, C.c_int, C.POINTER(u8p),
                                                   C.POINTER(TbResult)]),

@@ -118,6 +118,7 @@ struct batch_context {
   cudaEvent_t  join[NOF_SIDE]  = {};
   uint32_t     slot_lo    = 0xffffffffU; // range of HARQ slots this batch touches (ordering between batches)
   uint32_t     slot_hi    = 0;
+  cudaEvent_t  wait_for   = nullptr; // set by a streamed submit: the batch's kernels wait for the ingest copies
   bool         open       = false;   // accepting operations, not launched
   bool         in_flight  = false;   // launched, results not yet consumed
   uint32_t     generation = 0;
@@ -159,6 +160,20 @@ struct batch_context {
   std::vector<copy_job> copies;
 };
 
+/// Streaming ingestion of the LLRs of one transport block (pusch_decoder_buffer::on_new_softbits): every pushed block is
+/// copied to the device at once on the ingest stream; the batch that decodes the transport block waits for `pushed`.
+struct ingest_slot {
+  static constexpr int NOF = 8;
+  cudaStream_t       stream = nullptr;
+  cudaEvent_t        pushed = nullptr;
+  device_buf<int8_t> d_llr;
+  uint32_t           used       = 0;
+  uint32_t           capacity   = 0;     // LLRs announced at stream_begin
+  bool               open       = false; // between stream_begin and stream_submit
+  int                ctx        = -1;    // batch context that reads d_llr (until it completes)
+  uint32_t           generation = 0;
+};
+
 struct hal_op {
   srsran_cuda_pusch_dec_cb_config cfg;
   bool                            configured = false;
@@ -197,6 +212,8 @@ struct srsran_cuda_pusch_dec {
   int           last_launched = -1;
 
   hal_op hal[SRSRAN_CUDA_MAX_NOF_SEGMENTS];
+
+  ingest_slot ingest[ingest_slot::NOF];
 
   // unit-level scratch
   device_buf<crc_job>  d_crc_jobs;
@@ -853,6 +870,10 @@ int launch_context(srsran_cuda_pusch_dec* h, int ci)
     CUDA_TRY(h, cudaMemcpyAsync(c.d_tbmap.p, c.h_tbmap.p, ncb * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
   }
   CUDA_TRY(h, cudaEventRecord(c.copied, s));
+  if (c.wait_for != nullptr) {
+    CUDA_TRY(h, cudaStreamWaitEvent(s, c.wait_for, 0));
+    c.wait_for = nullptr;
+  }
   // 3. HARQ ordering: kernels of this context run after the kernels of the previously launched context.
   //    Batches whose HARQ slot ranges are disjoint share no state (soft bits, data bits, CRC flags are per slot; every other
   //    buffer is per context), so they may overlap: the next batch's dematching fills the tail of this batch's decoding.
@@ -967,11 +988,11 @@ int launch_context(srsran_cuda_pusch_dec* h, int ci)
   CUDA_TRY(h, cudaEventRecord(c.decoded, s));
   CUDA_TRY(h, cudaStreamWaitEvent(ts, c.decoded, 0));
   if (ntb != 0) {
-    tb_gather_kernel<<<(ncb + TBG_WARPS - 1) / TBG_WARPS, TBG_WARPS * 32, 0, ts>>>(c.d_tb.p, c.d_tbmap.p, ncb, h->d_bits.p,
+    tb_gather_kernel<<<(ncb + TBG_WARPS - 1) / TBG_WARPS, TBG_WARPS * 32, 0, ts>>>(c.d_tb.p, c.d_desc.p, c.d_tbmap.p, ncb, h->d_bits.p,
                                                                                   c.d_tbout.p, c.d_tbshare.p);
     ++h->launches;
     CUDA_TRY(h, cudaGetLastError());
-    tb_finalize_kernel<<<(ntb + 7) / 8, 256, 0, ts>>>(c.d_tb.p, ntb, c.d_tbres.p, c.d_tbshare.p, h->d_crc_flags.p);
+    tb_finalize_kernel<<<(ntb + 7) / 8, 256, 0, ts>>>(c.d_tb.p, c.d_desc.p, ntb, c.d_tbres.p, c.d_tbshare.p, h->d_crc_flags.p);
     ++h->launches;
     CUDA_TRY(h, cudaGetLastError());
   }
@@ -1054,7 +1075,7 @@ int segment(uint32_t tbs, uint32_t bg, uint32_t Qm, uint32_t nof_layers, uint32_
 
 /// Adds all code blocks of one TB to the open context. `llr_dev` = device address of the TB's LLRs.
 int add_tb(srsran_cuda_pusch_dec* h, batch_context& c, const srsran_cuda_pusch_dec_tb_config& cfg, const int8_t* llr_dev,
-           uint32_t nof_llrs)
+           uint32_t nof_llrs, const uint32_t* cb_slots = nullptr, uint32_t nof_cb_slots = 0)
 {
   srsran_cuda_pusch_dec_cb_meta metas[SRSRAN_CUDA_MAX_NOF_SEGMENTS];
   if (cfg.tbs_bits % 8 != 0) {
@@ -1071,6 +1092,10 @@ int add_tb(srsran_cuda_pusch_dec* h, batch_context& c, const srsran_cuda_pusch_d
     h->last_error = "too many transport blocks in one batch";
     return SRSRAN_CUDA_ERR_STATE;
   }
+  if (cb_slots != nullptr && nof_cb_slots < static_cast<uint32_t>(C)) {
+    h->last_error = "fewer HARQ code-block ids than code blocks";
+    return SRSRAN_CUDA_ERR_INVALID;
+  }
   // pusch_decoder_impl.cpp:35-46.
   uint32_t crc_poly = (C > 1) ? SRSRAN_CUDA_CRC24B : ((cfg.tbs_bits > 3824) ? SRSRAN_CUDA_CRC24A : SRSRAN_CUDA_CRC16);
   uint32_t first_cb = static_cast<uint32_t>(c.cb_meta.size());
@@ -1079,7 +1104,7 @@ int add_tb(srsran_cuda_pusch_dec* h, batch_context& c, const srsran_cuda_pusch_d
   bool     have_prev = false;
   uint32_t prev_E = 0, prev_F = 0, prev_ext_before = 0, prev_ext_after = 0;
   for (int i = 0; i != C; ++i) {
-    const uint32_t slot = cfg.harq_first_slot + i;
+    const uint32_t slot = (cb_slots != nullptr) ? cb_slots[i] : cfg.harq_first_slot + i;
     if (have_prev && metas[i].rm_length == prev_E && metas[i].nof_filler_bits == prev_F && slot < h->nof_slots &&
         h->extent[slot] == prev_ext_before) {
       const uint32_t idx = static_cast<uint32_t>(c.cb_meta.size());
@@ -1111,7 +1136,7 @@ int add_tb(srsran_cuda_pusch_dec* h, batch_context& c, const srsran_cuda_pusch_d
     p.max_it    = cfg.nof_ldpc_iterations;
     p.mode      = cfg.use_early_stop ? MODE_EARLY_STOP : MODE_CRC_AT_END;
     p.new_data  = cfg.new_data;
-    p.slot      = cfg.harq_first_slot + i;
+    p.slot      = slot;
     p.flags     = FLAG_DEMATCH | FLAG_DECODE | FLAG_USE_HARQ | FLAG_TRACK_CRC;
     p.scaling   = 0.8F; // pusch_codeblock_decoder.cpp:47-50 keeps the default scaling factor
     uint32_t idx;
@@ -1128,7 +1153,7 @@ int add_tb(srsran_cuda_pusch_dec* h, batch_context& c, const srsran_cuda_pusch_d
   tb_desc  t        = {};
   t.first_cb        = first_cb;
   t.nof_cbs         = C;
-  t.first_slot      = cfg.harq_first_slot;
+  t.first_slot      = (cb_slots != nullptr) ? cb_slots[0] : cfg.harq_first_slot;
   t.tbs_bits        = cfg.tbs_bits;
   t.cb_data_bits    = K - metas[0].nof_crc_bits - metas[0].nof_filler_bits;
   t.out_offset      = static_cast<uint32_t>(c.tbout_used);
@@ -1294,6 +1319,15 @@ void srsran_cuda_pusch_dec_destroy(srsran_cuda_pusch_dec_t* h)
   }
   cudaSetDevice(h->device);
   cudaDeviceSynchronize();
+  for (ingest_slot& g : h->ingest) {
+    if (g.stream != nullptr) {
+      cudaStreamDestroy(g.stream);
+    }
+    if (g.pushed != nullptr) {
+      cudaEventDestroy(g.pushed);
+    }
+    g.d_llr.release();
+  }
   for (batch_context& c : h->ctx) {
     c.h_llr.release();
     c.d_llr.release();
@@ -1625,7 +1659,9 @@ int srsran_cuda_pusch_dec_segment(uint32_t tbs_bits, uint32_t base_graph, uint32
 }
 
 static int submit_common(srsran_cuda_pusch_dec_t* h, uint32_t nof_tbs, const srsran_cuda_pusch_dec_tb_config* configs,
-                         const int8_t* const* llrs, const uint32_t* nof_llrs, int* tickets, bool device_resident)
+                         const int8_t* const* llrs, const uint32_t* nof_llrs, int* tickets, bool device_resident,
+                         const uint32_t* cb_slots = nullptr, uint32_t nof_cb_slots = 0, cudaEvent_t wait_for = nullptr,
+                         int* ctx_out = nullptr)
 {
   if (h == nullptr || configs == nullptr || llrs == nullptr || nof_llrs == nullptr || tickets == nullptr ||
       nof_tbs == 0 || nof_tbs > MAX_TBS_PER_CTX) {
@@ -1673,13 +1709,17 @@ static int submit_common(srsran_cuda_pusch_dec_t* h, uint32_t nof_tbs, const srs
   }
   for (uint32_t i = 0; i != nof_tbs; ++i) {
     const int8_t* dev = device_resident ? llrs[i] : c.d_llr.p + offs[i];
-    r                 = add_tb(h, c, configs[i], dev, nof_llrs[i]);
+    r                 = add_tb(h, c, configs[i], dev, nof_llrs[i], cb_slots, nof_cb_slots);
     if (r != SRSRAN_CUDA_OK) {
       c.open      = false;
       h->open_ctx = -1;
       return r;
     }
     tickets[i] = make_ticket(ci, static_cast<uint32_t>(c.tb_meta.size() - 1), c.generation);
+  }
+  c.wait_for = wait_for;
+  if (ctx_out != nullptr) {
+    *ctx_out = ci;
   }
   PROF_T(p1);
   r = launch_context(h, ci);
@@ -1716,6 +1756,96 @@ int srsran_cuda_pusch_dec_submit_tb(srsran_cuda_pusch_dec_t* h, const srsran_cud
   int ticket = -1;
   int r      = submit_common(h, 1, config, &llrs, &nof_llrs, &ticket, false);
   return (r == SRSRAN_CUDA_OK) ? ticket : r;
+}
+
+int srsran_cuda_pusch_dec_submit_tb_cb_ids(srsran_cuda_pusch_dec_t* h, const srsran_cuda_pusch_dec_tb_config* config,
+                                           const int8_t* llrs, uint32_t nof_llrs, const uint32_t* absolute_cb_ids,
+                                           uint32_t nof_cb_ids)
+{
+  if (absolute_cb_ids == nullptr) {
+    return SRSRAN_CUDA_ERR_INVALID;
+  }
+  int ticket = -1;
+  int r      = submit_common(h, 1, config, &llrs, &nof_llrs, &ticket, false, absolute_cb_ids, nof_cb_ids);
+  return (r == SRSRAN_CUDA_OK) ? ticket : r;
+}
+
+int srsran_cuda_pusch_dec_stream_begin(srsran_cuda_pusch_dec_t* h, uint32_t max_nof_llrs)
+{
+  if (h == nullptr || max_nof_llrs == 0) {
+    return SRSRAN_CUDA_ERR_INVALID;
+  }
+  cudaSetDevice(h->device);
+  for (int i = 0; i != ingest_slot::NOF; ++i) {
+    ingest_slot& g = h->ingest[i];
+    if (g.open) {
+      continue;
+    }
+    if (g.ctx >= 0) {
+      // The device buffer is free again once the batch that read it has completed (or its context was recycled).
+      batch_context& c = h->ctx[g.ctx];
+      if (c.in_flight && c.generation == g.generation && cudaEventQuery(c.done) == cudaErrorNotReady) {
+        continue;
+      }
+      g.ctx = -1;
+    }
+    if (g.stream == nullptr) {
+      CUDA_TRY(h, cudaStreamCreateWithFlags(&g.stream, cudaStreamNonBlocking));
+      CUDA_TRY(h, cudaEventCreateWithFlags(&g.pushed, cudaEventDisableTiming));
+    }
+    CUDA_TRY(h, g.d_llr.reserve((static_cast<size_t>(max_nof_llrs) + 15) & ~size_t(15)));
+    g.used     = 0;
+    g.capacity = max_nof_llrs;
+    g.open     = true;
+    return i;
+  }
+  h->last_error = "all ingest streams are busy";
+  return SRSRAN_CUDA_ERR_STATE;
+}
+
+int srsran_cuda_pusch_dec_stream_push(srsran_cuda_pusch_dec_t* h, int stream, const int8_t* llrs, uint32_t nof_llrs)
+{
+  if (h == nullptr || stream < 0 || stream >= ingest_slot::NOF || (llrs == nullptr && nof_llrs != 0)) {
+    return SRSRAN_CUDA_ERR_INVALID;
+  }
+  ingest_slot& g = h->ingest[stream];
+  if (!g.open || g.used + nof_llrs > g.capacity) {
+    h->last_error = "ingest stream not open or more LLRs than announced";
+    return SRSRAN_CUDA_ERR_STATE;
+  }
+  if (nof_llrs != 0) {
+    cudaSetDevice(h->device);
+    CUDA_TRY(h, cudaMemcpyAsync(g.d_llr.p + g.used, llrs, nof_llrs, cudaMemcpyHostToDevice, g.stream));
+    g.used += nof_llrs;
+  }
+  return SRSRAN_CUDA_OK;
+}
+
+int srsran_cuda_pusch_dec_stream_submit(srsran_cuda_pusch_dec_t* h, int stream, const srsran_cuda_pusch_dec_tb_config* config,
+                                        const uint32_t* absolute_cb_ids, uint32_t nof_cb_ids)
+{
+  if (h == nullptr || stream < 0 || stream >= ingest_slot::NOF || config == nullptr) {
+    return SRSRAN_CUDA_ERR_INVALID;
+  }
+  ingest_slot& g = h->ingest[stream];
+  if (!g.open) {
+    h->last_error = "ingest stream not open";
+    return SRSRAN_CUDA_ERR_STATE;
+  }
+  cudaSetDevice(h->device);
+  g.open = false;
+  CUDA_TRY(h, cudaEventRecord(g.pushed, g.stream));
+  const int8_t* dev    = g.d_llr.p;
+  uint32_t      n      = g.used;
+  int           ticket = -1, ci = -1;
+  int r = submit_common(h, 1, config, &dev, &n, &ticket, true, absolute_cb_ids, absolute_cb_ids ? nof_cb_ids : 0, g.pushed,
+                        &ci);
+  if (r != SRSRAN_CUDA_OK) {
+    return r;
+  }
+  g.ctx        = ci;
+  g.generation = h->ctx[ci].generation;
+  return ticket;
 }
 
 int srsran_cuda_pusch_dec_poll_tb(srsran_cuda_pusch_dec_t* h, int ticket, int block, uint8_t* tb,
@@ -1829,6 +1959,43 @@ int srsran_cuda_pusch_dec_tb_data(srsran_cuda_pusch_dec_t* h, int ticket, const 
   }
   *data = c.h_tbres.p[ti].written ? c.h_tbout.p + c.tb_meta[ti].out_offset : nullptr;
   return SRSRAN_CUDA_OK;
+}
+
+int srsran_cuda_pusch_dec_tb_cb_outputs(srsran_cuda_pusch_dec_t* h, int ticket, uint8_t* crc_ok, uint32_t* nof_iterations,
+                                        uint32_t nof_cbs)
+{
+  if (h == nullptr || ticket < 0 || crc_ok == nullptr) {
+    return SRSRAN_CUDA_ERR_INVALID;
+  }
+  int      ci  = (ticket >> 16) & 0xf;
+  uint32_t ti  = static_cast<uint32_t>(ticket) & 0xffff;
+  uint32_t gen = (static_cast<uint32_t>(ticket) >> 20) & 0x3ff;
+  if (ci >= NOF_CONTEXTS) {
+    return SRSRAN_CUDA_ERR_INVALID;
+  }
+  batch_context& c = h->ctx[ci];
+  if ((c.generation & 0x3ff) != gen || ti >= c.tb_meta.size() || !c.in_flight || cudaEventQuery(c.done) != cudaSuccess) {
+    h->last_error = "stale, unknown or unfinished ticket";
+    return SRSRAN_CUDA_ERR_STATE;
+  }
+  const tb_host_meta& m = c.tb_meta[ti];
+  if (nof_cbs < m.nof_cbs) {
+    return SRSRAN_CUDA_ERR_INVALID;
+  }
+  bool all_ok = true;
+  for (uint32_t i = 0; i != m.nof_cbs; ++i) {
+    const cb_result& r = c.h_res.p[m.first_cb + i];
+    crc_ok[i]          = r.crc_ok ? 1 : 0;
+    all_ok             = all_ok && crc_ok[i];
+    if (nof_iterations != nullptr) {
+      nof_iterations[i] = (r.status == 2) ? 0xffffffffU : ((r.iters >= 0) ? static_cast<uint32_t>(r.iters) : m.max_it);
+    }
+  }
+  // A TB whose code blocks all pass but whose own CRC fails resets every flag (pusch_decoder_impl.cpp:425-428).
+  if (all_ok && m.nof_cbs > 1 && !c.h_tbres.p[ti].tb_crc_ok) {
+    std::memset(crc_ok, 0, m.nof_cbs);
+  }
+  return static_cast<int>(m.nof_cbs);
 }
 
 int srsran_cuda_pusch_dec_ticket_timing(srsran_cuda_pusch_dec_t* h, int ticket, float* stage_ms)

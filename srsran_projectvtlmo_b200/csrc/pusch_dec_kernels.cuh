@@ -1029,6 +1029,7 @@ __device__ __forceinline__ uint32_t warp_xpow(uint32_t e, int poly, int lane)
 }
 
 __global__ void __launch_bounds__(TBG_WARPS * 32) tb_gather_kernel(const tb_desc* __restrict__ tbs,
+                                                                   const cb_desc* __restrict__ descs,
                                                                    const uint32_t* __restrict__ tb_of_cb,
                                                                    uint32_t nof_cbs,
                                                                    const uint8_t* __restrict__ bits_base,
@@ -1050,7 +1051,7 @@ __global__ void __launch_bounds__(TBG_WARPS * 32) tb_gather_kernel(const tb_desc
   }
   const tb_desc   tb   = tbs[tbi];
   const uint32_t  r    = cb - tb.first_cb;
-  const uint32_t* src  = reinterpret_cast<const uint32_t*>(bits_base + (size_t)(tb.first_slot + r) * BITS_STRIDE);
+  const uint32_t* src  = reinterpret_cast<const uint32_t*>(bits_base + (size_t)descs[cb].slot * BITS_STRIDE);
   uint32_t*       out  = reinterpret_cast<uint32_t*>(tb_out + tb.out_offset);
   if (tb.nof_cbs == 1) {
     // The code-block CRC is the TB CRC: the payload is the first TBS bits.
@@ -1075,7 +1076,8 @@ __global__ void __launch_bounds__(TBG_WARPS * 32) tb_gather_kernel(const tb_desc
   const uint32_t  m0    = (o + 31) / 32;
   const uint32_t  m1    = (o + Lp + 31) / 32;
   const bool      last  = (r + 1 == tb.nof_cbs);
-  const uint32_t* nxt   = reinterpret_cast<const uint32_t*>(bits_base + (size_t)(tb.first_slot + r + 1) * BITS_STRIDE);
+  // The HARQ slots of a TB's code blocks need not be consecutive (rx_buffer absolute code-block ids): cb_desc::slot.
+  const uint32_t* nxt   = reinterpret_cast<const uint32_t*>(bits_base + (size_t)descs[last ? cb : cb + 1].slot * BITS_STRIDE);
   for (uint32_t m = m0 + lane; m < m1; m += 32) {
     uint32_t w  = 32 * m - o;
     uint32_t sw = w >> 5, sh = w & 31;
@@ -1095,6 +1097,7 @@ __global__ void __launch_bounds__(TBG_WARPS * 32) tb_gather_kernel(const tb_desc
 }
 
 __global__ void __launch_bounds__(256) tb_finalize_kernel(const tb_desc* __restrict__ tbs,
+                                                          const cb_desc* __restrict__ descs,
                                                           uint32_t nof_tbs,
                                                           tb_result_dev* __restrict__ tb_results,
                                                           const uint32_t* __restrict__ crc_share,
@@ -1109,7 +1112,7 @@ __global__ void __launch_bounds__(256) tb_finalize_kernel(const tb_desc* __restr
   bool          ok  = true;
   uint32_t      crc = 0;
   for (uint32_t i = lane; i < tb.nof_cbs; i += 32) {
-    ok = ok && (crc_flags[tb.first_slot + i] != 0);
+    ok = ok && (crc_flags[descs[tb.first_cb + i].slot] != 0);
     crc ^= crc_share[tb.first_cb + i];
   }
   const uint32_t all_ok = __all_sync(0xffffffffU, ok) ? 1U : 0U;
@@ -1127,7 +1130,7 @@ __global__ void __launch_bounds__(256) tb_finalize_kernel(const tb_desc* __restr
   if (crc != 0) {
     // At least one code block is a false positive: reset them all (pusch_decoder_impl.cpp:425-428).
     for (uint32_t i = lane; i < tb.nof_cbs; i += 32) {
-      crc_flags[tb.first_slot + i] = 0;
+      crc_flags[descs[tb.first_cb + i].slot] = 0;
     }
   }
 }

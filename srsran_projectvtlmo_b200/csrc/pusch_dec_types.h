@@ -62,7 +62,7 @@ struct cb_result {
 struct tb_desc {
   uint32_t first_cb;      ///< index of code block 0 in the batch's cb_desc / cb_result arrays
   uint32_t nof_cbs;
-  uint32_t first_slot;    ///< HARQ slot of code block 0 (slots are consecutive)
+  uint32_t first_slot;    ///< HARQ slot of code block 0 (informative: the kernels take every slot from cb_desc::slot)
   uint32_t tbs_bits;
   uint32_t cb_data_bits;  ///< payload bits per code block (K - crc - filler)
   uint32_t out_offset;    ///< byte offset of this TB in the batch TB output buffer

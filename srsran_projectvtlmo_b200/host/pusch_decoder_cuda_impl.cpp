@@ -1,0 +1,258 @@
+#include "pusch_decoder_cuda_impl.h"
+#include "srsran/phy/upper/channel_processors/pusch/pusch_decoder_result.h"
+#include "srsran/ran/pusch/pusch_constants.h"
+#include "srsran/ran/sch/sch_segmentation.h"
+#include "srsran/support/srsran_assert.h"
+#include <algorithm>
+#include <cstring>
+#include <mutex>
+
+using namespace srsran;
+
+namespace {
+/// Blocks smaller than this are merged with the next one before they are copied to the device.
+constexpr unsigned MIN_PUSH_SOFTBITS = 16384;
+} // namespace
+
+pusch_decoder_cuda_impl::pusch_decoder_cuda_impl(std::shared_ptr<hal::cuda_pusch_dec_device> device_,
+                                                 task_executor*                              executor_,
+                                                 unsigned                                    nof_prb,
+                                                 unsigned                                    nof_layers) :
+  device(std::move(device_)),
+  executor(executor_),
+  softbits_capacity(pusch_constants::get_max_codeword_size(nof_prb, nof_layers).value())
+{
+  srsran_assert(device, "Invalid CUDA device context.");
+  static_assert(sizeof(log_likelihood_ratio) == sizeof(int8_t), "LLRs are int8");
+  softbits_buffer = static_cast<log_likelihood_ratio*>(srsran_cuda_pusch_dec_host_alloc(softbits_capacity));
+  report_fatal_error_if_not(softbits_buffer != nullptr, "Cannot allocate page-locked soft-bit staging memory.");
+}
+
+pusch_decoder_cuda_impl::~pusch_decoder_cuda_impl()
+{
+  srsran_cuda_pusch_dec_host_free(softbits_buffer);
+}
+
+pusch_decoder_buffer& pusch_decoder_cuda_impl::new_data(span<uint8_t>           transport_block_,
+                                                        unique_rx_buffer        unique_rm_buffer_,
+                                                        pusch_decoder_notifier& notifier,
+                                                        const configuration&    cfg)
+{
+  internal_states previous_state = current_state.exchange(internal_states::collecting);
+  srsran_assert(previous_state == internal_states::idle, "Invalid state: a transport block is already being processed.");
+
+  transport_block  = transport_block_;
+  unique_rm_buffer = std::move(unique_rm_buffer_);
+  result_notifier  = &notifier;
+  current_config   = cfg;
+  softbits_count   = 0;
+  softbits_pushed  = 0;
+  ingest_stream    = -1;
+  nof_ulsch_softbits.reset();
+
+  unsigned tb_size = transport_block.size() * 8;
+  nof_codeblocks   = ldpc::compute_nof_codeblocks(units::bits(tb_size), cfg.base_graph);
+  srsran_assert(nof_codeblocks == unique_rm_buffer->get_nof_codeblocks(),
+                "Wrong number of codeblocks {} (expected {}).",
+                unique_rm_buffer->get_nof_codeblocks(),
+                nof_codeblocks);
+
+  // Reset CRCs if new data is flagged (pusch_decoder_impl.cpp:131-135). The device ignores its own flags of a slot when
+  // the configuration says new data, so only the host view needs clearing.
+  if (cfg.new_data) {
+    unique_rm_buffer->reset_codeblocks_crc();
+  }
+  return *this;
+}
+
+void pusch_decoder_cuda_impl::set_nof_softbits(units::bits nof_softbits)
+{
+  // No effect before new_data or once decoding has started (pusch_decoder.h:91-97).
+  if (current_state.load() != internal_states::collecting || nof_ulsch_softbits.has_value()) {
+    return;
+  }
+  nof_ulsch_softbits = nof_softbits;
+  // From now on every block is copied to the device as it arrives.
+  std::lock_guard<std::mutex> lock(device->mutex());
+  ingest_stream = srsran_cuda_pusch_dec_stream_begin(device->get(), nof_softbits.value());
+  report_fatal_error_if_not(ingest_stream >= 0, "CUDA PUSCH decoder: {}", srsran_cuda_pusch_dec_last_error(device->get()));
+}
+
+span<log_likelihood_ratio> pusch_decoder_cuda_impl::get_next_block_view(unsigned block_size)
+{
+  srsran_assert(current_state.load() == internal_states::collecting, "Invalid state: not collecting soft bits.");
+  srsran_assert(softbits_count + block_size <= softbits_capacity,
+                "The sum of current buffer number of elements (i.e., {}) and the block size (i.e., {}), exceeds the "
+                "total number of elements of the buffer (i.e., {}).",
+                softbits_count,
+                block_size,
+                softbits_capacity);
+  return span<log_likelihood_ratio>(softbits_buffer + softbits_count, block_size);
+}
+
+void pusch_decoder_cuda_impl::on_new_softbits(span<const log_likelihood_ratio> softbits)
+{
+  srsran_assert(current_state.load() == internal_states::collecting, "Invalid state: not collecting soft bits.");
+  span<log_likelihood_ratio> block = get_next_block_view(softbits.size());
+  // Copy only if the soft bits were not written through the view (pusch_decoder_impl.cpp:188-191).
+  if (block.data() != softbits.data()) {
+    std::copy(softbits.begin(), softbits.end(), block.begin());
+  }
+  softbits_count += softbits.size();
+  if (ingest_stream >= 0 && softbits_count - softbits_pushed >= MIN_PUSH_SOFTBITS) {
+    push_pending();
+  }
+}
+
+void pusch_decoder_cuda_impl::push_pending()
+{
+  if (ingest_stream < 0 || softbits_pushed == softbits_count) {
+    return;
+  }
+  std::lock_guard<std::mutex> lock(device->mutex());
+  int st = srsran_cuda_pusch_dec_stream_push(device->get(),
+                                             ingest_stream,
+                                             reinterpret_cast<const int8_t*>(softbits_buffer + softbits_pushed),
+                                             softbits_count - softbits_pushed);
+  report_fatal_error_if_not(st == SRSRAN_CUDA_OK, "CUDA PUSCH decoder: {}", srsran_cuda_pusch_dec_last_error(device->get()));
+  softbits_pushed = softbits_count;
+}
+
+void pusch_decoder_cuda_impl::on_end_softbits()
+{
+  internal_states previous_state = current_state.exchange(internal_states::decoding);
+  srsran_assert(previous_state == internal_states::collecting, "Invalid state: not collecting soft bits.");
+  if (nof_ulsch_softbits.has_value()) {
+    srsran_assert(nof_ulsch_softbits->value() == softbits_count,
+                  "The number of soft bits (i.e., {}) is not the announced one (i.e., {}).",
+                  softbits_count,
+                  nof_ulsch_softbits->value());
+  }
+
+  srsran_cuda_pusch_dec_tb_config cfg = {};
+  cfg.tbs_bits                        = transport_block.size() * 8;
+  cfg.base_graph                      = (current_config.base_graph == ldpc_base_graph_type::BG1) ? 1 : 2;
+  cfg.rv                              = current_config.rv;
+  cfg.modulation                      = get_bits_per_symbol(current_config.mod);
+  cfg.Nref                            = current_config.Nref;
+  cfg.nof_layers                      = current_config.nof_layers;
+  cfg.nof_ldpc_iterations             = current_config.nof_ldpc_iterations;
+  cfg.use_early_stop                  = current_config.use_early_stop ? 1 : 0;
+  cfg.new_data                        = current_config.new_data ? 1 : 0;
+  // HARQ slots: the rx buffer's absolute code-block identifiers (rx_buffer.h:50-53), not necessarily consecutive.
+  uint32_t cb_ids[SRSRAN_CUDA_MAX_NOF_SEGMENTS];
+  for (unsigned i = 0; i != nof_codeblocks; ++i) {
+    cb_ids[i] = unique_rm_buffer->get_absolute_codeblock_id(i);
+  }
+
+  int ticket;
+  if (ingest_stream >= 0) {
+    push_pending();
+    std::lock_guard<std::mutex> lock(device->mutex());
+    ticket        = srsran_cuda_pusch_dec_stream_submit(device->get(), ingest_stream, &cfg, cb_ids, nof_codeblocks);
+    ingest_stream = -1;
+  } else {
+    std::lock_guard<std::mutex> lock(device->mutex());
+    ticket = srsran_cuda_pusch_dec_submit_tb_cb_ids(
+        device->get(), &cfg, reinterpret_cast<const int8_t*>(softbits_buffer), softbits_count, cb_ids, nof_codeblocks);
+  }
+  report_fatal_error_if_not(ticket >= 0, "CUDA PUSCH decoder: {}", srsran_cuda_pusch_dec_last_error(device->get()));
+
+  if (executor != nullptr) {
+    bool success = executor->execute([this, ticket]() { complete(ticket); });
+    if (success) {
+      return;
+    }
+  }
+  complete(ticket);
+}
+
+void pusch_decoder_cuda_impl::complete(int ticket)
+{
+  pusch_decoder_result            stats;
+  srsran_cuda_pusch_dec_tb_result result = {};
+  uint8_t                         cb_crc[SRSRAN_CUDA_MAX_NOF_SEGMENTS];
+  uint32_t                        cb_iterations[SRSRAN_CUDA_MAX_NOF_SEGMENTS];
+  {
+    // Wait without holding the device: other decoder instances keep submitting while this TB is in flight.
+    int st = 0;
+    while (st == 0) {
+      std::lock_guard<std::mutex> lock(device->mutex());
+      st = srsran_cuda_pusch_dec_poll_tb(device->get(), ticket, 0, nullptr, &result);
+      if (st == 1) {
+        const uint8_t* data = nullptr;
+        st = srsran_cuda_pusch_dec_tb_cb_outputs(device->get(), ticket, cb_crc, cb_iterations, nof_codeblocks);
+        if (st >= 0 && srsran_cuda_pusch_dec_tb_data(device->get(), ticket, &data) == SRSRAN_CUDA_OK && data != nullptr) {
+          // The reference writes the transport block only when every code block is ok (pusch_decoder_impl.cpp:405-418).
+          std::memcpy(transport_block.data(), data, transport_block.size());
+        }
+        st = (st >= 0) ? 1 : st;
+      }
+      report_fatal_error_if_not(st >= 0, "CUDA PUSCH decoder: {}", srsran_cuda_pusch_dec_last_error(device->get()));
+    }
+  }
+
+  stats.tb_crc_ok            = result.tb_crc_ok != 0;
+  stats.nof_codeblocks_total = nof_codeblocks;
+  // sample_statistics keeps a running mean: feed the observations code block by code block, in order
+  // (pusch_decoder_impl.cpp:357-363).
+  span<bool> cb_crcs = unique_rm_buffer->get_codeblocks_crc();
+  for (unsigned i = 0; i != nof_codeblocks; ++i) {
+    if (cb_iterations[i] != 0xffffffffU) {
+      stats.ldpc_decoder_stats.update(cb_iterations[i]);
+    }
+    cb_crcs[i] = cb_crc[i] != 0;
+  }
+
+  // Release soft buffer if the CRC is OK, otherwise unlock (pusch_decoder_impl.cpp:431-436).
+  if (stats.tb_crc_ok) {
+    unique_rm_buffer.release();
+  } else {
+    unique_rm_buffer.unlock();
+  }
+
+  internal_states previous_state = current_state.exchange(internal_states::idle);
+  srsran_assert(previous_state == internal_states::decoding, "Invalid state: not decoding.");
+
+  // Finally report decoding result.
+  result_notifier->on_sch_data(stats);
+}
+
+namespace {
+
+class pusch_decoder_factory_cuda : public pusch_decoder_factory
+{
+public:
+  pusch_decoder_factory_cuda(std::shared_ptr<hal::cuda_pusch_dec_device> device_,
+                             task_executor*                              executor_,
+                             unsigned                                    nof_prb_,
+                             unsigned                                    nof_layers_) :
+    device(std::move(device_)), executor(executor_), nof_prb(nof_prb_), nof_layers(nof_layers_)
+  {
+  }
+
+  std::unique_ptr<pusch_decoder> create() override
+  {
+    return std::make_unique<pusch_decoder_cuda_impl>(device, executor, nof_prb, nof_layers);
+  }
+
+private:
+  std::shared_ptr<hal::cuda_pusch_dec_device> device;
+  task_executor*                              executor;
+  unsigned                                    nof_prb;
+  unsigned                                    nof_layers;
+};
+
+} // namespace
+
+std::shared_ptr<pusch_decoder_factory>
+srsran::create_pusch_decoder_factory_cuda(std::shared_ptr<hal::cuda_pusch_dec_device> device,
+                                          task_executor*                              executor,
+                                          unsigned                                    nof_prb,
+                                          unsigned                                    nof_layers)
+{
+  if (!device) {
+    return nullptr;
+  }
+  return std::make_shared<pusch_decoder_factory_cuda>(std::move(device), executor, nof_prb, nof_layers);
+}
