@@ -100,7 +100,9 @@ struct lane_state {
 };
 static_assert(sizeof(lane_state) == 64, "lane_state is 64 bytes");
 
-template <int TPC>
+/// ZT: lifting size known at compile time (0 = taken from the descriptor). The specialisation for Z = 384 - the lifting size
+/// of every full-size transport block - turns the per-edge message offsets into immediates and the shift wrap into a compare.
+template <int TPC, int ZT = 0>
 __global__ void __launch_bounds__(TPC, 1) ldpc_decode4_kernel(const cb_desc* __restrict__ descs,
                                                                const grp_desc* __restrict__ groups,
                                                                cb_result* __restrict__ results,
@@ -116,7 +118,7 @@ __global__ void __launch_bounds__(TPC, 1) ldpc_decode4_kernel(const cb_desc* __r
   constexpr int   NW   = TPC / 32;
   const grp_desc& g    = groups[blockIdx.x];
   const cb_desc&  d0   = descs[g.cb[0]];
-  const uint32_t  Z = d0.Z, bg = d0.bg, Kb = (bg == 1) ? 22 : 10, K = Kb * Z, L = g.layer_cap;
+  const uint32_t  Z = ZT ? (uint32_t)ZT : (uint32_t)d0.Z, bg = d0.bg, Kb = (bg == 1) ? 22 : 10, K = Kb * Z, L = g.layer_cap;
   const uint32_t  mode = d0.mode, max_it = d0.max_it, mult = d0.scale_mult;
   const int       poly = d0.crc_poly;
   const uint32_t  HBW  = K / 32;

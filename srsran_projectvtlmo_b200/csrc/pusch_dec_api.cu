@@ -317,9 +317,13 @@ cudaError_t launch_decode(srsran_cuda_pusch_dec* h, cudaStream_t s, const cb_des
 
 template <int TPC>
 cudaError_t launch_decode4(srsran_cuda_pusch_dec* h, cudaStream_t s, const cb_desc* descs, const grp_desc* groups,
-                           cb_result* res, uint8_t* bits_base, uint32_t n, uint32_t smem)
+                           cb_result* res, uint8_t* bits_base, uint32_t n, uint32_t smem, bool z384 = false)
 {
-  ldpc_decode4_kernel<TPC><<<n, TPC, smem, s>>>(descs, groups, res, h->d_soft.p, bits_base, h->d_crc_flags.p);
+  if (TPC == 384 && z384) {
+    ldpc_decode4_kernel<384, 384><<<n, 384, smem, s>>>(descs, groups, res, h->d_soft.p, bits_base, h->d_crc_flags.p);
+  } else {
+    ldpc_decode4_kernel<TPC><<<n, TPC, smem, s>>>(descs, groups, res, h->d_soft.p, bits_base, h->d_crc_flags.p);
+  }
   ++h->launches;
   return cudaGetLastError();
 }
@@ -692,6 +696,7 @@ int launch_context(srsran_cuda_pusch_dec* h, int ci)
     uint32_t lanes; // code blocks per CTA: 4, or 2 when the state of four does not fit in shared memory
     uint32_t smem;
     uint32_t first, count; // range in h_grp
+    uint32_t z;            // lifting size (one per class: the Z = 384 specialisation of the kernel)
   };
   uint32_t grp_lanes = 4;
   std::vector<pklass> pclasses;
@@ -768,8 +773,9 @@ int launch_context(srsran_cuda_pusch_dec* h, int ci)
     const cb_desc&  d  = c.h_desc.p[g.cb[0]];
     uint32_t        sm = (dec4_smem_layout(d.bg, d.Z, g.layer_cap, grp_lanes).total + 1023) & ~1023U;
     int             tp = d.Z <= 256 ? 256 : 384;
-    if (pclasses.empty() || pclasses.back().tpc != tp || pclasses.back().smem != sm || pclasses.back().lanes != grp_lanes) {
-      pclasses.push_back({tp, grp_lanes, sm, ngrp, 0});
+    if (pclasses.empty() || pclasses.back().tpc != tp || pclasses.back().smem != sm || pclasses.back().lanes != grp_lanes ||
+        pclasses.back().z != d.Z) {
+      pclasses.push_back({tp, grp_lanes, sm, ngrp, 0, d.Z});
     }
     ++pclasses.back().count;
     ++ngrp;
@@ -935,7 +941,7 @@ int launch_context(srsran_cuda_pusch_dec* h, int ci)
                          : launch_decode4h<384, 2>(h, st, c.d_desc.p, grp, c.d_res.p, c.bits_base, k.count, k.smem);
     } else {
       e = (k.tpc == 256) ? launch_decode4<256>(h, st, c.d_desc.p, grp, c.d_res.p, c.bits_base, k.count, k.smem)
-                         : launch_decode4<384>(h, st, c.d_desc.p, grp, c.d_res.p, c.bits_base, k.count, k.smem);
+                         : launch_decode4<384>(h, st, c.d_desc.p, grp, c.d_res.p, c.bits_base, k.count, k.smem, k.z == 384);
     }
     CUDA_TRY(h, e);
   }
@@ -1242,6 +1248,7 @@ int srsran_cuda_pusch_dec_create(int device, uint32_t max_cbs_in_flight, uint32_
   }
   if (cudaFuncSetAttribute(ldpc_decode4_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess ||
       cudaFuncSetAttribute(ldpc_decode4_kernel<384>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess ||
+      cudaFuncSetAttribute(ldpc_decode4_kernel<384, 384>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess ||
       cudaFuncSetAttribute(ldpc_decode4h_kernel<256, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess ||
       cudaFuncSetAttribute(ldpc_decode4h_kernel<384, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess ||
       cudaFuncSetAttribute(ldpc_decode_q4_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess ||

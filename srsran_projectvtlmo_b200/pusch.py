@@ -306,6 +306,30 @@ def submit_tbs(acc: Accelerator, configs, llrs_list=None, device_resident=False)
     return list(a.tickets)
 
 
+def submit_tb_streamed(acc: Accelerator, config, llr_blocks, cb_ids=None):
+    """One TB whose LLRs arrive in blocks (pusch_decoder_buffer::on_new_softbits): every block's host -> device copy starts
+    when it is pushed. `llr_blocks`: numpy int8 arrays that stay alive until the ticket completes; `cb_ids`: the rx
+    buffer's absolute code-block ids (HARQ slots), or None for config.harq_first_slot + i. Returns the ticket."""
+    total = sum(b.size for b in llr_blocks)
+    sid = acc._check(acc._lib.srsran_cuda_pusch_dec_stream_begin(acc.h, total), "stream_begin")
+    for b in llr_blocks:
+        acc._check(acc._lib.srsran_cuda_pusch_dec_stream_push(acc.h, sid, b.ctypes.data_as(capi.i8p), b.size), "stream_push")
+    ids, n = None, 0
+    if cb_ids is not None:
+        n = len(cb_ids)
+        ids = (C.c_uint32 * n)(*cb_ids)
+    return acc._check(acc._lib.srsran_cuda_pusch_dec_stream_submit(acc.h, sid, C.byref(config), ids, n), "stream_submit")
+
+
+def tb_cb_outputs(acc: Accelerator, ticket, nof_cbs):
+    """(crc flags, iteration observations) per code block of a completed TB; 0xffffffff = no observation."""
+    crc = np.zeros(nof_cbs, np.uint8)
+    its = np.zeros(nof_cbs, np.uint32)
+    acc._check(acc._lib.srsran_cuda_pusch_dec_tb_cb_outputs(acc.h, ticket, crc.ctypes.data_as(capi.u8p),
+                                                           its.ctypes.data_as(capi.u32p), nof_cbs), "tb_cb_outputs")
+    return crc, its
+
+
 def poll_tb(acc: Accelerator, ticket, tb_out=None, block=True):
     res = TbResult()
     p = tb_out.ctypes.data_as(capi.u8p) if tb_out is not None else None

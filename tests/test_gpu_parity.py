@@ -290,6 +290,40 @@ def test_pusch_batch_of_tbs_device_resident_and_host(acc):
             assert np.array_equal(out, tbs_bytes[i])
 
 
+def test_pusch_streamed_tb_with_scattered_harq_slots(acc):
+    """stream_begin / stream_push / stream_submit with non-consecutive HARQ slots (rx_buffer absolute code-block ids):
+    same TB result as the oracle over rv0 -> rv2, per-code-block CRC flags and iteration observations included."""
+    rng = np.random.default_rng(62)
+    prb, qm, R, nl, bg, nref = 106, 6, 873, 2, 1, 0
+    tbs = synth.tbs_for(prb, qm, R, nl)
+    nllr = prb * 156 * qm * nl
+    nseg = len(pusch.segment(tbs, bg, qm, nl, nllr))
+    ids = [3000 + 7 * i + (i % 3) for i in range(nseg)]  # scattered, increasing
+    payload = rng.integers(0, 256, tbs // 8, dtype=np.uint8)
+    port = ob.PortPusch()
+    for rv, new_data, mu in ((0, 1, 1.3), (2, 0, 1.3)):
+        llr = awgn_llrs(rng, synth.encode_tb(payload, bg, rv, qm, nref, nl, nllr), mu)
+        cuts = sorted(rng.choice(np.arange(1, nllr), 9, replace=False).tolist())
+        blocks = [np.ascontiguousarray(b) for b in np.split(llr, cuts)]
+        cfg = pusch.TbConfig(tbs, bg, rv, qm, nref, nl, 6, 1, new_data, 0)
+        ticket = pusch.submit_tb_streamed(acc, cfg, blocks, ids)
+        out = np.zeros(tbs // 8, np.uint8)
+        res = pusch.poll_tb(acc, ticket, out)
+        crc, its = pusch.tb_cb_outputs(acc, ticket, nseg)
+        tb_p, res_p = port.decode(0, tbs // 8, llr, bg, rv, qm, nref, nl, 6, True, bool(new_data))
+        assert res.tb_crc_ok == res_p.tb_crc_ok
+        assert (res.iter_min, res.iter_max, res.nof_observations) == (res_p.iter_min, res_p.iter_max, res_p.nof_observations)
+        obs = its[its != 0xffffffff]
+        assert obs.size == res_p.nof_observations
+        if obs.size:
+            assert (obs.min(), obs.max()) == (res_p.iter_min, res_p.iter_max)
+        for i, slot in enumerate(ids):
+            assert acc.read_cb_crc(slot) == bool(crc[i])
+        if res_p.tb_crc_ok:
+            assert np.array_equal(out, payload)
+            assert crc.all()
+
+
 def test_pusch_poll_tbs_whole_batch(acc):
     """poll_tbs (one call per batch, all or nothing when not blocking) returns what poll_tb returns ticket by ticket; a
     retransmission batch (rv2, same HARQ slots) exercises the descriptor fast path with a non-zero soft-buffer extent."""
