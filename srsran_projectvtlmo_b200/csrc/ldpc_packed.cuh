@@ -345,8 +345,12 @@ __global__ void __launch_bounds__(TPC, 1) ldpc_decode4_kernel(const cb_desc* __r
         const uint32_t d0 = pk::hadd2(s.x, PK_REP2(0xe481U)), d1 = pk::hadd2(s.y, PK_REP2(0xe481U));
         z0 = pk::minu2(z0, s.x ^ pk::SOFT_ZERO2);
         z1 = pk::minu2(z1, s.y ^ pk::SOFT_ZERO2);
-        const uint32_t b0 = __ballot_sync(0xffffffffU, (d0 & 0x8000U) != 0);
-        const uint32_t b1 = __ballot_sync(0xffffffffU, (d1 & 0x8000U) != 0);
+        // (the AND is opaque to the optimiser, which would turn the test into shift + and + compare: 3 instructions)
+        uint32_t l0, l1;
+        asm("and.b32 %0, %1, 0x8000;" : "=r"(l0) : "r"(d0));
+        asm("and.b32 %0, %1, 0x8000;" : "=r"(l1) : "r"(d1));
+        const uint32_t b0 = __ballot_sync(0xffffffffU, l0 != 0);
+        const uint32_t b1 = __ballot_sync(0xffffffffU, l1 != 0);
         const uint32_t b2 = __ballot_sync(0xffffffffU, (int32_t)d0 < 0);
         const uint32_t b3 = __ballot_sync(0xffffffffU, (int32_t)d1 < 0);
         if (lane < 4) {

@@ -407,6 +407,7 @@ int upload_tables(srsran_cuda_pusch_dec* h)
   CUDA_TRY(h, cudaMemcpyToSymbol(c_col, col, sizeof(col)));
   CUDA_TRY(h, cudaMemcpyToSymbol(c_shift, shift, sizeof(shift)));
   CUDA_TRY(h, cudaMemcpyToSymbol(c_xpow32, xp32, sizeof(xp32)));
+  CUDA_TRY(h, cudaMemcpyToSymbol(g_xpow32, xp32, sizeof(xp32)));
   CUDA_TRY(h, cudaMemcpyToSymbol(c_xpow128, xp128, sizeof(xp128)));
   uint32_t xp2[3][32];
   for (int poly = 1; poly <= 3; ++poly) {

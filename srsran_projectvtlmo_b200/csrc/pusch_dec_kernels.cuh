@@ -24,6 +24,9 @@ __constant__ uint8_t  c_col[2][MAX_EDGES];
 __constant__ uint16_t c_shift[2][8][MAX_EDGES];
 /// x^(32 i) mod g, i = 0..271, for CRC24A, CRC24B, CRC16 (index poly - 1).
 __constant__ uint32_t c_xpow32[3][272];
+/// The same table in global memory, for lookups whose index differs from lane to lane (a constant-bank access with
+/// divergent addresses is replayed once per distinct address).
+__device__ uint32_t g_xpow32[3][272];
 /// x^(128 i) mod g, i = 0..1023.
 __constant__ uint32_t c_xpow128[3][1024];
 /// x^(2^i) mod g, i = 0..31 (square-and-multiply ladders).
@@ -53,6 +56,20 @@ __host__ __device__ __forceinline__ uint32_t gf2_mulmod(uint32_t a, uint32_t b, 
     if ((b >> i) & 1U) {
       acc ^= a;
     }
+  }
+  return acc;
+}
+
+/// gf2_mulmod with the degree of the generator known at compile time (fully unrolled, branch-free).
+template <int ORDER>
+__device__ __forceinline__ uint32_t gf2_mulmod_fixed(uint32_t a, uint32_t b, uint32_t gen)
+{
+  uint32_t acc = 0;
+#pragma unroll
+  for (int i = ORDER - 1; i >= 0; --i) {
+    acc <<= 1;
+    acc ^= gen & (0U - ((acc >> ORDER) & 1U));
+    acc ^= a & (0U - ((b >> i) & 1U));
   }
   return acc;
 }
@@ -1011,7 +1028,8 @@ __device__ __forceinline__ uint32_t crc_share_words(const uint32_t* words, uint3
     acc = m ^ r;
   }
   if (w1 > w0 && w1 != nw) {
-    acc = gf2_mulmod(acc, c_xpow32[poly - 1][nw - w1], gen, order);
+    const uint32_t m = __ldg(&g_xpow32[poly - 1][nw - w1]);
+    acc              = (order == 24) ? gf2_mulmod_fixed<24>(acc, m, gen) : gf2_mulmod_fixed<16>(acc, m, gen);
   }
   return acc;
 }
