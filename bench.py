@@ -426,23 +426,23 @@ def main():
                                              "tb_assemble_crc": iso_ms[3], "d2h_results": iso_ms[4]},
             "roofline": {"kernel": "ldpc_decode4_kernel", "bound": "smem", "achieved": smem_ach, "peak": smem_peak,
                          "unit": "GB/s", "frac": smem_ach / smem_peak if smem_peak else None,
-                         "traffic": 95.2e6 * B / 64, "traffic_note": "dram__bytes_read+write of one launch (ncu, 64 TBs): "
+                         "traffic": 94.7e6 * B / 64, "traffic_note": "dram__bytes_read+write of one launch (ncu, 64 TBs): "
                          "the soft buffers are read once (89 MB), decoded bits written (6 MB)",
                          "peak_source": "128 B/clk/SM x 148 SMs x SM clock sampled during the run (B300_MICROARCH.md: "
                                         "smem crossbar 128 B/cyc/SM)",
                          "algorithmic": f"4 B per edge update, U = {mean_it:.2f} it x 384 x {edges} edges x {ncb * B} CBs",
                          "share_of_step": iso_ms[2] / sum(iso_ms[1:4]) if sum(iso_ms[1:4]) else None,
                          "share_note": "decode span / kernel spans (dematch + decode + TB assembly) of a batch processed alone"},
-            # The decoder is bound by instruction issue, not by shared-memory bandwidth: the layer body executes 51.2 warp
-            # instructions per (thread, edge) for four code blocks = 12.8 per code-block edge update (ncu instruction counts
-            # of the layer lines, profiles/r1_v6_packed_decode_ncu_summary.txt), split over the ALU pipe (HMNMX2, HSET2, PRMT,
+            # The decoder is bound by instruction issue, not by shared-memory bandwidth: the layer body executes 46.8 warp
+            # instructions per (thread, edge) for four code blocks = 11.7 per code-block edge update (ncu instruction counts
+            # of the layer lines, profiles/r1_v8_packed_decode_ncu_summary.txt), split over the ALU pipe (HMNMX2, HSET2, PRMT,
             # LOP3), the FMA pipe (HFMA2, HADD2, IMAD) and the LSU; a scheduler issues at most one warp instruction per clock.
             "roofline_issue": {"kernel": "ldpc_decode4_kernel", "bound": "instruction-issue",
-                               "achieved": 12.8 * U / dec_s / 1e12 if dec_s > 0 else 0.0,
+                               "achieved": 11.7 * U / dec_s / 1e12 if dec_s > 0 else 0.0,
                                "peak": 148 * 4 * 32 * sm_clk / 1e12, "unit": "T thread-instr/s",
-                               "frac": (12.8 * U / dec_s) / (148 * 4 * 32 * sm_clk) if dec_s > 0 else None,
-                               "algorithmic": "12.8 instructions per edge update x U (mean iterations, not executed ones)",
-                               "ncu_issue_slots_busy": 0.52, "ncu_alu_pipe_busy": 0.46, "ncu_fma_pipe_busy": 0.53},
+                               "frac": (11.7 * U / dec_s) / (148 * 4 * 32 * sm_clk) if dec_s > 0 else None,
+                               "algorithmic": "11.7 instructions per edge update x U (mean iterations, not executed ones)",
+                               "ncu_issue_slots_busy": 0.53, "ncu_alu_pipe_busy": 0.44, "ncu_fma_pipe_busy": 0.56},
             "roofline_dematch": {"kernel": "rate_dematch_kernel", "bound": "hbm", "achieved": hbm_ach,
                                  "peak": peaks.get("hbm_gbs"), "unit": "GB/s",
                                  "frac": hbm_ach / peaks["hbm_gbs"] if peaks.get("hbm_gbs") else None, "traffic": None,
