@@ -102,8 +102,15 @@ static_assert(sizeof(lane_state) == 64, "lane_state is 64 bytes");
 
 /// ZT: lifting size known at compile time (0 = taken from the descriptor). The specialisation for Z = 384 - the lifting size
 /// of every full-size transport block - turns the per-edge message offsets into immediates and the shift wrap into a compare.
+/// Launch bound of TPC + 32 threads: the kernel is launched with TPC threads, the slack only caps the registers at
+/// 152 per thread (65536 / 416 rounded down to the allocation unit) so that, next to one decoder CTA (384 x 152 registers,
+/// 207 KB of shared memory), an SM still has room for one 128-thread rate-dematcher CTA of the NEXT batch: the dematcher
+/// then runs in the issue slots the decoder leaves idle instead of after it.
+#ifndef DEC4_LB_EXTRA
+#define DEC4_LB_EXTRA 32
+#endif
 template <int TPC, int ZT = 0>
-__global__ void __launch_bounds__(TPC, 1) ldpc_decode4_kernel(const cb_desc* __restrict__ descs,
+__global__ void __launch_bounds__(TPC + DEC4_LB_EXTRA, 1) ldpc_decode4_kernel(const cb_desc* __restrict__ descs,
                                                                const grp_desc* __restrict__ groups,
                                                                cb_result* __restrict__ results,
                                                                const int8_t* __restrict__ soft_base,

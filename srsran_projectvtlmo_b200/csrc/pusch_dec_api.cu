@@ -15,6 +15,10 @@
 using namespace pusch_dec;
 
 namespace {
+// Threads per rate-dematcher CTA (one code block): 128 so that a CTA fits beside a packed-decoder CTA on the same SM.
+#ifndef DM_THREADS
+#define DM_THREADS 128
+#endif
 #ifdef PUSCH_DEC_HOST_PROF
 static double g_prof[8];
 static long   g_prof_n;
@@ -899,7 +903,7 @@ int launch_context(srsran_cuda_pusch_dec* h, int ci)
   if (dm_stage_bytes != 0) {
     // + 32: the de-interleaved image is read with aligned 32-bit loads that may run a few bytes past E.
     uint32_t smem = ((dm_stage_bytes + 15) & ~15U) + 32;
-    rate_dematch_kernel<true><<<ncb, 256, smem, s>>>(c.d_desc.p, h->d_soft.p, h->combine_block);
+    rate_dematch_kernel<true><<<ncb, DM_THREADS, smem, s>>>(c.d_desc.p, h->d_soft.p, h->combine_block);
     ++h->launches;
     CUDA_TRY(h, cudaGetLastError());
   }
