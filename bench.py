@@ -448,8 +448,9 @@ def main():
                                  "frac": hbm_ach / peaks["hbm_gbs"] if peaks.get("hbm_gbs") else None, "traffic": None,
                                  "peak_source": peak_src, "algorithmic": "E + 12611 B per code block",
                                  "timed": "batches processed one at a time after the timed region (stage_ms_one_batch_in_flight)"},
-            "tb_latency_us": {"p50": float(np.percentile(lat, 50)), "p99": float(np.percentile(lat, 99)),
-                              "max": float(lat.max()), "n": int(lat.size),
+            "tb_latency_us": {"p50": float(np.percentile(lat, 50)) if lat.size else None,
+                              "p99": float(np.percentile(lat, 99)) if lat.size else None,
+                              "max": float(lat.max()) if lat.size else None, "n": int(lat.size),
                               "what": "one TB, host LLRs -> TB bytes, idle GPU, wall clock; slot budget 500 us"},
         }
         if n_gpus == 1 and not args.no_cpu_baseline:
