@@ -844,7 +844,6 @@ __global__ void __launch_bounds__(TPB, (TPB == 96) ? 4 : 6) ldpc_decode_q4_kerne
                                                                                    uint32_t* __restrict__ crc_flags)
 {
   extern __shared__ __align__(16) uint8_t smem_raw[];
-  constexpr int  NW   = TPB / 32;
   const int      t    = threadIdx.x;
   const int      lane = t & 31;
   const int      warp = __shfl_sync(0xffffffffU, t >> 5, 0);

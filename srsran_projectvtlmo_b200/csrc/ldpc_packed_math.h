@@ -37,9 +37,15 @@
 #if defined(__CUDACC__)
 #define PK_FN __host__ __device__ __forceinline__
 #define PK_MFN __host__ __device__ __forceinline__
+#if defined(__CUDA_ARCH__)
+#define PK_UNROLL _Pragma("unroll")
+#else
+#define PK_UNROLL
+#endif
 #else
 #define PK_FN static inline
 #define PK_MFN inline
+#define PK_UNROLL
 #endif
 
 namespace pusch_dec {
@@ -358,7 +364,7 @@ struct check_lanes {
 
   PK_MFN void begin()
   {
-#pragma unroll
+PK_UNROLL
     for (int r = 0; r != NR; ++r) {
       m1[r] = m2[r] = PK_REP2(H_120);
       x[r]          = 0;
@@ -368,7 +374,7 @@ struct check_lanes {
   /// Edge e: soft words s[r] (half S + 1152 per lane) and messages of the previous iteration c[r] (half c + 1152 per lane).
   PK_MFN void gather(int e, const uint32_t* s, const uint32_t* c)
   {
-#pragma unroll
+PK_UNROLL
     for (int r = 0; r != NR; ++r) {
       uint32_t qq = hsub2(s[r], c[r]);
       q[e][r]     = qq;
@@ -388,7 +394,7 @@ struct check_lanes {
 
   PK_MFN void reduce(uint32_t mult)
   {
-#pragma unroll
+PK_UNROLL
     for (int r = 0; r != NR; ++r) {
       // The two minima are integers in [0, 120]: the half 1024 + m has m in its low mantissa bits, and back.
       uint32_t i1  = hadd2(m1[r], PK_REP2(H_1024)) & 0x00ff00ffU;
@@ -407,7 +413,7 @@ struct check_lanes {
   /// every lane) of edge e.
   PK_MFN void scatter(int e, uint32_t* sn, uint32_t* cn)
   {
-#pragma unroll
+PK_UNROLL
     for (int r = 0; r != NR; ++r) {
       uint32_t qq = q[e][r];
       // 1: |q| > min1 -> min1, 0: this edge is the minimum -> min2
