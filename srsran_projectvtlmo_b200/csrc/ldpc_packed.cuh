@@ -56,36 +56,59 @@ __device__ __forceinline__ uint32_t edge_addr(uint2 te, uint32_t j, uint32_t Z, 
   return te.x + k - __umulhi(k, zmagic) * Z;
 }
 
-/// One lifted check (thread j) of a layer of degree DEG for the four code blocks of the group. `tab_row[e]` = (byte offset
-/// of the edge's variable node in the soft array, circulant shift); the soft addresses are computed once and kept for
-/// the write-back (the modulo by a multiply-high: the address arithmetic issues on the FMA pipe).
-template <int DEG>
-__device__ __forceinline__ void process_check4(uint8_t* __restrict__     soft_bytes,
-                                               uint32_t* __restrict__    c2v_j,
-                                               const uint2* __restrict__ tab_row,
-                                               uint32_t                  j,
-                                               uint32_t                  Z,
-                                               uint32_t                  zmagic,
-                                               uint32_t                  mult)
+/// One lifted check (thread j) of a layer of degree DEG for the 2 * NR code blocks of the group (NR registers of two lanes
+/// per thread). `tab_row[e]` = (byte offset of the edge's variable node in the soft array, circulant shift); the soft
+/// addresses are computed once and kept for the write-back (the modulo by a multiply-high: the address arithmetic issues on
+/// the FMA pipe). Soft values: 4 * NR bytes per variable lift, messages: 2 * NR bytes per lifted edge.
+template <int DEG, int NR>
+__device__ __forceinline__ void process_check_n(uint8_t* __restrict__     soft_bytes,
+                                                uint8_t* __restrict__     c2v_j,
+                                                const uint2* __restrict__ tab_row,
+                                                uint32_t                  j,
+                                                uint32_t                  Z,
+                                                uint32_t                  zmagic,
+                                                uint32_t                  mult)
 {
-  pk::check4<DEG> ck;
-  uint32_t        addr[DEG];
-  ck.begin();
+  uint32_t addr[DEG];
+  if constexpr (NR == 2) {
+    pk::check4<DEG> ck;
+    uint32_t*       cj = reinterpret_cast<uint32_t*>(c2v_j);
+    ck.begin();
 #pragma unroll
-  for (int e = 0; e != DEG; ++e) {
-    const uint2 te = tab_row[e];
-    uint32_t    k  = j + te.y;
-    k -= __umulhi(k, zmagic) * Z;
-    addr[e]       = te.x + k * 8;
-    const uint2 s = *reinterpret_cast<const uint2*>(soft_bytes + addr[e]);
-    ck.gather(e, s.x, s.y, c2v_j[e * Z]);
-  }
-  ck.reduce(mult);
+    for (int e = 0; e != DEG; ++e) {
+      const uint2 te = tab_row[e];
+      uint32_t    k  = j + te.y;
+      k -= __umulhi(k, zmagic) * Z;
+      addr[e]       = te.x + k * 8;
+      const uint2 s = *reinterpret_cast<const uint2*>(soft_bytes + addr[e]);
+      ck.gather(e, s.x, s.y, cj[e * Z]);
+    }
+    ck.reduce(mult);
 #pragma unroll
-  for (int e = 0; e != DEG; ++e) {
-    uint32_t s0, s1;
-    c2v_j[e * Z]                                       = ck.scatter(e, s0, s1);
-    *reinterpret_cast<uint2*>(soft_bytes + addr[e]) = make_uint2(s0, s1);
+    for (int e = 0; e != DEG; ++e) {
+      uint32_t s0, s1;
+      cj[e * Z]                                        = ck.scatter(e, s0, s1);
+      *reinterpret_cast<uint2*>(soft_bytes + addr[e]) = make_uint2(s0, s1);
+    }
+  } else {
+    pk::check2<DEG> ck;
+    uint16_t*       cj = reinterpret_cast<uint16_t*>(c2v_j);
+    ck.begin();
+#pragma unroll
+    for (int e = 0; e != DEG; ++e) {
+      const uint2 te = tab_row[e];
+      uint32_t    k  = j + te.y;
+      k -= __umulhi(k, zmagic) * Z;
+      addr[e] = te.x + k * 4;
+      ck.gather(e, *reinterpret_cast<const uint32_t*>(soft_bytes + addr[e]), cj[e * Z]);
+    }
+    ck.reduce(mult);
+#pragma unroll
+    for (int e = 0; e != DEG; ++e) {
+      uint32_t s0;
+      cj[e * Z]                                           = (uint16_t)ck.scatter(e, s0);
+      *reinterpret_cast<uint32_t*>(soft_bytes + addr[e]) = s0;
+    }
   }
 }
 
@@ -109,8 +132,12 @@ static_assert(sizeof(lane_state) == 64, "lane_state is 64 bytes");
 #ifndef DEC4_LB_EXTRA
 #define DEC4_LB_EXTRA 32
 #endif
-template <int TPC, int ZT = 0>
-__global__ void __launch_bounds__(TPC + DEC4_LB_EXTRA, 1) ldpc_decode4_kernel(const cb_desc* __restrict__ descs,
+/// NR: registers (of two code blocks each) per thread: 2 = four code blocks per CTA, one CTA per SM; 1 = two code blocks per
+/// CTA with half the shared memory, two CTAs per SM - for groups whose state does not fit four code blocks (HARQ
+/// retransmissions whose combined buffer spans many layers) and for small batches (a single transport block spreads over
+/// twice as many SMs).
+template <int TPC, int ZT = 0, int NR = 2>
+__global__ void __launch_bounds__((NR == 2) ? TPC + DEC4_LB_EXTRA : TPC, (NR == 2) ? 1 : 2) ldpc_decode4_kernel(const cb_desc* __restrict__ descs,
                                                                const grp_desc* __restrict__ groups,
                                                                cb_result* __restrict__ results,
                                                                const int8_t* __restrict__ soft_base,
@@ -123,6 +150,9 @@ __global__ void __launch_bounds__(TPC + DEC4_LB_EXTRA, 1) ldpc_decode4_kernel(co
   // Broadcast from lane 0 so that the compiler knows the warp index is warp-uniform (uniform loop bounds around ballots).
   const int       warp = __shfl_sync(0xffffffffU, t >> 5, 0);
   constexpr int   NW   = TPC / 32;
+  constexpr int   NC   = 2 * NR;  // code blocks per CTA
+  constexpr int   SE   = 4 * NR;  // bytes of soft values per variable lift
+  constexpr int   CE   = 2 * NR;  // bytes of messages per lifted edge
   const grp_desc& g    = groups[blockIdx.x];
   const cb_desc&  d0   = descs[g.cb[0]];
   const uint32_t  Z = ZT ? (uint32_t)ZT : (uint32_t)d0.Z, bg = d0.bg, Kb = (bg == 1) ? 22 : 10, K = Kb * Z, L = g.layer_cap;
@@ -130,10 +160,10 @@ __global__ void __launch_bounds__(TPC + DEC4_LB_EXTRA, 1) ldpc_decode4_kernel(co
   const int       poly = d0.crc_poly;
   const uint32_t  HBW  = K / 32;
 
-  const dec4_layout lay  = dec4_smem_layout(bg, Z, L);
+  const dec4_layout lay  = dec4_smem_layout(bg, Z, L, NC);
   uint2*            tab  = reinterpret_cast<uint2*>(smem_raw + lay.tab_off);
-  uint2*            soft = reinterpret_cast<uint2*>(smem_raw + lay.soft_off);
-  uint32_t*         c2v  = reinterpret_cast<uint32_t*>(smem_raw + lay.c2v_off);
+  uint8_t*          soft = smem_raw + lay.soft_off; // SE bytes per variable lift
+  uint8_t*          c2v  = smem_raw + lay.c2v_off;  // CE bytes per lifted edge, check order
   uint32_t*         hb   = reinterpret_cast<uint32_t*>(smem_raw + lay.hb_off);
   uint32_t*         tabs = reinterpret_cast<uint32_t*>(smem_raw + lay.crc_off);
   uint32_t*         misc = reinterpret_cast<uint32_t*>(smem_raw + lay.misc_off);
@@ -146,7 +176,7 @@ __global__ void __launch_bounds__(TPC + DEC4_LB_EXTRA, 1) ldpc_decode4_kernel(co
   }
   if (t < 4) {
     const int      c      = t;
-    const bool     valid  = c < (int)g.n;
+    const bool     valid  = c < (int)g.n && c < NC;
     const cb_desc& d      = descs[g.cb[valid ? c : 0]];
     const uint32_t cap_in = (Kb + L) * Z - 2 * Z;
     lane_state     ls;
@@ -191,30 +221,31 @@ __global__ void __launch_bounds__(TPC + DEC4_LB_EXTRA, 1) ldpc_decode4_kernel(co
   // ---- prologue ----------------------------------------------------------------------------------------------------------
   const uint32_t nedges = c_row_ptr[bg - 1][L];
   for (uint32_t e = t; e < nedges; e += TPC) {
-    tab[e] = make_uint2((uint32_t)c_col[bg - 1][e] * Z * 8, c_shift[bg - 1][d0.ils][e] % Z);
+    tab[e] = make_uint2((uint32_t)c_col[bg - 1][e] * Z * SE, c_shift[bg - 1][d0.ils][e] % Z);
   }
   {
-    // Input of the four code blocks, 16 variable nodes per code block and step (Z % 16 == 0): the 128-bit loads of a
+    // Input of the code blocks, 16 variable nodes per code block and step (Z % 16 == 0): the 128-bit loads of a
     // step are all in flight together, the messages are cleared while they travel.
     const uint32_t n16   = (Kb + L) * Z / 16;
     const uint32_t punct = 2 * Z / 16;
-    uint32_t       nz[4] = {0, 0, 0, 0};
-    const int8_t*  src[4];
-    uint32_t       n_load[4];
+    uint32_t       nz[NC];
+    const int8_t*  src[NC];
+    uint32_t       n_load[NC];
 #pragma unroll
-    for (int c = 0; c != 4; ++c) {
+    for (int c = 0; c != NC; ++c) {
+      nz[c]     = 0;
       src[c]    = st[c].src;
       n_load[c] = st[c].n_load;
     }
     auto fetch = [&](uint32_t v, uint4* w) {
 #pragma unroll
-      for (int c = 0; c != 4; ++c) {
+      for (int c = 0; c != NC; ++c) {
         w[c] = make_uint4(0, 0, 0, 0);
       }
       if (v >= punct && v < n16) {
         const uint32_t p = (v - punct) * 16;
 #pragma unroll
-        for (int c = 0; c != 4; ++c) {
+        for (int c = 0; c != NC; ++c) {
           if (p + 16 <= n_load[c]) {
             w[c] = __ldg(reinterpret_cast<const uint4*>(src[c] + p));
           } else if (p < n_load[c]) {
@@ -228,11 +259,11 @@ __global__ void __launch_bounds__(TPC + DEC4_LB_EXTRA, 1) ldpc_decode4_kernel(co
         }
       }
     };
-    uint4 w[4];
+    uint4 w[NC];
     fetch(t, w);
     {
       uint4*         c4 = reinterpret_cast<uint4*>(c2v);
-      const uint32_t n4 = nedges * Z / 4;
+      const uint32_t n4 = nedges * Z * CE / 16;
       const uint4    zz = make_uint4(pk::C2V_ZERO4, pk::C2V_ZERO4, pk::C2V_ZERO4, pk::C2V_ZERO4);
       for (uint32_t i = t; i < n4; i += TPC) {
         c4[i] = zz;
@@ -242,9 +273,9 @@ __global__ void __launch_bounds__(TPC + DEC4_LB_EXTRA, 1) ldpc_decode4_kernel(co
       build_crc_tables(tabs, poly, t, TPC);
     }
     for (uint32_t v = t; v < n16; v += TPC) {
-      uint32_t ww[4][4];
+      uint32_t ww[NC][4];
 #pragma unroll
-      for (int c = 0; c != 4; ++c) {
+      for (int c = 0; c != NC; ++c) {
         nz[c] |= w[c].x | w[c].y | w[c].z | w[c].w;
         ww[c][0] = w[c].x ^ 0x80808080U;
         ww[c][1] = w[c].y ^ 0x80808080U;
@@ -254,21 +285,31 @@ __global__ void __launch_bounds__(TPC + DEC4_LB_EXTRA, 1) ldpc_decode4_kernel(co
       fetch(v + TPC, w); // next step's loads travel while this one is converted
 #pragma unroll
       for (int i = 0; i != 4; ++i) {
+        // selb: byte b of the first operand -> bytes 0,1; of the second -> bytes 2,3 (then masked to the lane's low byte)
+        if constexpr (NR == 2) {
 #pragma unroll
-        for (int b = 0; b != 4; b += 2) {
-          uint32_t sel0 = (uint32_t)b * 0x11U + 0x4400U + (uint32_t)b * 0x1100U; // byte b of x -> bytes 0,1; of y -> 2,3
-          uint32_t sel1 = sel0 + 0x1111U;
-          uint4    o;
-          o.x = pk::soft_from_biased_bytes(__byte_perm(ww[0][i], ww[2][i], sel0) & 0x00ff00ffU);
-          o.y = pk::soft_from_biased_bytes(__byte_perm(ww[1][i], ww[3][i], sel0) & 0x00ff00ffU);
-          o.z = pk::soft_from_biased_bytes(__byte_perm(ww[0][i], ww[2][i], sel1) & 0x00ff00ffU);
-          o.w = pk::soft_from_biased_bytes(__byte_perm(ww[1][i], ww[3][i], sel1) & 0x00ff00ffU);
-          *reinterpret_cast<uint4*>(&soft[v * 16 + i * 4 + b]) = o;
+          for (int b = 0; b != 4; b += 2) {
+            uint32_t sel0 = (uint32_t)b * 0x11U + 0x4400U + (uint32_t)b * 0x1100U;
+            uint32_t sel1 = sel0 + 0x1111U;
+            uint4    o;
+            o.x = pk::soft_from_biased_bytes(__byte_perm(ww[0][i], ww[2][i], sel0) & 0x00ff00ffU);
+            o.y = pk::soft_from_biased_bytes(__byte_perm(ww[1][i], ww[3][i], sel0) & 0x00ff00ffU);
+            o.z = pk::soft_from_biased_bytes(__byte_perm(ww[0][i], ww[2][i], sel1) & 0x00ff00ffU);
+            o.w = pk::soft_from_biased_bytes(__byte_perm(ww[1][i], ww[3][i], sel1) & 0x00ff00ffU);
+            *reinterpret_cast<uint4*>(soft + (size_t)(v * 16 + i * 4 + b) * SE) = o;
+          }
+        } else {
+          uint4 o;
+          o.x = pk::soft_from_biased_bytes(__byte_perm(ww[0][i], ww[1][i], 0x4400U) & 0x00ff00ffU);
+          o.y = pk::soft_from_biased_bytes(__byte_perm(ww[0][i], ww[1][i], 0x5511U) & 0x00ff00ffU);
+          o.z = pk::soft_from_biased_bytes(__byte_perm(ww[0][i], ww[1][i], 0x6622U) & 0x00ff00ffU);
+          o.w = pk::soft_from_biased_bytes(__byte_perm(ww[0][i], ww[1][i], 0x7733U) & 0x00ff00ffU);
+          *reinterpret_cast<uint4*>(soft + (size_t)(v * 16 + i * 4) * SE) = o;
         }
       }
     }
 #pragma unroll
-    for (int c = 0; c != 4; ++c) {
+    for (int c = 0; c != NC; ++c) {
       uint32_t any = __reduce_or_sync(0xffffffffU, nz[c]);
       if (lane == 0 && any != 0) {
         atomicOr(&misc[c], 1U);
@@ -293,7 +334,7 @@ __global__ void __launch_bounds__(TPC + DEC4_LB_EXTRA, 1) ldpc_decode4_kernel(co
   }
 
   // ---- iterations --------------------------------------------------------------------------------------------------------
-  constexpr int  WPC    = NW / 4; // warps per code block in the CRC step
+  constexpr int  WPC    = NW / NC; // warps per code block in the CRC step
   const uint32_t j      = t;
   const uint32_t zmagic = 0xffffffffU / Z + 1; // ceil(2^32 / Z): floor(k / Z) = umulhi(k, zmagic) for k < 2 Z
   uint32_t       checks = 0;                   // hard-decision rounds so far (parity selects the "any zero" flag set)
@@ -302,36 +343,36 @@ __global__ void __launch_bounds__(TPC + DEC4_LB_EXTRA, 1) ldpc_decode4_kernel(co
       uint32_t e0  = c_row_ptr[bg - 1][l];
       int      deg = (int)c_row_ptr[bg - 1][l + 1] - (int)e0;
       if (j < Z) {
-        uint32_t*    c2v_row = c2v + (size_t)e0 * Z + j;
+        uint8_t*     c2v_row = c2v + ((size_t)e0 * Z + j) * CE;
         const uint2* tab_row = tab + e0;
-        uint8_t*     sb      = reinterpret_cast<uint8_t*>(soft);
+        uint8_t*     sb      = soft;
         switch (deg) {
           case 3:
-            process_check4<3>(sb, c2v_row, tab_row, j, Z, zmagic, mult);
+            process_check_n<3, NR>(sb, c2v_row, tab_row, j, Z, zmagic, mult);
             break;
           case 4:
-            process_check4<4>(sb, c2v_row, tab_row, j, Z, zmagic, mult);
+            process_check_n<4, NR>(sb, c2v_row, tab_row, j, Z, zmagic, mult);
             break;
           case 5:
-            process_check4<5>(sb, c2v_row, tab_row, j, Z, zmagic, mult);
+            process_check_n<5, NR>(sb, c2v_row, tab_row, j, Z, zmagic, mult);
             break;
           case 6:
-            process_check4<6>(sb, c2v_row, tab_row, j, Z, zmagic, mult);
+            process_check_n<6, NR>(sb, c2v_row, tab_row, j, Z, zmagic, mult);
             break;
           case 7:
-            process_check4<7>(sb, c2v_row, tab_row, j, Z, zmagic, mult);
+            process_check_n<7, NR>(sb, c2v_row, tab_row, j, Z, zmagic, mult);
             break;
           case 8:
-            process_check4<8>(sb, c2v_row, tab_row, j, Z, zmagic, mult);
+            process_check_n<8, NR>(sb, c2v_row, tab_row, j, Z, zmagic, mult);
             break;
           case 9:
-            process_check4<9>(sb, c2v_row, tab_row, j, Z, zmagic, mult);
+            process_check_n<9, NR>(sb, c2v_row, tab_row, j, Z, zmagic, mult);
             break;
           case 10:
-            process_check4<10>(sb, c2v_row, tab_row, j, Z, zmagic, mult);
+            process_check_n<10, NR>(sb, c2v_row, tab_row, j, Z, zmagic, mult);
             break;
           default:
-            process_check4<19>(sb, c2v_row, tab_row, j, Z, zmagic, mult);
+            process_check_n<19, NR>(sb, c2v_row, tab_row, j, Z, zmagic, mult);
             break;
         }
       }
@@ -348,44 +389,60 @@ __global__ void __launch_bounds__(TPC + DEC4_LB_EXTRA, 1) ldpc_decode4_kernel(co
       // is negative exactly for soft <= 0; a running unsigned minimum of pattern ^ pattern(0) finds zero soft values.
       uint32_t z0 = 0xffffffffU, z1 = 0xffffffffU;
       for (uint32_t w = warp; w < HBW; w += NW) {
-        const uint2    s  = soft[w * 32 + 31 - lane];
-        const uint32_t d0 = pk::hadd2(s.x, PK_REP2(0xe481U)), d1 = pk::hadd2(s.y, PK_REP2(0xe481U));
-        z0 = pk::minu2(z0, s.x ^ pk::SOFT_ZERO2);
-        z1 = pk::minu2(z1, s.y ^ pk::SOFT_ZERO2);
-        // (the AND is opaque to the optimiser, which would turn the test into shift + and + compare: 3 instructions)
-        uint32_t l0, l1;
-        asm("and.b32 %0, %1, 0x8000;" : "=r"(l0) : "r"(d0));
-        asm("and.b32 %0, %1, 0x8000;" : "=r"(l1) : "r"(d1));
-        const uint32_t b0 = __ballot_sync(0xffffffffU, l0 != 0);
-        const uint32_t b1 = __ballot_sync(0xffffffffU, l1 != 0);
-        const uint32_t b2 = __ballot_sync(0xffffffffU, (int32_t)d0 < 0);
-        const uint32_t b3 = __ballot_sync(0xffffffffU, (int32_t)d1 < 0);
-        if (lane < 4) {
-          const uint32_t blo = (lane & 1) ? b1 : b0, bhi = (lane & 1) ? b3 : b2;
-          hb[lane * HBW + w] = (lane & 2) ? bhi : blo;
+        if constexpr (NR == 2) {
+          const uint2    s  = *reinterpret_cast<const uint2*>(soft + (size_t)(w * 32 + 31 - lane) * SE);
+          const uint32_t d0 = pk::hadd2(s.x, PK_REP2(0xe481U)), d1 = pk::hadd2(s.y, PK_REP2(0xe481U));
+          z0 = pk::minu2(z0, s.x ^ pk::SOFT_ZERO2);
+          z1 = pk::minu2(z1, s.y ^ pk::SOFT_ZERO2);
+          // (the AND is opaque to the optimiser, which would turn the test into shift + and + compare: 3 instructions)
+          uint32_t l0, l1;
+          asm("and.b32 %0, %1, 0x8000;" : "=r"(l0) : "r"(d0));
+          asm("and.b32 %0, %1, 0x8000;" : "=r"(l1) : "r"(d1));
+          const uint32_t b0 = __ballot_sync(0xffffffffU, l0 != 0);
+          const uint32_t b1 = __ballot_sync(0xffffffffU, l1 != 0);
+          const uint32_t b2 = __ballot_sync(0xffffffffU, (int32_t)d0 < 0);
+          const uint32_t b3 = __ballot_sync(0xffffffffU, (int32_t)d1 < 0);
+          if (lane < 4) {
+            const uint32_t blo = (lane & 1) ? b1 : b0, bhi = (lane & 1) ? b3 : b2;
+            hb[lane * HBW + w] = (lane & 2) ? bhi : blo;
+          }
+        } else {
+          const uint32_t s  = *reinterpret_cast<const uint32_t*>(soft + (size_t)(w * 32 + 31 - lane) * SE);
+          const uint32_t d0 = pk::hadd2(s, PK_REP2(0xe481U));
+          z0                = pk::minu2(z0, s ^ pk::SOFT_ZERO2);
+          uint32_t l0;
+          asm("and.b32 %0, %1, 0x8000;" : "=r"(l0) : "r"(d0));
+          const uint32_t b0 = __ballot_sync(0xffffffffU, l0 != 0);
+          const uint32_t b1 = __ballot_sync(0xffffffffU, (int32_t)d0 < 0);
+          if (lane < 2) {
+            hb[lane * HBW + w] = lane ? b1 : b0;
+          }
         }
       }
       z0 = pk::minu2(z0, __shfl_xor_sync(0xffffffffU, z0, 16));
-      z1 = pk::minu2(z1, __shfl_xor_sync(0xffffffffU, z1, 16));
       z0 = pk::minu2(z0, __shfl_xor_sync(0xffffffffU, z0, 8));
-      z1 = pk::minu2(z1, __shfl_xor_sync(0xffffffffU, z1, 8));
       z0 = pk::minu2(z0, __shfl_xor_sync(0xffffffffU, z0, 4));
-      z1 = pk::minu2(z1, __shfl_xor_sync(0xffffffffU, z1, 4));
       z0 = pk::minu2(z0, __shfl_xor_sync(0xffffffffU, z0, 2));
-      z1 = pk::minu2(z1, __shfl_xor_sync(0xffffffffU, z1, 2));
       z0 = pk::minu2(z0, __shfl_xor_sync(0xffffffffU, z0, 1));
-      z1 = pk::minu2(z1, __shfl_xor_sync(0xffffffffU, z1, 1));
+      if constexpr (NR == 2) {
+        z1 = pk::minu2(z1, __shfl_xor_sync(0xffffffffU, z1, 16));
+        z1 = pk::minu2(z1, __shfl_xor_sync(0xffffffffU, z1, 8));
+        z1 = pk::minu2(z1, __shfl_xor_sync(0xffffffffU, z1, 4));
+        z1 = pk::minu2(z1, __shfl_xor_sync(0xffffffffU, z1, 2));
+        z1 = pk::minu2(z1, __shfl_xor_sync(0xffffffffU, z1, 1));
+      }
       if (lane == 0) {
+        // code block of a lane: NR == 2: (s.x low, s.y low, s.x high, s.y high) = 0..3; NR == 1: (low, high) = 0, 1
         if ((z0 & 0xffffU) == 0) {
           atomicOr(&zflag[0], 1U);
         }
-        if ((z1 & 0xffffU) == 0) {
+        if ((z0 >> 16) == 0) {
+          atomicOr(&zflag[NR == 2 ? 2 : 1], 1U);
+        }
+        if (NR == 2 && (z1 & 0xffffU) == 0) {
           atomicOr(&zflag[1], 1U);
         }
-        if ((z0 >> 16) == 0) {
-          atomicOr(&zflag[2], 1U);
-        }
-        if ((z1 >> 16) == 0) {
+        if (NR == 2 && (z1 >> 16) == 0) {
           atomicOr(&zflag[3], 1U);
         }
       }

@@ -332,6 +332,20 @@ cudaError_t launch_decode4(srsran_cuda_pusch_dec* h, cudaStream_t s, const cb_de
   return cudaGetLastError();
 }
 
+/// Two code blocks per CTA (two CTAs per SM): the same kernel with one register of two lanes per thread.
+template <int TPC>
+cudaError_t launch_decode2(srsran_cuda_pusch_dec* h, cudaStream_t s, const cb_desc* descs, const grp_desc* groups,
+                           cb_result* res, uint8_t* bits_base, uint32_t n, uint32_t smem, bool z384 = false)
+{
+  if (TPC == 384 && z384) {
+    ldpc_decode4_kernel<384, 384, 1><<<n, 384, smem, s>>>(descs, groups, res, h->d_soft.p, bits_base, h->d_crc_flags.p);
+  } else {
+    ldpc_decode4_kernel<TPC, 0, 1><<<n, TPC, smem, s>>>(descs, groups, res, h->d_soft.p, bits_base, h->d_crc_flags.p);
+  }
+  ++h->launches;
+  return cudaGetLastError();
+}
+
 template <int TPC, int NP>
 cudaError_t launch_decode4h(srsran_cuda_pusch_dec* h, cudaStream_t s, const cb_desc* descs, const grp_desc* groups,
                             cb_result* res, uint8_t* bits_base, uint32_t n, uint32_t smem)
@@ -939,8 +953,8 @@ int launch_context(srsran_cuda_pusch_dec* h, int ci)
     cudaStream_t    st  = class_stream();
     cudaError_t     e;
     if (k.lanes == 2) {
-      e = (k.tpc == 256) ? launch_decode4h<256, 1>(h, st, c.d_desc.p, grp, c.d_res.p, c.bits_base, k.count, k.smem)
-                         : launch_decode4h<384, 1>(h, st, c.d_desc.p, grp, c.d_res.p, c.bits_base, k.count, k.smem);
+      e = (k.tpc == 256) ? launch_decode2<256>(h, st, c.d_desc.p, grp, c.d_res.p, c.bits_base, k.count, k.smem)
+                         : launch_decode2<384>(h, st, c.d_desc.p, grp, c.d_res.p, c.bits_base, k.count, k.smem, k.z == 384);
     } else if (h->packed_half) {
       e = (k.tpc == 256) ? launch_decode4h<256, 2>(h, st, c.d_desc.p, grp, c.d_res.p, c.bits_base, k.count, k.smem)
                          : launch_decode4h<384, 2>(h, st, c.d_desc.p, grp, c.d_res.p, c.bits_base, k.count, k.smem);
@@ -1259,8 +1273,9 @@ int srsran_cuda_pusch_dec_create(int device, uint32_t max_cbs_in_flight, uint32_
       cudaFuncSetAttribute(ldpc_decode_q4_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess ||
       cudaFuncSetAttribute(ldpc_decode_q4_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess ||
       cudaFuncSetAttribute(ldpc_decode_q4_kernel<96>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess ||
-      cudaFuncSetAttribute(ldpc_decode4h_kernel<256, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess ||
-      cudaFuncSetAttribute(ldpc_decode4h_kernel<384, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) {
+      cudaFuncSetAttribute(ldpc_decode4_kernel<256, 0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess ||
+      cudaFuncSetAttribute(ldpc_decode4_kernel<384, 0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess ||
+      cudaFuncSetAttribute(ldpc_decode4_kernel<384, 384, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) {
     h->last_error = "cudaFuncSetAttribute(ldpc_decode4_kernel) failed";
     return fail(SRSRAN_CUDA_ERR_CUDA);
   }
