@@ -204,8 +204,14 @@ __device__ __forceinline__ int dm_byte(const dm_geom& g, const int8_t* __restric
   return val;
 }
 
+#ifndef DM_UNR
+#define DM_UNR 4
+#endif
+#ifndef DM_MINB
+#define DM_MINB 6 // caps the registers at 42: sixteen 128-thread CTAs per SM
+#endif
 template <bool STAGED>
-__global__ void __launch_bounds__(256) rate_dematch_kernel(const cb_desc* __restrict__ descs, int8_t* __restrict__ soft_base,
+__global__ void __launch_bounds__(256, DM_MINB) rate_dematch_kernel(const cb_desc* __restrict__ descs, int8_t* __restrict__ soft_base,
                                                            uint32_t combine_block)
 {
   extern __shared__ __align__(16) int8_t dm_sm[];
@@ -257,13 +263,12 @@ __global__ void __launch_bounds__(256) rate_dematch_kernel(const cb_desc* __rest
     const uint32_t mis  = (uint32_t)(reinterpret_cast<uintptr_t>(in) & 15U); // bytes before `in` in its 16-byte line
     const uint32_t nvec = (mis + g.E + 15) / 16;
     const int8_t*  base = in - mis;
-    for (uint32_t v = threadIdx.x; v < nvec; v += blockDim.x) {
+    // Vector v of this thread: `whole` = entirely inside the code block (all but the first / last one), then `w` holds it.
+    auto scatter = [&](uint32_t v, bool whole, const uint4& w) {
       int      first = (int)(v * 16) - (int)mis; // index into `in` of byte 0 of this vector
       uint32_t lo    = first < 0 ? (uint32_t)(-first) : 0U;
       uint32_t hi    = min(16U, (uint32_t)((int)g.E - first));
-      if (lo == 0 && hi == 16) {
-        // Whole vector inside the code block (all but the first / last one).
-        const uint4    w   = __ldg(reinterpret_cast<const uint4*>(base) + v);
+      if (whole) {
         const uint32_t idx = (uint32_t)first;
         if (g.Qm == 8 && (idx & 15U) == 0 && (g.S & 1U) == 0) {
           // Two modulation symbols (rows i, i + 1; i even) x 8 bits: bit j of both rows lands on d[j S + i], d[j S + i + 1].
@@ -296,7 +301,7 @@ __global__ void __launch_bounds__(256) rate_dematch_kernel(const cb_desc* __rest
             }
           }
         }
-        continue;
+        return;
       }
       // Partial vector at either end of the code block: byte by byte.
       for (uint32_t b = lo; b < hi; ++b) {
@@ -307,6 +312,27 @@ __global__ void __launch_bounds__(256) rate_dematch_kernel(const cb_desc* __rest
           p          = (idx - i * g.Qm) * g.S + i;
         }
         dm_sm[p] = __ldg(in + idx);
+      }
+    };
+    // Four vectors per thread and round: their loads are all issued before the first one is consumed, so that a code block
+    // costs about one HBM round trip instead of one per vector (the kernel is latency-bound: one dependent chain per CTA).
+    constexpr uint32_t UNR = DM_UNR;
+    for (uint32_t v0 = threadIdx.x; v0 < nvec; v0 += UNR * blockDim.x) {
+      uint4 w[UNR];
+      bool  whole[UNR];
+#pragma unroll
+      for (uint32_t u = 0; u != UNR; ++u) {
+        const uint32_t v     = v0 + u * blockDim.x;
+        const int      first = (int)(v * 16) - (int)mis;
+        whole[u]             = v < nvec && first >= 0 && first + 16 <= (int)g.E;
+        w[u]                 = whole[u] ? __ldg(reinterpret_cast<const uint4*>(base) + v) : make_uint4(0, 0, 0, 0);
+      }
+#pragma unroll
+      for (uint32_t u = 0; u != UNR; ++u) {
+        const uint32_t v = v0 + u * blockDim.x;
+        if (v < nvec) {
+          scatter(v, whole[u], w[u]);
+        }
       }
     }
     __syncthreads();
