@@ -415,7 +415,7 @@ def _cb_llrs(rng, bg, z, F, crc_poly, E, qm, rv, nref, mu):
     return awgn_llrs(rng, synth.rate_match(cw, bg, z, F, E, rv, qm, nref), mu)
 
 
-@pytest.mark.parametrize("variant", [0, 1, 2, 3])
+@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4])
 def test_packed_decoder_groups_via_hal(acc, variant):
     rng = np.random.default_rng(40 + variant)
     hw = pusch.hw_accelerator_pusch_dec_cuda(acc)
@@ -473,6 +473,56 @@ def test_packed_decoder_groups_via_hal(acc, variant):
                 assert iters == (it if it >= 0 else max_it), key
                 if not (early_stop and not llr.any()):
                     assert np.array_equal(bits, want_bits), key
+            hw.free_queue()
+    finally:
+        acc.set_decoder_variant(0)
+
+
+@pytest.mark.parametrize("variant", [0, 4])
+def test_packed_decoder_many_iterations_saturated_inputs(acc, variant):
+    """Groups of four / two with up to 40 iterations, many layers and inputs that drive soft values to +-infinity in both
+    directions (strong wrong parity bits, +-127 and +-120 everywhere): a promoted value is updated dozens of times, its
+    binary16 representation grows up to the IEEE infinities and must behave like the reference's sticky +-127."""
+    rng = np.random.default_rng(70 + variant)
+    hw = pusch.hw_accelerator_pusch_dec_cuda(acc)
+    acc.set_decoder_variant(variant)
+    try:
+        for (bg, z, max_it) in [(1, 144, 40), (2, 208, 25), (1, 160, 12)]:
+            K, N = ob.kb(bg) * z, ob.ns(bg) * z
+            F, qm, nref = 16, 2, 0
+            E = (int((K - 2 * z - F) * 1.8) // qm) * qm
+            ops = []
+            for c in range(7):
+                if c % 3 == 0:
+                    llr = _cb_llrs(rng, bg, z, F, pusch.CRC24B, E, qm, 0, nref, 28.0)
+                    flip = rng.choice(np.arange(E // 2, E), 30, replace=False)
+                    llr[flip] = -llr[flip]
+                elif c % 3 == 1:
+                    llr = rng.choice(np.array([-127, 127, -120, 120, 119, -119], np.int8), E)
+                else:
+                    llr = np.where(rng.random(E) < 0.5, 120, -120).astype(np.int8)
+                ops.append(llr)
+            hw.reserve_queue()
+            for i, llr in enumerate(ops):
+                cfg = pusch.CbConfig(bg, qm, len(ops), 0, E, z, N, nref, K - 24 - F, F, max_it, 1, 1, 24, pusch.CB_CRC24B,
+                                     7400 + i)
+                hw.configure_operation(cfg, i)
+                assert hw.enqueue_operation(llr, None, i)
+            for i, llr in enumerate(ops):
+                bits = np.full(K // 8, 0x5A, np.uint8)
+                soft = np.zeros(N, np.int8)
+                while not hw.dequeue_operation(bits, soft, i):
+                    pass
+                crc_ok, iters = hw.read_operation_outputs(i, 7400 + i)
+                want_soft = np.zeros(N, np.int8)
+                want_bits = np.full(K // 8, 0x5A, np.uint8)
+                it = ob.port().oracle_cb_decode(ob._p8(want_bits), ob._pi(want_soft), N, ob._pi(llr), E, 1, 0, qm, nref, F,
+                                                bg, z, pusch.CRC24B, 1, max_it)
+                key = (variant, bg, z, max_it, i)
+                assert np.array_equal(soft, want_soft), key
+                assert crc_ok == (it >= 0), key
+                assert iters == (it if it >= 0 else max_it), key
+                assert np.array_equal(bits, want_bits), key
             hw.free_queue()
     finally:
         acc.set_decoder_variant(0)

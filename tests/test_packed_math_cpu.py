@@ -127,6 +127,32 @@ def test_packed_math_saturating_inputs(emu):
                 assert iters[c] == it and np.array_equal(outs[c], want), (bg, z, c, max_it)
 
 
+def test_packed_math_many_updates_of_infinite_values(emu):
+    """Full-length code words (all 46 / 42 layers, column degrees up to 30) and many iterations: a promoted soft value is
+    updated dozens of times, its binary16 representation runs up to the IEEE infinities and must stay infinite, with no
+    NaN on the way; inputs that never converge keep the decoder running to the last iteration."""
+    emu.pk_host_set_lanes_per_thread(4)
+    rng = np.random.default_rng(9)
+    for (bg, z, max_it) in [(1, 48, 40), (2, 80, 25), (1, 144, 12)]:
+        K, N = ob.kb(bg) * z, ob.ns(bg) * z
+        lanes = []
+        llr, F = make_lane(rng, bg, z, 2, 28.0)
+        bad = llr.copy()
+        flip = rng.choice(np.arange(K - 2 * z, N - 2 * z), 40, replace=False)
+        bad[flip] = -bad[flip]  # strong wrong parity bits: promoted values of both signs, no convergence for a while
+        lanes.append((bad, F))
+        lanes.append((rng.choice(np.array([-127, 127, -120, 120, 119, -119], np.int8), N - 2 * z), 0))
+        sat = np.where(rng.random(N - 2 * z) < 0.5, 120, -120).astype(np.int8)
+        lanes.append((sat, 0))
+        lanes.append((llr, F))
+        layers = 46 if bg == 1 else 42
+        outs, iters = run_group(emu, lanes, bg, z, 2, max_it, 1, layers)
+        for c, (l, Fc) in enumerate(lanes):
+            want = np.full((K + 7) // 8, 0x5A, np.uint8)
+            it, want, _ = ob.port_decode(l, bg, z, Fc, 2, max_it, want)
+            assert iters[c] == it and np.array_equal(outs[c], want), (bg, z, c, max_it, it, iters[c])
+
+
 def test_packed_math_no_scaling(emu):
     rng = np.random.default_rng(8)
     bg, z = 2, 64
