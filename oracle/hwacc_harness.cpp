@@ -167,8 +167,11 @@ int main()
   //      ids with a stride of 3 so that the code blocks of a TB do not sit in consecutive slots) --------------------------------
   hal::cuda_hwacc_pusch_dec_configuration cu_cfg = acc_cfg;
   cu_cfg.nof_harq_cb_slots                       = 8192;
-  auto                    cu_device = std::make_shared<hal::cuda_pusch_dec_device>(cu_cfg);
-  auto                    cu_factory = create_pusch_decoder_factory_cuda(cu_device, nullptr, MAX_RB, 4);
+  // Two device contexts (on one GPU here; one per GPU in a multi-GPU host): transport blocks are sharded by the rx buffer's
+  // first code-block id, and a HARQ retransmission only decodes if it lands on the context that holds its soft bits.
+  std::vector<std::shared_ptr<hal::cuda_pusch_dec_device>> cu_devices = {
+      std::make_shared<hal::cuda_pusch_dec_device>(cu_cfg), std::make_shared<hal::cuda_pusch_dec_device>(cu_cfg)};
+  auto cu_factory = create_pusch_decoder_factory_cuda(cu_devices, nullptr, MAX_RB, 4);
   std::unique_ptr<pusch_decoder> cu_decoder = cu_factory->create();
 
   // ---- oracle: reference software decoder ---------------------------------------------------------------------------------
@@ -206,11 +209,11 @@ int main()
   };
   std::mt19937 rgen(2026);
   int          failures = 0;
-  unsigned     next_abs = 0;
+  unsigned     next_abs = 0, case_no = 0; // even / odd first code-block ids alternate between the two device contexts
   for (const tb_case& c : cases) {
     unsigned nof_cbs = ldpc::compute_nof_codeblocks(units::bits(c.tbs_bits),
                                                     (c.bg == 1) ? ldpc_base_graph_type::BG1 : ldpc_base_graph_type::BG2);
-    harness_rx_buffer sw_buffer(nof_cbs, 0), hw_buffer(nof_cbs, next_abs), cu_buffer(nof_cbs, 3 * next_abs + 1, 3);
+    harness_rx_buffer sw_buffer(nof_cbs, 0), hw_buffer(nof_cbs, next_abs), cu_buffer(nof_cbs, 6 * next_abs + 2 + (case_no++ & 1), 3);
     next_abs += nof_cbs;
     std::vector<uint8_t> tb(c.tbs_bits / 8), tb_sw(tb.size()), tb_hw(tb.size()), tb_cu(tb.size()), cw(c.nof_llrs);
     for (uint8_t& b : tb) {

@@ -18,11 +18,25 @@ pusch_decoder_cuda_impl::pusch_decoder_cuda_impl(std::shared_ptr<hal::cuda_pusch
                                                  task_executor*                              executor_,
                                                  unsigned                                    nof_prb,
                                                  unsigned                                    nof_layers) :
-  device(std::move(device_)),
+  pusch_decoder_cuda_impl(std::vector<std::shared_ptr<hal::cuda_pusch_dec_device>>{std::move(device_)},
+                          executor_,
+                          nof_prb,
+                          nof_layers)
+{
+}
+
+pusch_decoder_cuda_impl::pusch_decoder_cuda_impl(std::vector<std::shared_ptr<hal::cuda_pusch_dec_device>> devices_,
+                                                 task_executor*                                           executor_,
+                                                 unsigned                                                 nof_prb,
+                                                 unsigned                                                 nof_layers) :
+  devices(std::move(devices_)),
   executor(executor_),
   softbits_capacity(pusch_constants::get_max_codeword_size(nof_prb, nof_layers).value())
 {
-  srsran_assert(device, "Invalid CUDA device context.");
+  srsran_assert(!devices.empty(), "No CUDA device context.");
+  for (const auto& d : devices) {
+    srsran_assert(d, "Invalid CUDA device context.");
+  }
   static_assert(sizeof(log_likelihood_ratio) == sizeof(int8_t), "LLRs are int8");
   softbits_buffer = static_cast<log_likelihood_ratio*>(srsran_cuda_pusch_dec_host_alloc(softbits_capacity));
   report_fatal_error_if_not(softbits_buffer != nullptr, "Cannot allocate page-locked soft-bit staging memory.");
@@ -56,6 +70,9 @@ pusch_decoder_buffer& pusch_decoder_cuda_impl::new_data(span<uint8_t>           
                 "Wrong number of codeblocks {} (expected {}).",
                 unique_rm_buffer->get_nof_codeblocks(),
                 nof_codeblocks);
+
+  // Sticky sharding: the HARQ process (its rx buffer's code-block ids) decides the GPU.
+  device = devices[unique_rm_buffer->get_absolute_codeblock_id(0) % devices.size()].get();
 
   // Reset CRCs if new data is flagged (pusch_decoder_impl.cpp:131-135). The device ignores its own flags of a slot when
   // the configuration says new data, so only the host view needs clearing.
@@ -223,21 +240,21 @@ namespace {
 class pusch_decoder_factory_cuda : public pusch_decoder_factory
 {
 public:
-  pusch_decoder_factory_cuda(std::shared_ptr<hal::cuda_pusch_dec_device> device_,
-                             task_executor*                              executor_,
-                             unsigned                                    nof_prb_,
-                             unsigned                                    nof_layers_) :
-    device(std::move(device_)), executor(executor_), nof_prb(nof_prb_), nof_layers(nof_layers_)
+  pusch_decoder_factory_cuda(std::vector<std::shared_ptr<hal::cuda_pusch_dec_device>> devices_,
+                             task_executor*                                           executor_,
+                             unsigned                                                 nof_prb_,
+                             unsigned                                                 nof_layers_) :
+    devices(std::move(devices_)), executor(executor_), nof_prb(nof_prb_), nof_layers(nof_layers_)
   {
   }
 
   std::unique_ptr<pusch_decoder> create() override
   {
-    return std::make_unique<pusch_decoder_cuda_impl>(device, executor, nof_prb, nof_layers);
+    return std::make_unique<pusch_decoder_cuda_impl>(devices, executor, nof_prb, nof_layers);
   }
 
 private:
-  std::shared_ptr<hal::cuda_pusch_dec_device> device;
+  std::vector<std::shared_ptr<hal::cuda_pusch_dec_device>> devices;
   task_executor*                              executor;
   unsigned                                    nof_prb;
   unsigned                                    nof_layers;
@@ -254,5 +271,23 @@ srsran::create_pusch_decoder_factory_cuda(std::shared_ptr<hal::cuda_pusch_dec_de
   if (!device) {
     return nullptr;
   }
-  return std::make_shared<pusch_decoder_factory_cuda>(std::move(device), executor, nof_prb, nof_layers);
+  return create_pusch_decoder_factory_cuda(
+      std::vector<std::shared_ptr<hal::cuda_pusch_dec_device>>{std::move(device)}, executor, nof_prb, nof_layers);
+}
+
+std::shared_ptr<pusch_decoder_factory>
+srsran::create_pusch_decoder_factory_cuda(std::vector<std::shared_ptr<hal::cuda_pusch_dec_device>> devices,
+                                          task_executor*                                           executor,
+                                          unsigned                                                 nof_prb,
+                                          unsigned                                                 nof_layers)
+{
+  if (devices.empty()) {
+    return nullptr;
+  }
+  for (const auto& d : devices) {
+    if (!d) {
+      return nullptr;
+    }
+  }
+  return std::make_shared<pusch_decoder_factory_cuda>(std::move(devices), executor, nof_prb, nof_layers);
 }

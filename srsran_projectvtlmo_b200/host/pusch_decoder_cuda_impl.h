@@ -15,6 +15,7 @@
 #include "srsran/support/executors/task_executor.h"
 #include <atomic>
 #include <optional>
+#include <vector>
 
 namespace srsran {
 
@@ -31,6 +32,13 @@ public:
                           task_executor*                              executor_,
                           unsigned                                    nof_prb,
                           unsigned                                    nof_layers);
+  /// Several GPUs: a transport block is decoded on devices_[first absolute code-block id % devices_.size()]. The rx buffer
+  /// of a HARQ process keeps its code-block ids from the first transmission to its release, so every retransmission finds
+  /// its soft bits on the device that holds them (sticky sharding, no device-to-device traffic).
+  pusch_decoder_cuda_impl(std::vector<std::shared_ptr<hal::cuda_pusch_dec_device>> devices_,
+                          task_executor*                                           executor_,
+                          unsigned                                                 nof_prb,
+                          unsigned                                                 nof_layers);
   ~pusch_decoder_cuda_impl() override;
 
   // See interface for the documentation.
@@ -56,8 +64,10 @@ private:
   /// Waits for the device, fills the transport block, updates the rx buffer and notifies.
   void complete(int ticket);
 
-  std::shared_ptr<hal::cuda_pusch_dec_device> device;
-  task_executor*                              executor;
+  std::vector<std::shared_ptr<hal::cuda_pusch_dec_device>> devices;
+  /// Device of the transport block in flight (chosen in new_data).
+  hal::cuda_pusch_dec_device* device = nullptr;
+  task_executor*              executor;
   /// Page-locked soft-bit staging (the UL-SCH demultiplexer writes into it through get_next_block_view).
   log_likelihood_ratio*        softbits_buffer = nullptr;
   unsigned                     softbits_capacity;
@@ -79,5 +89,11 @@ std::shared_ptr<pusch_decoder_factory> create_pusch_decoder_factory_cuda(std::sh
                                                                          task_executor* executor,
                                                                          unsigned       nof_prb,
                                                                          unsigned       nof_layers);
+/// The same over several GPUs (one device context each); nullptr if the list is empty or holds a null context.
+std::shared_ptr<pusch_decoder_factory>
+create_pusch_decoder_factory_cuda(std::vector<std::shared_ptr<hal::cuda_pusch_dec_device>> devices,
+                                  task_executor*                                           executor,
+                                  unsigned                                                 nof_prb,
+                                  unsigned                                                 nof_layers);
 
 } // namespace srsran

@@ -33,20 +33,20 @@ __global__ void kern(const uint32_t* s_in, const uint32_t* c_in, uint32_t* s_out
   }
 }
 
+/// One soft value in the decoder's storage format: the binary16 number S + 1152 (S in [-120, 120]), or an "infinite" value:
+/// the loader's +-infinity, a grown one, or an IEEE infinity.
 static uint32_t soft_lane(int mode)
 {
   int r = rand() % 100;
-  int v;
   if (r < 10) {
-    v = 0;
-  } else if (r < 15) {
-    v = (rand() & 1) ? 8192 : -8192;
-  } else if (mode == 0) {
-    v = rand() % 241 - 120;
-  } else {
-    v = rand() % 21 - 10;
+    return H_1152; // S = 0
   }
-  return (uint32_t)(v + 0x8080) & 0xffff;
+  if (r < 15) {
+    static const uint32_t inf[6] = {H_POS_INF, H_NEG_INF, 0x7c00U, 0xfc00U, 0x7a00U, 0xf9f0U};
+    return inf[rand() % 6];
+  }
+  int v = (mode == 0) ? rand() % 241 - 120 : rand() % 21 - 10;
+  return (H_1024 | (uint32_t)(v + 128)) & 0xffffU;
 }
 
 template <int DEG>
