@@ -78,7 +78,7 @@ __device__ __forceinline__ void process_check_n(uint8_t* __restrict__     soft_b
     for (int e = 0; e != DEG; ++e) {
       const uint2 te = tab_row[e];
       uint32_t    k  = j + te.y;
-      k -= __umulhi(k, zmagic) * Z;
+      k = __viaddmin_u32(k, 0U - Z, k); // (j + shift) mod Z: min(k - Z, k) on unsigned values, one VIADDMNMX
       addr[e]       = te.x + k * 8;
       const uint2 s = *reinterpret_cast<const uint2*>(soft_bytes + addr[e]);
       ck.gather(e, s.x, s.y, cj[e * Z]);
@@ -98,7 +98,7 @@ __device__ __forceinline__ void process_check_n(uint8_t* __restrict__     soft_b
     for (int e = 0; e != DEG; ++e) {
       const uint2 te = tab_row[e];
       uint32_t    k  = j + te.y;
-      k -= __umulhi(k, zmagic) * Z;
+      k = __viaddmin_u32(k, 0U - Z, k); // (j + shift) mod Z: min(k - Z, k) on unsigned values, one VIADDMNMX
       addr[e] = te.x + k * 4;
       ck.gather(e, *reinterpret_cast<const uint32_t*>(soft_bytes + addr[e]), cj[e * Z]);
     }
