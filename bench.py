@@ -223,6 +223,7 @@ def main():
     ap.add_argument("--ref-seconds", type=float, default=20.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--latency-reps", type=int, default=200)
+    ap.add_argument("--depth", type=int, default=3, help="batches in flight (1..5)")
     ap.add_argument("--clock-period-ms", type=float, default=4.0, help="NVML clock sampling period inside the timed region")
     ap.add_argument("--decoder-variant", type=int, default=0, help="0 auto, 1 general kernel only, 2 packed groups with 2 threads per check, 3 one code block per CTA packed kernel everywhere, 4 pairs of code blocks per CTA (two CTAs per SM)")
     args = ap.parse_args()
@@ -298,16 +299,16 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    DEPTH = 3  # batches in flight (the handle has 4 batch contexts)
+    DEPTH = args.depth  # batches in flight (the handle has 6 batch contexts)
 
     # ---- warm-up + correctness gate: every TB of the warm-up must decode to its payload; every batch context is touched ----
-    for i in range(max(args.warmup, 4)):
+    for i in range(max(args.warmup, 6)):  # every batch context of the handle allocates its buffers on first use
         tk = step_device(i)
         for k, t in enumerate(tk):
             r = pusch.poll_tb(acc, t, tb_out)
             if i == 0 and r.tb_crc_ok and not np.array_equal(tb_out, payloads[k % len(payloads)]):
                 raise SystemExit("decoded TB differs from the transmitted payload")
-    for i in range(max(args.warmup, 4)):
+    for i in range(max(args.warmup, 6)):
         drain(step_host(i))
 
     # ---- value: device-resident inputs, K steps back to back (<= DEPTH in flight), device stopwatch ---------------------
@@ -412,11 +413,11 @@ def main():
             "config": {"workload": w["name"], "tbs_bits": tbs, "codeblocks_per_tb": ncb, "tbs_per_step_per_gpu": B,
                        "lifting_size": 384, "base_graph": 1, "max_iterations": w["max_it"], "early_stop": True,
                        "mu": args.mu, "decoder_variant": args.decoder_variant, "mean_iterations": mean_it, "tb_crc_ok_fraction": ok_tbs / (B * args.steps),
-                       "timing": "device stopwatch (CUDA events on the library streams) over all steps, <= 3 batches in flight; "
+                       "timing": f"device stopwatch (CUDA events on the library streams) over all steps, <= {DEPTH} batches in flight; "
                                  "inputs alternate between two sets larger than L2 (no flush needed)"},
             "e2e": {"value": e2e, "unit": "Gbit/s", "h2d_bytes_per_step": B * nllr,
                     "d2h_bytes_per_step": B * (tbs // 8 + 3 + 8 + ncb * 16),
-                    "note": "pinned host LLRs -> submit_tbs -> poll_tb (TB bytes + results), <= 3 batches in flight, wall clock"},
+                    "note": f"pinned host LLRs -> submit_tbs -> poll_tb (TB bytes + results), <= {DEPTH} batches in flight, wall clock"},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "stage_ms": {"h2d_descriptors": stage_ms[0], "rate_dematch": stage_ms[1], "ldpc_decode": stage_ms[2],

@@ -32,7 +32,7 @@ static inline double prof_now() { return std::chrono::duration<double, std::micr
 
 thread_local std::string g_create_error;
 
-constexpr int      NOF_CONTEXTS   = 4;
+constexpr int      NOF_CONTEXTS   = 6;
 constexpr uint32_t MAX_TBS_PER_CTX = 1024;
 
 template <typename T>
