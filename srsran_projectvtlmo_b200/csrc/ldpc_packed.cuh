@@ -1,17 +1,20 @@
-// Kernel 2b: packed layered LDPC decoder - FOUR code blocks per CTA, one thread per lifted check, the four code blocks
-// in the 16-bit lanes of two registers (arithmetic: ldpc_packed_math.h, verified on the CPU against the oracle by
+// Kernel 2b: packed layered LDPC decoder - FOUR (or two) code blocks per CTA, one thread per lifted check, the code blocks
+// in the binary16 lanes of two (one) registers (arithmetic: ldpc_packed_math.h, verified on the CPU against the oracle by
 // tests/test_packed_math_cpu.py). Used for groups of code blocks that share base graph, lifting size (Z >= 144,
 // Z % 16 == 0), CRC, mode, iteration limit and scaling, whose state fits in shared memory - i.e. the high-rate PUSCH
-// transport blocks of BASELINE config 2 (BG1, Z = 384, 4 layers). Everything else runs on ldpc_decode_kernel.
+// transport blocks of BASELINE config 2 (BG1, Z = 384, 4 layers). Single code blocks run on ldpc_decode_q4_kernel (four
+// lifted checks of ONE code block per thread, same arithmetic), the remaining shapes on ldpc_decode_kernel.
 //
 // The number of layers is NOT derived from the data here (ldpc_decoder_impl.cpp:86-114 trims trailing zero LLRs): the
 // host's upper bound (layer_cap) is processed, because a layer whose extension node holds only zero LLRs is a no-op
 // for every other node (min1 = 0 => all its messages are 0, soft' = clamp(soft - 0) + 0), see DESIGN.md.
 //
-// Shared memory per CTA:  tab   per edge: node base | shift << 16
-//                         soft  (K_b + L) * Z x 8 bytes: 4 biased u16 lanes per variable node lift
-//                         c2v   edges * Z x 4 bytes: 4 biased u8 lanes per lifted edge, check order (thread-private)
-//                         hb    4 x K/32 words of hard decisions, crc tables 4 x 256 words, misc
+// Shared memory per CTA (NR = registers per thread, 2 or 1):
+//   tab    per edge: (byte offset of the variable node in `soft`, circulant shift)
+//   soft   (K_b + L) * Z x 4 NR bytes: the halves S + 1152 of the 2 NR code blocks per variable-node lift
+//   c2v    edges * Z x 2 NR bytes: the message bytes c + 128 of the 2 NR code blocks per lifted edge, check order
+//          (thread-private between barriers)
+//   hb     4 x K/32 words of hard decisions, crc byte tables 4 x 256 words, flags / CRC shares, four lane_state records
 #pragma once
 #include "ldpc_packed_math.h"
 
