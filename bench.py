@@ -106,6 +106,23 @@ class ClockSampler:
                 "samples": len(sm), "source": "NVML, sampled inside the timed value region"}
 
 
+def bind_to_gpu_cpus(index):
+    """Pins this process (and the threads it starts later, CUDA's included) to the CPUs NVML names as closest to the GPU, before
+    anything is allocated: page-locked buffers then land on the GPU's NUMA node and launches do not cross sockets. What
+    `numactl` does for a one-process-per-GPU job; a no-op where the container's cpuset does not allow it."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        try:
+            h = pynvml.nvmlDeviceGetHandleByUUID("GPU-" + str(torch_uuid(index)))
+        except Exception:
+            h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        pynvml.nvmlDeviceSetCpuAffinity(h)
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return None
+
+
 def torch_uuid(index):
     import torch
     return torch.cuda.get_device_properties(index).uuid
@@ -223,6 +240,7 @@ def main():
     ap.add_argument("--ref-seconds", type=float, default=20.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--latency-reps", type=int, default=200)
+    ap.add_argument("--bind-cpus", type=int, default=1, help="1: pin the process to the GPU's closest CPUs (NVML), 0: leave it")
     ap.add_argument("--depth", type=int, default=3, help="batches in flight (1..5)")
     ap.add_argument("--clock-period-ms", type=float, default=4.0, help="NVML clock sampling period inside the timed region")
     ap.add_argument("--decoder-variant", type=int, default=0, help="0 auto, 1 general kernel only, 2 packed groups with 2 threads per check, 3 one code block per CTA packed kernel everywhere, 4 pairs of code blocks per CTA (two CTAs per SM)")
@@ -244,6 +262,8 @@ def main():
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the product has no CPU fallback")
+    all_cpus = os.sched_getaffinity(0)
+    ncpus_bound = bind_to_gpu_cpus(local_rank) if args.bind_cpus else None
     torch.cuda.set_device(local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
@@ -412,7 +432,7 @@ def main():
             "scaling": "weak", "vs_baseline": None, "dtype": "int8", "data": "synthetic",
             "config": {"workload": w["name"], "tbs_bits": tbs, "codeblocks_per_tb": ncb, "tbs_per_step_per_gpu": B,
                        "lifting_size": 384, "base_graph": 1, "max_iterations": w["max_it"], "early_stop": True,
-                       "mu": args.mu, "decoder_variant": args.decoder_variant, "mean_iterations": mean_it, "tb_crc_ok_fraction": ok_tbs / (B * args.steps),
+                       "mu": args.mu, "decoder_variant": args.decoder_variant, "cpus_bound_to_gpu": ncpus_bound, "mean_iterations": mean_it, "tb_crc_ok_fraction": ok_tbs / (B * args.steps),
                        "timing": f"device stopwatch (CUDA events on the library streams) over all steps, <= {DEPTH} batches in flight; "
                                  "inputs alternate between two sets larger than L2 (no flush needed)"},
             "e2e": {"value": e2e, "unit": "Gbit/s", "h2d_bytes_per_step": B * nllr,
@@ -455,6 +475,7 @@ def main():
                               "what": "one TB, host LLRs -> TB bytes, idle GPU, wall clock; slot budget 500 us"},
         }
         if n_gpus == 1 and not args.no_cpu_baseline:
+            os.sched_setaffinity(0, all_cpus)  # the CPU baseline gets every host thread, not only the GPU's neighbours
             line["cpu_baseline"] = cpu_baseline(args, tbs, nllr, sets[0][0])
         print(json.dumps(line), flush=True)
 
