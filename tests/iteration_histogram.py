@@ -8,7 +8,7 @@ from pathlib import Path
 
 import numpy as np
 
-sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
+sys.path.insert(0, str(Path(__file__).resolve().parent.parent))  # test-side analysis: the only place besides tests that may use oracle/
 import bench  # noqa: E402
 from oracle import bindings as ob  # noqa: E402
 from srsran_projectvtlmo_b200 import pusch  # noqa: E402
