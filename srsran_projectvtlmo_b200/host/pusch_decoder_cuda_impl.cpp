@@ -92,7 +92,11 @@ void pusch_decoder_cuda_impl::set_nof_softbits(units::bits nof_softbits)
   // From now on every block is copied to the device as it arrives.
   std::lock_guard<std::mutex> lock(device->mutex());
   ingest_stream = srsran_cuda_pusch_dec_stream_begin(device->get(), nof_softbits.value());
-  report_fatal_error_if_not(ingest_stream >= 0, "CUDA PUSCH decoder: {}", srsran_cuda_pusch_dec_last_error(device->get()));
+  if (ingest_stream < 0) {
+    // Every ingest stream of the device is taken by other decoders: this transport block is copied in one piece at
+    // on_end_softbits instead (same result, only the overlap with the reception is lost).
+    ingest_stream = -1;
+  }
 }
 
 span<log_likelihood_ratio> pusch_decoder_cuda_impl::get_next_block_view(unsigned block_size)
