@@ -16,12 +16,16 @@ HERE = Path(__file__).resolve().parent / "host_emul"
 MULT = 52428  # (uint16)(0.8f * 65536), avx512_support.h:69-83
 
 
-@pytest.fixture(scope="module")
-def emu():
+def load_emu():
     subprocess.run(["make", "-s", "-C", str(HERE)], check=True)
     lib = C.CDLL(str(HERE / "libpacked_math_host.so"))
     lib.pk_host_decode_group.restype = C.c_int
     return lib
+
+
+@pytest.fixture(scope="module")
+def emu():
+    return load_emu()
 
 
 def make_lane(rng, bg, z, crc_poly, mu):
