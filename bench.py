@@ -432,7 +432,7 @@ def main():
             "scaling": "weak", "vs_baseline": None, "dtype": "int8", "data": "synthetic",
             "config": {"workload": w["name"], "tbs_bits": tbs, "codeblocks_per_tb": ncb, "tbs_per_step_per_gpu": B,
                        "lifting_size": 384, "base_graph": 1, "max_iterations": w["max_it"], "early_stop": True,
-                       "mu": args.mu, "decoder_variant": args.decoder_variant, "cpus_bound_to_gpu": ncpus_bound, "mean_iterations": mean_it, "tb_crc_ok_fraction": ok_tbs / (B * args.steps),
+                       "mu": args.mu, "arithmetic": "int8 LLR algebra of the reference, bit-exact; the decoder holds the (integer) values in binary16 lanes", "decoder_variant": args.decoder_variant, "cpus_bound_to_gpu": ncpus_bound, "mean_iterations": mean_it, "tb_crc_ok_fraction": ok_tbs / (B * args.steps),
                        "timing": f"device stopwatch (CUDA events on the library streams) over all steps, <= {DEPTH} batches in flight; "
                                  "inputs alternate between two sets larger than L2 (no flush needed)"},
             "e2e": {"value": e2e, "unit": "Gbit/s", "h2d_bytes_per_step": B * nllr,
