@@ -31,8 +31,33 @@ struct dec4_layout {
   uint32_t tab_off, soft_off, c2v_off, hb_off, crc_off, misc_off, total;
 };
 
-/// `lanes` = code blocks per CTA (4, or 2 for the single-plane variant of ldpc_decode4h_kernel).
-__host__ __device__ inline dec4_layout dec4_smem_layout(uint32_t bg, uint32_t Z, uint32_t layer_cap, uint32_t lanes = 4)
+/// Columns of tensor memory one thread needs for its messages of layers [0, layer_cap): one 32-bit column per lifted
+/// edge (the message bytes of the four code blocks), every layer padded to a multiple of four columns (the granule of the
+/// tcgen05.ld / tcgen05.st shapes used).
+__host__ __device__ inline uint32_t dec4_tmem_cols(uint32_t bg, uint32_t layer_cap)
+{
+  uint32_t n = 0;
+  for (uint32_t l = 0; l != layer_cap; ++l) {
+#ifdef __CUDA_ARCH__
+    uint32_t deg = c_row_ptr[bg - 1][l + 1] - c_row_ptr[bg - 1][l];
+#else
+    const uint16_t* rp  = (bg == 1) ? NR_BG1_ROW_PTR : NR_BG2_ROW_PTR;
+    uint32_t        deg = rp[l + 1] - rp[l];
+#endif
+    n += (deg + 3U) & ~3U;
+  }
+  return n;
+}
+
+/// Tensor-memory columns per warp when `tm_cols` columns are shared by the TPC / 128 warps of a lane quadrant.
+__host__ __device__ inline uint32_t dec4_tmem_cols_per_warp(uint32_t tm_cols, uint32_t tpc)
+{
+  return (tm_cols / (tpc / 128U)) & ~3U;
+}
+
+/// `lanes` = code blocks per CTA (4 or 2). `tmem`: the messages live in tensor memory, not in shared memory.
+__host__ __device__ inline dec4_layout dec4_smem_layout(uint32_t bg, uint32_t Z, uint32_t layer_cap, uint32_t lanes = 4,
+                                                         bool tmem = false)
 {
 #ifdef __CUDA_ARCH__
   uint32_t nedges = c_row_ptr[bg - 1][layer_cap];
@@ -44,19 +69,14 @@ __host__ __device__ inline dec4_layout dec4_smem_layout(uint32_t bg, uint32_t Z,
   l.tab_off  = 0;
   l.soft_off = (nedges * 8 + 15) & ~15U;
   l.c2v_off  = l.soft_off + (Kb + layer_cap) * Z * 2 * lanes;
-  l.hb_off   = l.c2v_off + nedges * Z * lanes;
+  l.hb_off   = l.c2v_off + (tmem ? 0U : nedges * Z * lanes);
   l.crc_off  = l.hb_off + 4 * (Kb * Z / 32) * 4;
   l.misc_off = l.crc_off + 4 * 256 * 4;
   l.total    = l.misc_off + 128 + 4 * 64; // 32 flag / scratch words + four lane_state records
+  if (tmem) {
+    l.total += 112; // first message column of every layer (up to 46 + 1 entries of 16 bits) + the TMEM base address
+  }
   return l;
-}
-
-/// Soft-buffer index of edge `te` = (node base, shift) for lifted check j: base + (j + shift) mod Z, the modulo by a
-/// multiply-high so that the address arithmetic issues on the FMA pipe (the ALU pipe is the bottleneck of this kernel).
-__device__ __forceinline__ uint32_t edge_addr(uint2 te, uint32_t j, uint32_t Z, uint32_t zmagic)
-{
-  uint32_t k = j + te.y;
-  return te.x + k - __umulhi(k, zmagic) * Z;
 }
 
 /// One lifted check (thread j) of a layer of degree DEG for the 2 * NR code blocks of the group (NR registers of two lanes
@@ -115,6 +135,191 @@ __device__ __forceinline__ void process_check_n(uint8_t* __restrict__     soft_b
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Tensor memory as the message store. The check-to-variable messages are thread-private (thread j owns lifted check j of
+// every layer), 117 KB per group of four BG1 / Z = 384 / 4-layer code blocks - more than half of the shared memory the
+// kernel needs, and the reason only one CTA fits on an SM. Blackwell's tensor memory (256 KB per SM, 128 lanes x 512
+// 32-bit columns, otherwise idle in a kernel without tcgen05.mma) has exactly that access shape: a warp reads and writes
+// the 32 lanes of its quadrant (warp % 4), one lane per thread, any run of columns per instruction (tcgen05.ld / st
+// 32x32b.xN -> LDTM / STTM). Thread (warp w, lane i) keeps its messages in TMEM lane 32 (w % 4) + i, columns
+// [(w / 4) * CPW, ...): one column per lifted edge (the four message bytes of the four code blocks), a whole layer is one
+// or two instructions instead of DEG shared-memory loads and stores. With the messages gone, shared memory holds the soft
+// values only (80 KB + 9 KB of hard bits / CRC tables) and two CTAs share an SM.
+// ---------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void tmem_alloc(uint32_t* smem_dst, uint32_t ncols)
+{
+  const uint32_t dst = (uint32_t)__cvta_generic_to_shared(smem_dst);
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols)
+{
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tmem_fence_before_sync()
+{
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_fence_after_sync()
+{
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_wait_ld()
+{
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_wait_st()
+{
+  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
+/// N consecutive columns of the calling thread's TMEM lane -> r[0..N) (N = 4, 8, 16). Warp-collective.
+template <int N>
+__device__ __forceinline__ void tmem_ld(uint32_t taddr, uint32_t* r)
+{
+  static_assert(N == 4 || N == 8 || N == 16, "unsupported shape");
+  if constexpr (N == 4) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+                 : "r"(taddr));
+  } else if constexpr (N == 8) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr));
+  } else {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+  }
+}
+template <int N>
+__device__ __forceinline__ void tmem_st(uint32_t taddr, const uint32_t* r)
+{
+  static_assert(N == 4 || N == 8 || N == 16, "unsupported shape");
+  if constexpr (N == 4) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%2,%3,%4};" ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]),
+                 "r"(r[3])
+                 : "memory");
+  } else if constexpr (N == 8) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(taddr), "r"(r[0]), "r"(r[1]),
+                 "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+                 : "memory");
+  } else {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(
+                     taddr),
+                 "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+                 "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+                 : "memory");
+  }
+}
+/// A run of DP (multiple of 4, <= 20) columns as at most two instructions.
+template <int DP>
+__device__ __forceinline__ void tmem_ld_row(uint32_t taddr, uint32_t* r)
+{
+  if constexpr (DP == 4) {
+    tmem_ld<4>(taddr, r);
+  } else if constexpr (DP == 8) {
+    tmem_ld<8>(taddr, r);
+  } else if constexpr (DP == 12) {
+    tmem_ld<8>(taddr, r);
+    tmem_ld<4>(taddr + 8, r + 8);
+  } else {
+    static_assert(DP == 20, "unsupported row length");
+    tmem_ld<16>(taddr, r);
+    tmem_ld<4>(taddr + 16, r + 16);
+  }
+}
+template <int DP>
+__device__ __forceinline__ void tmem_st_row(uint32_t taddr, const uint32_t* r)
+{
+  if constexpr (DP == 4) {
+    tmem_st<4>(taddr, r);
+  } else if constexpr (DP == 8) {
+    tmem_st<8>(taddr, r);
+  } else if constexpr (DP == 12) {
+    tmem_st<8>(taddr, r);
+    tmem_st<4>(taddr + 8, r + 8);
+  } else {
+    static_assert(DP == 20, "unsupported row length");
+    tmem_st<16>(taddr, r);
+    tmem_st<4>(taddr + 16, r + 16);
+  }
+}
+
+/// One lifted check (thread j) of a layer of degree DEG for four code blocks, messages in tensor memory (`taddr` = the
+/// calling warp's lane quadrant and the first column of this layer). The v2c values are not kept in registers between the
+/// two passes: the first pass leaves them in the soft array IN PLACE of the soft values they were computed from (the
+/// lifted variable (column, (j + shift) mod Z) is touched by this thread only during a layer), the second pass reads them
+/// back and overwrites them with the new soft values. That costs one 64-bit store and load per edge and saves 38
+/// registers, which is what lets two 384-thread CTAs (80 registers per thread) share an SM. The last QR edges keep their
+/// v2c in registers.
+template <int DEG, int QR>
+__device__ __forceinline__ void process_check_t(uint8_t* __restrict__     soft_bytes,
+                                                uint32_t                  taddr,
+                                                const uint2* __restrict__ tab_row,
+                                                uint32_t                  j,
+                                                uint32_t                  Z,
+                                                uint32_t                  mult)
+{
+  constexpr int    DP = (DEG + 3) & ~3;
+  constexpr int    QS = (QR < DEG) ? DEG - QR : 0; // edges [0, QS) park their v2c in shared memory
+  uint32_t         addr[DEG];
+  uint32_t         cw[DP];
+  uint32_t         qk[(DEG - QS) > 0 ? (DEG - QS) : 1][2];
+  pk::check_acc<2> ck;
+  tmem_ld_row<DP>(taddr, cw);
+  ck.begin();
+  tmem_wait_ld();
+#pragma unroll
+  for (int e = 0; e != DEG; ++e) {
+    const uint2 te = tab_row[e];
+    uint32_t    k  = j + te.y;
+    k = __viaddmin_u32(k, 0U - Z, k); // (j + shift) mod Z: min(k - Z, k) on unsigned values, one VIADDMNMX
+    addr[e]        = te.x + k * 8;
+    const uint2 sv = *reinterpret_cast<const uint2*>(soft_bytes + addr[e]);
+    uint32_t    s[2] = {sv.x, sv.y};
+    uint32_t    c[2] = {pk::prmt2(cw[e], 0x64646464U, 0x4240U), pk::prmt2(cw[e], 0x64646464U, 0x4341U)};
+    uint32_t    q[2];
+    ck.gather_q(s, c, q);
+    if (e < QS) {
+      *reinterpret_cast<uint2*>(soft_bytes + addr[e]) = make_uint2(q[0], q[1]);
+    } else {
+      qk[e - QS][0] = q[0];
+      qk[e - QS][1] = q[1];
+    }
+  }
+  ck.reduce(mult);
+#pragma unroll
+  for (int e = 0; e != DEG; ++e) {
+    uint32_t q[2], sn[2], cn[2];
+    if (e < QS) {
+      const uint2 qv = *reinterpret_cast<const uint2*>(soft_bytes + addr[e]);
+      q[0]           = qv.x;
+      q[1]           = qv.y;
+    } else {
+      q[0] = qk[e - QS][0];
+      q[1] = qk[e - QS][1];
+    }
+    ck.scatter_q(q, sn, cn);
+    cw[e]                                           = pk::prmt2(cn[0], cn[1], 0x6240U);
+    *reinterpret_cast<uint2*>(soft_bytes + addr[e]) = make_uint2(sn[0], sn[1]);
+  }
+#pragma unroll
+  for (int e = DEG; e < DP; ++e) {
+    cw[e] = pk::C2V_ZERO4;
+  }
+  tmem_st_row<DP>(taddr, cw);
+  // The messages are read again one iteration (several barriers) later; the wait makes the stores complete before the
+  // layer barrier, which is the ordering the tcgen05 memory model asks for between a store and a later load.
+  tmem_wait_st();
+}
+
+#ifndef DEC4T_QR
+#define DEC4T_QR 0
+#endif
+
 /// Per code block state of a packed group, kept in shared memory so that it does not occupy registers in the layer loop.
 struct lane_state {
   const int8_t* src;       ///< decoder input (HARQ slot)
@@ -139,14 +344,18 @@ static_assert(sizeof(lane_state) == 64, "lane_state is 64 bytes");
 /// CTA with half the shared memory, two CTAs per SM - for groups whose state does not fit four code blocks (HARQ
 /// retransmissions whose combined buffer spans many layers) and for small batches (a single transport block spreads over
 /// twice as many SMs).
-template <int TPC, int ZT = 0, int NR = 2>
-__global__ void __launch_bounds__((NR == 2) ? TPC + DEC4_LB_EXTRA : TPC, (NR == 2) ? 1 : 2) ldpc_decode4_kernel(const cb_desc* __restrict__ descs,
+/// TM: the messages live in tensor memory (`tm_cols` columns allocated by the CTA: 256 -> two CTAs per SM, 512 -> one),
+/// the v2c values pass through the soft array, 80 registers per thread: two four-code-block CTAs (24 warps) per SM.
+template <int TPC, int ZT = 0, int NR = 2, int TM = 0>
+__global__ void __launch_bounds__((NR == 2 && !TM) ? TPC + DEC4_LB_EXTRA : TPC, (NR == 2 && !TM) ? 1 : 2) ldpc_decode4_kernel(const cb_desc* __restrict__ descs,
                                                                const grp_desc* __restrict__ groups,
                                                                cb_result* __restrict__ results,
                                                                const int8_t* __restrict__ soft_base,
                                                                uint8_t* __restrict__ bits_base,
-                                                               uint32_t* __restrict__ crc_flags)
+                                                               uint32_t* __restrict__ crc_flags,
+                                                               uint32_t tm_cols)
 {
+  static_assert(!TM || NR == 2, "the tensor-memory variant packs four code blocks per thread");
   extern __shared__ __align__(16) uint8_t smem_raw[];
   const int       t    = threadIdx.x;
   const int       lane = t & 31;
@@ -163,14 +372,20 @@ __global__ void __launch_bounds__((NR == 2) ? TPC + DEC4_LB_EXTRA : TPC, (NR == 
   const int       poly = d0.crc_poly;
   const uint32_t  HBW  = K / 32;
 
-  const dec4_layout lay  = dec4_smem_layout(bg, Z, L, NC);
+  const dec4_layout lay  = dec4_smem_layout(bg, Z, L, NC, TM != 0);
   uint2*            tab  = reinterpret_cast<uint2*>(smem_raw + lay.tab_off);
   uint8_t*          soft = smem_raw + lay.soft_off; // SE bytes per variable lift
-  uint8_t*          c2v  = smem_raw + lay.c2v_off;  // CE bytes per lifted edge, check order
+  uint8_t*          c2v  = smem_raw + lay.c2v_off;  // CE bytes per lifted edge, check order (TM: unused)
   uint32_t*         hb   = reinterpret_cast<uint32_t*>(smem_raw + lay.hb_off);
   uint32_t*         tabs = reinterpret_cast<uint32_t*>(smem_raw + lay.crc_off);
   uint32_t*         misc = reinterpret_cast<uint32_t*>(smem_raw + lay.misc_off);
   lane_state*       st   = reinterpret_cast<lane_state*>(smem_raw + lay.misc_off + 128);
+  // TM: first message column of every layer, then the TMEM base address the allocation returned.
+  uint16_t*         lcol   = reinterpret_cast<uint16_t*>(smem_raw + lay.misc_off + 128 + 4 * 64);
+  uint32_t*         tm_ptr = reinterpret_cast<uint32_t*>(smem_raw + lay.misc_off + 128 + 4 * 64 + 96);
+  (void)c2v;
+  (void)lcol;
+  (void)tm_ptr;
   // misc: [0..3] any non-zero input, [4..7] / [8..11] any zero soft bit (even / odd check rounds), [16..16+NW) CRC shares
 
   // ---- per code block setup (one thread each; the state lives in shared memory, not in registers) ---------------------------
@@ -226,6 +441,16 @@ __global__ void __launch_bounds__((NR == 2) ? TPC + DEC4_LB_EXTRA : TPC, (NR == 
   for (uint32_t e = t; e < nedges; e += TPC) {
     tab[e] = make_uint2((uint32_t)c_col[bg - 1][e] * Z * SE, c_shift[bg - 1][d0.ils][e] % Z);
   }
+  if constexpr (TM != 0) {
+    // Tensor memory for the messages (every thread of the CTA returns together above, so the allocation is always paired
+    // with the release at the end). Two co-resident CTAs take 256 columns each; nothing else on the SM allocates.
+    if (warp == 0) {
+      tmem_alloc(tm_ptr, tm_cols);
+    }
+    if (t <= (int)L) {
+      lcol[t] = (uint16_t)dec4_tmem_cols(bg, (uint32_t)t);
+    }
+  }
   {
     // Input of the code blocks, 16 variable nodes per code block and step (Z % 16 == 0): the 128-bit loads of a
     // step are all in flight together, the messages are cleared while they travel.
@@ -264,7 +489,7 @@ __global__ void __launch_bounds__((NR == 2) ? TPC + DEC4_LB_EXTRA : TPC, (NR == 
     };
     uint4 w[NC];
     fetch(t, w);
-    {
+    if constexpr (TM == 0) {
       uint4*         c4 = reinterpret_cast<uint4*>(c2v);
       const uint32_t n4 = nedges * Z * CE / 16;
       const uint4    zz = make_uint4(pk::C2V_ZERO4, pk::C2V_ZERO4, pk::C2V_ZERO4, pk::C2V_ZERO4);
@@ -319,7 +544,22 @@ __global__ void __launch_bounds__((NR == 2) ? TPC + DEC4_LB_EXTRA : TPC, (NR == 
       }
     }
   }
+  if constexpr (TM != 0) {
+    tmem_fence_before_sync();
+  }
   __syncthreads();
+  uint32_t tm_warp = 0; // TMEM address of this warp's lane quadrant and column range
+  if constexpr (TM != 0) {
+    tmem_fence_after_sync();
+    tm_warp = *tm_ptr + ((uint32_t)(warp & 3) << 21) + (uint32_t)(warp >> 2) * dec4_tmem_cols_per_warp(tm_cols, TPC);
+    // Messages of the first iteration: zero (byte 0x80 per code block).
+    uint32_t zz[4] = {pk::C2V_ZERO4, pk::C2V_ZERO4, pk::C2V_ZERO4, pk::C2V_ZERO4};
+    const uint32_t used = lcol[L];
+    for (uint32_t col = 0; col < used; col += 4) {
+      tmem_st<4>(tm_warp + col, zz);
+    }
+    tmem_wait_st();
+  }
   // Code blocks that are not decoded: not live, or all-zero input with early stop (the reference returns before touching
   // the output, ldpc_decoder_impl.cpp:88-94). Every thread keeps the same mask of finished code blocks.
   uint32_t done_mask = 0;
@@ -345,7 +585,42 @@ __global__ void __launch_bounds__((NR == 2) ? TPC + DEC4_LB_EXTRA : TPC, (NR == 
     for (uint32_t l = 0; l != L; ++l) {
       uint32_t e0  = c_row_ptr[bg - 1][l];
       int      deg = (int)c_row_ptr[bg - 1][l + 1] - (int)e0;
-      if (j < Z) {
+      if constexpr (TM != 0) {
+        // Z is a multiple of 32 here: whole warps are in or out (tcgen05.ld / st are warp-collective).
+        if (j < Z) {
+          const uint2*   tab_row = tab + e0;
+          const uint32_t ta      = tm_warp + lcol[l];
+          switch (deg) {
+            case 3:
+              process_check_t<3, DEC4T_QR>(soft, ta, tab_row, j, Z, mult);
+              break;
+            case 4:
+              process_check_t<4, DEC4T_QR>(soft, ta, tab_row, j, Z, mult);
+              break;
+            case 5:
+              process_check_t<5, DEC4T_QR>(soft, ta, tab_row, j, Z, mult);
+              break;
+            case 6:
+              process_check_t<6, DEC4T_QR>(soft, ta, tab_row, j, Z, mult);
+              break;
+            case 7:
+              process_check_t<7, DEC4T_QR>(soft, ta, tab_row, j, Z, mult);
+              break;
+            case 8:
+              process_check_t<8, DEC4T_QR>(soft, ta, tab_row, j, Z, mult);
+              break;
+            case 9:
+              process_check_t<9, DEC4T_QR>(soft, ta, tab_row, j, Z, mult);
+              break;
+            case 10:
+              process_check_t<10, DEC4T_QR>(soft, ta, tab_row, j, Z, mult);
+              break;
+            default:
+              process_check_t<19, DEC4T_QR>(soft, ta, tab_row, j, Z, mult);
+              break;
+          }
+        }
+      } else if (j < Z) {
         uint8_t*     c2v_row = c2v + ((size_t)e0 * Z + j) * CE;
         const uint2* tab_row = tab + e0;
         uint8_t*     sb      = soft;
@@ -509,312 +784,12 @@ __global__ void __launch_bounds__((NR == 2) ? TPC + DEC4_LB_EXTRA : TPC, (NR == 
       crc_flags[st[t].slot] = st[t].crc_ok;
     }
   }
-}
-
-// ---------------------------------------------------------------------------------------------------------------------
-// Kernel 2c: same four-code-block group per CTA, but TWO threads per lifted check (2 x TPC threads): thread (h, j) owns
-// code blocks h and h + 2 (one register of two 16-bit lanes). Twice the warps per scheduler (6 instead of 3) and half the
-// registers per thread hide the fixed ALU / shared-memory latencies the 4-lanes-per-thread kernel stalls on; the price is
-// one extra address computation and narrower shared-memory accesses per edge. Shared memory holds two planes of soft
-// values (4 bytes per variable lift each) and two planes of messages (2 bytes per lifted edge each).
-// ---------------------------------------------------------------------------------------------------------------------
-template <int DEG>
-__device__ __forceinline__ void process_check2(uint32_t* __restrict__    soft,
-                                               uint16_t* __restrict__    c2v_row,
-                                               const uint2* __restrict__ tab_row,
-                                               uint32_t                  j,
-                                               uint32_t                  Z,
-                                               uint32_t                  zmagic,
-                                               uint32_t                  mult)
-{
-  pk::check2<DEG> ck;
-  ck.begin();
-#pragma unroll
-  for (int e = 0; e != DEG; ++e) {
-    ck.gather(e, soft[edge_addr(tab_row[e], j, Z, zmagic)], c2v_row[e * Z + j]);
-  }
-  ck.reduce(mult);
-#pragma unroll
-  for (int e = 0; e != DEG; ++e) {
-    uint32_t s0;
-    c2v_row[e * Z + j]                        = (uint16_t)ck.scatter(e, s0);
-    soft[edge_addr(tab_row[e], j, Z, zmagic)] = s0;
-  }
-}
-
-/// NP = number of planes: 2 -> four code blocks per CTA on 2 x TPC threads, 1 -> two code blocks per CTA on TPC threads
-/// (half the shared memory: groups whose state does not fit four code blocks, e.g. HARQ retransmissions with many layers).
-template <int TPC, int NP>
-__global__ void __launch_bounds__(NP * TPC, (NP == 1) ? 2 : 1) ldpc_decode4h_kernel(const cb_desc* __restrict__ descs,
-                                                                     const grp_desc* __restrict__ groups,
-                                                                     cb_result* __restrict__ results,
-                                                                     const int8_t* __restrict__ soft_base,
-                                                                     uint8_t* __restrict__ bits_base,
-                                                                     uint32_t* __restrict__ crc_flags)
-{
-  extern __shared__ __align__(16) uint8_t smem_raw[];
-  constexpr int  NT   = NP * TPC;
-  constexpr int  NC   = 2 * NP; // code blocks per CTA
-  constexpr int  NW   = NT / 32;
-  const int      t    = threadIdx.x;
-  const int      lane = t & 31;
-  const int      warp = __shfl_sync(0xffffffffU, t >> 5, 0);
-  const int      h    = warp / (NW / NP); // plane: code blocks h and h + NP
-  const grp_desc& g   = groups[blockIdx.x];
-  const cb_desc& d0   = descs[g.cb[0]];
-  const uint32_t Z = d0.Z, bg = d0.bg, Kb = (bg == 1) ? 22 : 10, K = Kb * Z, L = g.layer_cap;
-  const uint32_t mode = d0.mode, max_it = d0.max_it, mult = d0.scale_mult;
-  const int      poly = d0.crc_poly;
-  const uint32_t HBW  = K / 32;
-  const uint32_t nvar = (Kb + L) * Z;
-
-  const dec4_layout lay    = dec4_smem_layout(bg, Z, L, NC);
-  uint2*            tab    = reinterpret_cast<uint2*>(smem_raw + lay.tab_off);
-  uint32_t*         soft   = reinterpret_cast<uint32_t*>(smem_raw + lay.soft_off) + (size_t)h * nvar;
-  const uint32_t    nedges = c_row_ptr[bg - 1][L];
-  uint16_t*         c2v    = reinterpret_cast<uint16_t*>(smem_raw + lay.c2v_off) + (size_t)h * nedges * Z;
-  uint32_t*         hb     = reinterpret_cast<uint32_t*>(smem_raw + lay.hb_off);
-  uint32_t*         tabs   = reinterpret_cast<uint32_t*>(smem_raw + lay.crc_off);
-  uint32_t*         misc   = reinterpret_cast<uint32_t*>(smem_raw + lay.misc_off);
-  lane_state*       st     = reinterpret_cast<lane_state*>(smem_raw + lay.misc_off + 64);
-  // misc: [0..3] any non-zero input, [4..7] any zero soft bit, [8..11] crc ok of this round, [12] nothing left to decode
-
-  // ---- per code block setup (one thread each) ------------------------------------------------------------------------------
-  if (t < 16) {
-    misc[t] = 0;
-  }
-  if (t < 4) {
-    const int      c      = t;
-    const bool     valid  = c < (int)g.n && c < NC;
-    const cb_desc& d      = descs[g.cb[valid ? c : 0]];
-    const uint32_t cap_in = (Kb + L) * Z - 2 * Z;
-    lane_state     ls;
-    ls.src       = soft_base + (size_t)d.slot * SOFT_STRIDE;
-    ls.bits_out  = d.bits_out;
-    ls.slot_bits = reinterpret_cast<uint32_t*>(bits_base + (size_t)d.slot * BITS_STRIDE);
-    ls.n_load    = valid ? min(min(d.n_in, d.scan_len), cap_in) : 0U;
-    ls.nbits     = K - d.nof_filler;
-    ls.cbi       = g.cb[valid ? c : 0];
-    ls.slot      = d.slot;
-    ls.flags     = d.flags;
-    ls.iters     = -1;
-    ls.crc_ok    = 0;
-    ls.live      = valid ? 1U : 0U;
-    ls.done      = 0; // 2 = skipped: decoded in an earlier transmission
-    if (valid && (d.flags & FLAG_TRACK_CRC) && !d.new_data && crc_flags[d.slot] != 0) {
-      // Already decoded in an earlier transmission: only dematched (pusch_decoder_impl.cpp:335-345).
-      ls.live           = 0;
-      ls.n_load         = 0;
-      ls.done           = 2;
-      results[ls.cbi] = {0, 1U, 0U, 2U};
-    }
-    st[c] = ls;
-  }
-  __syncthreads();
-  {
-    uint32_t any_live = 0;
-#pragma unroll
-    for (int c = 0; c != 4; ++c) {
-      any_live |= st[c].live;
-      if (st[c].done == 2 && st[c].bits_out != nullptr) {
-        for (uint32_t i = t; i < HBW; i += NT) {
-          reinterpret_cast<uint32_t*>(st[c].bits_out)[i] = st[c].slot_bits[i];
-        }
-      }
-    }
-    if (any_live == 0) {
-      return; // every code block of the group was already decoded (retransmission of an acknowledged TB)
-    }
-  }
-
-  // ---- prologue ----------------------------------------------------------------------------------------------------------
-  for (uint32_t e = t; e < nedges; e += NT) {
-    tab[e] = make_uint2((uint32_t)c_col[bg - 1][e] * Z, c_shift[bg - 1][d0.ils][e] % Z);
-  }
-  {
-    uint4*         c4 = reinterpret_cast<uint4*>(smem_raw + lay.c2v_off);
-    const uint32_t n4 = nedges * Z * NC / 16; // all planes: nedges * Z * NC bytes
-    const uint4    zz = make_uint4(pk::C2V_ZERO4, pk::C2V_ZERO4, pk::C2V_ZERO4, pk::C2V_ZERO4);
-    for (uint32_t i = t; i < n4; i += NT) {
-      c4[i] = zz;
-    }
-  }
-  if (poly != 0) {
-    build_crc_tables(tabs, poly, t, NT);
-  }
-  {
-    const uint32_t nq    = nvar / 4; // quads of variable nodes
-    const uint32_t punct = 2 * Z / 4;
-    uint32_t       nz0 = 0, nz1 = 0;
-    const int      tl = t - h * TPC; // index within the plane's threads
-    const int8_t*  s0 = st[h].src;
-    const int8_t*  s1 = st[h + NP].src;
-    const uint32_t l0 = st[h].n_load, l1 = st[h + NP].n_load;
-    for (uint32_t v = tl; v < nq; v += TPC) {
-      uint32_t w0 = 0, w1 = 0;
-      if (v >= punct) {
-        uint32_t p = (v - punct) * 4;
-        if (p < l0) {
-          w0 = __ldg(reinterpret_cast<const uint32_t*>(s0 + p));
-        }
-        if (p < l1) {
-          w1 = __ldg(reinterpret_cast<const uint32_t*>(s1 + p));
-        }
-        nz0 |= w0;
-        nz1 |= w1;
-      }
-      w0 ^= 0x80808080U;
-      w1 ^= 0x80808080U;
-      uint4 o;
-      o.x = pk::soft_from_biased_bytes(__byte_perm(w0, w1, 0x4400) & 0x00ff00ffU);
-      o.y = pk::soft_from_biased_bytes(__byte_perm(w0, w1, 0x5511) & 0x00ff00ffU);
-      o.z = pk::soft_from_biased_bytes(__byte_perm(w0, w1, 0x6622) & 0x00ff00ffU);
-      o.w = pk::soft_from_biased_bytes(__byte_perm(w0, w1, 0x7733) & 0x00ff00ffU);
-      reinterpret_cast<uint4*>(soft)[v] = o;
-    }
-    nz0 = __reduce_or_sync(0xffffffffU, nz0);
-    nz1 = __reduce_or_sync(0xffffffffU, nz1);
-    if (lane == 0) {
-      if (nz0 != 0) {
-        atomicOr(&misc[h], 1U);
-      }
-      if (nz1 != 0) {
-        atomicOr(&misc[h + NP], 1U);
-      }
-    }
-  }
-  __syncthreads();
-  if (t < 4) {
-    // All-zero input with early stop: the reference returns before touching the output (ldpc_decoder_impl.cpp:88-94).
-    if (!st[t].live || (misc[t] == 0 && mode == MODE_EARLY_STOP)) {
-      st[t].done = max(st[t].done, st[t].live ? 3U : 1U);
-    }
-  }
-  __syncthreads();
-#pragma unroll
-  for (int c = 0; c != 4; ++c) {
-    if (st[c].done == 3 && st[c].bits_out != nullptr) {
-      for (uint32_t i = t; i < HBW; i += blockDim.x) {
-        reinterpret_cast<uint32_t*>(st[c].bits_out)[i] = st[c].slot_bits[i]; // untouched output
-      }
-    }
-  }
-
-  // ---- iterations --------------------------------------------------------------------------------------------------------
-  const uint32_t j      = t - h * TPC;
-  const uint32_t zmagic = 0xffffffffU / Z + 1;
-  for (uint32_t it = 0; it != max_it; ++it) {
-    for (uint32_t l = 0; l != L; ++l) {
-      uint32_t e0  = c_row_ptr[bg - 1][l];
-      int      deg = (int)c_row_ptr[bg - 1][l + 1] - (int)e0;
-      if (j < Z) {
-        uint16_t*    c2v_row = c2v + (size_t)e0 * Z;
-        const uint2* tab_row = tab + e0;
-        switch (deg) {
-          case 3:
-            process_check2<3>(soft, c2v_row, tab_row, j, Z, zmagic, mult);
-            break;
-          case 4:
-            process_check2<4>(soft, c2v_row, tab_row, j, Z, zmagic, mult);
-            break;
-          case 5:
-            process_check2<5>(soft, c2v_row, tab_row, j, Z, zmagic, mult);
-            break;
-          case 6:
-            process_check2<6>(soft, c2v_row, tab_row, j, Z, zmagic, mult);
-            break;
-          case 7:
-            process_check2<7>(soft, c2v_row, tab_row, j, Z, zmagic, mult);
-            break;
-          case 8:
-            process_check2<8>(soft, c2v_row, tab_row, j, Z, zmagic, mult);
-            break;
-          case 9:
-            process_check2<9>(soft, c2v_row, tab_row, j, Z, zmagic, mult);
-            break;
-          case 10:
-            process_check2<10>(soft, c2v_row, tab_row, j, Z, zmagic, mult);
-            break;
-          default:
-            process_check2<19>(soft, c2v_row, tab_row, j, Z, zmagic, mult);
-            break;
-        }
-      }
-      __syncthreads();
-    }
-    const bool last_it = (it + 1 == max_it);
-    if (mode != MODE_EARLY_STOP && !last_it) {
-      continue;
-    }
-    {
-      // Plane h by its own warps; lane l takes variable 32 w + 31 - l: ballot bit l is already in MSB-first order.
-      uint32_t nz = 0x00010001U;
-      for (uint32_t w = warp - h * (NW / NP); w < HBW; w += NW / NP) {
-        uint32_t s  = soft[w * 32 + 31 - lane];
-        uint32_t p  = pk::positive_lanes(s); // 1 where soft > 0
-        nz &= pk::minu2(s ^ pk::SOFT_ZERO2, 0x00010001U);
-        uint32_t blo = __ballot_sync(0xffffffffU, (p & 0xffffU) == 0);
-        uint32_t bhi = __ballot_sync(0xffffffffU, (p >> 16) == 0);
-        if (lane < 2) {
-          hb[(h + NP * lane) * HBW + w] = lane ? bhi : blo;
-        }
-      }
-      nz = __reduce_and_sync(0xffffffffU, nz);
-      if (lane == 0) {
-        if (!(nz & 1U)) {
-          atomicOr(&misc[4 + h], 1U);
-        }
-        if (!(nz >> 16)) {
-          atomicOr(&misc[4 + NP + h], 1U);
-        }
-      }
-    }
+  if constexpr (TM != 0) {
+    tmem_wait_st();
+    tmem_fence_before_sync();
     __syncthreads();
-    if (warp < 4) {
-      uint32_t ok = 0;
-      if (!st[warp].done) {
-        uint32_t crc = warp_crc_words<false>(hb + warp * HBW, st[warp].nbits, poly, tabs, lane);
-        ok           = (crc == 0 && (mode != MODE_EARLY_STOP || misc[4 + warp] == 0)) ? 1U : 0U;
-      }
-      if (lane == 0) {
-        misc[8 + warp] = ok;
-      }
-    }
-    __syncthreads();
-#pragma unroll
-    for (int c = 0; c != 4; ++c) {
-      if (!st[c].done && (misc[8 + c] != 0 || last_it)) {
-        // The output holds the hard decision of the last iteration run (ldpc_decoder_impl.cpp:126-146).
-        uint32_t* slot = st[c].slot_bits;
-        uint32_t* out  = reinterpret_cast<uint32_t*>(st[c].bits_out);
-        for (uint32_t i = t; i < HBW; i += NT) {
-          uint32_t wd = __byte_perm(hb[c * HBW + i], 0, 0x0123);
-          slot[i]     = wd;
-          if (out != nullptr) {
-            out[i] = wd;
-          }
-        }
-      }
-    }
-    __syncthreads();
-    if (t < 4) {
-      if (!st[t].done && misc[8 + t] != 0) {
-        st[t].done   = 1;
-        st[t].crc_ok = 1;
-        st[t].iters  = (mode == MODE_EARLY_STOP) ? (int)it + 1 : (int)max_it;
-      }
-      misc[4 + t] = 0; // "any zero" flags of the next round
-    }
-    __syncthreads();
-    if (st[0].done && st[1].done && st[2].done && st[3].done) {
-      break;
-    }
-  }
-
-  if (t < 4 && st[t].live) {
-    results[st[t].cbi] = {st[t].iters, st[t].crc_ok, L, 0U};
-    if (st[t].flags & FLAG_TRACK_CRC) {
-      crc_flags[st[t].slot] = st[t].crc_ok;
+    if (warp == 0) {
+      tmem_dealloc(*tm_ptr, tm_cols);
     }
   }
 }

@@ -355,10 +355,12 @@ PK_FN uint32_t soft_from_biased_bytes(uint32_t ub2)
   return lane + tp * (H_POS_INF - 0x64ffU) + tn * (H_NEG_INF - 0x6401U);           // no carry between the lanes
 }
 
-/// State of one lifted check while a layer is processed, for 2 * NR code blocks (NR registers of two binary16 lanes).
-template <int DEG, int NR>
-struct check_lanes {
-  uint32_t q[DEG][NR]; ///< v2c
+/// Running state of one lifted check while a layer is processed, for 2 * NR code blocks (NR registers of two binary16
+/// lanes): minima, sign product and the two candidate output magnitudes. The v2c values themselves are not kept here:
+/// check_lanes (below) holds them in registers between the two passes; the TMEM-message kernel (ldpc_packed.cuh) parks
+/// them in the soft array instead.
+template <int NR>
+struct check_acc {
   uint32_t m1[NR], m2[NR], x[NR];
   uint32_t pm2[NR], dpm[NR];
 
@@ -371,13 +373,14 @@ PK_UNROLL
     }
   }
 
-  /// Edge e: soft words s[r] (half S + 1152 per lane) and messages of the previous iteration c[r] (half c + 1152 per lane).
-  PK_MFN void gather(int e, const uint32_t* s, const uint32_t* c)
+  /// One edge: soft words s[r] (half S + 1152 per lane) and messages of the previous iteration c[r] (half c + 1152 per
+  /// lane); returns the v2c words in qq[r].
+  PK_MFN void gather_q(const uint32_t* s, const uint32_t* c, uint32_t* qo)
   {
 PK_UNROLL
     for (int r = 0; r != NR; ++r) {
       uint32_t qq = hsub2(s[r], c[r]);
-      q[e][r]     = qq;
+      qo[r]       = qq;
       x[r] ^= qq; // bit 15 of every lane: parity of the negative v2c (a zero v2c is +0: it counts as positive)
       if (r < PK_GATHER_FMA_REGS) {
         uint32_t d = habs_rsub_relu(qq, m1[r]); // max(min1 - |q|, 0): exact, 0 for an infinite |q|
@@ -410,12 +413,12 @@ PK_UNROLL
   }
 
   /// New soft words sn[r] (half S + 1152) and new messages cn[r] (half c + 1152: the message byte is the low byte of
-  /// every lane) of edge e.
-  PK_MFN void scatter(int e, uint32_t* sn, uint32_t* cn)
+  /// every lane) of the edge whose v2c words are qi[r].
+  PK_MFN void scatter_q(const uint32_t* qi, uint32_t* sn, uint32_t* cn)
   {
 PK_UNROLL
     for (int r = 0; r != NR; ++r) {
-      uint32_t qq = q[e][r];
+      uint32_t qq = qi[r];
       // 1: |q| > min1 -> min1, 0: this edge is the minimum -> min2
       uint32_t t  = PK_SCATTER_T_ALU ? habs_gt_set(qq, m1[r]) : habs_gt(qq, m1[r]);
       uint32_t pm = hfma2(t, dpm[r], pm2[r]);                 // P * M
@@ -437,6 +440,25 @@ PK_UNROLL
       uint32_t w  = hfma2(t2, PK_REP2(H_8192), v);
       sn[r]       = hfma2(sq, w, PK_REP2(H_1152));
     }
+  }
+};
+
+/// State of one lifted check while a layer is processed, v2c values kept in registers between the passes.
+template <int DEG, int NR>
+struct check_lanes : check_acc<NR> {
+  uint32_t q[DEG][NR]; ///< v2c
+
+  /// Edge e: soft words s[r] (half S + 1152 per lane) and messages of the previous iteration c[r] (half c + 1152 per lane).
+  PK_MFN void gather(int e, const uint32_t* s, const uint32_t* c)
+  {
+    check_acc<NR>::gather_q(s, c, q[e]);
+  }
+
+  /// New soft words sn[r] (half S + 1152) and new messages cn[r] (half c + 1152: the message byte is the low byte of
+  /// every lane) of edge e.
+  PK_MFN void scatter(int e, uint32_t* sn, uint32_t* cn)
+  {
+    check_acc<NR>::scatter_q(q[e], sn, cn);
   }
 };
 

@@ -196,7 +196,7 @@ struct srsran_cuda_pusch_dec {
   uint32_t combine_block     = 64; // AVX-512 flavour of the reference's combine (32 = AVX2, 0 = generic)
   uint64_t launches          = 0;
   bool     use_packed        = true; // route eligible code blocks to the packed (4 per CTA) decoder
-  bool     packed_half       = false; // packed decoder with two threads per lifted check (measured slower: A/B only)
+  bool     use_tmem          = true;  // packed decoder with the messages in tensor memory (two CTAs per SM) where eligible
   bool     force_pairs       = false; // groups of two code blocks per CTA (two CTAs per SM) also for large batches
   bool     prefer_q4         = false; // one code block per CTA on the packed arithmetic also where groups of four would fit
   cudaEvent_t timer_begin    = nullptr;
@@ -324,9 +324,23 @@ cudaError_t launch_decode4(srsran_cuda_pusch_dec* h, cudaStream_t s, const cb_de
                            cb_result* res, uint8_t* bits_base, uint32_t n, uint32_t smem, bool z384 = false)
 {
   if (TPC == 384 && z384) {
-    ldpc_decode4_kernel<384, 384><<<n, 384, smem, s>>>(descs, groups, res, h->d_soft.p, bits_base, h->d_crc_flags.p);
+    ldpc_decode4_kernel<384, 384><<<n, 384, smem, s>>>(descs, groups, res, h->d_soft.p, bits_base, h->d_crc_flags.p, 0U);
   } else {
-    ldpc_decode4_kernel<TPC><<<n, TPC, smem, s>>>(descs, groups, res, h->d_soft.p, bits_base, h->d_crc_flags.p);
+    ldpc_decode4_kernel<TPC><<<n, TPC, smem, s>>>(descs, groups, res, h->d_soft.p, bits_base, h->d_crc_flags.p, 0U);
+  }
+  ++h->launches;
+  return cudaGetLastError();
+}
+
+/// Four code blocks per CTA with the messages in tensor memory (`tm_cols` columns per CTA: 256 -> two CTAs per SM).
+template <int TPC>
+cudaError_t launch_decode4t(srsran_cuda_pusch_dec* h, cudaStream_t s, const cb_desc* descs, const grp_desc* groups,
+                            cb_result* res, uint8_t* bits_base, uint32_t n, uint32_t smem, uint32_t tm_cols, bool z384 = false)
+{
+  if (TPC == 384 && z384) {
+    ldpc_decode4_kernel<384, 384, 2, 1><<<n, 384, smem, s>>>(descs, groups, res, h->d_soft.p, bits_base, h->d_crc_flags.p, tm_cols);
+  } else {
+    ldpc_decode4_kernel<TPC, 0, 2, 1><<<n, TPC, smem, s>>>(descs, groups, res, h->d_soft.p, bits_base, h->d_crc_flags.p, tm_cols);
   }
   ++h->launches;
   return cudaGetLastError();
@@ -338,19 +352,10 @@ cudaError_t launch_decode2(srsran_cuda_pusch_dec* h, cudaStream_t s, const cb_de
                            cb_result* res, uint8_t* bits_base, uint32_t n, uint32_t smem, bool z384 = false)
 {
   if (TPC == 384 && z384) {
-    ldpc_decode4_kernel<384, 384, 1><<<n, 384, smem, s>>>(descs, groups, res, h->d_soft.p, bits_base, h->d_crc_flags.p);
+    ldpc_decode4_kernel<384, 384, 1><<<n, 384, smem, s>>>(descs, groups, res, h->d_soft.p, bits_base, h->d_crc_flags.p, 0U);
   } else {
-    ldpc_decode4_kernel<TPC, 0, 1><<<n, TPC, smem, s>>>(descs, groups, res, h->d_soft.p, bits_base, h->d_crc_flags.p);
+    ldpc_decode4_kernel<TPC, 0, 1><<<n, TPC, smem, s>>>(descs, groups, res, h->d_soft.p, bits_base, h->d_crc_flags.p, 0U);
   }
-  ++h->launches;
-  return cudaGetLastError();
-}
-
-template <int TPC, int NP>
-cudaError_t launch_decode4h(srsran_cuda_pusch_dec* h, cudaStream_t s, const cb_desc* descs, const grp_desc* groups,
-                            cb_result* res, uint8_t* bits_base, uint32_t n, uint32_t smem)
-{
-  ldpc_decode4h_kernel<TPC, NP><<<n, NP * TPC, smem, s>>>(descs, groups, res, h->d_soft.p, bits_base, h->d_crc_flags.p);
   ++h->launches;
   return cudaGetLastError();
 }
@@ -381,6 +386,28 @@ bool packed_eligible(const srsran_cuda_pusch_dec* h, const cb_desc& d, uint32_t 
     return false;
   }
   return dec4_smem_layout(d.bg, d.Z, cap, lanes).total <= static_cast<uint32_t>(h->max_smem_optin);
+}
+
+/// Tensor-memory columns a group of four such code blocks needs per CTA (256 or 512), 0 if the tensor-memory variant of the
+/// packed decoder does not apply: whole warps only (Z % 32 == 0), and the messages of `cap` layers must fit in the columns
+/// of a warp (the TPC / 128 warps of a lane quadrant share the CTA's columns).
+uint32_t packed_tmem_cols(const srsran_cuda_pusch_dec* h, const cb_desc& d, uint32_t cap)
+{
+  if (!h->use_tmem || !packed_eligible(h, d, 4, 2) || (d.Z % 32) != 0) {
+    return 0;
+  }
+  if (dec4_smem_layout(d.bg, d.Z, cap, 4, true).total > static_cast<uint32_t>(h->max_smem_optin)) {
+    return 0;
+  }
+  const uint32_t tpc  = d.Z <= 256 ? 256 : 384;
+  const uint32_t need = dec4_tmem_cols(d.bg, cap);
+  if (need <= dec4_tmem_cols_per_warp(256, tpc)) {
+    return 256;
+  }
+  if (need <= dec4_tmem_cols_per_warp(512, tpc)) {
+    return 512;
+  }
+  return 0;
 }
 
 template <int TPC, int CBS>
@@ -716,8 +743,10 @@ int launch_context(srsran_cuda_pusch_dec* h, int ci)
     uint32_t smem;
     uint32_t first, count; // range in h_grp
     uint32_t z;            // lifting size (one per class: the Z = 384 specialisation of the kernel)
+    uint32_t tm_cols;      // tensor-memory columns per CTA (0: messages in shared memory)
   };
   uint32_t grp_lanes = 4;
+  bool     grp_tm    = false; // the open group runs on the tensor-memory variant
   std::vector<pklass> pclasses;
   uint32_t            ngrp     = 0;
   bool                grp_open = false;
@@ -790,11 +819,12 @@ int launch_context(srsran_cuda_pusch_dec* h, int ci)
       return;
     }
     const cb_desc&  d  = c.h_desc.p[g.cb[0]];
-    uint32_t        sm = (dec4_smem_layout(d.bg, d.Z, g.layer_cap, grp_lanes).total + 1023) & ~1023U;
+    const uint32_t  tm = grp_tm ? packed_tmem_cols(h, d, g.layer_cap) : 0U;
+    uint32_t        sm = (dec4_smem_layout(d.bg, d.Z, g.layer_cap, grp_lanes, tm != 0).total + 1023) & ~1023U;
     int             tp = d.Z <= 256 ? 256 : 384;
     if (pclasses.empty() || pclasses.back().tpc != tp || pclasses.back().smem != sm || pclasses.back().lanes != grp_lanes ||
-        pclasses.back().z != d.Z) {
-      pclasses.push_back({tp, grp_lanes, sm, ngrp, 0, d.Z});
+        pclasses.back().z != d.Z || pclasses.back().tm_cols != tm) {
+      pclasses.push_back({tp, grp_lanes, sm, ngrp, 0, d.Z, tm});
     }
     ++pclasses.back().count;
     ++ngrp;
@@ -821,6 +851,7 @@ int launch_context(srsran_cuda_pusch_dec* h, int ci)
   }
   const cb_desc* memo_desc  = nullptr;
   uint32_t       memo_lanes = 0;
+  bool           memo_tm    = false;
   const bool small_batch = h->force_pairs || (nof_packable + 3) / 4 <= static_cast<uint32_t>(h->nof_sms) / 2;
   for (uint32_t i = 0; i != ncb; ++i) {
     const cb_desc& d = c.h_desc.p[i];
@@ -836,7 +867,10 @@ int launch_context(srsran_cuda_pusch_dec* h, int ci)
     }
     if (memo_desc == nullptr || !same_class(*memo_desc, d)) {
       const bool inter_cb = !(h->prefer_q4 && q4_eligible(h, d));
-      memo_lanes = !inter_cb ? 0U : (!small_batch && packed_eligible(h, d, d.layer_cap, 4))
+      // Groups of four on the tensor-memory variant where it applies (also for shapes whose messages would not fit in
+      // shared memory four at a time), else groups of four / two with the messages in shared memory.
+      memo_tm    = inter_cb && !small_batch && packed_tmem_cols(h, d, d.layer_cap) != 0;
+      memo_lanes = !inter_cb ? 0U : (memo_tm || (!small_batch && packed_eligible(h, d, d.layer_cap, 4)))
                                   ? 4U
                                   : (packed_eligible(h, d, d.layer_cap, 2) ? 2U : 0U);
       memo_desc  = &d;
@@ -847,8 +881,10 @@ int launch_context(srsran_cuda_pusch_dec* h, int ci)
         grp_desc&      g   = c.h_grp.p[ngrp];
         const cb_desc& f   = c.h_desc.p[g.cb[0]];
         uint32_t       cap = std::max(g.layer_cap, d.layer_cap);
-        if (g.n < grp_lanes && ((same_class(f, d) && g.layer_cap == d.layer_cap) ||
-                                 (same_shape(f, d) && packed_eligible(h, d, cap, grp_lanes)))) {
+        if (g.n < grp_lanes && lanes_fit == grp_lanes && memo_tm == grp_tm &&
+            ((same_class(f, d) && g.layer_cap == d.layer_cap) ||
+             (same_shape(f, d) &&
+              (grp_tm ? packed_tmem_cols(h, d, cap) != 0 : packed_eligible(h, d, cap, grp_lanes))))) {
           g.cb[g.n++] = i;
           g.layer_cap = cap;
           continue;
@@ -861,6 +897,7 @@ int launch_context(srsran_cuda_pusch_dec* h, int ci)
       g.n         = 1;
       g.layer_cap = d.layer_cap;
       grp_lanes   = lanes_fit;
+      grp_tm      = memo_tm;
       grp_open    = true;
       continue;
     }
@@ -955,9 +992,10 @@ int launch_context(srsran_cuda_pusch_dec* h, int ci)
     if (k.lanes == 2) {
       e = (k.tpc == 256) ? launch_decode2<256>(h, st, c.d_desc.p, grp, c.d_res.p, c.bits_base, k.count, k.smem)
                          : launch_decode2<384>(h, st, c.d_desc.p, grp, c.d_res.p, c.bits_base, k.count, k.smem, k.z == 384);
-    } else if (h->packed_half) {
-      e = (k.tpc == 256) ? launch_decode4h<256, 2>(h, st, c.d_desc.p, grp, c.d_res.p, c.bits_base, k.count, k.smem)
-                         : launch_decode4h<384, 2>(h, st, c.d_desc.p, grp, c.d_res.p, c.bits_base, k.count, k.smem);
+    } else if (k.tm_cols != 0) {
+      e = (k.tpc == 256)
+              ? launch_decode4t<256>(h, st, c.d_desc.p, grp, c.d_res.p, c.bits_base, k.count, k.smem, k.tm_cols)
+              : launch_decode4t<384>(h, st, c.d_desc.p, grp, c.d_res.p, c.bits_base, k.count, k.smem, k.tm_cols, k.z == 384);
     } else {
       e = (k.tpc == 256) ? launch_decode4<256>(h, st, c.d_desc.p, grp, c.d_res.p, c.bits_base, k.count, k.smem)
                          : launch_decode4<384>(h, st, c.d_desc.p, grp, c.d_res.p, c.bits_base, k.count, k.smem, k.z == 384);
@@ -1268,8 +1306,9 @@ int srsran_cuda_pusch_dec_create(int device, uint32_t max_cbs_in_flight, uint32_
   if (cudaFuncSetAttribute(ldpc_decode4_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess ||
       cudaFuncSetAttribute(ldpc_decode4_kernel<384>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess ||
       cudaFuncSetAttribute(ldpc_decode4_kernel<384, 384>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess ||
-      cudaFuncSetAttribute(ldpc_decode4h_kernel<256, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess ||
-      cudaFuncSetAttribute(ldpc_decode4h_kernel<384, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess ||
+      cudaFuncSetAttribute(ldpc_decode4_kernel<256, 0, 2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess ||
+      cudaFuncSetAttribute(ldpc_decode4_kernel<384, 0, 2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess ||
+      cudaFuncSetAttribute(ldpc_decode4_kernel<384, 384, 2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess ||
       cudaFuncSetAttribute(ldpc_decode_q4_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess ||
       cudaFuncSetAttribute(ldpc_decode_q4_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess ||
       cudaFuncSetAttribute(ldpc_decode_q4_kernel<96>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess ||
@@ -1453,7 +1492,7 @@ int srsran_cuda_pusch_dec_set_decoder_variant(srsran_cuda_pusch_dec_t* h, uint32
     return SRSRAN_CUDA_ERR_INVALID;
   }
   h->use_packed  = (variant != 1);
-  h->packed_half = (variant == 2);
+  h->use_tmem    = (variant != 2); // 2: the round-1 packed decoder (messages in shared memory, one CTA per SM) for A/B runs
   h->prefer_q4   = (variant == 3);
   h->force_pairs = (variant == 4);
   return SRSRAN_CUDA_OK;
