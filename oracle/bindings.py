@@ -248,6 +248,18 @@ class PortPusch:
         assert r == 0
         return tb, res
 
+    def harq_state(self, key, metas):
+        """(CRC flags, soft buffers) per code block of the HARQ buffer `key`: the first full_length soft bits each."""
+
+        class H(C.Structure):
+            _fields_ = [("nof_cbs", C.c_uint32), ("crc", C.c_uint8 * 162), ("soft", C.POINTER(C.c_int8)),
+                        ("data", C.POINTER(C.c_uint8))]
+
+        hb = C.cast(self.harq[key][0], C.POINTER(H)).contents
+        all_soft = np.ctypeslib.as_array(hb.soft, shape=(len(metas) * 25344,))
+        return ([bool(hb.crc[cb]) for cb in range(len(metas))],
+                [all_soft[cb * 25344:cb * 25344 + m.full_length].copy() for cb, m in enumerate(metas)])
+
     def __del__(self):
         for h, _ in self.harq.values():
             port().oracle_harq_destroy(h)

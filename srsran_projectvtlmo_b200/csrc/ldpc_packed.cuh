@@ -248,6 +248,13 @@ __device__ __forceinline__ void tmem_st_row(uint32_t taddr, const uint32_t* r)
   }
 }
 
+#ifndef DEC4T_QR
+#define DEC4T_QR 0 ///< trailing edges of a check whose v2c values stay in registers
+#endif
+#ifndef DEC4T_PF
+#define DEC4T_PF 3 ///< shared-memory loads issued ahead of the edge being processed
+#endif
+
 /// One lifted check (thread j) of a layer of degree DEG for four code blocks, messages in tensor memory (`taddr` = the
 /// calling warp's lane quadrant and the first column of this layer). The v2c values are not kept in registers between the
 /// two passes: the first pass leaves them in the soft array IN PLACE of the soft values they were computed from (the
@@ -255,33 +262,50 @@ __device__ __forceinline__ void tmem_st_row(uint32_t taddr, const uint32_t* r)
 /// back and overwrites them with the new soft values. That costs one 64-bit store and load per edge and saves 38
 /// registers, which is what lets two 384-thread CTAs (80 registers per thread) share an SM. The last QR edges keep their
 /// v2c in registers.
+/// `tab_row[e]` = (byte offset of the edge's variable node from `smem`, 8 x circulant shift), `j8` = 8 j, `Z8` = 8 Z.
 template <int DEG, int QR>
 __device__ __forceinline__ void process_check_t(uint8_t* __restrict__     soft_bytes,
                                                 uint32_t                  taddr,
                                                 const uint2* __restrict__ tab_row,
-                                                uint32_t                  j,
-                                                uint32_t                  Z,
+                                                uint32_t                  j8,
+                                                uint32_t                  Z8,
                                                 uint32_t                  mult)
 {
   constexpr int    DP = (DEG + 3) & ~3;
   constexpr int    QS = (QR < DEG) ? DEG - QR : 0; // edges [0, QS) park their v2c in shared memory
+  constexpr int    PF = (DEC4T_PF < DEG) ? DEC4T_PF : DEG; // loads in flight ahead of the edge being processed
   uint32_t         addr[DEG];
   uint32_t         cw[DP];
   uint32_t         qk[(DEG - QS) > 0 ? (DEG - QS) : 1][2];
+  uint2            ring[PF];
   pk::check_acc<2> ck;
   tmem_ld_row<DP>(taddr, cw);
+  // The parked v2c values share the soft array with the soft values, so the compiler must keep every load behind the
+  // stores that precede it in program order: the loads of the next PF edges are therefore issued BEFORE the store of the
+  // current edge (software pipeline), else every edge would wait for a full shared-memory round trip.
+  auto edge_addr = [&](int e) {
+    const uint2 te = tab_row[e];
+    uint32_t    k  = j8 + te.y;
+    k = __viaddmin_u32(k, 0U - Z8, k); // 8 ((j + shift) mod Z): min(k - 8 Z, k) on unsigned values, one VIADDMNMX
+    addr[e]        = te.x + k;
+  };
+#pragma unroll
+  for (int e = 0; e != PF; ++e) {
+    edge_addr(e);
+    ring[e] = *reinterpret_cast<const uint2*>(soft_bytes + addr[e]);
+  }
   ck.begin();
   tmem_wait_ld();
 #pragma unroll
   for (int e = 0; e != DEG; ++e) {
-    const uint2 te = tab_row[e];
-    uint32_t    k  = j + te.y;
-    k = __viaddmin_u32(k, 0U - Z, k); // (j + shift) mod Z: min(k - Z, k) on unsigned values, one VIADDMNMX
-    addr[e]        = te.x + k * 8;
-    const uint2 sv = *reinterpret_cast<const uint2*>(soft_bytes + addr[e]);
-    uint32_t    s[2] = {sv.x, sv.y};
-    uint32_t    c[2] = {pk::prmt2(cw[e], 0x64646464U, 0x4240U), pk::prmt2(cw[e], 0x64646464U, 0x4341U)};
-    uint32_t    q[2];
+    const uint2 sv = ring[e % PF];
+    if (e + PF < DEG) {
+      edge_addr(e + PF);
+      ring[e % PF] = *reinterpret_cast<const uint2*>(soft_bytes + addr[e + PF]);
+    }
+    uint32_t s[2] = {sv.x, sv.y};
+    uint32_t c[2] = {pk::prmt2(cw[e], 0x64646464U, 0x4240U), pk::prmt2(cw[e], 0x64646464U, 0x4341U)};
+    uint32_t q[2];
     ck.gather_q(s, c, q);
     if (e < QS) {
       *reinterpret_cast<uint2*>(soft_bytes + addr[e]) = make_uint2(q[0], q[1]);
@@ -290,14 +314,21 @@ __device__ __forceinline__ void process_check_t(uint8_t* __restrict__     soft_b
       qk[e - QS][1] = q[1];
     }
   }
+  constexpr int PQ = (PF < QS) ? PF : QS;
+#pragma unroll
+  for (int e = 0; e != PQ; ++e) {
+    ring[e] = *reinterpret_cast<const uint2*>(soft_bytes + addr[e]);
+  }
   ck.reduce(mult);
 #pragma unroll
   for (int e = 0; e != DEG; ++e) {
     uint32_t q[2], sn[2], cn[2];
     if (e < QS) {
-      const uint2 qv = *reinterpret_cast<const uint2*>(soft_bytes + addr[e]);
-      q[0]           = qv.x;
-      q[1]           = qv.y;
+      q[0] = ring[e % PF].x;
+      q[1] = ring[e % PF].y;
+      if (e + PF < QS) {
+        ring[e % PF] = *reinterpret_cast<const uint2*>(soft_bytes + addr[e + PF]);
+      }
     } else {
       q[0] = qk[e - QS][0];
       q[1] = qk[e - QS][1];
@@ -316,9 +347,6 @@ __device__ __forceinline__ void process_check_t(uint8_t* __restrict__     soft_b
   tmem_wait_st();
 }
 
-#ifndef DEC4T_QR
-#define DEC4T_QR 0
-#endif
 
 /// Per code block state of a packed group, kept in shared memory so that it does not occupy registers in the layer loop.
 struct lane_state {
@@ -439,7 +467,12 @@ __global__ void __launch_bounds__((NR == 2 && !TM) ? TPC + DEC4_LB_EXTRA : TPC, 
   // ---- prologue ----------------------------------------------------------------------------------------------------------
   const uint32_t nedges = c_row_ptr[bg - 1][L];
   for (uint32_t e = t; e < nedges; e += TPC) {
-    tab[e] = make_uint2((uint32_t)c_col[bg - 1][e] * Z * SE, c_shift[bg - 1][d0.ils][e] % Z);
+    if constexpr (TM != 0) {
+      // absolute offset in the CTA's shared memory, shift in bytes: three instructions from here to the address
+      tab[e] = make_uint2(lay.soft_off + (uint32_t)c_col[bg - 1][e] * Z * SE, (c_shift[bg - 1][d0.ils][e] % Z) * SE);
+    } else {
+      tab[e] = make_uint2((uint32_t)c_col[bg - 1][e] * Z * SE, c_shift[bg - 1][d0.ils][e] % Z);
+    }
   }
   if constexpr (TM != 0) {
     // Tensor memory for the messages (every thread of the CTA returns together above, so the allocation is always paired
@@ -592,31 +625,31 @@ __global__ void __launch_bounds__((NR == 2 && !TM) ? TPC + DEC4_LB_EXTRA : TPC, 
           const uint32_t ta      = tm_warp + lcol[l];
           switch (deg) {
             case 3:
-              process_check_t<3, DEC4T_QR>(soft, ta, tab_row, j, Z, mult);
+              process_check_t<3, DEC4T_QR>(smem_raw, ta, tab_row, j * SE, Z * SE, mult);
               break;
             case 4:
-              process_check_t<4, DEC4T_QR>(soft, ta, tab_row, j, Z, mult);
+              process_check_t<4, DEC4T_QR>(smem_raw, ta, tab_row, j * SE, Z * SE, mult);
               break;
             case 5:
-              process_check_t<5, DEC4T_QR>(soft, ta, tab_row, j, Z, mult);
+              process_check_t<5, DEC4T_QR>(smem_raw, ta, tab_row, j * SE, Z * SE, mult);
               break;
             case 6:
-              process_check_t<6, DEC4T_QR>(soft, ta, tab_row, j, Z, mult);
+              process_check_t<6, DEC4T_QR>(smem_raw, ta, tab_row, j * SE, Z * SE, mult);
               break;
             case 7:
-              process_check_t<7, DEC4T_QR>(soft, ta, tab_row, j, Z, mult);
+              process_check_t<7, DEC4T_QR>(smem_raw, ta, tab_row, j * SE, Z * SE, mult);
               break;
             case 8:
-              process_check_t<8, DEC4T_QR>(soft, ta, tab_row, j, Z, mult);
+              process_check_t<8, DEC4T_QR>(smem_raw, ta, tab_row, j * SE, Z * SE, mult);
               break;
             case 9:
-              process_check_t<9, DEC4T_QR>(soft, ta, tab_row, j, Z, mult);
+              process_check_t<9, DEC4T_QR>(smem_raw, ta, tab_row, j * SE, Z * SE, mult);
               break;
             case 10:
-              process_check_t<10, DEC4T_QR>(soft, ta, tab_row, j, Z, mult);
+              process_check_t<10, DEC4T_QR>(smem_raw, ta, tab_row, j * SE, Z * SE, mult);
               break;
             default:
-              process_check_t<19, DEC4T_QR>(soft, ta, tab_row, j, Z, mult);
+              process_check_t<19, DEC4T_QR>(smem_raw, ta, tab_row, j * SE, Z * SE, mult);
               break;
           }
         }

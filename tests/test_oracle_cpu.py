@@ -182,7 +182,7 @@ def iter_tb_golden():
 def test_golden_tb_harq_sequences():
     port = ob.PortPusch()
     for key, (payload, txs) in enumerate(iter_tb_golden()):
-        for i, (m, llr, want_tb, _soft) in enumerate(txs):
+        for i, (m, llr, want_tb, want_soft) in enumerate(txs):
             (prb, qm, R, nl, bg, nref, es, max_it, rv, tbs, nllr, crc_ok, ncb, nobs, imin, imax, imean1000) = [int(x) for x in m[:17]]
             tb, res = port.decode(key, tbs // 8, llr, bg, rv, qm, nref, nl, max_it, bool(es), i == 0)
             assert res.tb_crc_ok == crc_ok, (key, rv)
@@ -190,6 +190,9 @@ def test_golden_tb_harq_sequences():
             assert int(round(res.iter_mean * 1000)) == imean1000
             if crc_ok:
                 assert np.array_equal(tb, want_tb) and np.array_equal(tb, payload)
+            # every combined soft-buffer byte the compiled reference held after this transmission
+            _, softs = port.harq_state(key, ob.port_segment(tbs, bg, qm, nl, nllr))
+            assert np.array_equal(np.concatenate(softs), want_soft), (key, rv)
 
 
 # ---- 3. differential against the compiled reference -------------------------------------------------------------------
