@@ -89,6 +89,12 @@ def port():
         lib.oracle_pusch_bench.restype = C.c_double
         lib.oracle_pusch_bench.argtypes = [C.c_uint32, i8p, C.c_uint32, C.c_int, C.c_int, C.c_uint32, C.c_int, C.c_int,
                                            C.c_int, C.c_int, C.POINTER(C.c_int)]
+        f32p, u32p = C.POINTER(C.c_float), C.POINTER(C.c_uint32)
+        lib.oracle_scrambling_sequence.argtypes = [C.c_uint32, u8p, C.c_uint32]
+        lib.oracle_demodulate_soft.argtypes = [C.c_int, C.c_int, i8p, f32p, f32p, C.c_uint32]
+        lib.oracle_pusch_demodulate.restype = C.c_int
+        lib.oracle_pusch_demodulate.argtypes = [C.c_int, C.c_int, C.c_uint32, C.c_uint32, C.c_uint32, u32p, C.c_uint32,
+                                                f32p, f32p, i8p]
         _port = lib
     return _port
 
@@ -141,6 +147,14 @@ def ref():
                                            C.c_uint32, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int)]
         lib.ref_ldpc_decode_bench.restype = C.c_double
         lib.ref_ldpc_decode_bench.argtypes = [C.c_char_p, i8p, C.c_uint32, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
+        f32p = C.POINTER(C.c_float)
+        if hasattr(lib, "ref_demodulate_soft"):
+            lib.ref_demodulate_soft.argtypes = [C.c_int, C.c_int, i8p, f32p, f32p, C.c_uint32]
+            lib.ref_scrambling_sequence.argtypes = [C.c_uint32, u8p, C.c_uint32]
+            lib.ref_pusch_demodulate.restype = C.c_int
+            lib.ref_pusch_demodulate.argtypes = [C.c_int, C.c_int, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32,
+                                                 C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, f32p, f32p, C.c_uint32,
+                                                 i8p, C.c_uint32]
         _ref = lib
     return _ref
 
@@ -295,3 +309,78 @@ def host_threads():
         return len(os.sched_getaffinity(0))
     except AttributeError:
         return os.cpu_count() or 1
+
+
+# ---- PUSCH soft-demodulation chain ---------------------------------------------------------------
+
+def _pf(a):
+    assert a.dtype == np.float32 and a.flags["C_CONTIGUOUS"]
+    return a.ctypes.data_as(C.POINTER(C.c_float))
+
+
+def _demod_args(symbols, noise_vars):
+    sym = np.ascontiguousarray(symbols.astype(np.complex64)).view(np.float32)
+    nv = np.ascontiguousarray(noise_vars, dtype=np.float32)
+    assert sym.size == 2 * nv.size
+    return sym, nv
+
+
+def port_demodulate_soft(symbols, noise_vars, qm, pi2=False):
+    """demodulation_mapper::demodulate_soft on one block (complex64 symbols, float32 noise variances) -> int8 LLRs."""
+    sym, nv = _demod_args(symbols, noise_vars)
+    out = np.zeros(nv.size * qm, np.int8)
+    port().oracle_demodulate_soft(qm, int(pi2), _pi(out), _pf(sym), _pf(nv), nv.size)
+    return out
+
+
+def ref_demodulate_soft(symbols, noise_vars, qm, pi2=False):
+    sym, nv = _demod_args(symbols, noise_vars)
+    out = np.zeros(nv.size * qm, np.int8)
+    ref().ref_demodulate_soft(qm, int(pi2), _pi(out), _pf(sym), _pf(nv), nv.size)
+    return out
+
+
+def port_scrambling_sequence(c_init, n):
+    out = np.zeros(n, np.uint8)
+    port().oracle_scrambling_sequence(c_init, _p8(out), n)
+    return out
+
+
+def ref_scrambling_sequence(c_init, n):
+    out = np.zeros(n, np.uint8)
+    ref().ref_scrambling_sequence(c_init, _p8(out), n)
+    return out
+
+
+def pusch_re_per_symbol(nof_prb, start_symbol, nof_symbols, dmrs_mask, nof_cdm_groups_without_data):
+    """Data REs per layer in every OFDM symbol of a DM-RS type 1 allocation (pusch_demodulator_impl.cpp:142-150)."""
+    out = []
+    for s in range(start_symbol, start_symbol + nof_symbols):
+        if (dmrs_mask >> s) & 1:
+            out.append(nof_prb * (12 - 6 * nof_cdm_groups_without_data))
+        else:
+            out.append(nof_prb * 12)
+    return np.array(out, np.uint32)
+
+
+def port_pusch_demodulate(symbols, noise_vars, qm, rnti, n_id, nof_layers, re_per_symbol, pi2=False):
+    sym, nv = _demod_args(symbols, noise_vars)
+    re_per_symbol = np.ascontiguousarray(re_per_symbol, dtype=np.uint32)
+    assert int(re_per_symbol.sum()) * nof_layers == nv.size
+    out = np.zeros(nv.size * qm, np.int8)
+    n = port().oracle_pusch_demodulate(qm, int(pi2), rnti, n_id, nof_layers,
+                                       re_per_symbol.ctypes.data_as(C.POINTER(C.c_uint32)), re_per_symbol.size, _pf(sym),
+                                       _pf(nv), _pi(out))
+    assert n == out.size
+    return out
+
+
+def ref_pusch_demodulate(symbols, noise_vars, qm, rnti, n_id, nof_layers, nof_prb, start_symbol, nof_symbols, dmrs_mask,
+                         nof_cdm_groups_without_data, pi2=False):
+    """The reference's pusch_demodulator_impl (stub equalizer) + ulsch_demultiplex_impl without UCI."""
+    sym, nv = _demod_args(symbols, noise_vars)
+    out = np.zeros(nv.size * qm, np.int8)
+    n = ref().ref_pusch_demodulate(qm, int(pi2), rnti, n_id, nof_layers, nof_prb, start_symbol, nof_symbols, dmrs_mask,
+                                   nof_cdm_groups_without_data, _pf(sym), _pf(nv), nv.size, _pi(out), out.size)
+    assert n == out.size, n
+    return out
