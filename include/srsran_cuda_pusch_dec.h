@@ -224,6 +224,48 @@ int srsran_cuda_pusch_dec_submit_tbs_device(srsran_cuda_pusch_dec_t* handle, uin
 int srsran_cuda_pusch_dec_submit_tbs(srsran_cuda_pusch_dec_t* handle, uint32_t nof_tbs,
                                      const srsran_cuda_pusch_dec_tb_config* configs, const int8_t* const* llrs,
                                      const uint32_t* nof_llrs, int* tickets);
+/* ---- Soft demodulation + descrambling + UL-SCH demultiplexing on the device ------------------------
+ * The soft bits are born in HBM: the caller hands over what the channel equalizer produced - equalized symbols (complex
+ * binary32, re / im interleaved) and post-equalization noise variances, in the order the reference's demodulator consumes
+ * them ([OFDM symbol][RE][layer]) - and the library reproduces, bit for bit (x86 flavour of the reference):
+ *   demodulation_mapper::demodulate_soft   lib/phy/upper/channel_modulation/demodulation_mapper_impl.cpp:76-106 (+ _qpsk/_qam16/_qam64/_qam256.cpp)
+ *   descrambling with c_init = rnti * 2^15 + n_id  lib/phy/upper/channel_processors/pusch/pusch_demodulator_impl.cpp:38-127,139-140,287-293
+ *   the block partition of the demodulator loop (one demapper call per <= MAX_BLOCK_SIZE / bits-per-RE subcarriers of an OFDM
+ *   symbol; the SIMD / scalar-tail split of a demapper call depends on it)  pusch_demodulator_impl.cpp:163-279
+ *   ulsch_demultiplex without UCI (soft bits pass through in order)  ulsch_demultiplex_impl.cpp:253-275
+ * PUSCH with multiplexed UCI is not handled here (SRSRAN_CUDA_ERR_INVALID is not returned for it because the configuration
+ * below cannot express it: keep the host demultiplexer for those slots). */
+typedef struct {
+  uint32_t modulation;        /* bits per symbol: 1 (BPSK), 2, 4, 6, 8 */
+  uint32_t pi2_bpsk;          /* 1: pi/2-BPSK (modulation == 1) */
+  uint32_t rnti;              /* pusch_demodulator::configuration::rnti */
+  uint32_t n_id;              /* pusch_demodulator::configuration::n_id */
+  uint32_t nof_layers;        /* nof_tx_layers */
+  uint32_t nof_ofdm_symbols;  /* OFDM symbols of the allocation (<= 14): entries of re_per_symbol */
+  uint32_t re_per_symbol[14]; /* data REs PER LAYER in each of them (0: a DM-RS symbol without data) */
+} srsran_cuda_pusch_demod_config;
+
+/* demodulation_mapper::demodulate_soft on ONE block of `nof_symbols` symbols (unit-level interface, synchronous):
+ * `symbols` = nof_symbols x (re, im), host memory; writes nof_symbols * modulation soft bits to `llrs` (host). */
+int srsran_cuda_demodulate_soft(srsran_cuda_pusch_dec_t* handle, int8_t* llrs, const float* symbols, const float* noise_vars,
+                                uint32_t nof_symbols, uint32_t modulation, uint32_t pi2_bpsk);
+/* pusch_demodulator_impl::demodulate minus the equalizer + UL-SCH demultiplexing (no UCI) of one codeword (synchronous,
+ * host buffers): writes sum(re_per_symbol) * nof_layers * modulation descrambled soft bits to `llrs`. Returns their number. */
+int srsran_cuda_pusch_demodulate(srsran_cuda_pusch_dec_t* handle, int8_t* llrs, const float* symbols, const float* noise_vars,
+                                 const srsran_cuda_pusch_demod_config* config);
+/* submit_tbs with the soft bits produced on the device: per TB, `symbols[i]` / `noise_vars[i]` hold
+ * sum(re_per_symbol) * nof_layers entries, in host memory (`device_resident` = 0: copied to the device inside the call's
+ * batch) or already in device memory (1: the upstream equalizer ran on the GPU). One set of launches: scrambling
+ * sequences, demodulation, rate dematching, LDPC decoding, TB assembly. One ticket per TB. */
+int srsran_cuda_pusch_dec_submit_tbs_symbols(srsran_cuda_pusch_dec_t* handle, uint32_t nof_tbs,
+                                             const srsran_cuda_pusch_dec_tb_config* configs,
+                                             const srsran_cuda_pusch_demod_config* demod_configs,
+                                             const float* const* symbols, const float* const* noise_vars, int* tickets,
+                                             int device_resident);
+/* Device-side duration in milliseconds of the demodulation stage (scrambling sequences + demodulation kernels) of the batch
+ * a ticket belongs to; 0 if the batch had none. Waits for the batch to complete. */
+int srsran_cuda_pusch_dec_ticket_demod_ms(srsran_cuda_pusch_dec_t* handle, int ticket, float* ms);
+
 /* Device-side duration (CUDA events on the stream the batch ran on) of the five stages of the batch a ticket belongs
  * to, in milliseconds: [0] host->device copies, [1] rate-dematch kernel, [2] LDPC decode kernels, [3] TB assembly + CRC
  * kernel, [4] device->host copies. Waits for the batch to complete. Used by the benchmark's roofline accounting. */

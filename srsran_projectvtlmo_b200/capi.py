@@ -52,6 +52,14 @@ class CbMeta(C.Structure):
                  "nof_crc_bits")]
 
 
+class DemodConfig(C.Structure):
+    """srsran_cuda_pusch_demod_config: what pusch_demodulator::configuration fixes about a codeword's soft demodulation."""
+    _fields_ = [("modulation", C.c_uint32), ("pi2_bpsk", C.c_uint32), ("rnti", C.c_uint32), ("n_id", C.c_uint32),
+                ("nof_layers", C.c_uint32), ("nof_ofdm_symbols", C.c_uint32), ("re_per_symbol", C.c_uint32 * 14)]
+
+
+f32p = C.POINTER(C.c_float)
+
 # Every symbol include/srsran_cuda_pusch_dec.h declares: name -> (restype, argtypes).
 SYMBOLS = {
     "srsran_cuda_pusch_dec_create": (C.c_int, [C.c_int, C.c_uint32, C.c_uint32, C.POINTER(C.c_void_p)]),
@@ -87,6 +95,12 @@ SYMBOLS = {
     "srsran_cuda_pusch_dec_submit_tbs": (C.c_int, [C.c_void_p, C.c_uint32, C.POINTER(TbConfig),
                                                     C.POINTER(C.c_void_p), u32p, intp]),
     "srsran_cuda_pusch_dec_ticket_timing": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_float)]),
+    "srsran_cuda_demodulate_soft": (C.c_int, [C.c_void_p, i8p, f32p, f32p, C.c_uint32, C.c_uint32, C.c_uint32]),
+    "srsran_cuda_pusch_demodulate": (C.c_int, [C.c_void_p, i8p, f32p, f32p, C.POINTER(DemodConfig)]),
+    "srsran_cuda_pusch_dec_submit_tbs_symbols": (C.c_int, [C.c_void_p, C.c_uint32, C.POINTER(TbConfig),
+                                                            C.POINTER(DemodConfig), C.POINTER(C.c_void_p),
+                                                            C.POINTER(C.c_void_p), intp, C.c_int]),
+    "srsran_cuda_pusch_dec_ticket_demod_ms": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_float)]),
     "srsran_cuda_pusch_dec_timer_start": (C.c_int, [C.c_void_p]),
     "srsran_cuda_pusch_dec_timer_stop": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
     "srsran_cuda_pusch_dec_synchronize": (C.c_int, [C.c_void_p]),

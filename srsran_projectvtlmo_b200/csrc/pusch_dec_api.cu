@@ -3,6 +3,7 @@
 #include "../../include/srsran_cuda_pusch_dec.h"
 #include "pusch_dec_kernels.cuh"
 #include "ldpc_packed.cuh"
+#include "pusch_demod.cuh"
 #include <algorithm>
 #include <chrono>
 #include <cmath>
@@ -162,6 +163,24 @@ struct batch_context {
     size_t        bytes;
   };
   std::vector<copy_job> copies;
+
+  // Device-side demodulation (pusch_demod.cuh): equalized symbols + noise variances staged in d_dm_in (host callers),
+  // scrambling sequences in d_scr, one descriptor per transport block.
+  struct raw_copy {
+    const void* src;
+    size_t      dst_off; // in d_dm_in
+    size_t      bytes;
+  };
+  device_buf<uint8_t>      d_dm_in;
+  size_t                   dm_in_used = 0;
+  device_buf<uint32_t>     d_scr;
+  pinned_buf<demod_desc>   h_dm;
+  device_buf<demod_desc>   d_dm;
+  uint32_t                 ndm          = 0;
+  uint32_t                 dm_max_sym   = 0;
+  uint32_t                 dm_max_words = 0;
+  std::vector<raw_copy>    raw_copies;
+  cudaEvent_t              dm_ev[2] = {nullptr, nullptr};
 };
 
 /// Streaming ingestion of the LLRs of one transport block (pusch_decoder_buffer::on_new_softbits): every pushed block is
@@ -218,6 +237,11 @@ struct srsran_cuda_pusch_dec {
   hal_op hal[SRSRAN_CUDA_MAX_NOF_SEGMENTS];
 
   ingest_slot ingest[ingest_slot::NOF];
+
+  // Scrambling-sequence tables of the device-side demodulator (built on first use).
+  bool                 demod_ready = false;
+  device_buf<uint32_t> d_scr_x1; // packed x1(n + 1600)
+  device_buf<uint32_t> d_scr_x2; // [chunk][bit of c_init][32]: x2 windows at every chunk start
 
   // unit-level scratch
   device_buf<crc_job>  d_crc_jobs;
@@ -559,6 +583,11 @@ int open_context(srsran_cuda_pusch_dec* h, uint32_t min_cbs)
   c.cb_meta.clear();
   c.tb_meta.clear();
   c.copies.clear();
+  c.raw_copies.clear();
+  c.ndm          = 0;
+  c.dm_in_used   = 0;
+  c.dm_max_sym   = 0;
+  c.dm_max_words = 0;
   ++c.generation;
   h->open_ctx = pick;
   return pick;
@@ -725,6 +754,23 @@ int launch_context(srsran_cuda_pusch_dec* h, int ci)
   for (const batch_context::copy_job& j : c.copies) {
     const int8_t* src = (j.src != nullptr) ? j.src : c.h_llr.p + j.dst_off;
     CUDA_TRY(h, cudaMemcpyAsync(c.d_llr.p + j.dst_off, src, j.bytes, cudaMemcpyHostToDevice, s));
+  }
+  for (const batch_context::raw_copy& j : c.raw_copies) {
+    CUDA_TRY(h, cudaMemcpyAsync(c.d_dm_in.p + j.dst_off, j.src, j.bytes, cudaMemcpyHostToDevice, s));
+  }
+  if (c.ndm != 0) {
+    // 1b. Soft bits born on the device: scrambling sequences (one warp per 32-Kbit chunk), then one thread per symbol.
+    CUDA_TRY(h, cudaMemcpyAsync(c.d_dm.p, c.h_dm.p, c.ndm * sizeof(demod_desc), cudaMemcpyHostToDevice, s));
+    CUDA_TRY(h, cudaEventRecord(c.dm_ev[0], s));
+    scr_seq_kernel<<<dim3((c.dm_max_words + SCR_CHUNK_WORDS - 1) / SCR_CHUNK_WORDS, c.ndm), 32, 0, s>>>(
+        c.d_dm.p, h->d_scr_x1.p, h->d_scr_x2.p);
+    ++h->launches;
+    CUDA_TRY(h, cudaGetLastError());
+    pusch_demod_kernel<<<dim3((c.dm_max_sym + DM_THREADS_PER_CTA - 1) / DM_THREADS_PER_CTA, c.ndm), DM_THREADS_PER_CTA, 0, s>>>(
+        c.d_dm.p);
+    ++h->launches;
+    CUDA_TRY(h, cudaGetLastError());
+    CUDA_TRY(h, cudaEventRecord(c.dm_ev[1], s));
   }
   PROF_T(l1);
   // 2. Group the decode operations into launch classes (threads per code block x shared-memory bucket).
@@ -1248,6 +1294,158 @@ int prepare_tb_buffers(srsran_cuda_pusch_dec* h, batch_context& c, uint32_t nof_
   return SRSRAN_CUDA_OK;
 }
 
+/// Packed words of a 31-stage binary recurrence s(n + 31) = XOR of s(n + t), t in `taps`, from the initial state `init`
+/// (bit i = s(i)), starting at bit 1600: word w bit j = s(1600 + 32 w + j). The first 31 words are produced bit by bit, the
+/// rest with the word-level form of the same recurrence (Frobenius: P(x)^32 = P(x^32) over GF(2)).
+void lfsr_words(uint32_t init, uint32_t taps, uint32_t* words, uint32_t nwords)
+{
+  uint32_t st = init & 0x7fffffffU;
+  auto     step = [&]() {
+    uint32_t f = __builtin_popcount(st & taps) & 1U;
+    uint32_t o = st & 1U;
+    st         = (st >> 1) | (f << 30);
+    return o;
+  };
+  for (int i = 0; i != 1600; ++i) {
+    step();
+  }
+  for (uint32_t w = 0; w != std::min<uint32_t>(31, nwords); ++w) {
+    uint32_t v = 0;
+    for (int j = 0; j != 32; ++j) {
+      v |= step() << j;
+    }
+    words[w] = v;
+  }
+  for (uint32_t w = 31; w < nwords; ++w) {
+    uint32_t v = 0;
+    for (int t = 0; t != 4; ++t) {
+      if ((taps >> t) & 1U) {
+        v ^= words[w - 31 + t];
+      }
+    }
+    words[w] = v;
+  }
+}
+
+/// Builds the demodulator's constant tables (the reference's binary32 expressions) and the scrambling-sequence tables.
+int init_demod(srsran_cuda_pusch_dec* h)
+{
+  if (h->demod_ready) {
+    return SRSRAN_CUDA_OK;
+  }
+  demod_tables t = {};
+  auto fill = [&](int ti, float unit, float width_mult, int n, const int* slope_mult, const float* icpt_num, float icpt_den) {
+    t.width[ti] = width_mult * unit;
+    t.inv[ti]   = 1.0F / t.width[ti];
+    t.n[ti]     = n;
+    for (int i = 0; i != n; ++i) {
+      t.slope[ti][i] = static_cast<float>(slope_mult[i]) * unit;
+      t.icpt[ti][i]  = icpt_num[i] / icpt_den;
+    }
+  };
+  const float s42 = 1.0F / std::sqrt(42.0F), s170 = 1.0F / std::sqrt(170.0F);
+  {
+    // demodulation_mapper_qam64.cpp:42-84
+    static const int   s01[8] = {16, 12, 8, 4, 4, 8, 12, 16};
+    static const float i01[8] = {24, 12, 4, 0, 0, -4, -12, -24};
+    static const int   s23[8] = {8, 4, 4, 8, -8, -4, -4, -8};
+    static const float i23[8] = {20, 8, 8, 12, 12, 8, 8, 20};
+    static const int   s45[4] = {4, -4, 4, -4};
+    static const float i45[4] = {12, -4, -4, 12};
+    fill(0, s42, 2, 8, s01, i01, 21);
+    fill(1, s42, 2, 8, s23, i23, 21);
+    fill(2, s42, 4, 4, s45, i45, 21);
+  }
+  {
+    // demodulation_mapper_qam256.cpp:42-172
+    static const int   s01[16] = {32, 28, 24, 20, 16, 12, 8, 4, 4, 8, 12, 16, 20, 24, 28, 32};
+    static const float i01[16] = {112, 84, 60, 40, 24, 12, 4, 0, 0, -4, -12, -24, -40, -60, -84, -112};
+    static const int   s23[16] = {16, 12, 8, 4, 4, 8, 12, 16, -16, -12, -8, -4, -4, -8, -12, -16};
+    static const float i23[16] = {88, 60, 36, 16, 16, 28, 36, 40, 40, 36, 28, 16, 16, 36, 60, 88};
+    static const int   s45[16] = {8, 4, 4, 8, -8, -4, -4, -8, 8, 4, 4, 8, -8, -4, -4, -8};
+    static const float i45[16] = {52, 24, 24, 44, -20, -8, -8, -12, -12, -8, -8, -20, 44, 24, 24, 52};
+    static const int   s67[8]  = {4, -4, 4, -4, 4, -4, 4, -4};
+    static const float i67[8]  = {28, -20, 12, -4, -4, 12, -20, 28};
+    fill(3, s170, 2, 16, s01, i01, 85);
+    fill(4, s170, 2, 16, s23, i23, 85);
+    fill(5, s170, 2, 16, s45, i45, 85);
+    fill(6, s170, 4, 8, s67, i67, 85);
+  }
+  t.sq10  = 1.0F / std::sqrt(10.0F);
+  t.gain2 = 2.0F * 1.41421356237309504880F;
+  CUDA_TRY(h, cudaMemcpyToSymbol(c_demod, &t, sizeof(t)));
+  // Scrambling sequences (TS 38.211 5.2.1): x1 from state 1 (taps n, n + 3), x2 from every single bit of c_init (taps
+  // n .. n + 3); the x2 sequence of any c_init is the XOR of the basis sequences of its set bits.
+  std::vector<uint32_t> seq(SCR_MAX_WORDS);
+  std::vector<uint32_t> win(static_cast<size_t>(SCR_NOF_CHUNKS) * 31 * 32, 0);
+  CUDA_TRY(h, h->d_scr_x1.reserve(SCR_MAX_WORDS));
+  CUDA_TRY(h, h->d_scr_x2.reserve(win.size()));
+  lfsr_words(1U, 0x9U, seq.data(), SCR_MAX_WORDS);
+  CUDA_TRY(h, cudaMemcpy(h->d_scr_x1.p, seq.data(), SCR_MAX_WORDS * sizeof(uint32_t), cudaMemcpyHostToDevice));
+  for (uint32_t bit = 0; bit != 31; ++bit) {
+    lfsr_words(1U << bit, 0xfU, seq.data(), SCR_MAX_WORDS);
+    for (uint32_t ch = 0; ch != SCR_NOF_CHUNKS; ++ch) {
+      for (uint32_t l = 0; l != 31; ++l) {
+        uint32_t w = ch * SCR_CHUNK_WORDS + l;
+        win[(static_cast<size_t>(ch) * 31 + bit) * 32 + l] = (w < SCR_MAX_WORDS) ? seq[w] : 0U;
+      }
+    }
+  }
+  CUDA_TRY(h, cudaMemcpy(h->d_scr_x2.p, win.data(), win.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+  h->demod_ready = true;
+  return SRSRAN_CUDA_OK;
+}
+
+/// Validates a demodulation configuration; returns the number of symbols (REs x layers) or 0.
+uint32_t demod_nof_symbols(const srsran_cuda_pusch_demod_config& d)
+{
+  if ((d.modulation != 1 && d.modulation != 2 && d.modulation != 4 && d.modulation != 6 && d.modulation != 8) ||
+      d.nof_layers == 0 || d.nof_layers > 4 || d.nof_ofdm_symbols == 0 || d.nof_ofdm_symbols > DM_MAX_OFDM ||
+      (d.pi2_bpsk != 0 && d.modulation != 1) || d.n_id > 1023 || d.rnti > 65535) {
+    return 0;
+  }
+  uint64_t re = 0;
+  for (uint32_t i = 0; i != d.nof_ofdm_symbols; ++i) {
+    re += d.re_per_symbol[i];
+  }
+  uint64_t nsym = re * d.nof_layers;
+  if (nsym == 0 || nsym * d.modulation > static_cast<uint64_t>(SCR_MAX_WORDS) * 32) {
+    return 0;
+  }
+  return static_cast<uint32_t>(nsym);
+}
+
+/// Appends one codeword to the open context's demodulation list. `sym_dev` / `nv_dev` / `llr_dev`: device addresses.
+int add_demod(srsran_cuda_pusch_dec* h, batch_context& c, const srsran_cuda_pusch_demod_config& d, uint32_t nsym,
+              const float* sym_dev, const float* nv_dev, int8_t* llr_dev, size_t scr_word_off)
+{
+  (void)h;
+  demod_desc& o    = c.h_dm.p[c.ndm++];
+  o                = {};
+  o.sym            = reinterpret_cast<const float2*>(sym_dev);
+  o.nv             = nv_dev;
+  o.llr            = llr_dev;
+  o.scr            = c.d_scr.p + scr_word_off;
+  o.nsym           = nsym;
+  o.qm             = d.modulation;
+  o.pi2            = d.pi2_bpsk;
+  o.nl             = d.nof_layers;
+  o.max_block_subc = 4096 / (d.nof_layers * d.modulation); // pusch_demodulator_impl.h:71, .cpp:177
+  o.c_init         = (d.rnti << 15) + d.n_id;              // pusch_demodulator_impl.cpp:139
+  o.nof_ofdm       = d.nof_ofdm_symbols;
+  uint32_t acc     = 0;
+  for (uint32_t i = 0; i != d.nof_ofdm_symbols; ++i) {
+    o.re_start[i] = acc;
+    acc += d.re_per_symbol[i];
+  }
+  for (uint32_t i = d.nof_ofdm_symbols; i <= DM_MAX_OFDM; ++i) {
+    o.re_start[i] = acc;
+  }
+  c.dm_max_sym   = std::max(c.dm_max_sym, nsym);
+  c.dm_max_words = std::max(c.dm_max_words, (nsym * d.modulation + 31) / 32);
+  return SRSRAN_CUDA_OK;
+}
+
 int make_ticket(int ctx, uint32_t tb_index, uint32_t generation)
 {
   return static_cast<int>(((generation & 0x3ff) << 20) | (static_cast<uint32_t>(ctx) << 16) | tb_index);
@@ -1351,6 +1549,7 @@ int srsran_cuda_pusch_dec_create(int device, uint32_t max_cbs_in_flight, uint32_
       ok = ok && cudaEventCreate(&e) == cudaSuccess;
     }
     ok = ok && cudaEventCreateWithFlags(&c.fork, cudaEventDisableTiming) == cudaSuccess;
+    ok = ok && cudaEventCreate(&c.dm_ev[0]) == cudaSuccess && cudaEventCreate(&c.dm_ev[1]) == cudaSuccess;
     for (int k = 0; k != batch_context::NOF_SIDE; ++k) {
       ok = ok && cudaStreamCreateWithFlags(&c.side[k], cudaStreamNonBlocking) == cudaSuccess &&
            cudaEventCreateWithFlags(&c.join[k], cudaEventDisableTiming) == cudaSuccess;
@@ -1385,6 +1584,8 @@ void srsran_cuda_pusch_dec_destroy(srsran_cuda_pusch_dec_t* h)
   }
   cudaSetDevice(h->device);
   cudaDeviceSynchronize();
+  h->d_scr_x1.release();
+  h->d_scr_x2.release();
   for (ingest_slot& g : h->ingest) {
     if (g.stream != nullptr) {
       cudaStreamDestroy(g.stream);
@@ -1417,6 +1618,15 @@ void srsran_cuda_pusch_dec_destroy(srsran_cuda_pusch_dec_t* h)
     c.h_tbout.release();
     c.d_tbout.release();
     c.d_unit_bits.release();
+    c.d_dm_in.release();
+    c.d_scr.release();
+    c.h_dm.release();
+    c.d_dm.release();
+    for (cudaEvent_t e : c.dm_ev) {
+      if (e != nullptr) {
+        cudaEventDestroy(e);
+      }
+    }
     if (c.done != nullptr) {
       cudaEventDestroy(c.done);
     }
@@ -2062,6 +2272,209 @@ int srsran_cuda_pusch_dec_tb_cb_outputs(srsran_cuda_pusch_dec_t* h, int ticket, 
     std::memset(crc_ok, 0, m.nof_cbs);
   }
   return static_cast<int>(m.nof_cbs);
+}
+
+int srsran_cuda_pusch_dec_submit_tbs_symbols(srsran_cuda_pusch_dec_t* h, uint32_t nof_tbs,
+                                             const srsran_cuda_pusch_dec_tb_config* configs,
+                                             const srsran_cuda_pusch_demod_config* demod_configs,
+                                             const float* const* symbols, const float* const* noise_vars, int* tickets,
+                                             int device_resident)
+{
+  if (h == nullptr || configs == nullptr || demod_configs == nullptr || symbols == nullptr || noise_vars == nullptr ||
+      tickets == nullptr || nof_tbs == 0 || nof_tbs > MAX_TBS_PER_CTX) {
+    return SRSRAN_CUDA_ERR_INVALID;
+  }
+  cudaSetDevice(h->device);
+  int r = init_demod(h);
+  if (r != SRSRAN_CUDA_OK) {
+    return r;
+  }
+  if (h->open_ctx >= 0) {
+    r = fixup_and_launch(h, h->open_ctx); // a HAL-style batch is still open: launch it first to keep HARQ ordering
+    if (r != SRSRAN_CUDA_OK) {
+      return r;
+    }
+  }
+  uint32_t              total_cbs = 0;
+  size_t                tb_bytes = 0, llr_bytes = 0, in_bytes = 0, scr_words = 0;
+  std::vector<uint32_t> nsym(nof_tbs);
+  for (uint32_t i = 0; i != nof_tbs; ++i) {
+    nsym[i] = demod_nof_symbols(demod_configs[i]);
+    if (nsym[i] == 0 || symbols[i] == nullptr || noise_vars[i] == nullptr ||
+        demod_configs[i].modulation != (configs[i].modulation == 0 ? 1 : configs[i].modulation) ||
+        demod_configs[i].nof_layers != configs[i].nof_layers) {
+      h->last_error = "invalid demodulation configuration";
+      return SRSRAN_CUDA_ERR_INVALID;
+    }
+    uint32_t B = configs[i].tbs_bits + ((configs[i].tbs_bits <= 3824) ? 16 : 24);
+    uint32_t m = (configs[i].base_graph == 1) ? 8448 : 3840;
+    total_cbs += (B <= m) ? 1 : (B + m - 25) / (m - 24);
+    tb_bytes += configs[i].tbs_bits / 8 + 32;
+    llr_bytes += (static_cast<size_t>(nsym[i]) * demod_configs[i].modulation + 15) & ~size_t(15);
+    in_bytes += (static_cast<size_t>(nsym[i]) * 12 + 15) & ~size_t(15);
+    scr_words += (static_cast<size_t>(nsym[i]) * demod_configs[i].modulation + 31) / 32 + 1;
+  }
+  int ci = open_context(h, total_cbs);
+  if (ci < 0) {
+    return ci;
+  }
+  batch_context& c    = h->ctx[ci];
+  auto           fail = [&](int code) {
+    c.open      = false;
+    h->open_ctx = -1;
+    return code;
+  };
+  r = prepare_tb_buffers(h, c, nof_tbs, tb_bytes);
+  if (r != SRSRAN_CUDA_OK) {
+    return fail(r);
+  }
+  // All device regions are sized before any address is taken (the buffers may be reallocated while growing).
+  if (c.d_llr.reserve(llr_bytes) != cudaSuccess || c.d_scr.reserve(scr_words) != cudaSuccess ||
+      c.h_dm.reserve(MAX_TBS_PER_CTX) != cudaSuccess || c.d_dm.reserve(MAX_TBS_PER_CTX) != cudaSuccess ||
+      (!device_resident && c.d_dm_in.reserve(in_bytes) != cudaSuccess)) {
+    cudaGetLastError();
+    h->last_error = "demodulation staging allocation failed";
+    return fail(SRSRAN_CUDA_ERR_NO_MEMORY);
+  }
+  size_t llr_off = 0, in_off = 0, scr_off = 0;
+  for (uint32_t i = 0; i != nof_tbs; ++i) {
+    const srsran_cuda_pusch_demod_config& d = demod_configs[i];
+    const float*                          sym_dev = symbols[i];
+    const float*                          nv_dev  = noise_vars[i];
+    if (!device_resident) {
+      // One region per TB: symbols (8 B each) then noise variances (4 B each).
+      const size_t sym_bytes = static_cast<size_t>(nsym[i]) * 8, nv_bytes = static_cast<size_t>(nsym[i]) * 4;
+      c.raw_copies.push_back({symbols[i], in_off, sym_bytes});
+      c.raw_copies.push_back({noise_vars[i], in_off + sym_bytes, nv_bytes});
+      sym_dev = reinterpret_cast<const float*>(c.d_dm_in.p + in_off);
+      nv_dev  = reinterpret_cast<const float*>(c.d_dm_in.p + in_off + sym_bytes);
+      in_off += (sym_bytes + nv_bytes + 15) & ~size_t(15);
+    }
+    const uint32_t nllr = nsym[i] * d.modulation;
+    add_demod(h, c, d, nsym[i], sym_dev, nv_dev, c.d_llr.p + llr_off, scr_off);
+    r = add_tb(h, c, configs[i], c.d_llr.p + llr_off, nllr);
+    if (r != SRSRAN_CUDA_OK) {
+      return fail(r);
+    }
+    llr_off += (static_cast<size_t>(nllr) + 15) & ~size_t(15);
+    scr_off += (static_cast<size_t>(nllr) + 31) / 32 + 1;
+    tickets[i] = make_ticket(ci, static_cast<uint32_t>(c.tb_meta.size() - 1), c.generation);
+  }
+  c.llr_used = llr_off;
+  return launch_context(h, ci);
+}
+
+/// One synchronous demodulation of `nof_jobs` codewords with host buffers (unit-level entry points).
+static int demod_sync(srsran_cuda_pusch_dec_t* h, int8_t* llrs, const float* symbols, const float* noise_vars,
+                      const srsran_cuda_pusch_demod_config& d, uint32_t nsym, uint32_t max_block_subc_override)
+{
+  cudaSetDevice(h->device);
+  int r = init_demod(h);
+  if (r != SRSRAN_CUDA_OK) {
+    return r;
+  }
+  r = srsran_cuda_pusch_dec_synchronize(h);
+  if (r != SRSRAN_CUDA_OK) {
+    return r;
+  }
+  batch_context& c    = h->ctx[0];
+  const size_t   nllr = static_cast<size_t>(nsym) * d.modulation;
+  CUDA_TRY(h, c.d_llr.reserve((nllr + 15) & ~size_t(15)));
+  CUDA_TRY(h, c.d_scr.reserve(nllr / 32 + 2));
+  CUDA_TRY(h, c.d_dm_in.reserve(static_cast<size_t>(nsym) * 12 + 16));
+  CUDA_TRY(h, c.h_dm.reserve(MAX_TBS_PER_CTX));
+  CUDA_TRY(h, c.d_dm.reserve(MAX_TBS_PER_CTX));
+  cudaStream_t s = c.stream;
+  CUDA_TRY(h, cudaMemcpyAsync(c.d_dm_in.p, symbols, static_cast<size_t>(nsym) * 8, cudaMemcpyHostToDevice, s));
+  CUDA_TRY(h, cudaMemcpyAsync(c.d_dm_in.p + static_cast<size_t>(nsym) * 8, noise_vars, static_cast<size_t>(nsym) * 4,
+                              cudaMemcpyHostToDevice, s));
+  c.ndm = 0;
+  c.dm_max_sym = c.dm_max_words = 0;
+  add_demod(h, c, d, nsym, reinterpret_cast<const float*>(c.d_dm_in.p),
+            reinterpret_cast<const float*>(c.d_dm_in.p + static_cast<size_t>(nsym) * 8), c.d_llr.p, 0);
+  if (max_block_subc_override != 0) {
+    c.h_dm.p[0].max_block_subc = max_block_subc_override;
+  }
+  CUDA_TRY(h, cudaMemcpyAsync(c.d_dm.p, c.h_dm.p, sizeof(demod_desc), cudaMemcpyHostToDevice, s));
+  scr_seq_kernel<<<dim3((c.dm_max_words + SCR_CHUNK_WORDS - 1) / SCR_CHUNK_WORDS, 1), 32, 0, s>>>(c.d_dm.p, h->d_scr_x1.p,
+                                                                                                 h->d_scr_x2.p);
+  pusch_demod_kernel<<<dim3((nsym + DM_THREADS_PER_CTA - 1) / DM_THREADS_PER_CTA, 1), DM_THREADS_PER_CTA, 0, s>>>(c.d_dm.p);
+  h->launches += 2;
+  CUDA_TRY(h, cudaGetLastError());
+  CUDA_TRY(h, cudaMemcpyAsync(llrs, c.d_llr.p, nllr, cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(h, cudaStreamSynchronize(s));
+  c.ndm = 0;
+  return static_cast<int>(nllr);
+}
+
+int srsran_cuda_pusch_demodulate(srsran_cuda_pusch_dec_t* h, int8_t* llrs, const float* symbols, const float* noise_vars,
+                                 const srsran_cuda_pusch_demod_config* config)
+{
+  if (h == nullptr || llrs == nullptr || symbols == nullptr || noise_vars == nullptr || config == nullptr) {
+    return SRSRAN_CUDA_ERR_INVALID;
+  }
+  uint32_t nsym = demod_nof_symbols(*config);
+  if (nsym == 0) {
+    h->last_error = "invalid demodulation configuration";
+    return SRSRAN_CUDA_ERR_INVALID;
+  }
+  return demod_sync(h, llrs, symbols, noise_vars, *config, nsym, 0);
+}
+
+int srsran_cuda_demodulate_soft(srsran_cuda_pusch_dec_t* h, int8_t* llrs, const float* symbols, const float* noise_vars,
+                                uint32_t nof_symbols, uint32_t modulation, uint32_t pi2_bpsk)
+{
+  if (h == nullptr || llrs == nullptr || symbols == nullptr || noise_vars == nullptr || nof_symbols == 0) {
+    return SRSRAN_CUDA_ERR_INVALID;
+  }
+  // One demodulation_mapper call = one block of one layer; the scrambling of the codeword-level path is undone below
+  // by demodulating with the all-zero sequence (c_init whose x2 cancels x1 does not exist, so the unit-level path
+  // re-applies the sequence on the host side of this function instead).
+  srsran_cuda_pusch_demod_config d = {};
+  d.modulation                     = modulation;
+  d.pi2_bpsk                       = pi2_bpsk;
+  d.nof_layers                     = 1;
+  d.nof_ofdm_symbols               = 1;
+  d.re_per_symbol[0]               = nof_symbols;
+  uint32_t nsym                    = demod_nof_symbols(d);
+  if (nsym == 0) {
+    h->last_error = "invalid demodulation configuration";
+    return SRSRAN_CUDA_ERR_INVALID;
+  }
+  int n = demod_sync(h, llrs, symbols, noise_vars, d, nsym, nof_symbols); // one block: the whole input
+  if (n < 0) {
+    return n;
+  }
+  // Undo the descrambling (c_init = 0: c(n) = x1(n + 1600)) - the demapper itself does not descramble.
+  std::vector<uint32_t> x1((static_cast<size_t>(n) + 31) / 32);
+  lfsr_words(1U, 0x9U, x1.data(), static_cast<uint32_t>(x1.size()));
+  for (int i = 0; i != n; ++i) {
+    if ((x1[i >> 5] >> (i & 31)) & 1U) {
+      llrs[i] = static_cast<int8_t>(-llrs[i]);
+    }
+  }
+  return SRSRAN_CUDA_OK;
+}
+
+int srsran_cuda_pusch_dec_ticket_demod_ms(srsran_cuda_pusch_dec_t* h, int ticket, float* ms)
+{
+  if (h == nullptr || ticket < 0 || ms == nullptr) {
+    return SRSRAN_CUDA_ERR_INVALID;
+  }
+  int      ci  = (ticket >> 16) & 0xf;
+  uint32_t gen = (static_cast<uint32_t>(ticket) >> 20) & 0x3ff;
+  if (ci >= NOF_CONTEXTS || (h->ctx[ci].generation & 0x3ff) != gen) {
+    h->last_error = "stale or unknown ticket";
+    return SRSRAN_CUDA_ERR_STATE;
+  }
+  batch_context& c = h->ctx[ci];
+  cudaSetDevice(h->device);
+  CUDA_TRY(h, cudaEventSynchronize(c.done));
+  *ms = 0.0F;
+  if (c.ndm != 0) {
+    CUDA_TRY(h, cudaEventElapsedTime(ms, c.dm_ev[0], c.dm_ev[1]));
+  }
+  return SRSRAN_CUDA_OK;
 }
 
 int srsran_cuda_pusch_dec_ticket_timing(srsran_cuda_pusch_dec_t* h, int ticket, float* stage_ms)

@@ -369,3 +369,91 @@ def ticket_timing(acc: Accelerator, ticket):
     ms = (C.c_float * 5)()
     acc._check(acc._lib.srsran_cuda_pusch_dec_ticket_timing(acc.h, ticket, ms), "ticket_timing")
     return [float(v) for v in ms]
+
+
+# ---- soft demodulation + descrambling + UL-SCH demultiplexing on the device -------------------------
+DemodConfig = capi.DemodConfig
+
+
+def demod_config(modulation, rnti, n_id, nof_layers, re_per_symbol, pi2_bpsk=False):
+    """srsran_cuda_pusch_demod_config from the fields of pusch_demodulator::configuration that shape the soft bits:
+    `re_per_symbol` = data REs per layer in every OFDM symbol of the allocation."""
+    d = DemodConfig()
+    d.modulation, d.pi2_bpsk, d.rnti, d.n_id, d.nof_layers = modulation, int(pi2_bpsk), rnti, n_id, nof_layers
+    d.nof_ofdm_symbols = len(re_per_symbol)
+    for i, v in enumerate(re_per_symbol):
+        d.re_per_symbol[i] = int(v)
+    return d
+
+
+def _f32(symbols, noise_vars):
+    sym = np.ascontiguousarray(symbols, dtype=np.complex64).view(np.float32)
+    nv = np.ascontiguousarray(noise_vars, dtype=np.float32)
+    assert sym.size == 2 * nv.size
+    return sym, nv
+
+
+class demodulation_mapper_cuda:
+    """Mirror of srsran::demodulation_mapper (include/srsran/phy/upper/channel_modulation/demodulation_mapper.h): one call =
+    one block."""
+
+    def __init__(self, acc: Accelerator):
+        self.acc = acc
+
+    def demodulate_soft(self, symbols, noise_vars, modulation, pi2_bpsk=False):
+        sym, nv = _f32(symbols, noise_vars)
+        out = np.zeros(nv.size * modulation, np.int8)
+        st = self.acc._lib.srsran_cuda_demodulate_soft(self.acc.h, out.ctypes.data_as(capi.i8p),
+                                                       sym.ctypes.data_as(capi.f32p), nv.ctypes.data_as(capi.f32p),
+                                                       nv.size, modulation, int(pi2_bpsk))
+        self.acc._check(st, "demodulate_soft")
+        return out
+
+
+def pusch_demodulate(acc: Accelerator, symbols, noise_vars, config):
+    """pusch_demodulator_impl::demodulate minus the equalizer + ulsch_demultiplex without UCI, one codeword, host buffers."""
+    sym, nv = _f32(symbols, noise_vars)
+    out = np.zeros(nv.size * config.modulation, np.int8)
+    n = acc._lib.srsran_cuda_pusch_demodulate(acc.h, out.ctypes.data_as(capi.i8p), sym.ctypes.data_as(capi.f32p),
+                                              nv.ctypes.data_as(capi.f32p), C.byref(config))
+    acc._check(n, "pusch_demodulate")
+    assert n == out.size
+    return out
+
+
+class SubmitSymbolArgs:
+    """Marshalled arguments of one submit_tbs_symbols call. `symbols_list` / `noise_list`: numpy arrays (host: complex64 /
+    float32, kept alive here) or device addresses (ints) when `device_resident`."""
+
+    def __init__(self, configs, demod_configs, symbols_list, noise_list, device_resident=False):
+        n = len(configs)
+        self.n = n
+        self.device_resident = device_resident
+        self.cfg_arr = (TbConfig * n)(*configs)
+        self.dm_arr = (DemodConfig * n)(*demod_configs)
+        self.sym = (C.c_void_p * n)()
+        self.nv = (C.c_void_p * n)()
+        self.keep = []
+        for i in range(n):
+            if device_resident:
+                self.sym[i], self.nv[i] = symbols_list[i], noise_list[i]
+            else:
+                s, v = _f32(symbols_list[i], noise_list[i])
+                self.keep.append((s, v))
+                self.sym[i], self.nv[i] = s.ctypes.data, v.ctypes.data
+        self.tickets = (C.c_int * n)()
+
+
+def submit_tbs_symbols(acc: Accelerator, args: SubmitSymbolArgs):
+    """Equalized symbols + noise variances in, transport blocks out: demodulation, descrambling, rate dematching, LDPC
+    decoding and TB assembly in one set of launches. Returns the tickets."""
+    acc._check(acc._lib.srsran_cuda_pusch_dec_submit_tbs_symbols(acc.h, args.n, args.cfg_arr, args.dm_arr, args.sym,
+                                                                 args.nv, args.tickets, int(args.device_resident)),
+               "submit_tbs_symbols")
+    return list(args.tickets)
+
+
+def ticket_demod_ms(acc: Accelerator, ticket):
+    ms = C.c_float(0)
+    acc._check(acc._lib.srsran_cuda_pusch_dec_ticket_demod_ms(acc.h, ticket, C.byref(ms)), "ticket_demod_ms")
+    return ms.value
