@@ -31,6 +31,8 @@ extern "C" {
 #define SRSRAN_CUDA_ERR_NO_MEMORY (-3)   /* device or pinned host allocation failed */
 #define SRSRAN_CUDA_ERR_CUDA (-4)        /* CUDA runtime error (see srsran_cuda_pusch_dec_last_error) */
 #define SRSRAN_CUDA_ERR_STATE (-5)       /* call sequence violated (e.g. dequeue of an operation never enqueued) */
+#define SRSRAN_CUDA_ERR_BUSY (-6)        /* every batch context holds transport blocks nobody has polled yet: consume older
+                                            tickets (poll_tb / poll_tbs) and submit again - like a full bbdev queue, not fatal */
 
 /* CRC polynomial selectors (crc_generator_poly of include/srsran/phy/upper/channel_coding/crc_calculator.h:31-39). */
 #define SRSRAN_CUDA_CRC_NONE 0
@@ -224,6 +226,24 @@ int srsran_cuda_pusch_dec_submit_tbs_device(srsran_cuda_pusch_dec_t* handle, uin
 int srsran_cuda_pusch_dec_submit_tbs(srsran_cuda_pusch_dec_t* handle, uint32_t nof_tbs,
                                      const srsran_cuda_pusch_dec_tb_config* configs, const int8_t* const* llrs,
                                      const uint32_t* nof_llrs, int* tickets);
+/* A batch of TBs whose HARQ slots are the rx buffers' absolute code-block ids (rx_buffer::get_absolute_codeblock_id,
+ * include/srsran/phy/upper/rx_buffer.h:50-53; not consecutive): `absolute_cb_ids` holds the ids of all TBs back to back,
+ * `nof_cb_ids[i]` of them for TB i. `ingest_streams` (may be NULL): >= 0 for a TB whose LLRs were streamed to the device with
+ * stream_begin / stream_push (llrs[i] / nof_llrs[i] are then ignored and the stream is closed by this call), -1 for host
+ * LLRs. This is what a slot aggregator above many pusch_decoder instances calls once per batch. SRSRAN_CUDA_ERR_BUSY: nothing
+ * was submitted (ingest streams stay open) - poll older tickets and call again. */
+int srsran_cuda_pusch_dec_submit_tbs_cb_ids(srsran_cuda_pusch_dec_t* handle, uint32_t nof_tbs,
+                                            const srsran_cuda_pusch_dec_tb_config* configs, const int8_t* const* llrs,
+                                            const uint32_t* nof_llrs, const int* ingest_streams,
+                                            const uint32_t* absolute_cb_ids, const uint32_t* nof_cb_ids, int* tickets);
+/* poll_tb without consuming the ticket: returns 1 and the result if the TB has completed, 0 if not. The batch context (and
+ * with it the buffer srsran_cuda_pusch_dec_tb_data points into) stays reserved until poll_tb / poll_tbs consume the ticket. */
+int srsran_cuda_pusch_dec_peek_tb(srsran_cuda_pusch_dec_t* handle, int ticket, srsran_cuda_pusch_dec_tb_result* result);
+/* Blocks until the batch of `ticket` has completed on the device. Unlike every other function it may be called while
+ * another thread uses the handle (it only waits on the batch's completion event): a completion thread waits here, then
+ * takes the handle for the short poll_tb calls. */
+int srsran_cuda_pusch_dec_wait_ticket(srsran_cuda_pusch_dec_t* handle, int ticket);
+
 /* ---- Soft demodulation + descrambling + UL-SCH demultiplexing on the device ------------------------
  * The soft bits are born in HBM: the caller hands over what the channel equalizer produced - equalized symbols (complex
  * binary32, re / im interleaved) and post-equalization noise variances, in the order the reference's demodulator consumes

@@ -14,7 +14,7 @@ HERE = Path(__file__).resolve().parent
 # SRSRAN_CUDA_PUSCH_DEC_LIB: another build of the same library (kernel A/B measurements); never a different implementation.
 LIB_PATH = Path(os.environ.get("SRSRAN_CUDA_PUSCH_DEC_LIB", HERE / "libsrsran_cuda_pusch_dec.so"))
 
-OK, ERR_NO_DEVICE, ERR_INVALID, ERR_NO_MEMORY, ERR_CUDA, ERR_STATE = 0, -1, -2, -3, -4, -5
+OK, ERR_NO_DEVICE, ERR_INVALID, ERR_NO_MEMORY, ERR_CUDA, ERR_STATE, ERR_BUSY = 0, -1, -2, -3, -4, -5, -6
 CRC_NONE, CRC24A, CRC24B, CRC16 = 0, 1, 2, 3
 CB_CRC16, CB_CRC24B, CB_CRC24A = 0, 1, 2
 MAX_NOF_SEGMENTS = 162
@@ -95,6 +95,10 @@ SYMBOLS = {
     "srsran_cuda_pusch_dec_submit_tbs": (C.c_int, [C.c_void_p, C.c_uint32, C.POINTER(TbConfig),
                                                     C.POINTER(C.c_void_p), u32p, intp]),
     "srsran_cuda_pusch_dec_ticket_timing": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_float)]),
+    "srsran_cuda_pusch_dec_submit_tbs_cb_ids": (C.c_int, [C.c_void_p, C.c_uint32, C.POINTER(TbConfig), C.POINTER(C.c_void_p),
+                                                           u32p, intp, u32p, u32p, intp]),
+    "srsran_cuda_pusch_dec_wait_ticket": (C.c_int, [C.c_void_p, C.c_int]),
+    "srsran_cuda_pusch_dec_peek_tb": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(TbResult)]),
     "srsran_cuda_demodulate_soft": (C.c_int, [C.c_void_p, i8p, f32p, f32p, C.c_uint32, C.c_uint32, C.c_uint32]),
     "srsran_cuda_pusch_demodulate": (C.c_int, [C.c_void_p, i8p, f32p, f32p, C.POINTER(DemodConfig)]),
     "srsran_cuda_pusch_dec_submit_tbs_symbols": (C.c_int, [C.c_void_p, C.c_uint32, C.POINTER(TbConfig),

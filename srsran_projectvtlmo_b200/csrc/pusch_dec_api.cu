@@ -33,7 +33,7 @@ static inline double prof_now() { return std::chrono::duration<double, std::micr
 
 thread_local std::string g_create_error;
 
-constexpr int      NOF_CONTEXTS   = 6;
+constexpr int      NOF_CONTEXTS   = 8;
 constexpr uint32_t MAX_TBS_PER_CTX = 1024;
 
 template <typename T>
@@ -123,9 +123,18 @@ struct batch_context {
   cudaEvent_t  join[NOF_SIDE]  = {};
   uint32_t     slot_lo    = 0xffffffffU; // range of HARQ slots this batch touches (ordering between batches)
   uint32_t     slot_hi    = 0;
+  // The HARQ slots themselves as runs [first, last]: the rx buffers of a slot's transport blocks own scattered runs of
+  // code-block ids, so two batches whose RANGES overlap usually share no slot at all and need no ordering.
+  std::vector<std::pair<uint32_t, uint32_t>> slot_runs;
+  bool                                       runs_sorted = false;
   cudaEvent_t  wait_for   = nullptr; // set by a streamed submit: the batch's kernels wait for the ingest copies
   bool         open       = false;   // accepting operations, not launched
   bool         in_flight  = false;   // launched, results not yet consumed
+  bool         hal_style  = false;   // descriptors hold staging OFFSETS until fixup_and_launch (enqueue path)
+  std::vector<cudaEvent_t> wait_events; // ingest copies the batch's kernels wait for (streamed transport blocks)
+  // Soft-buffer extents this (not yet launched) batch has advanced: (slot, previous value). Committed when the batch is
+  // launched, restored if it is abandoned - the host-side extents must describe what the device actually wrote.
+  std::vector<std::pair<uint32_t, uint32_t>> extent_undo;
   uint32_t     generation = 0;
 
   pinned_buf<int8_t>        h_llr;
@@ -186,7 +195,7 @@ struct batch_context {
 /// Streaming ingestion of the LLRs of one transport block (pusch_decoder_buffer::on_new_softbits): every pushed block is
 /// copied to the device at once on the ingest stream; the batch that decodes the transport block waits for `pushed`.
 struct ingest_slot {
-  static constexpr int NOF = 8;
+  static constexpr int NOF = 32;
   cudaStream_t       stream = nullptr;
   cudaEvent_t        pushed = nullptr;
   device_buf<int8_t> d_llr;
@@ -550,8 +559,9 @@ int open_context(srsran_cuda_pusch_dec* h, uint32_t min_cbs)
     break;
   }
   if (pick < 0) {
+    // Not an error of the caller: the accelerator is busy. Poll (consume) older tickets and submit again.
     h->last_error = "all batch contexts hold unpolled transport blocks";
-    return SRSRAN_CUDA_ERR_STATE;
+    return SRSRAN_CUDA_ERR_BUSY;
   }
   batch_context& c = h->ctx[pick];
   if (c.in_flight) {
@@ -576,6 +586,8 @@ int open_context(srsran_cuda_pusch_dec* h, uint32_t min_cbs)
   c.open       = true;
   c.slot_lo    = 0xffffffffU;
   c.slot_hi    = 0;
+  c.slot_runs.clear();
+  c.runs_sorted = false;
   c.llr_used   = 0;
   c.tbout_used = 0;
   c.want_bits  = false;
@@ -584,6 +596,9 @@ int open_context(srsran_cuda_pusch_dec* h, uint32_t min_cbs)
   c.tb_meta.clear();
   c.copies.clear();
   c.raw_copies.clear();
+  c.wait_events.clear();
+  c.extent_undo.clear();
+  c.hal_style    = false;
   c.ndm          = 0;
   c.dm_in_used   = 0;
   c.dm_max_sym   = 0;
@@ -591,6 +606,59 @@ int open_context(srsran_cuda_pusch_dec* h, uint32_t min_cbs)
   ++c.generation;
   h->open_ctx = pick;
   return pick;
+}
+
+/// Notes that the open batch touches HARQ slot `slot` (soft bits, data bits or CRC flag).
+inline void note_slot(batch_context& c, uint32_t slot)
+{
+  c.slot_lo = std::min(c.slot_lo, slot);
+  c.slot_hi = std::max(c.slot_hi, slot);
+  if (!c.slot_runs.empty() && c.slot_runs.back().second + 1 == slot) {
+    c.slot_runs.back().second = slot; // the code blocks of a transport block mostly take consecutive slots
+  } else if (c.slot_runs.empty() || slot < c.slot_runs.back().first || slot > c.slot_runs.back().second) {
+    c.slot_runs.emplace_back(slot, slot);
+  }
+}
+
+/// True if the two batches share a HARQ slot.
+bool slots_overlap(batch_context& a, batch_context& b)
+{
+  if (a.slot_lo > a.slot_hi || b.slot_lo > b.slot_hi || a.slot_lo > b.slot_hi || b.slot_lo > a.slot_hi) {
+    return false;
+  }
+  for (batch_context* c : {&a, &b}) {
+    if (!c->runs_sorted) {
+      std::sort(c->slot_runs.begin(), c->slot_runs.end());
+      c->runs_sorted = true;
+    }
+  }
+  size_t i = 0, j = 0;
+  while (i != a.slot_runs.size() && j != b.slot_runs.size()) {
+    if (a.slot_runs[i].second < b.slot_runs[j].first) {
+      ++i;
+    } else if (b.slot_runs[j].second < a.slot_runs[i].first) {
+      ++j;
+    } else {
+      return true;
+    }
+  }
+  return false;
+}
+
+/// Drops a batch that was never launched: the soft-buffer extents it advanced are restored and the context is closed, so
+/// that no later call finds it half built.
+void abandon_context(srsran_cuda_pusch_dec* h, batch_context& c)
+{
+  for (auto it = c.extent_undo.rbegin(); it != c.extent_undo.rend(); ++it) {
+    h->extent[it->first] = it->second;
+  }
+  c.extent_undo.clear();
+  c.wait_events.clear();
+  c.wait_for = nullptr;
+  c.open     = false;
+  if (h->open_ctx >= 0 && &h->ctx[h->open_ctx] == &c) {
+    h->open_ctx = -1;
+  }
 }
 
 /// Reserves `bytes` (rounded to 16) of LLR staging in the open context; returns the offset.
@@ -693,6 +761,7 @@ int add_cb(srsran_cuda_pusch_dec* h, batch_context& c, const cb_params& p, const
     }
     d.Ncb = Ncb;
     d.k0  = compute_k0(p.bg, p.rv, Ncb, N, p.Z);
+    c.extent_undo.emplace_back(p.slot, h->extent[p.slot]);
     h->extent[p.slot] =
         extent_after_dematch(h->extent[p.slot], N, Ncb, d.k0, p.E, sys - p.F, sys, p.new_data != 0);
   }
@@ -718,8 +787,7 @@ int add_cb(srsran_cuda_pusch_dec* h, batch_context& c, const cb_params& p, const
   c.h_desc.p[idx]  = d;
   c.h_tbmap.p[idx] = 0xffffffffU;
   if (p.flags & (FLAG_DEMATCH | FLAG_USE_HARQ | FLAG_TRACK_CRC)) {
-    c.slot_lo = std::min(c.slot_lo, p.slot);
-    c.slot_hi = std::max(c.slot_hi, p.slot);
+    note_slot(c, p.slot);
   } else {
     // unit-level decode: scratch data-bit slots of this context only, no HARQ state
   }
@@ -949,6 +1017,8 @@ int launch_context(srsran_cuda_pusch_dec* h, int ci)
     }
     close_group();
     if (!add_single(i)) {
+      // Nothing of this batch has reached the device yet: undo it (extents included).
+      abandon_context(h, c);
       h->last_error = "code block does not fit in shared memory";
       return SRSRAN_CUDA_ERR_INVALID;
     }
@@ -982,15 +1052,19 @@ int launch_context(srsran_cuda_pusch_dec* h, int ci)
     CUDA_TRY(h, cudaStreamWaitEvent(s, c.wait_for, 0));
     c.wait_for = nullptr;
   }
+  for (cudaEvent_t e : c.wait_events) {
+    CUDA_TRY(h, cudaStreamWaitEvent(s, e, 0));
+  }
+  c.wait_events.clear();
   // 3. HARQ ordering: kernels of this context run after the kernels of the previously launched context.
   //    Batches whose HARQ slot ranges are disjoint share no state (soft bits, data bits, CRC flags are per slot; every other
   //    buffer is per context), so they may overlap: the next batch's dematching fills the tail of this batch's decoding.
   for (int k = 0; k != NOF_CONTEXTS; ++k) {
-    const batch_context& o = h->ctx[k];
+    batch_context& o = h->ctx[k];
     if (k == ci || !o.in_flight || o.slot_lo > o.slot_hi) {
       continue;
     }
-    if (c.slot_lo <= o.slot_hi && o.slot_lo <= c.slot_hi) {
+    if (slots_overlap(c, o)) {
       CUDA_TRY(h, cudaStreamWaitEvent(s, o.kernels, 0));
     }
   }
@@ -1123,6 +1197,7 @@ int launch_context(srsran_cuda_pusch_dec* h, int ci)
   PROF_ADD(3, l1, l2);
   PROF_ADD(4, l2, l3);
   PROF_ADD(5, l3, l4);
+  c.extent_undo.clear(); // the dematcher of this batch is on the device: the extents stand
   c.in_flight      = true;
   h->last_launched = ci;
   return SRSRAN_CUDA_OK;
@@ -1225,9 +1300,9 @@ int add_tb(srsran_cuda_pusch_dec* h, batch_context& c, const srsran_cuda_pusch_d
       d.llr             = llr_dev + metas[i].cw_offset;
       d.slot            = slot;
       c.h_desc.p[idx]   = d;
+      c.extent_undo.emplace_back(slot, h->extent[slot]);
       h->extent[slot]   = prev_ext_after;
-      c.slot_lo         = std::min(c.slot_lo, slot);
-      c.slot_hi         = std::max(c.slot_hi, slot);
+      note_slot(c, slot);
       const cb_host_meta pm = c.cb_meta.back();
       c.cb_meta.push_back({pm.K, pm.max_it, slot});
       continue;
@@ -1773,6 +1848,7 @@ int srsran_cuda_pusch_dec_enqueue(srsran_cuda_pusch_dec_t* h, uint32_t cb_index,
     return ci;
   }
   batch_context& c = h->ctx[ci];
+  c.hal_style      = true;
   if (c.cb_meta.size() >= h->max_cbs) {
     return 0; // queue full: the caller dequeues first
   }
@@ -1818,6 +1894,12 @@ int srsran_cuda_pusch_dec_enqueue(srsran_cuda_pusch_dec_t* h, uint32_t cb_index,
 static int fixup_and_launch(srsran_cuda_pusch_dec_t* h, int ci)
 {
   batch_context& c = h->ctx[ci];
+  if (!c.hal_style) {
+    // An open context with absolute device pointers can only be the remains of a call that failed half way: it must not be
+    // launched (its descriptors are not offsets) - drop it.
+    abandon_context(h, c);
+    return SRSRAN_CUDA_OK;
+  }
   for (size_t i = 0; i != c.cb_meta.size(); ++i) {
     cb_desc& d = c.h_desc.p[i];
     d.llr      = c.d_llr.p + reinterpret_cast<size_t>(d.llr);
@@ -1934,15 +2016,22 @@ int srsran_cuda_pusch_dec_segment(uint32_t tbs_bits, uint32_t base_graph, uint32
   return segment(tbs_bits, base_graph, modulation == 0 ? 1 : modulation, nof_layers, nof_llrs, out);
 }
 
-static int submit_common(srsran_cuda_pusch_dec_t* h, uint32_t nof_tbs, const srsran_cuda_pusch_dec_tb_config* configs,
-                         const int8_t* const* llrs, const uint32_t* nof_llrs, int* tickets, bool device_resident,
-                         const uint32_t* cb_slots = nullptr, uint32_t nof_cb_slots = 0, cudaEvent_t wait_for = nullptr,
-                         int* ctx_out = nullptr)
+namespace {
+/// Where the LLRs of one transport block of a batch come from and which HARQ slots it uses.
+struct tb_source {
+  const int8_t*   llrs;         ///< host memory (copied inside the batch) or device memory
+  uint32_t        nof_llrs;
+  bool            device;       ///< `llrs` is a device address
+  const uint32_t* cb_slots;     ///< absolute code-block ids, or null: harq_first_slot + i
+  uint32_t        nof_cb_slots;
+};
+} // namespace
+
+/// One batch: every transport block becomes one ticket; one set of launches.
+static int submit_batch(srsran_cuda_pusch_dec_t* h, uint32_t nof_tbs, const srsran_cuda_pusch_dec_tb_config* configs,
+                        const tb_source* src, int* tickets, const std::vector<cudaEvent_t>* waits = nullptr,
+                        int* ctx_out = nullptr)
 {
-  if (h == nullptr || configs == nullptr || llrs == nullptr || nof_llrs == nullptr || tickets == nullptr ||
-      nof_tbs == 0 || nof_tbs > MAX_TBS_PER_CTX) {
-    return SRSRAN_CUDA_ERR_INVALID;
-  }
   PROF_T(p0);
   cudaSetDevice(h->device);
   if (h->open_ctx >= 0) {
@@ -1967,33 +2056,33 @@ static int submit_common(srsran_cuda_pusch_dec_t* h, uint32_t nof_tbs, const srs
   batch_context& c = h->ctx[ci];
   int            r = prepare_tb_buffers(h, c, nof_tbs, tb_bytes);
   if (r != SRSRAN_CUDA_OK) {
-    c.open      = false;
-    h->open_ctx = -1;
+    abandon_context(h, c);
     return r;
   }
   // Stage first (the device staging buffer may be reallocated while growing), then build the descriptors.
   std::vector<size_t> offs(nof_tbs, 0);
-  if (!device_resident) {
-    for (uint32_t i = 0; i != nof_tbs; ++i) {
-      r = stage_llrs(h, c, llrs[i], nof_llrs[i], &offs[i]);
-      if (r != SRSRAN_CUDA_OK) {
-        c.open      = false;
-        h->open_ctx = -1;
-        return r;
-      }
+  for (uint32_t i = 0; i != nof_tbs; ++i) {
+    if (src[i].device) {
+      continue;
+    }
+    r = stage_llrs(h, c, src[i].llrs, src[i].nof_llrs, &offs[i]);
+    if (r != SRSRAN_CUDA_OK) {
+      abandon_context(h, c);
+      return r;
     }
   }
   for (uint32_t i = 0; i != nof_tbs; ++i) {
-    const int8_t* dev = device_resident ? llrs[i] : c.d_llr.p + offs[i];
-    r                 = add_tb(h, c, configs[i], dev, nof_llrs[i], cb_slots, nof_cb_slots);
+    const int8_t* dev = src[i].device ? src[i].llrs : c.d_llr.p + offs[i];
+    r                 = add_tb(h, c, configs[i], dev, src[i].nof_llrs, src[i].cb_slots, src[i].nof_cb_slots);
     if (r != SRSRAN_CUDA_OK) {
-      c.open      = false;
-      h->open_ctx = -1;
+      abandon_context(h, c);
       return r;
     }
     tickets[i] = make_ticket(ci, static_cast<uint32_t>(c.tb_meta.size() - 1), c.generation);
   }
-  c.wait_for = wait_for;
+  if (waits != nullptr) {
+    c.wait_events = *waits;
+  }
   if (ctx_out != nullptr) {
     *ctx_out = ci;
   }
@@ -2010,6 +2099,95 @@ static int submit_common(srsran_cuda_pusch_dec_t* h, uint32_t nof_tbs, const srs
   }
 #endif
   return r;
+}
+
+static int submit_common(srsran_cuda_pusch_dec_t* h, uint32_t nof_tbs, const srsran_cuda_pusch_dec_tb_config* configs,
+                         const int8_t* const* llrs, const uint32_t* nof_llrs, int* tickets, bool device_resident,
+                         const uint32_t* cb_slots = nullptr, uint32_t nof_cb_slots = 0, cudaEvent_t wait_for = nullptr,
+                         int* ctx_out = nullptr)
+{
+  if (h == nullptr || configs == nullptr || llrs == nullptr || nof_llrs == nullptr || tickets == nullptr ||
+      nof_tbs == 0 || nof_tbs > MAX_TBS_PER_CTX) {
+    return SRSRAN_CUDA_ERR_INVALID;
+  }
+  thread_local std::vector<tb_source> src;
+  src.resize(nof_tbs);
+  for (uint32_t i = 0; i != nof_tbs; ++i) {
+    src[i] = {llrs[i], nof_llrs[i], device_resident, cb_slots, nof_cb_slots};
+  }
+  std::vector<cudaEvent_t> waits;
+  if (wait_for != nullptr) {
+    waits.push_back(wait_for);
+  }
+  return submit_batch(h, nof_tbs, configs, src.data(), tickets, wait_for != nullptr ? &waits : nullptr, ctx_out);
+}
+
+int srsran_cuda_pusch_dec_submit_tbs_cb_ids(srsran_cuda_pusch_dec_t* h, uint32_t nof_tbs,
+                                            const srsran_cuda_pusch_dec_tb_config* configs, const int8_t* const* llrs,
+                                            const uint32_t* nof_llrs, const int* ingest_streams,
+                                            const uint32_t* absolute_cb_ids, const uint32_t* nof_cb_ids, int* tickets)
+{
+  if (h == nullptr || configs == nullptr || llrs == nullptr || nof_llrs == nullptr || absolute_cb_ids == nullptr ||
+      nof_cb_ids == nullptr || tickets == nullptr || nof_tbs == 0 || nof_tbs > MAX_TBS_PER_CTX) {
+    return SRSRAN_CUDA_ERR_INVALID;
+  }
+  cudaSetDevice(h->device);
+  std::vector<tb_source>   src(nof_tbs);
+  std::vector<cudaEvent_t> waits;
+  size_t                   id_off = 0;
+  for (uint32_t i = 0; i != nof_tbs; ++i) {
+    const int k = (ingest_streams != nullptr) ? ingest_streams[i] : -1;
+    if (k >= 0) {
+      if (k >= ingest_slot::NOF || !h->ingest[k].open) {
+        h->last_error = "ingest stream not open";
+        return SRSRAN_CUDA_ERR_STATE;
+      }
+      src[i] = {h->ingest[k].d_llr.p, h->ingest[k].used, true, absolute_cb_ids + id_off, nof_cb_ids[i]};
+    } else {
+      if (llrs[i] == nullptr) {
+        return SRSRAN_CUDA_ERR_INVALID;
+      }
+      src[i] = {llrs[i], nof_llrs[i], false, absolute_cb_ids + id_off, nof_cb_ids[i]};
+    }
+    id_off += nof_cb_ids[i];
+  }
+  // The streamed transport blocks: their copies are ordered before the batch's kernels by an event each.
+  for (uint32_t i = 0; i != nof_tbs; ++i) {
+    const int k = (ingest_streams != nullptr) ? ingest_streams[i] : -1;
+    if (k >= 0) {
+      CUDA_TRY(h, cudaEventRecord(h->ingest[k].pushed, h->ingest[k].stream));
+      waits.push_back(h->ingest[k].pushed);
+    }
+  }
+  int ci = -1;
+  int r  = submit_batch(h, nof_tbs, configs, src.data(), tickets, waits.empty() ? nullptr : &waits, &ci);
+  if (r != SRSRAN_CUDA_OK) {
+    return r; // (BUSY: the ingest streams stay open, the caller submits again)
+  }
+  for (uint32_t i = 0; i != nof_tbs; ++i) {
+    const int k = (ingest_streams != nullptr) ? ingest_streams[i] : -1;
+    if (k >= 0) {
+      h->ingest[k].open       = false;
+      h->ingest[k].ctx        = ci;
+      h->ingest[k].generation = h->ctx[ci].generation;
+    }
+  }
+  return SRSRAN_CUDA_OK;
+}
+
+int srsran_cuda_pusch_dec_wait_ticket(srsran_cuda_pusch_dec_t* h, int ticket)
+{
+  if (h == nullptr || ticket < 0) {
+    return SRSRAN_CUDA_ERR_INVALID;
+  }
+  const int ci = (ticket >> 16) & 0xf;
+  if (ci >= NOF_CONTEXTS) {
+    return SRSRAN_CUDA_ERR_INVALID;
+  }
+  // Touches nothing but the completion event of the ticket's batch (which exists from create to destroy and is not
+  // re-recorded before the ticket has been polled): safe beside any other call on the handle.
+  cudaSetDevice(h->device);
+  return cudaEventSynchronize(h->ctx[ci].done) == cudaSuccess ? SRSRAN_CUDA_OK : SRSRAN_CUDA_ERR_CUDA;
 }
 
 int srsran_cuda_pusch_dec_submit_tbs(srsran_cuda_pusch_dec_t* h, uint32_t nof_tbs,
@@ -2124,8 +2302,22 @@ int srsran_cuda_pusch_dec_stream_submit(srsran_cuda_pusch_dec_t* h, int stream, 
   return ticket;
 }
 
+static int poll_tb_impl(srsran_cuda_pusch_dec_t* h, int ticket, int block, uint8_t* tb,
+                        srsran_cuda_pusch_dec_tb_result* result, bool consume);
+
 int srsran_cuda_pusch_dec_poll_tb(srsran_cuda_pusch_dec_t* h, int ticket, int block, uint8_t* tb,
                                   srsran_cuda_pusch_dec_tb_result* result)
+{
+  return poll_tb_impl(h, ticket, block, tb, result, true);
+}
+
+int srsran_cuda_pusch_dec_peek_tb(srsran_cuda_pusch_dec_t* h, int ticket, srsran_cuda_pusch_dec_tb_result* result)
+{
+  return poll_tb_impl(h, ticket, 0, nullptr, result, false);
+}
+
+static int poll_tb_impl(srsran_cuda_pusch_dec_t* h, int ticket, int block, uint8_t* tb,
+                        srsran_cuda_pusch_dec_tb_result* result, bool consume)
 {
   if (h == nullptr || ticket < 0) {
     return SRSRAN_CUDA_ERR_INVALID;
@@ -2186,16 +2378,19 @@ int srsran_cuda_pusch_dec_poll_tb(srsran_cuda_pusch_dec_t* h, int ticket, int bl
     result->iter_max             = nobs ? imax : 0;
     result->iter_mean            = nobs ? mean : 0;
   }
-  m.polled = true;
+  if (consume) {
+    m.polled = true;
+  }
   return 1;
 }
 
 int srsran_cuda_pusch_dec_poll_tbs(srsran_cuda_pusch_dec_t* h, uint32_t nof_tickets, const int* tickets, int block,
                                    uint8_t* const* tbs, srsran_cuda_pusch_dec_tb_result* results)
 {
-  if (h == nullptr || tickets == nullptr || (nof_tickets != 0 && results == nullptr)) {
+  if (h == nullptr || tickets == nullptr) {
     return SRSRAN_CUDA_ERR_INVALID;
   }
+  // (`results` may be null: the caller has read them with peek_tb and only consumes the tickets.)
   // All or nothing: without `block`, nothing is consumed unless every ticket's batch has completed.
   if (!block) {
     for (uint32_t i = 0; i != nof_tickets; ++i) {
@@ -2209,7 +2404,8 @@ int srsran_cuda_pusch_dec_poll_tbs(srsran_cuda_pusch_dec_t* h, uint32_t nof_tick
     }
   }
   for (uint32_t i = 0; i != nof_tickets; ++i) {
-    int r = srsran_cuda_pusch_dec_poll_tb(h, tickets[i], 1, tbs != nullptr ? tbs[i] : nullptr, &results[i]);
+    int r = srsran_cuda_pusch_dec_poll_tb(h, tickets[i], 1, tbs != nullptr ? tbs[i] : nullptr,
+                                          results != nullptr ? &results[i] : nullptr);
     if (r < 0) {
       return r;
     }
@@ -2320,8 +2516,7 @@ int srsran_cuda_pusch_dec_submit_tbs_symbols(srsran_cuda_pusch_dec_t* h, uint32_
   }
   batch_context& c    = h->ctx[ci];
   auto           fail = [&](int code) {
-    c.open      = false;
-    h->open_ctx = -1;
+    abandon_context(h, c);
     return code;
   };
   r = prepare_tb_buffers(h, c, nof_tbs, tb_bytes);
@@ -2611,8 +2806,7 @@ int srsran_cuda_ldpc_rate_dematch(srsran_cuda_pusch_dec_t* h, int8_t* softbuf, u
   uint32_t idx;
   r = add_cb(h, c, p, c.d_llr.p + off, false, &idx);
   if (r != SRSRAN_CUDA_OK) {
-    c.open      = false;
-    h->open_ctx = -1;
+    abandon_context(h, c);
     return r;
   }
   r = run_unit_batch(h, ci);
@@ -2681,8 +2875,7 @@ int srsran_cuda_ldpc_decode_batch(srsran_cuda_pusch_dec_t* h, uint8_t* bits, con
       uint32_t idx;
       r = add_cb(h, c, p, c.d_llr.p + offs[i], true, &idx);
       if (r != SRSRAN_CUDA_OK) {
-        c.open      = false;
-        h->open_ctx = -1;
+        abandon_context(h, c);
         return r;
       }
     }

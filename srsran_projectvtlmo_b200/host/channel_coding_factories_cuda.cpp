@@ -37,7 +37,7 @@ public:
     uint32_t    poly    = (crc != nullptr) ? to_cuda_poly(crc->get_generator_poly()) : SRSRAN_CUDA_CRC_NONE;
     int         nof_its = -1;
     srsran_assert((crc == nullptr) || (poly != SRSRAN_CUDA_CRC_NONE), "CRC polynomial not used by PUSCH.");
-    std::lock_guard<std::mutex> lock(device->mutex());
+    std::lock_guard<std::recursive_mutex> lock(device->mutex());
     int st = srsran_cuda_ldpc_decode(device->get(),
                                      output.get_buffer().data(),
                                      reinterpret_cast<const int8_t*>(input.data()),
@@ -71,7 +71,7 @@ public:
                     bool                             new_data,
                     const codeblock_metadata&        cfg) override
   {
-    std::lock_guard<std::mutex> lock(device->mutex());
+    std::lock_guard<std::recursive_mutex> lock(device->mutex());
     int st = srsran_cuda_ldpc_rate_dematch(device->get(),
                                            reinterpret_cast<int8_t*>(output.data()),
                                            output.size(),
@@ -120,7 +120,7 @@ private:
   crc_calculator_checksum_t run(const uint8_t* bytes, size_t nof_bits)
   {
     uint32_t                    checksum = 0;
-    std::lock_guard<std::mutex> lock(device->mutex());
+    std::lock_guard<std::recursive_mutex> lock(device->mutex());
     int st = srsran_cuda_crc_calculate(device->get(), to_cuda_poly(poly), bytes, nof_bits, &checksum);
     srsran_assert(st == SRSRAN_CUDA_OK, "CUDA CRC calculator failed ({}).", st);
     return checksum;

@@ -6,7 +6,9 @@ using namespace hal;
 
 void hw_accelerator_pusch_dec_cuda_impl::reserve_queue()
 {
-  queue_lock = std::unique_lock<std::mutex>(device->mutex());
+  if (!queue_lock.owns_lock()) {
+    queue_lock = std::unique_lock<std::recursive_mutex>(device->mutex());
+  }
   int st     = srsran_cuda_pusch_dec_reserve_queue(device->get());
   srsran_assert(st == SRSRAN_CUDA_OK, "CUDA PUSCH decoder: reserve_queue failed ({}).", st);
 }

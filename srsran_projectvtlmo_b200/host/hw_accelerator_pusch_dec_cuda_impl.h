@@ -31,8 +31,11 @@ public:
 
 private:
   std::shared_ptr<cuda_pusch_dec_device> device;
-  /// Held from reserve_queue() to free_queue(): one transport block owns the handle's operation table at a time.
-  std::unique_lock<std::mutex> queue_lock;
+  /// Held from reserve_queue() to free_queue(): one transport block owns the handle's operation table at a time. The lock is
+  /// owned by this object (released by free_queue, or by the destructor if the owner never got there), and the device mutex
+  /// is recursive: pusch_decoder_hw_impl recomputes CRC16 / CRC24A between reserve_queue and free_queue
+  /// (pusch_decoder_hw_impl.cpp:353-360,384), which may be "cuda" crc_calculators of the same device.
+  std::unique_lock<std::recursive_mutex> queue_lock;
 };
 
 } // namespace hal

@@ -90,7 +90,7 @@ void pusch_decoder_cuda_impl::set_nof_softbits(units::bits nof_softbits)
   }
   nof_ulsch_softbits = nof_softbits;
   // From now on every block is copied to the device as it arrives.
-  std::lock_guard<std::mutex> lock(device->mutex());
+  std::lock_guard<std::recursive_mutex> lock(device->mutex());
   ingest_stream = srsran_cuda_pusch_dec_stream_begin(device->get(), nof_softbits.value());
   if (ingest_stream < 0) {
     // Every ingest stream of the device is taken by other decoders: this transport block is copied in one piece at
@@ -130,7 +130,7 @@ void pusch_decoder_cuda_impl::push_pending()
   if (ingest_stream < 0 || softbits_pushed == softbits_count) {
     return;
   }
-  std::lock_guard<std::mutex> lock(device->mutex());
+  std::lock_guard<std::recursive_mutex> lock(device->mutex());
   int st = srsran_cuda_pusch_dec_stream_push(device->get(),
                                              ingest_stream,
                                              reinterpret_cast<const int8_t*>(softbits_buffer + softbits_pushed),
@@ -150,70 +150,68 @@ void pusch_decoder_cuda_impl::on_end_softbits()
                   nof_ulsch_softbits->value());
   }
 
-  srsran_cuda_pusch_dec_tb_config cfg = {};
-  cfg.tbs_bits                        = transport_block.size() * 8;
-  cfg.base_graph                      = (current_config.base_graph == ldpc_base_graph_type::BG1) ? 1 : 2;
-  cfg.rv                              = current_config.rv;
-  cfg.modulation                      = get_bits_per_symbol(current_config.mod);
-  cfg.Nref                            = current_config.Nref;
-  cfg.nof_layers                      = current_config.nof_layers;
-  cfg.nof_ldpc_iterations             = current_config.nof_ldpc_iterations;
-  cfg.use_early_stop                  = current_config.use_early_stop ? 1 : 0;
-  cfg.new_data                        = current_config.new_data ? 1 : 0;
+  hal::cuda_tb_request req;
+  req.cfg.tbs_bits            = transport_block.size() * 8;
+  req.cfg.base_graph          = (current_config.base_graph == ldpc_base_graph_type::BG1) ? 1 : 2;
+  req.cfg.rv                  = current_config.rv;
+  req.cfg.modulation          = get_bits_per_symbol(current_config.mod);
+  req.cfg.Nref                = current_config.Nref;
+  req.cfg.nof_layers          = current_config.nof_layers;
+  req.cfg.nof_ldpc_iterations = current_config.nof_ldpc_iterations;
+  req.cfg.use_early_stop      = current_config.use_early_stop ? 1 : 0;
+  req.cfg.new_data            = current_config.new_data ? 1 : 0;
   // HARQ slots: the rx buffer's absolute code-block identifiers (rx_buffer.h:50-53), not necessarily consecutive.
-  uint32_t cb_ids[SRSRAN_CUDA_MAX_NOF_SEGMENTS];
+  req.nof_cbs = nof_codeblocks;
   for (unsigned i = 0; i != nof_codeblocks; ++i) {
-    cb_ids[i] = unique_rm_buffer->get_absolute_codeblock_id(i);
+    req.cb_ids[i] = unique_rm_buffer->get_absolute_codeblock_id(i);
   }
-
-  int ticket;
   if (ingest_stream >= 0) {
     push_pending();
-    std::lock_guard<std::mutex> lock(device->mutex());
-    ticket        = srsran_cuda_pusch_dec_stream_submit(device->get(), ingest_stream, &cfg, cb_ids, nof_codeblocks);
-    ingest_stream = -1;
-  } else {
-    std::lock_guard<std::mutex> lock(device->mutex());
-    ticket = srsran_cuda_pusch_dec_submit_tb_cb_ids(
-        device->get(), &cfg, reinterpret_cast<const int8_t*>(softbits_buffer), softbits_count, cb_ids, nof_codeblocks);
   }
-  report_fatal_error_if_not(ticket >= 0, "CUDA PUSCH decoder: {}", srsran_cuda_pusch_dec_last_error(device->get()));
+  req.llrs          = reinterpret_cast<const int8_t*>(softbits_buffer);
+  req.nof_llrs      = softbits_count;
+  req.ingest_stream = ingest_stream;
+  ingest_stream     = -1;
 
+  // The transport block joins the device's open batch (slot aggregator); the completion thread of the device copies the
+  // result out and either posts the notification to the executor or wakes this thread up.
+  completed.store(false);
+  device->submit(req, [this](const hal::cuda_tb_completion& c) { on_device_completion(c); }, executor);
   if (executor != nullptr) {
-    bool success = executor->execute([this, ticket]() { complete(ticket); });
-    if (success) {
-      return;
-    }
+    return;
   }
-  complete(ticket);
+  {
+    std::unique_lock<std::mutex> lock(completion_mutex);
+    completion_cv.wait(lock, [this]() { return completed.load(); });
+  }
+  finish_and_notify();
 }
 
-void pusch_decoder_cuda_impl::complete(int ticket)
+void pusch_decoder_cuda_impl::on_device_completion(const hal::cuda_tb_completion& c)
 {
-  pusch_decoder_result            stats;
-  srsran_cuda_pusch_dec_tb_result result = {};
-  uint8_t                         cb_crc[SRSRAN_CUDA_MAX_NOF_SEGMENTS];
-  uint32_t                        cb_iterations[SRSRAN_CUDA_MAX_NOF_SEGMENTS];
-  {
-    // Wait without holding the device: other decoder instances keep submitting while this TB is in flight.
-    int st = 0;
-    while (st == 0) {
-      std::lock_guard<std::mutex> lock(device->mutex());
-      st = srsran_cuda_pusch_dec_poll_tb(device->get(), ticket, 0, nullptr, &result);
-      if (st == 1) {
-        const uint8_t* data = nullptr;
-        st = srsran_cuda_pusch_dec_tb_cb_outputs(device->get(), ticket, cb_crc, cb_iterations, nof_codeblocks);
-        if (st >= 0 && srsran_cuda_pusch_dec_tb_data(device->get(), ticket, &data) == SRSRAN_CUDA_OK && data != nullptr) {
-          // The reference writes the transport block only when every code block is ok (pusch_decoder_impl.cpp:405-418).
-          std::memcpy(transport_block.data(), data, transport_block.size());
-        }
-        st = (st >= 0) ? 1 : st;
-      }
-      report_fatal_error_if_not(st >= 0, "CUDA PUSCH decoder: {}", srsran_cuda_pusch_dec_last_error(device->get()));
-    }
+  // Runs as a task of the executor (asynchronous decoders) or on the device's completion thread.
+  if (c.tb_data != nullptr) {
+    // The reference writes the transport block only when every code block is ok (pusch_decoder_impl.cpp:405-418).
+    std::memcpy(transport_block.data(), c.tb_data, transport_block.size());
   }
+  device_result = c.result;
+  std::memcpy(cb_crc, c.cb_crc, nof_codeblocks);
+  std::memcpy(cb_iterations, c.cb_iterations, nof_codeblocks * sizeof(uint32_t));
+  if (executor != nullptr) {
+    finish_and_notify(); // already a task of the executor (cuda_pusch_dec_device::submit)
+    return;
+  }
+  {
+    std::lock_guard<std::mutex> lock(completion_mutex);
+    completed.store(true);
+  }
+  completion_cv.notify_one();
+}
 
-  stats.tb_crc_ok            = result.tb_crc_ok != 0;
+void pusch_decoder_cuda_impl::finish_and_notify()
+{
+  pusch_decoder_result stats;
+  stats.tb_crc_ok            = device_result.tb_crc_ok != 0;
   stats.nof_codeblocks_total = nof_codeblocks;
   // sample_statistics keeps a running mean: feed the observations code block by code block, in order
   // (pusch_decoder_impl.cpp:357-363).
@@ -232,11 +230,12 @@ void pusch_decoder_cuda_impl::complete(int ticket)
     unique_rm_buffer.unlock();
   }
 
-  internal_states previous_state = current_state.exchange(internal_states::idle);
+  pusch_decoder_notifier* notifier = result_notifier;
+  internal_states previous_state   = current_state.exchange(internal_states::idle);
   srsran_assert(previous_state == internal_states::decoding, "Invalid state: not decoding.");
 
   // Finally report decoding result.
-  result_notifier->on_sch_data(stats);
+  notifier->on_sch_data(stats);
 }
 
 namespace {

@@ -14,6 +14,8 @@
 #include "srsran/phy/upper/unique_rx_buffer.h"
 #include "srsran/support/executors/task_executor.h"
 #include <atomic>
+#include <condition_variable>
+#include <mutex>
 #include <optional>
 #include <vector>
 
@@ -61,8 +63,11 @@ private:
 
   /// Pushes the soft bits collected since the last push to the device (no-op while the total is unknown).
   void push_pending();
-  /// Waits for the device, fills the transport block, updates the rx buffer and notifies.
-  void complete(int ticket);
+  /// Completion callback of the device's slot aggregator (completion thread): copies the transport block and the per
+  /// code block outputs, then hands over to the executor or to the thread blocked in on_end_softbits.
+  void on_device_completion(const hal::cuda_tb_completion& completion);
+  /// Updates the rx buffer (CRC flags, release / unlock), returns to idle and notifies.
+  void finish_and_notify();
 
   std::vector<std::shared_ptr<hal::cuda_pusch_dec_device>> devices;
   /// Device of the transport block in flight (chosen in new_data).
@@ -81,6 +86,13 @@ private:
   configuration                current_config;
   unsigned                     nof_codeblocks = 0;
   std::atomic<internal_states> current_state{internal_states::idle};
+  /// Result of the transport block in flight (written by the completion thread before it signals).
+  srsran_cuda_pusch_dec_tb_result device_result = {};
+  uint8_t                         cb_crc[SRSRAN_CUDA_MAX_NOF_SEGMENTS];
+  uint32_t                        cb_iterations[SRSRAN_CUDA_MAX_NOF_SEGMENTS];
+  std::mutex                      completion_mutex;
+  std::condition_variable         completion_cv;
+  std::atomic<bool>               completed{false};
 };
 
 /// Factory of CUDA PUSCH decoders ("cuda" flavour next to create_pusch_decoder_factory_sw / _hw, pusch/factories.h:57-80).
