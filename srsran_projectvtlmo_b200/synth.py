@@ -260,3 +260,48 @@ def tbs_for(nof_prb, qm, rate_x1024, nof_layers, nof_re_per_prb=156):
     else:
         c = 1
     return 8 * c * (-(-(n_info_q + 24) // (8 * c))) - 24
+
+
+# ---- transmitter side of the soft demodulator's input (TS 38.211 5.1, 5.2.1, 6.3.1.1-2): scrambling and QAM mapping --------
+def scrambling_sequence(c_init, n):
+    """First n bits of the pseudo-random sequence of TS 38.211 5.2.1 (x1 from 1, x2 from c_init, Nc = 1600), numpy uint8.
+    Word-level form of the two recurrences (they hold between 32-bit words of the packed sequences as well)."""
+    def words(init, taps, nwords):
+        st = init & 0x7fffffff
+        bits = []
+        for _ in range(1600 + 31 * 32):
+            bits.append(st & 1)
+            f = bin(st & taps).count("1") & 1
+            st = (st >> 1) | (f << 30)
+        w = np.zeros(max(nwords, 31), np.uint32)
+        b = np.array(bits[1600:], np.uint32).reshape(31, 32)
+        w[:31] = (b << np.arange(32, dtype=np.uint32)).sum(axis=1, dtype=np.uint64).astype(np.uint32)
+        tl = [t for t in range(4) if (taps >> t) & 1]
+        for i in range(31, nwords):
+            v = np.uint32(0)
+            for t in tl:
+                v ^= w[i - 31 + t]
+            w[i] = v
+        return w[:nwords]
+
+    nwords = (n + 31) // 32
+    c = words(1, 0x9, nwords) ^ words(c_init, 0xf, nwords)
+    return ((c[:, None] >> np.arange(32, dtype=np.uint32)) & 1).astype(np.uint8).reshape(-1)[:n]
+
+
+def modulate(bits, qm):
+    """TS 38.211 5.1.3-5.1.6: QPSK / 16QAM / 64QAM / 256QAM, unit average power, complex64."""
+    b = 1.0 - 2.0 * bits.reshape(-1, qm).astype(np.float32)
+    if qm == 2:
+        re, im, s = b[:, 0], b[:, 1], np.sqrt(2.0)
+    elif qm == 4:
+        re, im, s = b[:, 0] * (2 - b[:, 2]), b[:, 1] * (2 - b[:, 3]), np.sqrt(10.0)
+    elif qm == 6:
+        re = b[:, 0] * (4 - b[:, 2] * (2 - b[:, 4]))
+        im = b[:, 1] * (4 - b[:, 3] * (2 - b[:, 5]))
+        s = np.sqrt(42.0)
+    else:
+        re = b[:, 0] * (8 - b[:, 2] * (4 - b[:, 4] * (2 - b[:, 6])))
+        im = b[:, 1] * (8 - b[:, 3] * (4 - b[:, 5] * (2 - b[:, 7])))
+        s = np.sqrt(170.0)
+    return ((re + 1j * im) / s).astype(np.complex64)
