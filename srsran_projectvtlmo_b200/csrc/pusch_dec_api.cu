@@ -188,6 +188,7 @@ struct batch_context {
   uint32_t                 ndm          = 0;
   uint32_t                 dm_max_sym   = 0;
   uint32_t                 dm_max_words = 0;
+  uint32_t                 dm_qm_mask   = 0; // modulation orders present (bit QM)
   std::vector<raw_copy>    raw_copies;
   cudaEvent_t              dm_ev[2] = {nullptr, nullptr};
 };
@@ -603,6 +604,7 @@ int open_context(srsran_cuda_pusch_dec* h, uint32_t min_cbs)
   c.dm_in_used   = 0;
   c.dm_max_sym   = 0;
   c.dm_max_words = 0;
+  c.dm_qm_mask   = 0;
   ++c.generation;
   h->open_ctx = pick;
   return pick;
@@ -834,10 +836,7 @@ int launch_context(srsran_cuda_pusch_dec* h, int ci)
         c.d_dm.p, h->d_scr_x1.p, h->d_scr_x2.p);
     ++h->launches;
     CUDA_TRY(h, cudaGetLastError());
-    pusch_demod_kernel<<<dim3((c.dm_max_sym + DM_THREADS_PER_CTA - 1) / DM_THREADS_PER_CTA, c.ndm), DM_THREADS_PER_CTA, 0, s>>>(
-        c.d_dm.p);
-    ++h->launches;
-    CUDA_TRY(h, cudaGetLastError());
+    CUDA_TRY(h, launch_pusch_demod(c.d_dm.p, c.ndm, c.dm_max_sym, c.dm_qm_mask, s, &h->launches));
     CUDA_TRY(h, cudaEventRecord(c.dm_ev[1], s));
   }
   PROF_T(l1);
@@ -1449,6 +1448,7 @@ int init_demod(srsran_cuda_pusch_dec* h)
   t.sq10  = 1.0F / std::sqrt(10.0F);
   t.gain2 = 2.0F * 1.41421356237309504880F;
   CUDA_TRY(h, cudaMemcpyToSymbol(c_demod, &t, sizeof(t)));
+  CUDA_TRY(h, cudaMemcpyToSymbol(g_demod_slope_icpt, &t, 2 * 7 * 16 * sizeof(float))); // slope[7][16] then icpt[7][16]
   // Scrambling sequences (TS 38.211 5.2.1): x1 from state 1 (taps n, n + 3), x2 from every single bit of c_init (taps
   // n .. n + 3); the x2 sequence of any c_init is the XOR of the basis sequences of its set bits.
   std::vector<uint32_t> seq(SCR_MAX_WORDS);
@@ -1506,6 +1506,7 @@ int add_demod(srsran_cuda_pusch_dec* h, batch_context& c, const srsran_cuda_pusc
   o.pi2            = d.pi2_bpsk;
   o.nl             = d.nof_layers;
   o.max_block_subc = 4096 / (d.nof_layers * d.modulation); // pusch_demodulator_impl.h:71, .cpp:177
+  o.mbs_magic      = static_cast<uint32_t>((0x100000000ULL + o.max_block_subc - 1) / o.max_block_subc);
   o.c_init         = (d.rnti << 15) + d.n_id;              // pusch_demodulator_impl.cpp:139
   o.nof_ofdm       = d.nof_ofdm_symbols;
   uint32_t acc     = 0;
@@ -1516,6 +1517,7 @@ int add_demod(srsran_cuda_pusch_dec* h, batch_context& c, const srsran_cuda_pusc
   for (uint32_t i = d.nof_ofdm_symbols; i <= DM_MAX_OFDM; ++i) {
     o.re_start[i] = acc;
   }
+  c.dm_qm_mask |= 1U << d.modulation;
   c.dm_max_sym   = std::max(c.dm_max_sym, nsym);
   c.dm_max_words = std::max(c.dm_max_words, (nsym * d.modulation + 31) / 32);
   return SRSRAN_CUDA_OK;
@@ -2584,7 +2586,7 @@ static int demod_sync(srsran_cuda_pusch_dec_t* h, int8_t* llrs, const float* sym
   CUDA_TRY(h, cudaMemcpyAsync(c.d_dm_in.p + static_cast<size_t>(nsym) * 8, noise_vars, static_cast<size_t>(nsym) * 4,
                               cudaMemcpyHostToDevice, s));
   c.ndm = 0;
-  c.dm_max_sym = c.dm_max_words = 0;
+  c.dm_max_sym = c.dm_max_words = c.dm_qm_mask = 0;
   add_demod(h, c, d, nsym, reinterpret_cast<const float*>(c.d_dm_in.p),
             reinterpret_cast<const float*>(c.d_dm_in.p + static_cast<size_t>(nsym) * 8), c.d_llr.p, 0);
   if (max_block_subc_override != 0) {
@@ -2593,9 +2595,8 @@ static int demod_sync(srsran_cuda_pusch_dec_t* h, int8_t* llrs, const float* sym
   CUDA_TRY(h, cudaMemcpyAsync(c.d_dm.p, c.h_dm.p, sizeof(demod_desc), cudaMemcpyHostToDevice, s));
   scr_seq_kernel<<<dim3((c.dm_max_words + SCR_CHUNK_WORDS - 1) / SCR_CHUNK_WORDS, 1), 32, 0, s>>>(c.d_dm.p, h->d_scr_x1.p,
                                                                                                  h->d_scr_x2.p);
-  pusch_demod_kernel<<<dim3((nsym + DM_THREADS_PER_CTA - 1) / DM_THREADS_PER_CTA, 1), DM_THREADS_PER_CTA, 0, s>>>(c.d_dm.p);
-  h->launches += 2;
-  CUDA_TRY(h, cudaGetLastError());
+  ++h->launches;
+  CUDA_TRY(h, launch_pusch_demod(c.d_dm.p, 1, nsym, c.dm_qm_mask, s, &h->launches));
   CUDA_TRY(h, cudaMemcpyAsync(llrs, c.d_llr.p, nllr, cudaMemcpyDeviceToHost, s));
   CUDA_TRY(h, cudaStreamSynchronize(s));
   c.ndm = 0;
