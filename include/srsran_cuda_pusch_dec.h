@@ -123,7 +123,8 @@ int srsran_cuda_pusch_dec_set_combine_flavour(srsran_cuda_pusch_dec_t* handle, u
  * registers, one thread per lifted check), single code blocks on the intra-code-block packed kernel (four lifted checks
  * of one code block per thread), the rest on the general kernel; 1 = general kernel only; 2 = packed groups with TWO
  * threads per lifted check; 3 = intra-code-block packed kernel wherever it fits; 4 = packed groups of TWO code blocks
- * per CTA, two CTAs per SM (what a small batch uses anyway). 2-4 exist for A/B measurements.
+ * per CTA, two CTAs per SM (what a small batch uses anyway); 5 = without the many-layer form (pairs of code blocks with up
+ * to 46 layers per CTA, messages in tensor memory). 2-5 exist for A/B measurements.
  * Results are identical: all variants are bit-exact to the reference (ldpc_decoder_avx512.cpp). */
 int srsran_cuda_pusch_dec_set_decoder_variant(srsran_cuda_pusch_dec_t* handle, uint32_t variant);
 /* Page-locked host memory for LLR buffers (what pusch_decoder_buffer::get_next_block_view hands to the demodulator,
@@ -290,6 +291,9 @@ int srsran_cuda_pusch_dec_ticket_demod_ms(srsran_cuda_pusch_dec_t* handle, int t
  * to, in milliseconds: [0] host->device copies, [1] rate-dematch kernel, [2] LDPC decode kernels, [3] TB assembly + CRC
  * kernel, [4] device->host copies. Waits for the batch to complete. Used by the benchmark's roofline accounting. */
 int srsran_cuda_pusch_dec_ticket_timing(srsran_cuda_pusch_dec_t* handle, int ticket, float* stage_ms);
+/* The same five durations for the last batch run through the unit-level interfaces (srsran_cuda_ldpc_decode_batch,
+ * srsran_cuda_ldpc_rate_dematch), which are synchronous and hand out no ticket. */
+int srsran_cuda_pusch_dec_last_unit_timing(srsran_cuda_pusch_dec_t* handle, float* stage_ms);
 /* Device-side stopwatch over several batches: timer_start arms an event that is recorded on the stream of the NEXT batch
  * launched, in front of its first copy; timer_stop records an event behind everything launched so far, waits for it and
  * returns the elapsed milliseconds between the two (CUDA events on the streams the work runs on). */

@@ -95,6 +95,7 @@ SYMBOLS = {
     "srsran_cuda_pusch_dec_submit_tbs": (C.c_int, [C.c_void_p, C.c_uint32, C.POINTER(TbConfig),
                                                     C.POINTER(C.c_void_p), u32p, intp]),
     "srsran_cuda_pusch_dec_ticket_timing": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_float)]),
+    "srsran_cuda_pusch_dec_last_unit_timing": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
     "srsran_cuda_pusch_dec_submit_tbs_cb_ids": (C.c_int, [C.c_void_p, C.c_uint32, C.POINTER(TbConfig), C.POINTER(C.c_void_p),
                                                            u32p, intp, u32p, u32p, intp]),
     "srsran_cuda_pusch_dec_wait_ticket": (C.c_int, [C.c_void_p, C.c_int]),

@@ -17,6 +17,7 @@
 //   hb     4 x K/32 words of hard decisions, crc byte tables 4 x 256 words, flags / CRC shares, four lane_state records
 #pragma once
 #include "ldpc_packed_math.h"
+#include <type_traits>
 
 namespace pusch_dec {
 
@@ -55,21 +56,52 @@ __host__ __device__ inline uint32_t dec4_tmem_cols_per_warp(uint32_t tm_cols, ui
   return (tm_cols / (tpc / 128U)) & ~3U;
 }
 
-/// `lanes` = code blocks per CTA (4 or 2). `tmem`: the messages live in tensor memory, not in shared memory.
+/// Two code blocks per thread (one register): columns of tensor memory for the messages of layers [0, layers) - two
+/// bytes per lifted edge, two edges per 32-bit column, every layer starting on a column of its own.
+__host__ __device__ inline uint32_t dec2_tmem_cols(uint32_t bg, uint32_t layers)
+{
+  uint32_t n = 0;
+  for (uint32_t l = 0; l != layers; ++l) {
+#ifdef __CUDA_ARCH__
+    uint32_t deg = c_row_ptr[bg - 1][l + 1] - c_row_ptr[bg - 1][l];
+#else
+    const uint16_t* rp  = (bg == 1) ? NR_BG1_ROW_PTR : NR_BG2_ROW_PTR;
+    uint32_t        deg = rp[l + 1] - rp[l];
+#endif
+    n += (deg + 1U) / 2U;
+  }
+  return n;
+}
+
+/// Layers (of `layer_cap`) whose messages fit in `cols_per_warp` columns of tensor memory with two code blocks per thread;
+/// the messages of the remaining layers stay in shared memory.
+__host__ __device__ inline uint32_t dec2_tm_layers(uint32_t bg, uint32_t layer_cap, uint32_t cols_per_warp)
+{
+  uint32_t lt = layer_cap;
+  while (lt != 0 && dec2_tmem_cols(bg, lt) > cols_per_warp) {
+    --lt;
+  }
+  return lt;
+}
+
+/// `lanes` = code blocks per CTA (4 or 2). `tmem`: the messages of layers [0, tm_layers) live in tensor memory, not in
+/// shared memory (tm_layers defaults to all of them).
 __host__ __device__ inline dec4_layout dec4_smem_layout(uint32_t bg, uint32_t Z, uint32_t layer_cap, uint32_t lanes = 4,
-                                                         bool tmem = false)
+                                                         bool tmem = false, uint32_t tm_layers = 0xffffffffU)
 {
 #ifdef __CUDA_ARCH__
   uint32_t nedges = c_row_ptr[bg - 1][layer_cap];
 #else
   uint32_t nedges = ((bg == 1) ? NR_BG1_ROW_PTR : NR_BG2_ROW_PTR)[layer_cap];
 #endif
+  // Two-code-block form only: 32-bit words (two edges each) of the layers whose messages stay in shared memory.
+  uint32_t spill_words = (tmem && tm_layers < layer_cap) ? dec2_tmem_cols(bg, layer_cap) - dec2_tmem_cols(bg, tm_layers) : 0U;
   uint32_t    Kb = (bg == 1) ? 22 : 10;
   dec4_layout l;
   l.tab_off  = 0;
   l.soft_off = (nedges * 8 + 15) & ~15U;
   l.c2v_off  = l.soft_off + (Kb + layer_cap) * Z * 2 * lanes;
-  l.hb_off   = l.c2v_off + (tmem ? 0U : nedges * Z * lanes);
+  l.hb_off   = l.c2v_off + (tmem ? spill_words * Z * 4 : nedges * Z * lanes);
   l.crc_off  = l.hb_off + 4 * (Kb * Z / 32) * 4;
   l.misc_off = l.crc_off + 4 * 256 * 4;
   l.total    = l.misc_off + 128 + 4 * 64; // 32 flag / scratch words + four lane_state records
@@ -248,6 +280,162 @@ __device__ __forceinline__ void tmem_st_row(uint32_t taddr, const uint32_t* r)
   }
 }
 
+/// N (1 .. 10) consecutive columns of the calling thread's TMEM lane as a sum of power-of-two shapes. Warp-collective.
+template <int N>
+__device__ __forceinline__ void tmem_ld_cols(uint32_t taddr, uint32_t* r)
+{
+  static_assert(N >= 1 && N <= 10, "unsupported run of columns");
+  if constexpr (N >= 8) {
+    tmem_ld<8>(taddr, r);
+    if constexpr (N > 8) {
+      tmem_ld_cols<N - 8>(taddr + 8, r + 8);
+    }
+  } else if constexpr (N >= 4) {
+    tmem_ld<4>(taddr, r);
+    if constexpr (N > 4) {
+      tmem_ld_cols<N - 4>(taddr + 4, r + 4);
+    }
+  } else if constexpr (N >= 2) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0,%1}, [%2];" : "=r"(r[0]), "=r"(r[1]) : "r"(taddr));
+    if constexpr (N > 2) {
+      tmem_ld_cols<N - 2>(taddr + 2, r + 2);
+    }
+  } else {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(r[0]) : "r"(taddr));
+  }
+}
+template <int N>
+__device__ __forceinline__ void tmem_st_cols(uint32_t taddr, const uint32_t* r)
+{
+  static_assert(N >= 1 && N <= 10, "unsupported run of columns");
+  if constexpr (N >= 8) {
+    tmem_st<8>(taddr, r);
+    if constexpr (N > 8) {
+      tmem_st_cols<N - 8>(taddr + 8, r + 8);
+    }
+  } else if constexpr (N >= 4) {
+    tmem_st<4>(taddr, r);
+    if constexpr (N > 4) {
+      tmem_st_cols<N - 4>(taddr + 4, r + 4);
+    }
+  } else if constexpr (N >= 2) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1,%2};" ::"r"(taddr), "r"(r[0]), "r"(r[1]) : "memory");
+    if constexpr (N > 2) {
+      tmem_st_cols<N - 2>(taddr + 2, r + 2);
+    }
+  } else {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x1.b32 [%0], {%1};" ::"r"(taddr), "r"(r[0]) : "memory");
+  }
+}
+
+/// One lifted check (thread j) of a layer of degree DEG for TWO code blocks (one register of two lanes), the form for code
+/// blocks with many layers (low code rates, HARQ retransmissions: up to all 46 layers of base graph 1 - the state of four
+/// such code blocks fits neither shared nor tensor memory). The messages (one byte per code block and lifted edge) are
+/// packed two edges per 32-bit word: in tensor memory (`MSG_TMEM`: `taddr` = the calling warp's lane quadrant and the
+/// first column of the layer, ceil(DEG / 2) columns) or, for the few layers that do not fit there, in shared memory
+/// (`msg_smem`: the thread's word 0, the words of a check Z words apart). One CTA of Z threads per SM: the v2c values
+/// and the soft addresses stay in registers between the two passes, and all DEG soft loads are in flight together.
+/// `tab_row[e]` = (byte offset of the edge's variable node from `smem`, 4 x circulant shift), `j4` = 4 j, `Z4` = 4 Z.
+template <int DEG, bool MSG_TMEM>
+__device__ __forceinline__ void process_check_t1(uint8_t* __restrict__     smem,
+                                                 uint32_t                  taddr,
+                                                 uint32_t* __restrict__    msg_smem,
+                                                 const uint2* __restrict__ tab_row,
+                                                 uint32_t                  j4,
+                                                 uint32_t                  Z4,
+                                                 uint32_t                  Z,
+                                                 uint32_t                  mult)
+{
+  constexpr int          DC = (DEG + 1) / 2;
+  uint32_t               addr[DEG];
+  uint32_t               sv[DEG];
+  uint32_t               cw[DC];
+  pk::check_lanes<DEG, 1> ck;
+  if constexpr (MSG_TMEM) {
+    tmem_ld_cols<DC>(taddr, cw);
+  } else {
+#pragma unroll
+    for (int i = 0; i != DC; ++i) {
+      cw[i] = msg_smem[i * Z];
+    }
+  }
+#pragma unroll
+  for (int e = 0; e != DEG; ++e) {
+    const uint2 te = tab_row[e];
+    uint32_t    k  = j4 + te.y;
+    k = __viaddmin_u32(k, 0U - Z4, k); // 4 ((j + shift) mod Z): min(k - 4 Z, k) on unsigned values, one VIADDMNMX
+    addr[e] = te.x + k;
+    sv[e]   = *reinterpret_cast<const uint32_t*>(smem + addr[e]);
+  }
+  ck.begin();
+  if constexpr (MSG_TMEM) {
+    tmem_wait_ld();
+  }
+#pragma unroll
+  for (int e = 0; e != DEG; ++e) {
+    // the half c + 1152 of both lanes: 0x64 above the two message bytes of edge e (low or high half of its word)
+    uint32_t c = pk::prmt2(cw[e / 2], 0x64646464U, (e & 1) ? 0x4342U : 0x4140U);
+    ck.gather(e, &sv[e], &c);
+  }
+  ck.reduce(mult);
+  uint32_t cn[DEG];
+#pragma unroll
+  for (int e = 0; e != DEG; ++e) {
+    uint32_t sn;
+    ck.scatter(e, &sn, &cn[e]);
+    *reinterpret_cast<uint32_t*>(smem + addr[e]) = sn;
+  }
+#pragma unroll
+  for (int i = 0; i != DC; ++i) {
+    // message bytes = the low bytes of the lanes: (edge 2i lane 0, lane 1, edge 2i + 1 lane 0, lane 1)
+    cw[i] = (2 * i + 1 < DEG) ? pk::prmt2(cn[2 * i], cn[2 * i + 1], 0x6420U) : pk::prmt2(cn[2 * i], pk::C2V_ZERO4, 0x4420U);
+  }
+  if constexpr (MSG_TMEM) {
+    tmem_st_cols<DC>(taddr, cw);
+    tmem_wait_st(); // complete before the layer barrier (see process_check_t)
+  } else {
+#pragma unroll
+    for (int i = 0; i != DC; ++i) {
+      msg_smem[i * Z] = cw[i];
+    }
+  }
+}
+
+/// Calls f(std::integral_constant<int, DEG>) for the degree of a base-graph row (3 .. 10 and 19; BG2's 3 .. 10).
+template <typename F>
+__device__ __forceinline__ void for_row_degree(int deg, F&& f)
+{
+  switch (deg) {
+    case 3:
+      f(std::integral_constant<int, 3>{});
+      break;
+    case 4:
+      f(std::integral_constant<int, 4>{});
+      break;
+    case 5:
+      f(std::integral_constant<int, 5>{});
+      break;
+    case 6:
+      f(std::integral_constant<int, 6>{});
+      break;
+    case 7:
+      f(std::integral_constant<int, 7>{});
+      break;
+    case 8:
+      f(std::integral_constant<int, 8>{});
+      break;
+    case 9:
+      f(std::integral_constant<int, 9>{});
+      break;
+    case 10:
+      f(std::integral_constant<int, 10>{});
+      break;
+    default:
+      f(std::integral_constant<int, 19>{});
+      break;
+  }
+}
+
 #ifndef DEC4T_QR
 #define DEC4T_QR 0 ///< trailing edges of a check whose v2c values stay in registers
 #endif
@@ -374,8 +562,11 @@ static_assert(sizeof(lane_state) == 64, "lane_state is 64 bytes");
 /// twice as many SMs).
 /// TM: the messages live in tensor memory (`tm_cols` columns allocated by the CTA: 256 -> two CTAs per SM, 512 -> one),
 /// the v2c values pass through the soft array, 80 registers per thread: two four-code-block CTAs (24 warps) per SM.
+/// TM with NR = 1: code blocks with MANY layers (up to all 46 of base graph 1: low code rates, BASELINE config 1, HARQ
+/// retransmissions), two per CTA, one CTA per SM: all 512 columns hold messages (two edges per column), the messages of the
+/// last layers that do not fit stay in shared memory, the v2c values stay in registers (168 per thread).
 template <int TPC, int ZT = 0, int NR = 2, int TM = 0>
-__global__ void __launch_bounds__((NR == 2 && !TM) ? TPC + DEC4_LB_EXTRA : TPC, (NR == 2 && !TM) ? 1 : 2) ldpc_decode4_kernel(const cb_desc* __restrict__ descs,
+__global__ void __launch_bounds__((NR == 2 && !TM) ? TPC + DEC4_LB_EXTRA : TPC, ((NR == 2 && !TM) || (NR == 1 && TM)) ? 1 : 2) ldpc_decode4_kernel(const cb_desc* __restrict__ descs,
                                                                const grp_desc* __restrict__ groups,
                                                                cb_result* __restrict__ results,
                                                                const int8_t* __restrict__ soft_base,
@@ -383,7 +574,6 @@ __global__ void __launch_bounds__((NR == 2 && !TM) ? TPC + DEC4_LB_EXTRA : TPC, 
                                                                uint32_t* __restrict__ crc_flags,
                                                                uint32_t tm_cols)
 {
-  static_assert(!TM || NR == 2, "the tensor-memory variant packs four code blocks per thread");
   extern __shared__ __align__(16) uint8_t smem_raw[];
   const int       t    = threadIdx.x;
   const int       lane = t & 31;
@@ -397,10 +587,13 @@ __global__ void __launch_bounds__((NR == 2 && !TM) ? TPC + DEC4_LB_EXTRA : TPC, 
   const cb_desc&  d0   = descs[g.cb[0]];
   const uint32_t  Z = ZT ? (uint32_t)ZT : (uint32_t)d0.Z, bg = d0.bg, Kb = (bg == 1) ? 22 : 10, K = Kb * Z, L = g.layer_cap;
   const uint32_t  mode = d0.mode, max_it = d0.max_it, mult = d0.scale_mult;
-  const int       poly = d0.crc_poly;
+  const int       poly = (mode == MODE_NO_CRC) ? 0 : (int)d0.crc_poly;
   const uint32_t  HBW  = K / 32;
+  // NR == 1 with TM: layers whose messages live in tensor memory (the host sized the shared memory with the same rule).
+  const uint32_t  cpw  = TM ? dec4_tmem_cols_per_warp(tm_cols, TPC) : 0U;
+  const uint32_t  Lt   = (TM != 0 && NR == 1) ? dec2_tm_layers(bg, L, cpw) : L;
 
-  const dec4_layout lay  = dec4_smem_layout(bg, Z, L, NC, TM != 0);
+  const dec4_layout lay  = dec4_smem_layout(bg, Z, L, NC, TM != 0, Lt);
   uint2*            tab  = reinterpret_cast<uint2*>(smem_raw + lay.tab_off);
   uint8_t*          soft = smem_raw + lay.soft_off; // SE bytes per variable lift
   uint8_t*          c2v  = smem_raw + lay.c2v_off;  // CE bytes per lifted edge, check order (TM: unused)
@@ -426,7 +619,7 @@ __global__ void __launch_bounds__((NR == 2 && !TM) ? TPC + DEC4_LB_EXTRA : TPC, 
     const cb_desc& d      = descs[g.cb[valid ? c : 0]];
     const uint32_t cap_in = (Kb + L) * Z - 2 * Z;
     lane_state     ls;
-    ls.src       = soft_base + (size_t)d.slot * SOFT_STRIDE;
+    ls.src       = (d.flags & FLAG_USE_HARQ) ? soft_base + (size_t)d.slot * SOFT_STRIDE : d.llr;
     ls.bits_out  = d.bits_out;
     ls.slot_bits = reinterpret_cast<uint32_t*>(bits_base + (size_t)d.slot * BITS_STRIDE);
     ls.n_load    = valid ? min(min(d.n_in, d.scan_len), cap_in) : 0U;
@@ -481,7 +674,16 @@ __global__ void __launch_bounds__((NR == 2 && !TM) ? TPC + DEC4_LB_EXTRA : TPC, 
       tmem_alloc(tm_ptr, tm_cols);
     }
     if (t <= (int)L) {
-      lcol[t] = (uint16_t)dec4_tmem_cols(bg, (uint32_t)t);
+      lcol[t] = (uint16_t)((NR == 2) ? dec4_tmem_cols(bg, (uint32_t)t) : dec2_tmem_cols(bg, (uint32_t)t));
+    }
+    if constexpr (NR == 1) {
+      // Messages of the layers kept in shared memory: zero (byte 0x80 per code block and edge).
+      uint4*         c4 = reinterpret_cast<uint4*>(c2v);
+      const uint32_t n4 = (lay.hb_off - lay.c2v_off) / 16;
+      const uint4    zz = make_uint4(pk::C2V_ZERO4, pk::C2V_ZERO4, pk::C2V_ZERO4, pk::C2V_ZERO4);
+      for (uint32_t i = t; i < n4; i += TPC) {
+        c4[i] = zz;
+      }
     }
   }
   {
@@ -584,10 +786,10 @@ __global__ void __launch_bounds__((NR == 2 && !TM) ? TPC + DEC4_LB_EXTRA : TPC, 
   uint32_t tm_warp = 0; // TMEM address of this warp's lane quadrant and column range
   if constexpr (TM != 0) {
     tmem_fence_after_sync();
-    tm_warp = *tm_ptr + ((uint32_t)(warp & 3) << 21) + (uint32_t)(warp >> 2) * dec4_tmem_cols_per_warp(tm_cols, TPC);
+    tm_warp = *tm_ptr + ((uint32_t)(warp & 3) << 21) + (uint32_t)(warp >> 2) * cpw;
     // Messages of the first iteration: zero (byte 0x80 per code block).
     uint32_t zz[4] = {pk::C2V_ZERO4, pk::C2V_ZERO4, pk::C2V_ZERO4, pk::C2V_ZERO4};
-    const uint32_t used = lcol[L];
+    const uint32_t used = lcol[Lt]; // (rounded up to four columns below: cpw is a multiple of four)
     for (uint32_t col = 0; col < used; col += 4) {
       tmem_st<4>(tm_warp + col, zz);
     }
@@ -618,7 +820,22 @@ __global__ void __launch_bounds__((NR == 2 && !TM) ? TPC + DEC4_LB_EXTRA : TPC, 
     for (uint32_t l = 0; l != L; ++l) {
       uint32_t e0  = c_row_ptr[bg - 1][l];
       int      deg = (int)c_row_ptr[bg - 1][l + 1] - (int)e0;
-      if constexpr (TM != 0) {
+      if constexpr (TM != 0 && NR == 1) {
+        if (j < Z) {
+          const uint2* tab_row = tab + e0;
+          if (l < Lt) {
+            const uint32_t ta = tm_warp + lcol[l];
+            for_row_degree(deg, [&](auto dg) {
+              process_check_t1<decltype(dg)::value, true>(smem_raw, ta, nullptr, tab_row, j * SE, Z * SE, Z, mult);
+            });
+          } else {
+            uint32_t* mw = reinterpret_cast<uint32_t*>(c2v) + (size_t)(lcol[l] - lcol[Lt]) * Z + j;
+            for_row_degree(deg, [&](auto dg) {
+              process_check_t1<decltype(dg)::value, false>(smem_raw, 0U, mw, tab_row, j * SE, Z * SE, Z, mult);
+            });
+          }
+        }
+      } else if constexpr (TM != 0) {
         // Z is a multiple of 32 here: whole warps are in or out (tcgen05.ld / st are warp-collective).
         if (j < Z) {
           const uint2*   tab_row = tab + e0;

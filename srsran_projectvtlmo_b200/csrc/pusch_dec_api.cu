@@ -226,6 +226,9 @@ struct srsran_cuda_pusch_dec {
   uint64_t launches          = 0;
   bool     use_packed        = true; // route eligible code blocks to the packed (4 per CTA) decoder
   bool     use_tmem          = true;  // packed decoder with the messages in tensor memory (two CTAs per SM) where eligible
+  bool     use_long          = true;  // many-layer code blocks two per CTA with the messages in tensor memory
+  bool     prefer_long       = false; // A/B: the many-layer pair form also where the shared-memory pair form fits
+  int      last_unit_ctx     = -1;    // context of the last unit-level batch (srsran_cuda_pusch_dec_last_unit_timing)
   bool     force_pairs       = false; // groups of two code blocks per CTA (two CTAs per SM) also for large batches
   bool     prefer_q4         = false; // one code block per CTA on the packed arithmetic also where groups of four would fit
   cudaEvent_t timer_begin    = nullptr;
@@ -394,6 +397,20 @@ cudaError_t launch_decode2(srsran_cuda_pusch_dec* h, cudaStream_t s, const cb_de
   return cudaGetLastError();
 }
 
+/// Two code blocks with many layers per CTA, messages in tensor memory (all 512 columns: one CTA per SM).
+template <int TPC>
+cudaError_t launch_decode2t(srsran_cuda_pusch_dec* h, cudaStream_t s, const cb_desc* descs, const grp_desc* groups,
+                            cb_result* res, uint8_t* bits_base, uint32_t n, uint32_t smem, uint32_t tm_cols, bool z384 = false)
+{
+  if (TPC == 384 && z384) {
+    ldpc_decode4_kernel<384, 384, 1, 1><<<n, 384, smem, s>>>(descs, groups, res, h->d_soft.p, bits_base, h->d_crc_flags.p, tm_cols);
+  } else {
+    ldpc_decode4_kernel<TPC, 0, 1, 1><<<n, TPC, smem, s>>>(descs, groups, res, h->d_soft.p, bits_base, h->d_crc_flags.p, tm_cols);
+  }
+  ++h->launches;
+  return cudaGetLastError();
+}
+
 template <int TPB>
 cudaError_t launch_decode_q4(srsran_cuda_pusch_dec* h, cudaStream_t s, const cb_desc* descs, const uint32_t* order,
                              cb_result* res, uint8_t* bits_base, uint32_t n, uint32_t smem)
@@ -442,6 +459,28 @@ uint32_t packed_tmem_cols(const srsran_cuda_pusch_dec* h, const cb_desc& d, uint
     return 512;
   }
   return 0;
+}
+
+/// Shared memory of a pair of such code blocks on the many-layer form of the packed decoder (two code blocks per CTA,
+/// messages in all 512 columns of tensor memory, the layers that do not fit there in shared memory); 0 if it does not
+/// apply: whole warps only (Z % 32 == 0), 16-byte aligned decoder input, and only where the one-code-block kernel would run
+/// fewer than three CTAs per SM (shorter code blocks are better off there). Any mode (with or without CRC) and any input
+/// (HARQ slot or the unit-level interface's staged soft bits).
+uint32_t packed_long_smem(const srsran_cuda_pusch_dec* h, const cb_desc& d, uint32_t cap)
+{
+  if (!h->use_packed || !h->use_tmem || !h->use_long || !(d.flags & FLAG_DECODE) || d.Z < 144 || (d.Z % 32) != 0) {
+    return 0;
+  }
+  if (!(d.flags & FLAG_USE_HARQ) && (reinterpret_cast<uintptr_t>(d.llr) & 15U) != 0) {
+    return 0;
+  }
+  if (3 * (decq_smem_layout(d.bg, d.Z, cap).total + 1024) <= static_cast<uint32_t>(h->max_smem_optin)) {
+    return 0;
+  }
+  const uint32_t tpc   = d.Z <= 256 ? 256 : 384;
+  const uint32_t lt    = dec2_tm_layers(d.bg, cap, dec4_tmem_cols_per_warp(512, tpc));
+  const uint32_t total = dec4_smem_layout(d.bg, d.Z, cap, 2, true, lt).total;
+  return total <= static_cast<uint32_t>(h->max_smem_optin) ? total : 0U;
 }
 
 template <int TPC, int CBS>
@@ -932,8 +971,10 @@ int launch_context(srsran_cuda_pusch_dec* h, int ci)
       return;
     }
     const cb_desc&  d  = c.h_desc.p[g.cb[0]];
-    const uint32_t  tm = grp_tm ? packed_tmem_cols(h, d, g.layer_cap) : 0U;
-    uint32_t        sm = (dec4_smem_layout(d.bg, d.Z, g.layer_cap, grp_lanes, tm != 0).total + 1023) & ~1023U;
+    const bool      lg = grp_tm && grp_lanes == 2; // many-layer form
+    const uint32_t  tm = lg ? 512U : (grp_tm ? packed_tmem_cols(h, d, g.layer_cap) : 0U);
+    uint32_t        sm = ((lg ? packed_long_smem(h, d, g.layer_cap)
+                              : dec4_smem_layout(d.bg, d.Z, g.layer_cap, grp_lanes, tm != 0).total) + 1023) & ~1023U;
     int             tp = d.Z <= 256 ? 256 : 384;
     if (pclasses.empty() || pclasses.back().tpc != tp || pclasses.back().smem != sm || pclasses.back().lanes != grp_lanes ||
         pclasses.back().z != d.Z || pclasses.back().tm_cols != tm) {
@@ -949,19 +990,24 @@ int launch_context(srsran_cuda_pusch_dec* h, int ci)
   auto same_class = [&same_shape](const cb_desc& a, const cb_desc& b) {
     return same_shape(a, b) && a.flags == b.flags && a.layer_cap == b.layer_cap;
   };
-  uint32_t nof_packable = 0;
+  uint32_t nof_packable = 0, nof_long = 0;
   {
     const cb_desc* prev = nullptr;
-    uint32_t       inc  = 0;
+    uint32_t       inc = 0, inc_long = 0;
     for (uint32_t i = 0; i != ncb; ++i) {
       const cb_desc& d = c.h_desc.p[i];
       if (prev == nullptr || !same_class(*prev, d)) {
-        inc  = ((d.flags & FLAG_DECODE) && packed_eligible(h, d, d.layer_cap, 2)) ? 1U : 0U;
-        prev = &d;
+        inc      = ((d.flags & FLAG_DECODE) && packed_eligible(h, d, d.layer_cap, 2)) ? 1U : 0U;
+        inc_long = (inc == 0 && packed_long_smem(h, d, d.layer_cap) != 0) ? 1U : 0U;
+        prev     = &d;
       }
       nof_packable += inc;
+      nof_long += inc_long;
     }
   }
+  // The many-layer pair form is a throughput form (one CTA of Z threads per SM works on two code blocks): with fewer such
+  // code blocks than SMs, one code block per CTA (four lifted checks per thread) on an SM of its own finishes earlier.
+  const bool long_batch = h->prefer_long || nof_long >= static_cast<uint32_t>(h->nof_sms);
   const cb_desc* memo_desc  = nullptr;
   uint32_t       memo_lanes = 0;
   bool           memo_tm    = false;
@@ -986,6 +1032,12 @@ int launch_context(srsran_cuda_pusch_dec* h, int ci)
       memo_lanes = !inter_cb ? 0U : (memo_tm || (!small_batch && packed_eligible(h, d, d.layer_cap, 4)))
                                   ? 4U
                                   : (packed_eligible(h, d, d.layer_cap, 2) ? 2U : 0U);
+      if (inter_cb && long_batch && (memo_lanes == 0 || (h->prefer_long && memo_lanes == 2 && !memo_tm)) &&
+          packed_long_smem(h, d, d.layer_cap) != 0) {
+        // Many layers: pairs with the messages in tensor memory instead of one code block per CTA.
+        memo_lanes = 2;
+        memo_tm    = true;
+      }
       memo_desc  = &d;
     }
     const uint32_t lanes_fit = memo_lanes;
@@ -997,7 +1049,8 @@ int launch_context(srsran_cuda_pusch_dec* h, int ci)
         if (g.n < grp_lanes && lanes_fit == grp_lanes && memo_tm == grp_tm &&
             ((same_class(f, d) && g.layer_cap == d.layer_cap) ||
              (same_shape(f, d) &&
-              (grp_tm ? packed_tmem_cols(h, d, cap) != 0 : packed_eligible(h, d, cap, grp_lanes))))) {
+              (grp_tm ? (grp_lanes == 2 ? packed_long_smem(h, d, cap) != 0 : packed_tmem_cols(h, d, cap) != 0)
+                      : packed_eligible(h, d, cap, grp_lanes))))) {
           g.cb[g.n++] = i;
           g.layer_cap = cap;
           continue;
@@ -1108,7 +1161,11 @@ int launch_context(srsran_cuda_pusch_dec* h, int ci)
     const grp_desc* grp = c.d_grp.p + k.first;
     cudaStream_t    st  = class_stream();
     cudaError_t     e;
-    if (k.lanes == 2) {
+    if (k.lanes == 2 && k.tm_cols != 0) {
+      e = (k.tpc == 256)
+              ? launch_decode2t<256>(h, st, c.d_desc.p, grp, c.d_res.p, c.bits_base, k.count, k.smem, k.tm_cols)
+              : launch_decode2t<384>(h, st, c.d_desc.p, grp, c.d_res.p, c.bits_base, k.count, k.smem, k.tm_cols, k.z == 384);
+    } else if (k.lanes == 2) {
       e = (k.tpc == 256) ? launch_decode2<256>(h, st, c.d_desc.p, grp, c.d_res.p, c.bits_base, k.count, k.smem)
                          : launch_decode2<384>(h, st, c.d_desc.p, grp, c.d_res.p, c.bits_base, k.count, k.smem, k.z == 384);
     } else if (k.tm_cols != 0) {
@@ -1584,6 +1641,9 @@ int srsran_cuda_pusch_dec_create(int device, uint32_t max_cbs_in_flight, uint32_
       cudaFuncSetAttribute(ldpc_decode4_kernel<256, 0, 2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess ||
       cudaFuncSetAttribute(ldpc_decode4_kernel<384, 0, 2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess ||
       cudaFuncSetAttribute(ldpc_decode4_kernel<384, 384, 2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess ||
+      cudaFuncSetAttribute(ldpc_decode4_kernel<256, 0, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess ||
+      cudaFuncSetAttribute(ldpc_decode4_kernel<384, 0, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess ||
+      cudaFuncSetAttribute(ldpc_decode4_kernel<384, 384, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess ||
       cudaFuncSetAttribute(ldpc_decode_q4_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess ||
       cudaFuncSetAttribute(ldpc_decode_q4_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess ||
       cudaFuncSetAttribute(ldpc_decode_q4_kernel<96>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess ||
@@ -1775,13 +1835,15 @@ int srsran_cuda_pusch_dec_set_combine_flavour(srsran_cuda_pusch_dec_t* h, uint32
 
 int srsran_cuda_pusch_dec_set_decoder_variant(srsran_cuda_pusch_dec_t* h, uint32_t variant)
 {
-  if (h == nullptr || variant > 4) {
+  if (h == nullptr || variant > 6) {
     return SRSRAN_CUDA_ERR_INVALID;
   }
   h->use_packed  = (variant != 1);
   h->use_tmem    = (variant != 2); // 2: the round-1 packed decoder (messages in shared memory, one CTA per SM) for A/B runs
   h->prefer_q4   = (variant == 3);
   h->force_pairs = (variant == 4);
+  h->use_long    = (variant != 5);
+  h->prefer_long = (variant == 6);
   return SRSRAN_CUDA_OK;
 }
 
@@ -2694,6 +2756,25 @@ int srsran_cuda_pusch_dec_ticket_timing(srsran_cuda_pusch_dec_t* h, int ticket, 
   return SRSRAN_CUDA_OK;
 }
 
+int srsran_cuda_pusch_dec_last_unit_timing(srsran_cuda_pusch_dec_t* h, float* stage_ms)
+{
+  if (h == nullptr || stage_ms == nullptr) {
+    return SRSRAN_CUDA_ERR_INVALID;
+  }
+  if (h->last_unit_ctx < 0 || h->ctx[h->last_unit_ctx].in_flight || h->ctx[h->last_unit_ctx].open) {
+    h->last_error = "no completed unit-level batch";
+    return SRSRAN_CUDA_ERR_STATE;
+  }
+  batch_context& c = h->ctx[h->last_unit_ctx];
+  cudaSetDevice(h->device);
+  CUDA_TRY(h, cudaEventSynchronize(c.done));
+  cudaEvent_t ev[6] = {c.stage[0], c.stage[1], c.stage[2], c.stage[3], c.kernels, c.done};
+  for (int i = 0; i != 5; ++i) {
+    CUDA_TRY(h, cudaEventElapsedTime(&stage_ms[i], ev[i], ev[i + 1]));
+  }
+  return SRSRAN_CUDA_OK;
+}
+
 int srsran_cuda_pusch_dec_timer_start(srsran_cuda_pusch_dec_t* h)
 {
   if (h == nullptr) {
@@ -2759,6 +2840,7 @@ static int run_unit_batch(srsran_cuda_pusch_dec_t* h, int ci)
   }
   CUDA_TRY(h, cudaEventSynchronize(h->ctx[ci].done));
   h->ctx[ci].in_flight = false;
+  h->last_unit_ctx     = ci;
   return SRSRAN_CUDA_OK;
 }
 

@@ -457,3 +457,10 @@ def ticket_demod_ms(acc: Accelerator, ticket):
     ms = C.c_float(0)
     acc._check(acc._lib.srsran_cuda_pusch_dec_ticket_demod_ms(acc.h, ticket, C.byref(ms)), "ticket_demod_ms")
     return ms.value
+
+
+def last_unit_timing(acc: Accelerator):
+    """Stage durations (ms) of the last unit-level batch (ldpc_decoder_cuda.decode_batch, ...): see ticket_timing."""
+    ms = (C.c_float * 5)()
+    acc._check(acc._lib.srsran_cuda_pusch_dec_last_unit_timing(acc.h, ms), "last_unit_timing")
+    return list(ms)

@@ -206,6 +206,95 @@ def test_config1_full_rate_batch_awgn_early_stop(acc):
 
 
 # ---------------------------------------------------------------------------------------------------------------------
+# Many-layer code blocks on the pair form of the packed decoder (two code blocks per CTA, messages in tensor memory, the
+# last layers' messages in shared memory): every lifting size it accepts (Z % 32 == 0, Z >= 160), both base graphs, with
+# and without CRC, odd batch sizes (the last code block runs alone on the one-code-block kernel), shortened inputs
+# (trailing zeros: fewer layers than the host's bound), an all-zero code block inside a batch, saturated inputs.
+# ---------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("bg,z,ncb", [(1, 384, 7), (1, 256, 6), (2, 384, 5), (1, 352, 4), (2, 160, 6), (1, 192, 4),
+                                       (2, 224, 3), (1, 288, 2), (1, 320, 4)])
+def test_many_layer_pairs_unit_batches(acc, bg, z, ncb):
+    rng = np.random.default_rng(7000 + z + bg)
+    dec = pusch.ldpc_decoder_cuda(acc)
+    K, N = ob.kb(bg) * z, ob.ns(bg) * z
+    # Variant 6 takes the pair form for every batch (by default it needs at least one code block per SM).
+    acc.set_decoder_variant(6)
+    try:
+        _many_layer_unit_batches(acc, dec, rng, bg, z, ncb, K, N)
+    finally:
+        acc.set_decoder_variant(0)
+
+
+def _many_layer_unit_batches(acc, dec, rng, bg, z, ncb, K, N):
+    for crc_poly, max_it in ((pusch.CRC24B, 6), (pusch.CRC_NONE, 3), (pusch.CRC16, 2)):
+        nb = {pusch.CRC24B: 24, pusch.CRC16: 16, pusch.CRC_NONE: 0}[crc_poly]
+        llr = np.zeros((ncb, N), np.int8)
+        for i in range(ncb):
+            msg = rng.integers(0, 2, K, dtype=np.uint8)
+            if nb:
+                c = ob.port_crc(crc_poly, np.packbits(msg[:K - nb]), K - nb)
+                msg[K - nb:] = [(c >> (nb - 1 - b)) & 1 for b in range(nb)]
+            cw = synth.ldpc_encode(msg, bg, z)
+            mu = [1.2, 2.0, 3.0, 0.6, 30.0][i % 5] * (1.0 if bg == 1 else 0.6)
+            llr[i] = awgn_llrs(rng, cw, mu)
+            if i % 5 == 4:
+                llr[i] = np.where(cw > 0, -127, 127).astype(np.int8)  # saturated ("infinite") inputs
+        if ncb > 2:
+            llr[1, N - 5 * z - 3:] = 0  # shortened: trailing zeros, not on a layer boundary
+        if ncb > 3:
+            llr[2, :] = 0  # all-zero input (ldpc_decoder_impl.cpp:88-94)
+        out = np.full((ncb, (K + 7) // 8), 0x5A, np.uint8)
+        its = dec.decode_batch(out, llr, ncb, crc_poly, bg, z, 0, max_it)
+        for i in range(ncb):
+            if HAVE_REF:
+                o = np.full((K + 7) // 8, 0x5A, np.uint8)
+                it, o = ob.ref_decode(llr[i], bg, z, 0, crc_poly, max_it, o)
+            else:
+                it, o, _ = ob.port_decode(llr[i], bg, z, 0, crc_poly, max_it, np.full((K + 7) // 8, 0x5A, np.uint8))
+            assert (it if it >= 0 else -1) == its[i], (bg, z, crc_poly, i, it, its[i])
+            assert np.array_equal(o, out[i]), (bg, z, crc_poly, i)
+
+
+@pytest.mark.parametrize("variant", [6, 5])
+def test_many_layer_tb_low_rate_harq_vs_reference(variant):
+    """Low-rate TBs (all 46 / 42 layers) through the TB path: rv0 -> rv2 -> rv3 with soft combining, every combined
+    soft-buffer byte and CRC flag compared; variant 6 = the pair form for every batch, 5 = without it (one code block per
+    CTA)."""
+    # (prb, Qm, R, layers, BG, Nref, mu)
+    shapes = [(273, 2, 308, 1, 1, 0, 0.7), (273, 4, 340, 2, 1, 0, 1.1), (273, 2, 193, 2, 2, 0, 0.65)]
+    rng = np.random.default_rng(909 + variant)
+    chk = _Checker()
+    acc = pusch.Accelerator(device=0, max_cbs_in_flight=256, nof_harq_cb_slots=256)
+    acc.set_decoder_variant(variant)
+    try:
+        gdec = pusch.pusch_decoder_cuda(acc)
+        failed_first = 0
+        for si, (prb, qm, R, nl, bg, nref, mu) in enumerate(shapes):
+            tbs = synth.tbs_for(prb, qm, R, nl)
+            nllr = prb * 156 * qm * nl
+            segs = pusch.segment(tbs, bg, qm, nl, nllr)
+            slot0 = 10 + 60 * si
+            slots = [slot0 + i for i in range(len(segs))]
+            payload = rng.integers(0, 256, tbs // 8, dtype=np.uint8)
+            tb_g = np.zeros(tbs // 8, np.uint8)
+            for i, rv in enumerate((0, 2, 3)):
+                llr = awgn_llrs(rng, synth.encode_tb(payload, bg, rv, qm, nref, nl, nllr), mu)
+                tb_r, res_r, crcs_r, softs_r = chk.decode(si, tbs // 8, llr, bg, rv, qm, nref, nl, 6, True, i == 0)
+                gdec.new_data(tb_g, slot0, None, pusch.pusch_decoder_configuration(bg, rv, qm, nref, nl, 6, True, i == 0))
+                gdec.on_new_softbits(llr)
+                res_g = gdec.on_end_softbits()
+                key = (variant, si, rv)
+                _assert_tb_equal(key, res_g, tb_g, res_r, tb_r, payload)
+                _assert_harq_equal(key, acc, slots, crcs_r, softs_r)
+                failed_first += int(i == 0 and not res_r.tb_crc_ok)
+                if res_r.tb_crc_ok:
+                    break
+        assert failed_first >= 1, "no first transmission failed: soft combining of many-layer code blocks not exercised"
+    finally:
+        acc.close()
+
+
+# ---------------------------------------------------------------------------------------------------------------------
 # Bounded slices of the hand-run seed sweeps (tests/seed_sweep_gpu.py, tests/seed_sweep_gpu_tb.py), so that the round-end
 # GPU run exercises them: random shapes / rates / SNRs / iteration limits / decoder variants / rv orders.
 # ---------------------------------------------------------------------------------------------------------------------
