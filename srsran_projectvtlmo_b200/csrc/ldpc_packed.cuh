@@ -111,6 +111,56 @@ __host__ __device__ inline dec4_layout dec4_smem_layout(uint32_t bg, uint32_t Z,
   return l;
 }
 
+/// Bulk-copy staging of the decoder inputs (forms that run one CTA per SM and have the room): the `lanes` inputs of a CTA
+/// are copied from their HARQ slots into shared memory behind the layout by one cp.async.bulk each (the TMA unit's 1-D
+/// path: no tensor map, 16-byte aligned source and size), completion on an mbarrier; the threads build tables, allocate
+/// and clear tensor memory meanwhile and then convert from shared memory. Stride per code block, and total bytes
+/// (staging + the mbarrier). Flagged to the kernel by DEC4_BULK_FLAG in its `tm_cols` argument.
+constexpr uint32_t DEC4_BULK_FLAG = 0x10000U;
+__host__ __device__ inline uint32_t dec4_bulk_stride(uint32_t bg, uint32_t Z, uint32_t layer_cap)
+{
+  return ((((bg == 1) ? 22U : 10U) + layer_cap - 2U) * Z + 15U) & ~15U;
+}
+__host__ __device__ inline uint32_t dec4_bulk_bytes(uint32_t bg, uint32_t Z, uint32_t layer_cap, uint32_t lanes)
+{
+  return lanes * dec4_bulk_stride(bg, Z, layer_cap) + 16U;
+}
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count)
+{
+  const uint32_t a = (uint32_t)__cvta_generic_to_shared(bar);
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(a), "r"(count) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); // visible to the async proxy
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes)
+{
+  const uint32_t a = (uint32_t)__cvta_generic_to_shared(bar);
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(a), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
+{
+  const uint32_t a = (uint32_t)__cvta_generic_to_shared(bar);
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(a),
+      "r"(parity)
+      : "memory");
+}
+/// `bytes` (multiple of 16) from global `src` (16-byte aligned) to shared `dst`, completion counted on `bar`.
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar)
+{
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(dst), b = (uint32_t)__cvta_generic_to_shared(bar);
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(d), "l"(src),
+               "r"(bytes), "r"(b)
+               : "memory");
+}
+
 /// One lifted check (thread j) of a layer of degree DEG for the 2 * NR code blocks of the group (NR registers of two lanes
 /// per thread). `tab_row[e]` = (byte offset of the edge's variable node in the soft array, circulant shift); the soft
 /// addresses are computed once and kept for the write-back (the modulo by a multiply-high: the address arithmetic issues on
@@ -590,6 +640,8 @@ __global__ void __launch_bounds__((NR == 2 && !TM) ? TPC + DEC4_LB_EXTRA : TPC, 
   const int       poly = (mode == MODE_NO_CRC) ? 0 : (int)d0.crc_poly;
   const uint32_t  HBW  = K / 32;
   // NR == 1 with TM: layers whose messages live in tensor memory (the host sized the shared memory with the same rule).
+  const bool      bulk    = (TM != 0) && (tm_cols & DEC4_BULK_FLAG) != 0; // inputs staged by bulk copies (see dec4_bulk_bytes)
+  tm_cols &= 0xffffU;
   const uint32_t  cpw  = TM ? dec4_tmem_cols_per_warp(tm_cols, TPC) : 0U;
   const uint32_t  Lt   = (TM != 0 && NR == 1) ? dec2_tm_layers(bg, L, cpw) : L;
 
@@ -641,6 +693,25 @@ __global__ void __launch_bounds__((NR == 2 && !TM) ? TPC + DEC4_LB_EXTRA : TPC, 
     st[c] = ls;
   }
   __syncthreads();
+  uint8_t*       stage        = smem_raw + lay.total;
+  const uint32_t stage_stride = dec4_bulk_stride(bg, Z, L);
+  uint64_t*      stage_bar    = reinterpret_cast<uint64_t*>(stage + NC * stage_stride);
+  if (TM != 0 && bulk && t == 0) {
+    mbar_init(stage_bar, 1);
+    uint32_t total = 0;
+#pragma unroll
+    for (int c = 0; c != NC; ++c) {
+      total += (st[c].n_load + 15U) & ~15U;
+    }
+    mbar_expect_tx(stage_bar, total);
+#pragma unroll
+    for (int c = 0; c != NC; ++c) {
+      const uint32_t len = (st[c].n_load + 15U) & ~15U; // (the bytes up to the 16-byte boundary belong to the same slot)
+      if (len != 0) {
+        bulk_g2s(stage + c * stage_stride, st[c].src, len, stage_bar);
+      }
+    }
+  }
   {
     uint32_t any_live = 0;
 #pragma unroll
@@ -707,6 +778,21 @@ __global__ void __launch_bounds__((NR == 2 && !TM) ? TPC + DEC4_LB_EXTRA : TPC, 
       }
       if (v >= punct && v < n16) {
         const uint32_t p = (v - punct) * 16;
+        if (TM != 0 && bulk) {
+          // staged by the bulk copies: the same bytes from shared memory (whole 16-byte units were copied)
+#pragma unroll
+          for (int c = 0; c != NC; ++c) {
+            if (p < n_load[c]) {
+              w[c] = *reinterpret_cast<const uint4*>(stage + c * stage_stride + p);
+              if (p + 16 > n_load[c]) {
+                w[c].y = (p + 4 < n_load[c]) ? w[c].y : 0U;
+                w[c].z = (p + 8 < n_load[c]) ? w[c].z : 0U;
+                w[c].w = (p + 12 < n_load[c]) ? w[c].w : 0U;
+              }
+            }
+          }
+          return;
+        }
 #pragma unroll
         for (int c = 0; c != NC; ++c) {
           if (p + 16 <= n_load[c]) {
@@ -723,7 +809,9 @@ __global__ void __launch_bounds__((NR == 2 && !TM) ? TPC + DEC4_LB_EXTRA : TPC, 
       }
     };
     uint4 w[NC];
-    fetch(t, w);
+    if (!(TM != 0 && bulk)) {
+      fetch(t, w);
+    }
     if constexpr (TM == 0) {
       uint4*         c4 = reinterpret_cast<uint4*>(c2v);
       const uint32_t n4 = nedges * Z * CE / 16;
@@ -734,6 +822,11 @@ __global__ void __launch_bounds__((NR == 2 && !TM) ? TPC + DEC4_LB_EXTRA : TPC, 
     }
     if (poly != 0) {
       build_crc_tables(tabs, poly, t, TPC);
+    }
+    if (TM != 0 && bulk) {
+      __syncthreads(); // the mbarrier was initialised by thread 0 after the previous barrier
+      mbar_wait(stage_bar, 0);
+      fetch(t, w);
     }
     for (uint32_t v = t; v < n16; v += TPC) {
       uint32_t ww[NC][4];

@@ -1,5 +1,6 @@
 // C ABI (include/srsran_cuda_pusch_dec.h) of the B200 PUSCH channel-decoding accelerator: batch contexts, HARQ state in
 // HBM, launch sequencing. No CPU fallback: every entry point needs a CUDA device.
+#include <nvtx3/nvToolsExt.h>
 #include "../../include/srsran_cuda_pusch_dec.h"
 #include "pusch_dec_kernels.cuh"
 #include "ldpc_packed.cuh"
@@ -227,6 +228,8 @@ struct srsran_cuda_pusch_dec {
   bool     use_packed        = true; // route eligible code blocks to the packed (4 per CTA) decoder
   bool     use_tmem          = true;  // packed decoder with the messages in tensor memory (two CTAs per SM) where eligible
   bool     use_long          = true;  // many-layer code blocks two per CTA with the messages in tensor memory
+  bool     use_bulk          = false; // one-CTA-per-SM forms stage their inputs with cp.async.bulk + mbarrier (variant 7):
+                                      // measured equal to plain 128-bit loads, kept selectable
   bool     prefer_long       = false; // A/B: the many-layer pair form also where the shared-memory pair form fits
   int      last_unit_ctx     = -1;    // context of the last unit-level batch (srsran_cuda_pusch_dec_last_unit_timing)
   bool     force_pairs       = false; // groups of two code blocks per CTA (two CTAs per SM) also for large batches
@@ -339,6 +342,16 @@ uint16_t scale_mult(float sf)
   constexpr unsigned FLOAT2INT = 1U << 16U;
   return static_cast<uint16_t>(sf * FLOAT2INT);
 }
+
+/// NVTX range over a host-side phase (submit / launch / poll), visible in Nsight Systems timelines next to the kernels -
+/// the counterpart of the reference's l1_tracer events around the PUSCH decoder. Without a tool
+/// attached the calls are a null-pointer test.
+struct nvtx_scope {
+  explicit nvtx_scope(const char* name) { nvtxRangePushA(name); }
+  ~nvtx_scope() { nvtxRangePop(); }
+  nvtx_scope(const nvtx_scope&)            = delete;
+  nvtx_scope& operator=(const nvtx_scope&) = delete;
+};
 
 int tpc_class(uint32_t Z)
 {
@@ -839,6 +852,7 @@ int add_cb(srsran_cuda_pusch_dec* h, batch_context& c, const cb_params& p, const
 
 int launch_context(srsran_cuda_pusch_dec* h, int ci)
 {
+  nvtx_scope nvtx_range("pusch_dec.launch_batch");
   batch_context& c   = h->ctx[ci];
   uint32_t       ncb = static_cast<uint32_t>(c.cb_meta.size());
   uint32_t       ntb = static_cast<uint32_t>(c.tb_meta.size());
@@ -972,9 +986,15 @@ int launch_context(srsran_cuda_pusch_dec* h, int ci)
     }
     const cb_desc&  d  = c.h_desc.p[g.cb[0]];
     const bool      lg = grp_tm && grp_lanes == 2; // many-layer form
-    const uint32_t  tm = lg ? 512U : (grp_tm ? packed_tmem_cols(h, d, g.layer_cap) : 0U);
-    uint32_t        sm = ((lg ? packed_long_smem(h, d, g.layer_cap)
-                              : dec4_smem_layout(d.bg, d.Z, g.layer_cap, grp_lanes, tm != 0).total) + 1023) & ~1023U;
+    uint32_t        tm = lg ? 512U : (grp_tm ? packed_tmem_cols(h, d, g.layer_cap) : 0U);
+    uint32_t        sm = lg ? packed_long_smem(h, d, g.layer_cap)
+                            : dec4_smem_layout(d.bg, d.Z, g.layer_cap, grp_lanes, tm != 0).total;
+    if (tm == 512 && h->use_bulk && sm + dec4_bulk_bytes(d.bg, d.Z, g.layer_cap, grp_lanes) <= static_cast<uint32_t>(h->max_smem_optin)) {
+      // One CTA per SM anyway (all 512 columns of tensor memory): room to stage the inputs by bulk copies.
+      sm += dec4_bulk_bytes(d.bg, d.Z, g.layer_cap, grp_lanes);
+      tm |= DEC4_BULK_FLAG;
+    }
+    sm = (sm + 1023) & ~1023U;
     int             tp = d.Z <= 256 ? 256 : 384;
     if (pclasses.empty() || pclasses.back().tpc != tp || pclasses.back().smem != sm || pclasses.back().lanes != grp_lanes ||
         pclasses.back().z != d.Z || pclasses.back().tm_cols != tm) {
@@ -1835,7 +1855,7 @@ int srsran_cuda_pusch_dec_set_combine_flavour(srsran_cuda_pusch_dec_t* h, uint32
 
 int srsran_cuda_pusch_dec_set_decoder_variant(srsran_cuda_pusch_dec_t* h, uint32_t variant)
 {
-  if (h == nullptr || variant > 6) {
+  if (h == nullptr || variant > 7) {
     return SRSRAN_CUDA_ERR_INVALID;
   }
   h->use_packed  = (variant != 1);
@@ -1844,6 +1864,7 @@ int srsran_cuda_pusch_dec_set_decoder_variant(srsran_cuda_pusch_dec_t* h, uint32
   h->force_pairs = (variant == 4);
   h->use_long    = (variant != 5);
   h->prefer_long = (variant == 6);
+  h->use_bulk    = (variant == 7);
   return SRSRAN_CUDA_OK;
 }
 
@@ -2191,6 +2212,7 @@ int srsran_cuda_pusch_dec_submit_tbs_cb_ids(srsran_cuda_pusch_dec_t* h, uint32_t
                                             const uint32_t* nof_llrs, const int* ingest_streams,
                                             const uint32_t* absolute_cb_ids, const uint32_t* nof_cb_ids, int* tickets)
 {
+  nvtx_scope nvtx_range("pusch_dec.submit_tbs");
   if (h == nullptr || configs == nullptr || llrs == nullptr || nof_llrs == nullptr || absolute_cb_ids == nullptr ||
       nof_cb_ids == nullptr || tickets == nullptr || nof_tbs == 0 || nof_tbs > MAX_TBS_PER_CTX) {
     return SRSRAN_CUDA_ERR_INVALID;
@@ -2241,6 +2263,7 @@ int srsran_cuda_pusch_dec_submit_tbs_cb_ids(srsran_cuda_pusch_dec_t* h, uint32_t
 
 int srsran_cuda_pusch_dec_wait_ticket(srsran_cuda_pusch_dec_t* h, int ticket)
 {
+  nvtx_scope nvtx_range("pusch_dec.wait_ticket");
   if (h == nullptr || ticket < 0) {
     return SRSRAN_CUDA_ERR_INVALID;
   }
@@ -2342,6 +2365,7 @@ int srsran_cuda_pusch_dec_stream_push(srsran_cuda_pusch_dec_t* h, int stream, co
 int srsran_cuda_pusch_dec_stream_submit(srsran_cuda_pusch_dec_t* h, int stream, const srsran_cuda_pusch_dec_tb_config* config,
                                         const uint32_t* absolute_cb_ids, uint32_t nof_cb_ids)
 {
+  nvtx_scope nvtx_range("pusch_dec.stream_submit");
   if (h == nullptr || stream < 0 || stream >= ingest_slot::NOF || config == nullptr) {
     return SRSRAN_CUDA_ERR_INVALID;
   }
@@ -2372,6 +2396,7 @@ static int poll_tb_impl(srsran_cuda_pusch_dec_t* h, int ticket, int block, uint8
 int srsran_cuda_pusch_dec_poll_tb(srsran_cuda_pusch_dec_t* h, int ticket, int block, uint8_t* tb,
                                   srsran_cuda_pusch_dec_tb_result* result)
 {
+  nvtx_scope nvtx_range("pusch_dec.poll_tb");
   return poll_tb_impl(h, ticket, block, tb, result, true);
 }
 
@@ -2451,6 +2476,7 @@ static int poll_tb_impl(srsran_cuda_pusch_dec_t* h, int ticket, int block, uint8
 int srsran_cuda_pusch_dec_poll_tbs(srsran_cuda_pusch_dec_t* h, uint32_t nof_tickets, const int* tickets, int block,
                                    uint8_t* const* tbs, srsran_cuda_pusch_dec_tb_result* results)
 {
+  nvtx_scope nvtx_range("pusch_dec.poll_tbs");
   if (h == nullptr || tickets == nullptr) {
     return SRSRAN_CUDA_ERR_INVALID;
   }
@@ -2540,6 +2566,7 @@ int srsran_cuda_pusch_dec_submit_tbs_symbols(srsran_cuda_pusch_dec_t* h, uint32_
                                              const float* const* symbols, const float* const* noise_vars, int* tickets,
                                              int device_resident)
 {
+  nvtx_scope nvtx_range("pusch_dec.submit_tbs_symbols");
   if (h == nullptr || configs == nullptr || demod_configs == nullptr || symbols == nullptr || noise_vars == nullptr ||
       tickets == nullptr || nof_tbs == 0 || nof_tbs > MAX_TBS_PER_CTX) {
     return SRSRAN_CUDA_ERR_INVALID;
@@ -2811,6 +2838,7 @@ int srsran_cuda_pusch_dec_timer_stop(srsran_cuda_pusch_dec_t* h, float* elapsed_
 
 int srsran_cuda_pusch_dec_synchronize(srsran_cuda_pusch_dec_t* h)
 {
+  nvtx_scope nvtx_range("pusch_dec.synchronize");
   if (h == nullptr) {
     return SRSRAN_CUDA_ERR_INVALID;
   }
@@ -2905,6 +2933,7 @@ int srsran_cuda_ldpc_decode_batch(srsran_cuda_pusch_dec_t* h, uint8_t* bits, con
                                   uint32_t nof_filler_bits, uint32_t crc_poly, uint32_t max_iterations,
                                   float scaling_factor, int* nof_iterations)
 {
+  nvtx_scope nvtx_range("pusch_dec.ldpc_decode_batch");
   if (h == nullptr || bits == nullptr || llrs == nullptr || nof_cbs == 0 || (base_graph != 1 && base_graph != 2)) {
     return SRSRAN_CUDA_ERR_INVALID;
   }

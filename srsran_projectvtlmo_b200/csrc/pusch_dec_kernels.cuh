@@ -540,50 +540,6 @@ process_check(int8_t* __restrict__ soft, int8_t* __restrict__ c2v, const uint32_
   }
 }
 
-/// Fallback with a run-time degree (two passes, recomputing v2c); never needed for the 3GPP graphs but kept for safety.
-__device__ __noinline__ void
-process_check_generic(int deg, int8_t* soft, int8_t* c2v, const uint32_t* tab, int j, int Z, uint32_t mult)
-{
-  int      m1 = 120, m2 = 120, amin = 0;
-  unsigned sg = 0;
-  for (int e = 0; e != deg; ++e) {
-    uint32_t te = tab[e];
-    int      k  = j + (int)(te >> 16);
-    k           = (k >= Z) ? k - Z : k;
-    int s       = soft[(int)(te & 0xffffU) + k];
-    int c       = c2v[e * Z + j];
-    int x       = max(-120, min(120, s - c));
-    x           = (s >= 127) ? 127 : x;
-    x           = (s <= -127) ? -127 : x;
-    int a       = abs(x);
-    sg ^= (unsigned)x;
-    m2   = min(m2, max(m1, a));
-    amin = (a < m1) ? e : amin;
-    m1   = min(m1, a);
-  }
-  int M1 = mult ? (int)(((uint32_t)m1 * mult) >> 16) : m1;
-  int M2 = mult ? (int)(((uint32_t)m2 * mult) >> 16) : m2;
-  for (int e = 0; e != deg; ++e) {
-    uint32_t te   = tab[e];
-    int      k    = j + (int)(te >> 16);
-    k             = (k >= Z) ? k - Z : k;
-    int      addr = (int)(te & 0xffffU) + k;
-    int      s    = soft[addr];
-    int      cold = c2v[e * Z + j];
-    int      x    = max(-120, min(120, s - cold));
-    x             = (s >= 127) ? 127 : x;
-    x             = (s <= -127) ? -127 : x;
-    int mag       = (e == amin) ? M2 : M1;
-    int c         = ((int)(sg ^ (unsigned)x) < 0) ? -mag : mag;
-    c2v[e * Z + j] = (int8_t)c;
-    int sum = c + x;
-    int r   = (sum > 120) ? 127 : ((sum < -120) ? -127 : sum);
-    r       = (x >= 127) ? 127 : r;
-    r       = (x <= -127) ? -127 : r;
-    soft[addr] = (int8_t)r;
-  }
-}
-
 /// Hard decision of the first K soft bits (MSB-first, bit = (llr <= 0)), "no zero LLR" test and CRC of the first
 /// K - F bits, cooperatively by the TPC threads of a group. Returns (to every thread of the group) 1 if the CRC is zero
 /// and no LLR is zero. get_hard_bits + hard_decision + crc->calculate (ldpc_decoder_impl.cpp:126-134).
@@ -852,7 +808,7 @@ __global__ void __launch_bounds__(TPC* CBS, (TPC * CBS >= 256) ? 2 : 4) ldpc_dec
               process_check<19>(soft, c2v_row, tab_row, j, Z, mult);
               break;
             default:
-              process_check_generic(deg, soft, c2v_row, tab_row, j, Z, mult);
+              __trap(); // the 3GPP base graphs have no other row degree
               break;
           }
         }

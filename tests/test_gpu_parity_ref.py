@@ -107,7 +107,8 @@ def test_headline_tb_vs_reference_harq_fresh_and_stale_slots(variant):
 # and CRC flags of every code block are verified after every transmission. UEs 0..15 carry the full 100 MHz / 4-layer TB
 # (152 code blocks of Z = 384: 13 layers after rv2), the others a mix of the 52 / 106 PRB allocations of config 3.
 # ---------------------------------------------------------------------------------------------------------------------
-def test_config4_64_ues_harq_rv0_rv2_rv3_soft_buffers():
+@pytest.mark.parametrize("variant", [0, 7])  # 7: the 13-layer retransmission groups stage their inputs by bulk copies
+def test_config4_64_ues_harq_rv0_rv2_rv3_soft_buffers(variant):
     # (prb, Qm, R, layers, BG, Nref, mu): mu at the waterfall of the rate (calibrated with the compiled reference)
     shapes = [(273, 8, 948, 4, 1, 12611, 12.8)] * 16 + [(106, 6, 873, 2, 1, 0, 8.0)] * 12 + \
              [(52, 4, 658, 1, 1, 25344, 4.4)] * 12 + [(52, 4, 378, 1, 1, 25344, 2.05)] * 8 + \
@@ -124,6 +125,7 @@ def test_config4_64_ues_harq_rv0_rv2_rv3_soft_buffers():
                         done=False))
         slot += nseg
     acc = pusch.Accelerator(device=0, max_cbs_in_flight=slot, nof_harq_cb_slots=slot)
+    acc.set_decoder_variant(variant)
     chk = _Checker()
     try:
         failed_first = 0
@@ -165,13 +167,18 @@ def _ref_or_port_decode(llr, bg, z, F, crc_poly, max_it):
     return it, out
 
 
-def test_config1_full_rate_batch_random_input(acc):
+@pytest.mark.parametrize("variant", [0, 7])  # 7: inputs staged by cp.async.bulk + mbarrier
+def test_config1_full_rate_batch_random_input(acc, variant):
     rng = np.random.default_rng(101)
     dec = pusch.ldpc_decoder_cuda(acc)
     ncb = 160
     llr = (rng.integers(0, 2, (ncb, 25344)) * 20 - 10).astype(np.int8)
     out = np.zeros((ncb, 1056), np.uint8)
-    its = dec.decode_batch(out, llr, ncb, pusch.CRC_NONE, 1, 384, 0, 6)
+    acc.set_decoder_variant(variant)
+    try:
+        its = dec.decode_batch(out, llr, ncb, pusch.CRC_NONE, 1, 384, 0, 6)
+    finally:
+        acc.set_decoder_variant(0)
     assert np.all(its == -1)
     step = 1 if HAVE_REF else 10  # the port needs ~0.1 s per full-rate code block
     for i in range(0, ncb, step):
