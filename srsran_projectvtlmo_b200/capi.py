@@ -52,6 +52,20 @@ class CbMeta(C.Structure):
                  "nof_crc_bits")]
 
 
+class PdschEncConfig(C.Structure):
+    """srsran_cuda_pdsch_enc_config == hal::hw_pdsch_encoder_configuration (include/srsran_cuda_pdsch_enc.h)."""
+    _fields_ = [(n, C.c_uint32) for n in (
+        "nof_tb_bits", "nof_tb_crc_bits", "base_graph", "modulation", "nof_segments", "nof_short_segments", "rv",
+        "cw_length_a", "cw_length_b", "lifting_size", "Ncb", "Nref", "nof_segment_bits", "nof_filler_bits",
+        "rm_length")] + [("tb_crc", C.c_uint8 * 3), ("cb_mode", C.c_uint8)]
+
+
+class PdschEncTbConfig(C.Structure):
+    """srsran_cuda_pdsch_enc_tb_config == pdsch_encoder::configuration + TBS."""
+    _fields_ = [(n, C.c_uint32) for n in
+                ("tbs_bits", "base_graph", "rv", "modulation", "Nref", "nof_layers", "nof_ch_symbols")]
+
+
 class DemodConfig(C.Structure):
     """srsran_cuda_pusch_demod_config: what pusch_demodulator::configuration fixes about a codeword's soft demodulation."""
     _fields_ = [("modulation", C.c_uint32), ("pi2_bpsk", C.c_uint32), ("rnti", C.c_uint32), ("n_id", C.c_uint32),
@@ -119,6 +133,20 @@ SYMBOLS = {
     "srsran_cuda_pusch_dec_read_softbuffer": (C.c_int, [C.c_void_p, C.c_uint32, i8p, C.c_uint32]),
     "srsran_cuda_pusch_dec_write_softbuffer": (C.c_int, [C.c_void_p, C.c_uint32, i8p, C.c_uint32]),
     "srsran_cuda_pusch_dec_read_cb_crc": (C.c_int, [C.c_void_p, C.c_uint32, intp]),
+    # ---- include/srsran_cuda_pdsch_enc.h ----
+    "srsran_cuda_pdsch_enc_create": (C.c_void_p, [C.c_int, C.c_uint32]),
+    "srsran_cuda_pdsch_enc_destroy": (None, [C.c_void_p]),
+    "srsran_cuda_pdsch_enc_last_error": (C.c_char_p, [C.c_void_p]),
+    "srsran_cuda_pdsch_enc_create_error": (C.c_char_p, []),
+    "srsran_cuda_pdsch_enc_configure": (C.c_int, [C.c_void_p, C.c_uint32, C.POINTER(PdschEncConfig)]),
+    "srsran_cuda_pdsch_enc_enqueue": (C.c_int, [C.c_void_p, C.c_uint32, u8p, C.c_uint32]),
+    "srsran_cuda_pdsch_enc_dequeue": (C.c_int, [C.c_void_p, C.c_uint32, u8p, C.c_uint32, u8p, C.c_uint32]),
+    "srsran_cuda_pdsch_enc_encode_tbs": (C.c_int, [C.c_void_p, C.c_uint32, C.POINTER(PdschEncTbConfig), C.POINTER(u8p),
+                                                   C.POINTER(u8p), C.POINTER(u8p)]),
+    "srsran_cuda_pdsch_enc_encode_tbs_resident": (C.c_int, [C.c_void_p, C.c_uint32, C.POINTER(PdschEncTbConfig), C.POINTER(u8p),
+                                                            C.POINTER(u8p), C.POINTER(C.c_uint64)]),
+    "srsran_cuda_pdsch_enc_last_timing": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
+    "srsran_cuda_pdsch_enc_launch_count": (C.c_uint64, [C.c_void_p]),
 }
 
 

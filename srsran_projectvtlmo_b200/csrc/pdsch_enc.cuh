@@ -1,0 +1,245 @@
+// PDSCH mirror of the decoding path: code-block CRC attachment, LDPC encoding, rate matching (bit
+// selection + bit interleaving) on the device, behind hal::hw_accelerator_pdsch_enc
+// (include/srsran/hal/phy/upper/channel_processors/hw_accelerator_pdsch_enc.h:36-97). Reference arithmetic reproduced bit
+// for bit:
+//   segmentation + CRCs  ldpc_segmenter_tx_impl.cpp (TB CRC from the caller, CRC24B per code block when C > 1, zero padding
+//                        of the last segment, filler bits)
+//   encoding             ldpc_encoder_impl.cpp / TS 38.212 5.3.2: systematic, the 4 core parity blocks through the
+//                        dual-diagonal structure, one independent parity block per extension row; fillers encode as 0
+//   rate matching        ldpc_rate_matcher_impl.cpp:37-147: circular buffer of Ncb = min(Nref, N) bits read from k0, filler
+//                        bits skipped, then f[i Qm + j] = e[j E/Qm + i]
+//
+// One CTA per code block. The lifted variable nodes live in shared memory as ONE BYTE PER BIT ((N_b + 2) Z <= 26112
+// bytes): a circulant shift is an index rotation, exactly as in the decoder, and every parity bit is an XOR of up to 19
+// byte loads. The kernel is bound by its output (E bytes of unpacked + E/8 bytes of packed bits per code block written to
+// HBM), the encoding itself is ~316 Z byte operations per code block.
+#pragma once
+#include "pusch_dec_kernels.cuh"
+
+namespace pusch_dec {
+
+/// One code-block encoding operation. 64 bytes.
+struct enc_cb_desc {
+  const uint8_t* src;        ///< CB mode: the code block's K' = K - F message bits, packed MSB first; TB mode: the packed TB
+  uint8_t*       out_bits;   ///< rate-matched bits, one per byte (E of them); may be null
+  uint8_t*       out_packed; ///< rate-matched bits packed MSB first (ceil(E / 8) bytes); may be null
+  uint32_t       E;          ///< rate-matched length
+  uint32_t       Ncb;        ///< circular buffer length: Nref ? min(Nref, N) : N
+  uint32_t       k0;         ///< starting position (ldpc_rate_matcher_impl.cpp:89-90)
+  uint32_t       nof_filler;
+  uint32_t       src_bit0;   ///< TB mode: first bit of this code block in the stream TB | TB CRC | zero padding
+  uint32_t       info_bits;  ///< bits taken from `src` (TB mode: without the code-block CRC; CB mode: K')
+  uint32_t       tbs_bits;   ///< TB mode: payload bits of the transport block
+  uint32_t       tb_crc;     ///< TB mode: checksum of the transport block (computed by the caller, as the reference's
+                             ///< pdsch_encoder_hw_impl does: pdsch_encoder_hw_impl.cpp:249-261)
+  uint16_t       Z;
+  uint8_t        bg;
+  uint8_t        ils;
+  uint8_t        Qm;
+  uint8_t        tb_mode;    ///< 0: code-block input, 1: TB input with `tb_crc` = checksum, 2: with `tb_crc` = CRC job index
+  uint8_t        tb_crc_len; ///< 16 or 24
+  uint8_t        cb_crc_len; ///< TB mode: 24 when the TB has several code blocks, else 0
+};
+static_assert(sizeof(enc_cb_desc) == 64, "enc_cb_desc must stay 64 bytes");
+
+/// Structure of the first core parity column per (base graph, lifting-set index): it has three entries in rows 0..3, two
+/// with equal shifts; summing the four rows leaves P^y p1 = sum of the lambdas. ent[r] = its shift in row r (-1: none).
+struct enc_core_desc {
+  int16_t y;
+  int16_t ent[4];
+};
+__constant__ enc_core_desc c_enc_core[2][8];
+
+constexpr int ENC_THREADS = 256;
+
+/// Shared memory of the encoder for a code block of base graph `bg` and lifting size Z.
+__host__ __device__ inline uint32_t enc_smem_bytes(uint32_t bg, uint32_t Z)
+{
+  const uint32_t nodes = (((bg == 1) ? 68U : 52U) * Z + 15U) & ~15U; // one byte per lifted variable node
+  const uint32_t lam   = (4U * Z + 15U) & ~15U;                       // the four core-row sums
+  const uint32_t tab   = MAX_EDGES * 8U;                              // (column offset, lifted shift) per edge
+  const uint32_t words = 272U * 4U;                                   // packed message words (code-block CRC)
+  return nodes + lam + tab + words + 4U * 1024U;                      // + CRC byte tables
+}
+
+__global__ void __launch_bounds__(ENC_THREADS) pdsch_encode_kernel(const enc_cb_desc* __restrict__ descs,
+                                                                   const uint32_t* __restrict__ tb_crcs)
+{
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  const enc_cb_desc& d    = descs[blockIdx.x];
+  const int          t    = threadIdx.x;
+  const int          lane = t & 31;
+  const uint32_t     Z = d.Z, bg = d.bg, Kb = (bg == 1) ? 22 : 10, Nb = (bg == 1) ? 68 : 52, K = Kb * Z;
+  const uint32_t     nrows = Nb - Kb;
+  uint8_t*           nodes = smem_raw;
+  uint8_t*           lam   = nodes + ((Nb * Z + 15U) & ~15U);
+  uint2*             tab   = reinterpret_cast<uint2*>(lam + ((4U * Z + 15U) & ~15U));
+  uint32_t*          msgw  = reinterpret_cast<uint32_t*>(tab + MAX_EDGES);
+  uint32_t*          tabs  = msgw + 272;
+
+  // ---- rate-matching geometry: which part of the code word is read at all -----------------------------------------------------
+  const uint32_t sys = (Kb - 2) * Z, F = d.nof_filler, Ncb = d.Ncb, E = d.E;
+  const uint32_t fs = min(sys - F, Ncb), fe = min(sys, Ncb), Fc = fe - fs; // filler positions inside the circular buffer
+  const uint32_t V  = Ncb - Fc;                                            // bits per lap
+  const uint32_t v0 = (d.k0 < fs) ? d.k0 : ((d.k0 < fe) ? fs : d.k0 - Fc); // valid index of the first selected bit
+  // Highest code-word position read: without a wrap only [k0, k0 + E + Fc) is needed - parity rows beyond it are skipped.
+  const uint32_t top   = (v0 + E <= V) ? min(Ncb, ((v0 + E <= fs) ? v0 + E : v0 + E + Fc)) : Ncb;
+  const uint32_t nodes_needed = (top + 2 * Z + Z - 1) / Z; // variable-node columns incl. the two punctured ones
+  const uint32_t rows_needed  = (nodes_needed > Kb) ? min(nrows, nodes_needed - Kb) : 0U;
+  const uint32_t rows_done    = max(rows_needed, 4U);
+
+  const uint32_t nedges = c_row_ptr[bg - 1][rows_done];
+  for (uint32_t e = t; e < nedges; e += ENC_THREADS) {
+    tab[e] = make_uint2((uint32_t)c_col[bg - 1][e] * Z, c_shift[bg - 1][d.ils][e] % Z);
+  }
+  if (d.tb_mode && d.cb_crc_len != 0) {
+    build_crc_tables(tabs, 2, t, ENC_THREADS);
+  }
+
+  // ---- message bits: one byte per bit; fillers and everything beyond K' are zero -----------------------------------------------
+  const uint8_t* __restrict__ src = d.src;
+  const uint32_t info = d.info_bits;
+  if (d.tb_mode) {
+    // tb_mode 2: the checksum was computed on the device by the CRC job of that index (crc_kernel, launched in front)
+    const uint32_t tbs = d.tbs_bits, crc_len = d.tb_crc_len, tb_crc = (d.tb_mode == 2) ? tb_crcs[d.tb_crc] : d.tb_crc;
+    for (uint32_t i = t; i < K; i += ENC_THREADS) {
+      uint32_t bit = 0;
+      if (i < info) {
+        const uint32_t s = d.src_bit0 + i;
+        if (s < tbs) {
+          bit = (__ldg(src + (s >> 3)) >> (7 - (s & 7))) & 1U;
+        } else if (s < tbs + crc_len) {
+          bit = (tb_crc >> (crc_len - 1 - (s - tbs))) & 1U;
+        }
+      }
+      nodes[i] = (uint8_t)bit;
+    }
+    if (d.cb_crc_len != 0) {
+      // CRC24B of the info bits (ldpc_segmenter_tx_impl.cpp: every segment of a multi-segment TB): pack them MSB first,
+      // one warp folds the words, the 24 checksum bits follow the info bits.
+      __syncthreads();
+      const uint32_t nw = (info + 31) / 32;
+      for (uint32_t w = t >> 5; w < nw; w += ENC_THREADS / 32) {
+        const uint32_t i   = w * 32 + 31 - lane; // ballot bit l <-> bit 31 - l of the word: MSB first
+        const uint32_t b   = (i < info) ? nodes[i] : 0U;
+        const uint32_t wd  = __ballot_sync(0xffffffffU, b != 0);
+        if (lane == 0) {
+          msgw[w] = wd;
+        }
+      }
+      __syncthreads();
+      if (t < 32) {
+        const uint32_t crc = warp_crc_words<false>(msgw, info, 2, tabs, lane);
+        if (lane < 24) {
+          nodes[info + lane] = (uint8_t)((crc >> (23 - lane)) & 1U);
+        }
+      }
+    }
+  } else {
+    for (uint32_t i = t; i < K; i += ENC_THREADS) {
+      nodes[i] = (i < info) ? (uint8_t)((__ldg(src + (i >> 3)) >> (7 - (i & 7))) & 1U) : (uint8_t)0;
+    }
+  }
+  __syncthreads();
+
+  auto rot_xor = [&](uint32_t e, uint32_t j) -> uint32_t {
+    const uint2 te = tab[e];
+    uint32_t    k  = j + te.y;
+    k              = (k >= Z) ? k - Z : k;
+    return nodes[te.x + k];
+  };
+
+  // ---- core rows: lambda_r = sum over the systematic columns ---------------------------------------------------------------------
+  for (uint32_t i = t; i < 4 * Z; i += ENC_THREADS) {
+    const uint32_t r = i / Z, j = i - r * Z;
+    uint32_t       acc = 0;
+    for (uint32_t e = c_row_ptr[bg - 1][r], e1 = c_row_ptr[bg - 1][r + 1]; e != e1; ++e) {
+      if (tab[e].x < K) {
+        acc ^= rot_xor(e, j);
+      }
+    }
+    lam[i] = (uint8_t)acc;
+  }
+  __syncthreads();
+  const enc_core_desc core = c_enc_core[bg - 1][d.ils];
+  const uint32_t      y    = (uint32_t)core.y % Z;
+  // p1 = P^-y (lambda_0 + lambda_1 + lambda_2 + lambda_3)
+  for (uint32_t j = t; j < Z; j += ENC_THREADS) {
+    uint32_t k = j + Z - y;
+    k          = (k >= Z) ? k - Z : k;
+    nodes[K + j] = lam[k] ^ lam[Z + k] ^ lam[2 * Z + k] ^ lam[3 * Z + k];
+  }
+  __syncthreads();
+  // Dual diagonal: row r (0..2) introduces column K_b + 1 + r with shift 0.
+  for (uint32_t j = t; j < Z; j += ENC_THREADS) {
+    uint32_t prev = 0;
+#pragma unroll
+    for (uint32_t r = 0; r != 3; ++r) {
+      uint32_t acc = lam[r * Z + j] ^ prev;
+      if (core.ent[r] >= 0) {
+        uint32_t k = j + (uint32_t)core.ent[r] % Z;
+        k          = (k >= Z) ? k - Z : k;
+        acc ^= nodes[K + k];
+      }
+      nodes[K + (1 + r) * Z + j] = (uint8_t)acc;
+      prev                       = acc;
+    }
+  }
+  __syncthreads();
+
+  // ---- extension rows: one new column each, independent of one another ---------------------------------------------------------
+  if (rows_needed > 4) {
+    const uint32_t ntask = (rows_needed - 4) * Z;
+    for (uint32_t i = t; i < ntask; i += ENC_THREADS) {
+      const uint32_t r = 4 + i / Z, j = i - (r - 4) * Z;
+      uint32_t       acc = 0;
+      // (the last edge of an extension row is its own new column)
+      for (uint32_t e = c_row_ptr[bg - 1][r], e1 = c_row_ptr[bg - 1][r + 1] - 1; e != e1; ++e) {
+        acc ^= rot_xor(e, j);
+      }
+      nodes[(Kb + r) * Z + j] = (uint8_t)acc;
+    }
+  }
+  __syncthreads();
+
+  // ---- rate matching: bit selection from k0 (fillers skipped, wrap at Ncb) + interleaving, eight output bits per thread ------------
+  const uint32_t Qm = d.Qm, EQ = E / Qm;
+  const uint8_t* cw = nodes + 2 * Z; // the two punctured columns are not part of the code word
+  auto out_bit = [&](uint32_t n) -> uint32_t {
+    // f[i Qm + j] = e[j E/Qm + i] (ldpc_rate_matcher_impl.cpp:149-270)
+    const uint32_t i = n / Qm, jq = n - i * Qm;
+    uint32_t       u = v0 + jq * EQ + i;
+    u                = (u >= V) ? u % V : u;
+    return cw[(u < fs) ? u : u + Fc];
+  };
+  uint8_t* __restrict__ ob = d.out_bits;
+  uint8_t* __restrict__ op = d.out_packed;
+  for (uint32_t b = t; b * 8 < E; b += ENC_THREADS) {
+    const uint32_t n0 = b * 8, cnt = min(8U, E - n0);
+    uint32_t       lo = 0, hi = 0, byte = 0;
+#pragma unroll
+    for (uint32_t k = 0; k != 8; ++k) {
+      const uint32_t bit = (k < cnt) ? out_bit(n0 + k) : 0U;
+      byte |= bit << (7 - k);
+      if (k < 4) {
+        lo |= bit << (8 * k);
+      } else {
+        hi |= bit << (8 * (k - 4));
+      }
+    }
+    if (op != nullptr) {
+      op[b] = (uint8_t)byte;
+    }
+    if (ob != nullptr) {
+      if (cnt == 8 && ((reinterpret_cast<uintptr_t>(ob) & 7U) == 0)) {
+        *reinterpret_cast<uint2*>(ob + n0) = make_uint2(lo, hi);
+      } else {
+        for (uint32_t k = 0; k != cnt; ++k) {
+          ob[n0 + k] = (uint8_t)((byte >> (7 - k)) & 1U);
+        }
+      }
+    }
+  }
+}
+
+} // namespace pusch_dec

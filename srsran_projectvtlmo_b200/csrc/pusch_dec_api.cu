@@ -502,7 +502,8 @@ cudaError_t set_smem_attr(int bytes)
   return cudaFuncSetAttribute(ldpc_decode_kernel<TPC, CBS>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
 }
 
-int upload_tables(srsran_cuda_pusch_dec* h)
+template <typename Handle>
+int upload_tables(Handle* h)
 {
   uint16_t row_ptr[2][48] = {};
   uint8_t  col[2][MAX_EDGES] = {};
@@ -3094,3 +3095,6 @@ int srsran_cuda_pusch_dec_read_cb_crc(srsran_cuda_pusch_dec_t* h, uint32_t absol
 }
 
 } // extern "C"
+
+// ---- PDSCH encoding accelerator: same translation unit, shares the constant tables -----------------
+#include "pdsch_enc_api.cuh"

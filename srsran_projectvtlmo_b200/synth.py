@@ -208,8 +208,9 @@ def rate_match(cw, bg, z, nfill, e_len, rv, qm, nref):
     return e
 
 
-def encode_tb(tb_bytes, bg, rv, qm, nref, nof_layers, nof_llrs):
-    """UL-SCH transmitter: TB bytes -> code word bits (one per element, nof_llrs of them)."""
+def tx_segments(tb_bytes, bg):
+    """Tx segmentation (TS 38.212 5.2.2, ldpc_segmenter_tx_impl.cpp): TB bytes -> (msg, z, kp, nfill, tb_crc) with msg the
+    (C, K) message bits of the code blocks (TB CRC and code-block CRCs attached, filler bits zero), kp = K - nfill."""
     tb_bits = np.unpackbits(np.asarray(tb_bytes, dtype=np.uint8))
     tbs = tb_bits.size
     c, z, k, kp, tb_crc, cb_crc, zero_pad = segmentation(tbs, bg)
@@ -221,7 +222,13 @@ def encode_tb(tb_bytes, bg, rv, qm, nref, nof_layers, nof_llrs):
     msg[:, :info] = segs
     if c > 1:
         msg[:, info:kp] = int_to_bits(crc_bits(segs, "24B"), 24)
-    nfill = k - kp
+    return msg, z, kp, k - kp, int(crc)
+
+
+def encode_tb(tb_bytes, bg, rv, qm, nref, nof_layers, nof_llrs):
+    """UL-SCH transmitter: TB bytes -> code word bits (one per element, nof_llrs of them)."""
+    msg, z, kp, nfill, _ = tx_segments(tb_bytes, bg)
+    c = msg.shape[0]
     cws = ldpc_encode(msg, bg, z)
     out = []
     for i, e_len in enumerate(rm_lengths(c, nof_llrs, qm, nof_layers)):

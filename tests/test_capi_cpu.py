@@ -15,7 +15,7 @@ ROOT = Path(__file__).resolve().parent.parent
 
 
 def declared_symbols():
-    text = (ROOT / "include" / "srsran_cuda_pusch_dec.h").read_text()
+    text = "".join(p.read_text() for p in sorted((ROOT / "include").glob("*.h")))
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
     return sorted(set(re.findall(r"\b(srsran_cuda_[a-z0-9_]+)\s*\(", text)))
 

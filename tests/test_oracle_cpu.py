@@ -289,3 +289,19 @@ def test_port_vs_reference_tb_harq():
                    (r2.tb_crc_ok, r2.nof_observations, r2.iter_min, r2.iter_max), (key, rv)
             if r2.tb_crc_ok:
                 assert np.array_equal(t1, t2)
+
+
+def test_golden_pdsch_encoder_codewords():
+    """tests/golden/pdsch_enc.npz (code words of the reference's pdsch_encoder_impl, made by make_golden_pdsch_enc.py) against
+    the numpy transmitter - the checker of the PDSCH encoding accelerator where the compiled reference is absent - and,
+    where it is present, against the compiled reference itself."""
+    g = np.load(GOLDEN / "pdsch_enc.npz")
+    for i, (prb, qm, R, nl, bg, nref, rv) in enumerate(g["cases"]):
+        prb, qm, R, nl, bg, nref, rv = (int(v) for v in (prb, qm, R, nl, bg, nref, rv))
+        tb = g[f"tb{i}"]
+        nbits = prb * 156 * qm * nl
+        assert tb.size * 8 == synth.tbs_for(prb, qm, R, nl)
+        cw = synth.encode_tb(tb, bg, rv, qm, nref, nl, nbits)
+        assert np.array_equal(np.packbits(cw), g[f"cw{i}"]), i
+        if ob.ref() is not None:
+            assert np.array_equal(ob.ref_encode_tb(tb, bg, rv, qm, nref, nl, nbits // qm), cw), i
