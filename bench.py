@@ -394,6 +394,56 @@ def other_configs(args, rng_seed=7):
                           "what": "reference pusch_decoder_impl, all host threads, the rv0 transmission of this TB at mu = 9 (fails: 6 iterations)"}}
     finally:
         acc.close()
+
+    # ---- PDSCH mirror: 64 TBs of config-2 size encoded in one launch -------------------------------------
+    from srsran_projectvtlmo_b200 import pdsch
+    enc = pdsch.EncoderAccelerator(device=0)
+    try:
+        rng = np.random.default_rng(rng_seed + 3)
+        B, tbs, nbits = 64, 1277992, 1362816
+        tb = [rng.integers(0, 256, tbs // 8, dtype=np.uint8) for _ in range(B)]
+        cfgs = [pdsch.pdsch_encoder_configuration(1, 0, 8, 12611, 4, nbits // 8) for _ in range(B)]
+        want = np.packbits(synth.encode_tb(tb[5], 1, 0, 8, 12611, 4, nbits))
+        stage, wall = np.zeros(3), 0.0
+        for rep in range(6):
+            t0 = time.perf_counter()
+            _, pk = pdsch.encode_tbs(enc, cfgs, tb, want_bits=False, want_packed=True)
+            if rep:
+                wall += time.perf_counter() - t0
+                stage += np.array(enc.last_timing())
+            assert np.array_equal(pk[5], want), "PDSCH code word differs from the transmitter restatement"
+        stage /= 5
+        wall /= 5
+        pe = {"workload": "64 TBs x 273 PRB / 256QAM / 4 layers / Nref 12611 (152 code blocks of BG1 Z = 384 each), rv 0: TB CRC + "
+                          "code-block CRCs + LDPC encoding + rate matching, packed code words back to the host",
+              "kernels_ms": float(stage[1]), "stage_ms": stage.tolist(), "info_gbit_per_s_kernels": B * tbs / (stage[1] * 1e-3) / 1e9,
+              "ms_host_buffers": wall * 1e3, "info_gbit_per_s_host_buffers": B * tbs / wall / 1e9,
+              "hbm_bytes_algorithmic": B * (tbs // 8 + nbits + nbits // 8),
+              "hbm_gbs": B * (tbs // 8 + nbits + nbits // 8) / (stage[1] * 1e-3) / 1e9,
+              "note": "the kernel writes the code word one bit per byte (the reference's pdsch_encoder output format, "
+                      "consumed by the modulation mapper) and a packing kernel re-reads it: E + E / 8 bytes out per code block"}
+        if ref is not None:
+            # The reference's Tx segmenter refuses this TBS (ldpc_segmenter_impl.cpp:77): the 2-layer TB of the same
+            # allocation stands in for it, all host threads, one pdsch_encoder_impl each.
+            from concurrent.futures import ThreadPoolExecutor
+            tbs2, nbits2 = 638984, 681408
+            tb2 = rng.integers(0, 256, tbs2 // 8, dtype=np.uint8)
+
+            def work(n):
+                for _ in range(n):
+                    ob.ref_encode_tb(tb2, 1, 0, 8, 25223, 2, nbits2 // 8)
+            work(2)
+            n_each = 40
+            t0 = time.perf_counter()
+            with ThreadPoolExecutor(threads) as ex:
+                list(ex.map(work, [n_each] * threads))
+            dt = time.perf_counter() - t0
+            pe["reference"] = {"value": threads * n_each * tbs2 / dt / 1e9, "unit": "Gbit/s info", "cores": threads,
+                               "what": "reference pdsch_encoder_impl (segmenter + AVX2 ldpc_encoder + rate matcher), one instance per "
+                                       "host thread, the 2-layer TB of the same allocation"}
+        out["pdsch_encode_64_tbs"] = pe
+    finally:
+        enc.close()
     return out
 
 

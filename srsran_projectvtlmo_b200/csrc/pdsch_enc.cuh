@@ -67,6 +67,9 @@ __global__ void __launch_bounds__(ENC_THREADS) pdsch_encode_kernel(const enc_cb_
 {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   const enc_cb_desc& d    = descs[blockIdx.x];
+  if ((d.Z & 31U) == 0) {
+    return; // handled by pdsch_encode_packed_kernel
+  }
   const int          t    = threadIdx.x;
   const int          lane = t & 31;
   const uint32_t     Z = d.Z, bg = d.bg, Kb = (bg == 1) ? 22 : 10, Nb = (bg == 1) ? 68 : 52, K = Kb * Z;
@@ -238,6 +241,278 @@ __global__ void __launch_bounds__(ENC_THREADS) pdsch_encode_kernel(const enc_cb_
           ob[n0 + k] = (uint8_t)((byte >> (7 - k)) & 1U);
         }
       }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Packed form for Z % 32 == 0 (every transport block large enough to matter: Z = 384 for full-size code blocks): a lifted
+// variable node is Z / 32 words of 32 bits (bit j of the column = bit j % 32 of word j / 32), a circulant shift is a word
+// rotation plus one funnel shift, a parity word is the XOR of up to 19 of them. The encoding proper then costs ~4
+// instructions per (edge, word) - 15 k thread instructions per full-size code block instead of 1.8 M with one byte per
+// bit - and the kernel is bound by what it has to write: E bytes of unpacked and E / 8 bytes of packed bits.
+// ---------------------------------------------------------------------------------------------------------------------
+/// TWO_LAPS: the selection covers at most two laps of the circular buffer (every practical code rate), so the wrap is one
+/// conditional subtraction.
+template <int QM, bool TWO_LAPS>
+__device__ __forceinline__ void enc_rate_match_packed(const uint32_t* __restrict__ cw, uint32_t v0, uint32_t V, uint32_t fs,
+                                                      uint32_t Fc, uint32_t E, uint8_t* __restrict__ ob, uint8_t* __restrict__ op,
+                                                      int t)
+{
+  const uint32_t EQ = E / QM;
+  const bool     aligned = (reinterpret_cast<uintptr_t>(ob) & 7U) == 0;
+  // Code-word bit behind output bit n: f[i QM + j] = e[j E/QM + i]; e[m] = the m-th non-filler position from k0, modulo the
+  // buffer (ldpc_rate_matcher_impl.cpp:101-147, 149-270).
+  auto src_bit = [&](uint32_t n) -> uint32_t {
+    const uint32_t i = n / QM, jq = n - i * QM;
+    uint32_t       u = v0 + jq * EQ + i;
+    if constexpr (TWO_LAPS) {
+      u = (u >= V) ? u - V : u;
+    } else {
+      u = (u >= V) ? u % V : u;
+    }
+    const uint32_t p = (u < fs) ? u : u + Fc;
+    return cw[p >> 5] >> (p & 31U);
+  };
+  for (uint32_t b = t; b * 8 < E; b += ENC_THREADS) {
+    const uint32_t n0 = b * 8;
+    if (n0 + 8 <= E) {
+      // Eight bits: shifted in from the top, so that bit k of the group ends in bit 24 + k.
+      uint32_t acc = 0;
+#pragma unroll
+      for (uint32_t k = 0; k != 8; ++k) {
+        acc = __funnelshift_r(acc, src_bit(n0 + k), 1);
+      }
+      const uint32_t r = acc >> 24; // bit k = output bit n0 + k
+      if (op != nullptr) {
+        op[b] = (uint8_t)(__brev(r) >> 24);
+      }
+      if (ob != nullptr) {
+        // one byte per bit: bits 0..3 of r into the four bytes of a word by one multiplication (distinct powers, no carries)
+        const uint32_t lo = ((r & 0xfU) * 0x00204081U) & 0x01010101U, hi = ((r >> 4) * 0x00204081U) & 0x01010101U;
+        if (aligned) {
+          *reinterpret_cast<uint2*>(ob + n0) = make_uint2(lo, hi);
+        } else {
+          for (uint32_t k = 0; k != 8; ++k) {
+            ob[n0 + k] = (uint8_t)((r >> k) & 1U);
+          }
+        }
+      }
+    } else {
+      uint32_t byte = 0;
+      for (uint32_t k = 0; n0 + k < E; ++k) {
+        const uint32_t bit = src_bit(n0 + k) & 1U;
+        byte |= bit << (7 - k);
+        if (ob != nullptr) {
+          ob[n0 + k] = (uint8_t)bit;
+        }
+      }
+      if (op != nullptr) {
+        op[b] = (uint8_t)byte;
+      }
+    }
+  }
+}
+
+/// Which descriptors a launch handles: the packed kernel those with Z % 32 == 0, the byte kernel the others.
+__device__ __forceinline__ bool enc_is_packed(const enc_cb_desc& d)
+{
+  return (d.Z & 31U) == 0;
+}
+
+__global__ void __launch_bounds__(ENC_THREADS) pdsch_encode_packed_kernel(const enc_cb_desc* __restrict__ descs,
+                                                                          const uint32_t* __restrict__ tb_crcs)
+{
+  // 68 columns x 12 words, the four core-row sums, the edge table, the CRC byte tables
+  __shared__ uint32_t colw[68 * 12];
+  __shared__ uint32_t lamw[4 * 12];
+  __shared__ uint2    tab[MAX_EDGES];
+  __shared__ uint32_t tabs[1024];
+  __shared__ uint32_t msgw[272];
+  const enc_cb_desc&  d = descs[blockIdx.x];
+  if (!enc_is_packed(d)) {
+    return;
+  }
+  const int      t    = threadIdx.x;
+  const int      lane = t & 31;
+  const uint32_t Z = d.Z, W = Z / 32, bg = d.bg, Kb = (bg == 1) ? 22 : 10, Nb = (bg == 1) ? 68 : 52, K = Kb * Z;
+  const uint32_t nrows = Nb - Kb;
+
+  const uint32_t sys = (Kb - 2) * Z, F = d.nof_filler, Ncb = d.Ncb, E = d.E;
+  const uint32_t fs = min(sys - F, Ncb), fe = min(sys, Ncb), Fc = fe - fs;
+  const uint32_t V  = Ncb - Fc;
+  const uint32_t v0 = (d.k0 < fs) ? d.k0 : ((d.k0 < fe) ? fs : d.k0 - Fc);
+  const uint32_t top = (v0 + E <= V) ? min(Ncb, ((v0 + E <= fs) ? v0 + E : v0 + E + Fc)) : Ncb;
+  const uint32_t nodes_needed = (top + 2 * Z + Z - 1) / Z;
+  const uint32_t rows_needed  = (nodes_needed > Kb) ? min(nrows, nodes_needed - Kb) : 0U;
+  const uint32_t rows_done    = max(rows_needed, 4U);
+
+  const uint32_t nedges = c_row_ptr[bg - 1][rows_done];
+  for (uint32_t e = t; e < nedges; e += ENC_THREADS) {
+    const uint32_t sh = c_shift[bg - 1][d.ils][e] % Z;
+    tab[e]            = make_uint2((uint32_t)c_col[bg - 1][e] * W, sh); // first word of the column, lifted shift
+  }
+  if (d.tb_mode && d.cb_crc_len != 0) {
+    build_crc_tables(tabs, 2, t, ENC_THREADS);
+  }
+
+  // ---- message words: bit i of the code block = bit i % 32 of word i / 32 -----------------------------------------------------
+  const uint8_t* __restrict__ src = d.src;
+  const uint32_t info = d.info_bits;
+  const uint32_t tbs = d.tbs_bits, crc_len = d.tb_crc_len;
+  const uint32_t tb_crc = (d.tb_mode == 2) ? tb_crcs[d.tb_crc] : d.tb_crc;
+  for (uint32_t w = t; w < K / 32; w += ENC_THREADS) {
+    const uint32_t i0 = w * 32;
+    uint32_t       msb = 0; // the 32 bits MSB first (bit i0 in bit 31)
+    if (i0 < info) {
+      const uint32_t s0 = d.tb_mode ? d.src_bit0 + i0 : i0;
+      if (!d.tb_mode || s0 + 32 <= tbs) {
+        const uint32_t by = s0 >> 3, sh = s0 & 7U;
+        // (a code block's last byte may be its input's last: the fifth byte is read only when it holds wanted bits)
+        const uint32_t v  = ((uint32_t)__ldg(src + by) << 24) | ((uint32_t)__ldg(src + by + 1) << 16) |
+                           ((uint32_t)__ldg(src + by + 2) << 8) | (uint32_t)__ldg(src + by + 3);
+        msb = v << sh;
+        if (sh != 0) {
+          msb |= (uint32_t)__ldg(src + by + 4) >> (8 - sh);
+        }
+      } else {
+        for (uint32_t k = 0; k != 32; ++k) {
+          const uint32_t s = s0 + k;
+          uint32_t       bit = 0;
+          if (s < tbs) {
+            bit = (__ldg(src + (s >> 3)) >> (7 - (s & 7))) & 1U;
+          } else if (s < tbs + crc_len) {
+            bit = (tb_crc >> (crc_len - 1 - (s - tbs))) & 1U;
+          }
+          msb |= bit << (31 - k);
+        }
+      }
+      if (i0 + 32 > info) {
+        msb &= 0xffffffffU << (i0 + 32 - info); // only the first info - i0 bits
+      }
+    }
+    msgw[w] = msb;
+    colw[w] = __brev(msb);
+  }
+  __syncthreads();
+  if (d.tb_mode && d.cb_crc_len != 0) {
+    // CRC24B of the info bits, appended behind them (ldpc_segmenter_tx_impl.cpp).
+    if (t < 32) {
+      const uint32_t crc = warp_crc_words<false>(msgw, info, 2, tabs, lane);
+      if (lane < 24) {
+        const uint32_t i = info + lane;
+        if ((crc >> (23 - lane)) & 1U) {
+          atomicOr(&colw[i >> 5], 1U << (i & 31U));
+        }
+      }
+    }
+    __syncthreads();
+  }
+
+  // Word w of P^s x (x = column starting at word c0): bits [(32 w + s) mod Z, ...) of x.
+  auto rot_word = [&](uint32_t c0, uint32_t s, uint32_t w) -> uint32_t {
+    uint32_t a = w + (s >> 5);
+    a          = (a >= W) ? a - W : a;
+    uint32_t b = a + 1;
+    b          = (b >= W) ? b - W : b;
+    return __funnelshift_r(colw[c0 + a], colw[c0 + b], s & 31U);
+  };
+
+  // ---- core rows ---------------------------------------------------------------------------------------------------------------
+  if (t < (int)(4 * W)) {
+    const uint32_t r = t / W, w = t - r * W;
+    uint32_t       acc = 0;
+    for (uint32_t e = c_row_ptr[bg - 1][r], e1 = c_row_ptr[bg - 1][r + 1]; e != e1; ++e) {
+      const uint2 te = tab[e];
+      if (te.x < Kb * W) {
+        acc ^= rot_word(te.x, te.y, w);
+      }
+    }
+    lamw[t] = acc;
+  }
+  __syncthreads();
+  const enc_core_desc core = c_enc_core[bg - 1][d.ils];
+  uint32_t*           p1   = colw + Kb * W;
+  if (t < (int)W) {
+    // p1 = P^-y (sum of the lambdas): word t of the rotation by Z - y
+    const uint32_t y = (uint32_t)core.y % Z, s = (y == 0) ? 0U : Z - y;
+    uint32_t       a = t + (s >> 5);
+    a                = (a >= W) ? a - W : a;
+    uint32_t b       = a + 1;
+    b                = (b >= W) ? b - W : b;
+    const uint32_t ta = lamw[a] ^ lamw[W + a] ^ lamw[2 * W + a] ^ lamw[3 * W + a];
+    const uint32_t tb = lamw[b] ^ lamw[W + b] ^ lamw[2 * W + b] ^ lamw[3 * W + b];
+    p1[t]             = __funnelshift_r(ta, tb, s & 31U);
+  }
+  __syncthreads();
+  if (t < (int)W) {
+    uint32_t prev = 0;
+#pragma unroll
+    for (uint32_t r = 0; r != 3; ++r) {
+      uint32_t acc = lamw[r * W + t] ^ prev;
+      if (core.ent[r] >= 0) {
+        acc ^= rot_word(Kb * W, (uint32_t)core.ent[r] % Z, t);
+      }
+      colw[(Kb + 1 + r) * W + t] = acc;
+      prev                       = acc;
+    }
+  }
+  __syncthreads();
+
+  // ---- extension rows ------------------------------------------------------------------------------------------------------------
+  if (rows_needed > 4) {
+    const uint32_t ntask = (rows_needed - 4) * W;
+    for (uint32_t i = t; i < ntask; i += ENC_THREADS) {
+      const uint32_t r = 4 + i / W, w = i - (r - 4) * W;
+      uint32_t       acc = 0;
+      for (uint32_t e = c_row_ptr[bg - 1][r], e1 = c_row_ptr[bg - 1][r + 1] - 1; e != e1; ++e) {
+        const uint2 te = tab[e];
+        acc ^= rot_word(te.x, te.y, w);
+      }
+      colw[(Kb + r) * W + w] = acc;
+    }
+  }
+  __syncthreads();
+
+  // ---- rate matching ---------------------------------------------------------------------------------------------------------------
+  const uint32_t* cw = colw + 2 * W;
+  uint8_t* const  ob = d.out_bits;
+  uint8_t* const  op = d.out_packed;
+  if (v0 + E <= 2 * V) {
+    switch (d.Qm) {
+      case 8:
+        enc_rate_match_packed<8, true>(cw, v0, V, fs, Fc, E, ob, op, t);
+        break;
+      case 6:
+        enc_rate_match_packed<6, true>(cw, v0, V, fs, Fc, E, ob, op, t);
+        break;
+      case 4:
+        enc_rate_match_packed<4, true>(cw, v0, V, fs, Fc, E, ob, op, t);
+        break;
+      case 2:
+        enc_rate_match_packed<2, true>(cw, v0, V, fs, Fc, E, ob, op, t);
+        break;
+      default:
+        enc_rate_match_packed<1, true>(cw, v0, V, fs, Fc, E, ob, op, t);
+        break;
+    }
+  } else {
+    switch (d.Qm) {
+      case 8:
+        enc_rate_match_packed<8, false>(cw, v0, V, fs, Fc, E, ob, op, t);
+        break;
+      case 6:
+        enc_rate_match_packed<6, false>(cw, v0, V, fs, Fc, E, ob, op, t);
+        break;
+      case 4:
+        enc_rate_match_packed<4, false>(cw, v0, V, fs, Fc, E, ob, op, t);
+        break;
+      case 2:
+        enc_rate_match_packed<2, false>(cw, v0, V, fs, Fc, E, ob, op, t);
+        break;
+      default:
+        enc_rate_match_packed<1, false>(cw, v0, V, fs, Fc, E, ob, op, t);
+        break;
     }
   }
 }

@@ -51,7 +51,8 @@ struct srsran_cuda_pdsch_enc {
   pinned_buf<uint64_t>     h_runs;
   device_buf<uint64_t>     d_runs;
   size_t                   bits_used = 0, packed_used = 0;
-  uint32_t                 max_z[2]  = {0, 0};
+  uint32_t                 max_z[2]  = {0, 0}; // largest lifting size among the code blocks of the byte-per-bit kernel
+  uint32_t                 n_packed = 0, n_bytewise = 0; // code blocks per kernel (Z % 32 == 0: packed words)
   device_buf<uint8_t>      d_bits, d_packed;
   pinned_buf<uint8_t>      h_bits, h_packed;
 };
@@ -141,6 +142,7 @@ void enc_begin(srsran_cuda_pdsch_enc* h)
   h->bits_used = h->packed_used = 0;
   h->ndesc = h->njobs = 0;
   h->max_z[0] = h->max_z[1] = 0;
+  h->n_packed = h->n_bytewise = 0;
   h->runs.clear();
 }
 
@@ -177,7 +179,12 @@ int enc_fill_desc(srsran_cuda_pdsch_enc* h, enc_cb_desc& d, uint32_t bg, uint32_
   d.bg         = static_cast<uint8_t>(bg);
   d.ils        = static_cast<uint8_t>(ils);
   d.Qm         = static_cast<uint8_t>(Qm);
-  h->max_z[bg - 1] = std::max(h->max_z[bg - 1], Z);
+  if (Z % 32 == 0) {
+    ++h->n_packed;
+  } else {
+    ++h->n_bytewise;
+    h->max_z[bg - 1] = std::max(h->max_z[bg - 1], Z);
+  }
   return SRSRAN_CUDA_OK;
 }
 
@@ -261,7 +268,7 @@ int enc_launch(srsran_cuda_pdsch_enc* h)
 {
   cudaStream_t s = h->stream;
   cudaSetDevice(h->device);
-  CUDA_TRY(h, h->d_in.reserve(std::max<size_t>(h->in_used, 16)));
+  CUDA_TRY(h, h->d_in.reserve(h->in_used + 16)); // (the kernels read whole words: up to four bytes past a message)
   CUDA_TRY(h, h->d_bits.reserve(h->bits_used + 16));
   CUDA_TRY(h, h->d_packed.reserve(h->packed_used + 16));
   CUDA_TRY(h, h->d_desc.reserve(h->ndesc));
@@ -300,10 +307,18 @@ int enc_launch(srsran_cuda_pdsch_enc* h)
     ++h->launches;
     CUDA_TRY(h, cudaGetLastError());
   }
-  const uint32_t smem = std::max(h->max_z[0] ? enc_smem_bytes(1, h->max_z[0]) : 0U, h->max_z[1] ? enc_smem_bytes(2, h->max_z[1]) : 0U);
-  pdsch_encode_kernel<<<h->ndesc, ENC_THREADS, smem, s>>>(h->d_desc.p, h->d_crcs.p);
-  ++h->launches;
-  CUDA_TRY(h, cudaGetLastError());
+  // Both kernels walk the same descriptor array and skip the code blocks of the other (Z % 32 == 0: packed words).
+  if (h->n_packed != 0) {
+    pdsch_encode_packed_kernel<<<h->ndesc, ENC_THREADS, 0, s>>>(h->d_desc.p, h->d_crcs.p);
+    ++h->launches;
+    CUDA_TRY(h, cudaGetLastError());
+  }
+  if (h->n_bytewise != 0) {
+    const uint32_t smem = std::max(h->max_z[0] ? enc_smem_bytes(1, h->max_z[0]) : 0U, h->max_z[1] ? enc_smem_bytes(2, h->max_z[1]) : 0U);
+    pdsch_encode_kernel<<<h->ndesc, ENC_THREADS, smem, s>>>(h->d_desc.p, h->d_crcs.p);
+    ++h->launches;
+    CUDA_TRY(h, cudaGetLastError());
+  }
   if (!h->runs.empty()) {
     uint64_t maxbits = 0;
     for (const enc_out_run& r : h->runs) {
@@ -592,12 +607,36 @@ int srsran_cuda_pdsch_enc_encode_tbs(srsran_cuda_pdsch_enc_t* h, uint32_t nof_tb
   if (r != SRSRAN_CUDA_OK) {
     return r;
   }
-  for (uint32_t i = 0; i != nof_tbs; ++i) {
-    if (codewords != nullptr && codewords[i] != nullptr) {
-      CUDA_TRY(h, cudaMemcpyAsync(codewords[i], h->d_bits.p + boff[i], nbits[i], cudaMemcpyDeviceToHost, h->stream));
+  // Outputs that are adjacent on both sides (the caller laid the code words of a slot back to back) leave in one copy.
+  auto copy_out = [&](uint8_t* const* dst, const uint8_t* dev, const std::vector<size_t>& off, bool pk) -> int {
+    uint32_t i = 0;
+    while (i != nof_tbs) {
+      if (dst[i] == nullptr) {
+        ++i;
+        continue;
+      }
+      auto   len = [&](uint32_t k) { return pk ? static_cast<size_t>((nbits[k] + 7) / 8) : static_cast<size_t>(nbits[k]); };
+      size_t n   = len(i);
+      uint32_t j = i + 1;
+      while (j != nof_tbs && dst[j] == dst[i] + n && off[j] == off[i] + n) {
+        n += len(j);
+        ++j;
+      }
+      CUDA_TRY(h, cudaMemcpyAsync(dst[i], dev + off[i], n, cudaMemcpyDeviceToHost, h->stream));
+      i = j;
     }
-    if (packed != nullptr && packed[i] != nullptr) {
-      CUDA_TRY(h, cudaMemcpyAsync(packed[i], h->d_packed.p + poff[i], (nbits[i] + 7) / 8, cudaMemcpyDeviceToHost, h->stream));
+    return SRSRAN_CUDA_OK;
+  };
+  if (codewords != nullptr) {
+    r = copy_out(codewords, h->d_bits.p, boff, false);
+    if (r != SRSRAN_CUDA_OK) {
+      return r;
+    }
+  }
+  if (packed != nullptr) {
+    r = copy_out(packed, h->d_packed.p, poff, true);
+    if (r != SRSRAN_CUDA_OK) {
+      return r;
     }
   }
   CUDA_TRY(h, cudaEventRecord(h->ev[3], h->stream));

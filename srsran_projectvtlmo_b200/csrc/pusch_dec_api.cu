@@ -2681,6 +2681,7 @@ static int demod_sync(srsran_cuda_pusch_dec_t* h, int8_t* llrs, const float* sym
             reinterpret_cast<const float*>(c.d_dm_in.p + static_cast<size_t>(nsym) * 8), c.d_llr.p, 0);
   if (max_block_subc_override != 0) {
     c.h_dm.p[0].max_block_subc = max_block_subc_override;
+    c.h_dm.p[0].mbs_magic      = static_cast<uint32_t>((0x100000000ULL + max_block_subc_override - 1) / max_block_subc_override);
   }
   CUDA_TRY(h, cudaMemcpyAsync(c.d_dm.p, c.h_dm.p, sizeof(demod_desc), cudaMemcpyHostToDevice, s));
   scr_seq_kernel<<<dim3((c.dm_max_words + SCR_CHUNK_WORDS - 1) / SCR_CHUNK_WORDS, 1), 32, 0, s>>>(c.d_dm.p, h->d_scr_x1.p,

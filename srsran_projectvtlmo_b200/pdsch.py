@@ -30,6 +30,7 @@ class EncoderAccelerator:
         if not self.h:
             raise capi.CudaPuschDecError("srsran_cuda_pdsch_enc_create: " + self._lib.srsran_cuda_pdsch_enc_create_error().decode())
         self.max_ops = max_ops
+        self._pinned_ptr, self._pinned_cap = None, 0
 
     def _check(self, st, what):
         if st < 0:
@@ -46,10 +47,26 @@ class EncoderAccelerator:
         self._check(self._lib.srsran_cuda_pdsch_enc_last_timing(self.h, ms), "last_timing")
         return [float(v) for v in ms]
 
+    def pinned(self, nbytes):
+        """A uint8 view of page-locked host memory owned by the accelerator object (grow-only; reused by the next call), so that
+        the outputs of a batch leave the device in one asynchronous copy."""
+        if nbytes > self._pinned_cap:
+            if self._pinned_ptr:
+                self._lib.srsran_cuda_pusch_dec_host_free(self._pinned_ptr)
+            self._pinned_ptr = self._lib.srsran_cuda_pusch_dec_host_alloc(nbytes)
+            if not self._pinned_ptr:
+                self._pinned_cap = 0
+                raise capi.CudaPuschDecError("pinned host allocation failed")
+            self._pinned_cap = nbytes
+        return np.ctypeslib.as_array(C.cast(self._pinned_ptr, capi.u8p), shape=(max(nbytes, 1),))[:nbytes]
+
     def close(self):
         if self.h:
             self._lib.srsran_cuda_pdsch_enc_destroy(self.h)
             self.h = None
+        if self._pinned_ptr:
+            self._lib.srsran_cuda_pusch_dec_host_free(self._pinned_ptr)
+            self._pinned_ptr, self._pinned_cap = None, 0
 
 
 class hw_accelerator_pdsch_enc_cuda:
@@ -103,23 +120,33 @@ class pdsch_encoder_configuration:
 
 def encode_tbs(acc: EncoderAccelerator, configs, tbs, want_bits=True, want_packed=True):
     """Encodes the transport blocks `tbs` (uint8 arrays of TBS / 8 bytes) in one launch. Returns (codewords, packed): lists of
-    uint8 arrays (one bit per byte / packed MSB first), None where not wanted."""
+    uint8 arrays (one bit per byte / packed MSB first), None where not wanted. The arrays are views of the accelerator
+    object's page-locked output buffer, laid out back to back (one device-to-host copy per kind): valid until the next
+    call."""
     n = len(tbs)
     cfgs = (PdschEncTbConfig * n)()
     tb_ptrs = (capi.u8p * n)()
     cw_ptrs = (capi.u8p * n)()
     pk_ptrs = (capi.u8p * n)()
+    nbits = [c.nof_ch_symbols * max(c.mod, 1) for c in configs]
+    tot_bits = sum(nbits) if want_bits else 0
+    tot_pk = sum((b + 7) // 8 for b in nbits) if want_packed else 0
+    buf = acc.pinned(tot_bits + tot_pk)
     keep, cws, pks = [], [], []
+    bo, po = 0, tot_bits
     for i, (c, tb) in enumerate(zip(configs, tbs)):
         tb = np.ascontiguousarray(tb, dtype=np.uint8)
         keep.append(tb)
-        nbits = c.nof_ch_symbols * max(c.mod, 1)
         cfgs[i] = PdschEncTbConfig(tb.size * 8, c.base_graph, c.rv, c.mod, c.Nref, c.nof_layers, c.nof_ch_symbols)
         tb_ptrs[i] = tb.ctypes.data_as(capi.u8p)
-        cws.append(np.empty(nbits, np.uint8) if want_bits else None)
-        pks.append(np.empty((nbits + 7) // 8, np.uint8) if want_packed else None)
+        cws.append(buf[bo:bo + nbits[i]] if want_bits else None)
+        pks.append(buf[po:po + (nbits[i] + 7) // 8] if want_packed else None)
         cw_ptrs[i] = cws[i].ctypes.data_as(capi.u8p) if want_bits else None
         pk_ptrs[i] = pks[i].ctypes.data_as(capi.u8p) if want_packed else None
+        if want_bits:
+            bo += nbits[i]
+        if want_packed:
+            po += (nbits[i] + 7) // 8
     acc._check(acc._lib.srsran_cuda_pdsch_enc_encode_tbs(acc.h, n, cfgs, tb_ptrs, cw_ptrs, pk_ptrs), "encode_tbs")
     return cws, pks
 
