@@ -121,8 +121,9 @@ int srsran_cuda_pusch_dec_set_combine_flavour(srsran_cuda_pusch_dec_t* handle, u
 /* Selects the LDPC decoder kernel: 0 (default) = automatic - groups of four same-shape code blocks with few layers
  * (high-rate PUSCH, Z >= 144) run on the packed kernel (four code blocks per CTA in the two binary16 lanes of two
  * registers, one thread per lifted check), single code blocks on the intra-code-block packed kernel (four lifted checks
- * of one code block per thread), the rest on the general kernel; 1 = general kernel only; 2 = packed groups with TWO
- * threads per lifted check; 3 = intra-code-block packed kernel wherever it fits; 4 = packed groups of TWO code blocks
+ * of one code block per thread), the rest on the general kernel; 1 = general kernel only; 2 = packed groups with the
+ * messages in shared memory instead of tensor memory (the round-1 kernel, one CTA per SM); 3 = intra-code-block packed
+ * kernel wherever it fits; 4 = packed groups of TWO code blocks
  * per CTA, two CTAs per SM (what a small batch uses anyway); 5 = without the many-layer form (pairs of code blocks with up
  * to 46 layers per CTA, messages in tensor memory); 6 = the many-layer form for every batch (by default it needs one code
  * block per SM); 7 = the forms that run one CTA per SM stage their inputs with cp.async.bulk + mbarrier instead of

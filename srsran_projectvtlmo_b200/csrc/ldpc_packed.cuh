@@ -492,6 +492,9 @@ __device__ __forceinline__ void for_row_degree(int deg, F&& f)
 #ifndef DEC4T_PF
 #define DEC4T_PF 3 ///< shared-memory loads issued ahead of the edge being processed
 #endif
+#ifndef DEC4T_LATE_WAIT
+#define DEC4T_LATE_WAIT 0 ///< 1: wait for a layer's message stores at the start of the NEXT layer instead of behind them
+#endif
 
 /// One lifted check (thread j) of a layer of degree DEG for four code blocks, messages in tensor memory (`taddr` = the
 /// calling warp's lane quadrant and the first column of this layer). The v2c values are not kept in registers between the
@@ -517,6 +520,9 @@ __device__ __forceinline__ void process_check_t(uint8_t* __restrict__     soft_b
   uint32_t         qk[(DEG - QS) > 0 ? (DEG - QS) : 1][2];
   uint2            ring[PF];
   pk::check_acc<2> ck;
+#if DEC4T_LATE_WAIT
+  tmem_wait_st(); // the previous layer's stores (the messages read below were stored an iteration ago)
+#endif
   tmem_ld_row<DP>(taddr, cw);
   // The parked v2c values share the soft array with the soft values, so the compiler must keep every load behind the
   // stores that precede it in program order: the loads of the next PF edges are therefore issued BEFORE the store of the
@@ -582,7 +588,9 @@ __device__ __forceinline__ void process_check_t(uint8_t* __restrict__     soft_b
   tmem_st_row<DP>(taddr, cw);
   // The messages are read again one iteration (several barriers) later; the wait makes the stores complete before the
   // layer barrier, which is the ordering the tcgen05 memory model asks for between a store and a later load.
+#if !DEC4T_LATE_WAIT
   tmem_wait_st();
+#endif
 }
 
 

@@ -314,6 +314,92 @@ __device__ __forceinline__ void enc_rate_match_packed(const uint32_t* __restrict
   }
 }
 
+/// Rate matching 32 output bits per thread for QM in {2, 4, 8} (QM divides 32): the 32 / QM symbols of a thread take NS =
+/// 32 / QM CONSECUTIVE bits from each of the QM streams e[j E/QM + i], i.e. one funnel-shifted word load per stream instead
+/// of one shared-memory bit extraction per output bit; the bits are then interleaved in registers. Runs that cross the end of
+/// the circular buffer or the filler gap (a handful per code block) are gathered bit by bit. Output: one packed word
+/// (four bytes, MSB first) and 32 unpacked bytes (two 16-byte stores) per thread, contiguous across the warp.
+template <int QM>
+__device__ __forceinline__ void enc_rate_match_words(const uint32_t* __restrict__ cw, uint32_t v0, uint32_t V, uint32_t fs,
+                                                     uint32_t Fc, uint32_t E, uint8_t* __restrict__ ob, uint8_t* __restrict__ op,
+                                                     int t)
+{
+  static_assert(QM == 2 || QM == 4 || QM == 8, "QM must divide 32");
+  constexpr uint32_t NS = 32 / QM;
+  const uint32_t     EQ = E / QM;
+  const uint32_t     nfull = E / 32; // whole 32-bit groups; the tail (< 32 bits) is done bit by bit below
+  auto bit_at = [&](uint32_t m) -> uint32_t { // e[m]
+    uint32_t u = v0 + m;
+    u          = (u >= V) ? u % V : u;
+    const uint32_t p = (u < fs) ? u : u + Fc;
+    return (cw[p >> 5] >> (p & 31U)) & 1U;
+  };
+  for (uint32_t g = t; g < nfull; g += ENC_THREADS) {
+    const uint32_t i0 = g * NS; // first symbol of the group
+    uint32_t       chunk[QM];   // NS bits of stream j, bit s = symbol i0 + s
+#pragma unroll
+    for (int j = 0; j != QM; ++j) {
+      const uint32_t m0 = (uint32_t)j * EQ + i0;
+      uint32_t       u  = v0 + m0;
+      u                 = (u >= V) ? u - V : u;
+      // fast: at most one lap behind, the NS positions neither wrap nor straddle the filler gap
+      if (u < V && u + NS <= V && (u >= fs || u + NS <= fs)) {
+        const uint32_t p = (u < fs) ? u : u + Fc;
+        chunk[j]         = __funnelshift_r(cw[p >> 5], cw[(p >> 5) + 1], p & 31U);
+      } else {
+        uint32_t c = 0;
+        for (uint32_t s2 = 0; s2 != NS; ++s2) {
+          c |= bit_at(m0 + s2) << s2;
+        }
+        chunk[j] = c;
+      }
+    }
+    // Output bit n = 32 g + s QM + j  <-  chunk[j] bit s. Packed MSB first: bit n of the group at position 31 - (s QM + j).
+    uint32_t word = 0;
+#pragma unroll
+    for (int s2 = 0; s2 != (int)NS; ++s2) {
+#pragma unroll
+      for (int j = 0; j != QM; ++j) {
+        word |= ((chunk[j] >> s2) & 1U) << (31 - (s2 * QM + j));
+      }
+    }
+    if (op != nullptr) {
+      // bytes in memory order: the first eight bits of the group are the first byte
+      reinterpret_cast<uint32_t*>(op)[g] = __byte_perm(word, 0, 0x0123);
+    }
+    if (ob != nullptr) {
+      uint32_t       w8[8];
+      const uint32_t rw = __brev(word); // bit n of the group at position n
+#pragma unroll
+      for (int k = 0; k != 8; ++k) {
+        // output bits 4k .. 4k + 3 as one byte each, by one multiplication (distinct powers, no carries)
+        w8[k] = (((rw >> (4 * k)) & 0xfU) * 0x00204081U) & 0x01010101U;
+      }
+      uint4* dst = reinterpret_cast<uint4*>(ob + (size_t)g * 32);
+      dst[0]     = make_uint4(w8[0], w8[1], w8[2], w8[3]);
+      dst[1]     = make_uint4(w8[4], w8[5], w8[6], w8[7]);
+    }
+  }
+  // Tail: the last E % 32 bits.
+  for (uint32_t n = nfull * 32 + t; n < E; n += ENC_THREADS) {
+    const uint32_t i = n / QM, j = n - i * QM;
+    const uint32_t bit = bit_at(j * EQ + i);
+    if (ob != nullptr) {
+      ob[n] = (uint8_t)bit;
+    }
+  }
+  if (op != nullptr) {
+    for (uint32_t b = nfull * 4 + t; b * 8 < E; b += ENC_THREADS) {
+      uint32_t byte = 0;
+      for (uint32_t k = 0; k != 8 && b * 8 + k < E; ++k) {
+        const uint32_t n = b * 8 + k, i = n / QM, j = n - i * QM;
+        byte |= bit_at(j * EQ + i) << (7 - k);
+      }
+      op[b] = (uint8_t)byte;
+    }
+  }
+}
+
 /// Which descriptors a launch handles: the packed kernel those with Z % 32 == 0, the byte kernel the others.
 __device__ __forceinline__ bool enc_is_packed(const enc_cb_desc& d)
 {
@@ -324,7 +410,7 @@ __global__ void __launch_bounds__(ENC_THREADS) pdsch_encode_packed_kernel(const 
                                                                           const uint32_t* __restrict__ tb_crcs)
 {
   // 68 columns x 12 words, the four core-row sums, the edge table, the CRC byte tables
-  __shared__ uint32_t colw[68 * 12];
+  __shared__ uint32_t colw[68 * 12 + 4]; // (+ one word: the rate matcher reads word pairs)
   __shared__ uint32_t lamw[4 * 12];
   __shared__ uint2    tab[MAX_EDGES];
   __shared__ uint32_t tabs[1024];
@@ -478,7 +564,15 @@ __global__ void __launch_bounds__(ENC_THREADS) pdsch_encode_packed_kernel(const 
   const uint32_t* cw = colw + 2 * W;
   uint8_t* const  ob = d.out_bits;
   uint8_t* const  op = d.out_packed;
-  if (v0 + E <= 2 * V) {
+  // Word-granular form where the outputs allow vector stores (buffers of a batch are 8-byte aligned; 16 needed here).
+  const bool      vec = (reinterpret_cast<uintptr_t>(ob) & 15U) == 0 && (reinterpret_cast<uintptr_t>(op) & 3U) == 0;
+  if (vec && d.Qm == 8) {
+    enc_rate_match_words<8>(cw, v0, V, fs, Fc, E, ob, op, t);
+  } else if (vec && d.Qm == 4) {
+    enc_rate_match_words<4>(cw, v0, V, fs, Fc, E, ob, op, t);
+  } else if (vec && d.Qm == 2) {
+    enc_rate_match_words<2>(cw, v0, V, fs, Fc, E, ob, op, t);
+  } else if (v0 + E <= 2 * V) {
     switch (d.Qm) {
       case 8:
         enc_rate_match_packed<8, true>(cw, v0, V, fs, Fc, E, ob, op, t);
