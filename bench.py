@@ -629,6 +629,28 @@ def main():
         iso += np.array(pusch.ticket_timing(acc, tk[0]))
     iso_ms = (iso / niso).tolist()
 
+    # ---- the same device-resident leg with the decoded TBs LEFT IN HBM (a consumer on the device side of the link): shows how
+    # much of `value` the return path of the decoded bits costs - at eight GPUs it is the box's PCIe fabric that limits the
+    # step, not the kernels. CRC verdicts and statistics still come back and are still enforced.
+    acc.set_tb_host_copy(False)
+    counters = {"ok": 0, "tbs": 0}
+    for i in range(4):
+        settle(step_device(i))
+    counters = {"ok": 0, "tbs": 0}
+    saved_min = args.min_seconds
+    args.min_seconds = min(args.min_seconds, 1.0)
+    barrier()
+    hbm_s, hbm_steps, _ = timed_region(step_device, settle, True)
+    barrier()
+    args.min_seconds = saved_min
+    acc.set_tb_host_copy(True)
+    if counters["ok"] != counters["tbs"]:
+        raise SystemExit("value leg (TBs left in HBM): transport blocks failed their CRC")
+    hbm_local = torch.tensor([hbm_s * 1e3 / hbm_steps], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(hbm_local, op=dist.ReduceOp.MAX)
+    hbm_step_ms = float(hbm_local.item())
+
     # ---- e2e: host LLRs in pinned memory, H2D + kernels + D2H of TB bytes and results, <= DEPTH batches in flight ------
     counters = {"ok": 0, "tbs": 0}
 
@@ -745,8 +767,9 @@ def main():
     # dispatcher (every rank evaluates the same pure function, no communication), every rank submitting its share of the same
     # slot at the same time; one slot at a time, host LLRs in, TB bytes out. Slot n + 1 retransmits nothing (all TBs decode),
     # so every HARQ process is released and re-hashed: the shares vary from slot to slot like in a live cell mix. --------------
-    slot_lat, share_sizes = [], []
-    if args.slot_latency_slots > 0:
+    def slot_leg(resident):
+        """One slot at a time; `resident`: the soft bits are already in HBM (born there by a device-side demodulator)."""
+        lats, shares = [], []
         disp = TbDispatcher(world, balance=True)
         barrier()
         for s in range(args.slot_latency_slots):
@@ -754,9 +777,9 @@ def main():
             mine = [c for c in range(64) if disp.assign(HarqKey(c, 0x4601 + (s % 16), s % 8), True, ncb) == rank]
             for c in range(64):
                 disp.release(HarqKey(c, 0x4601 + (s % 16), s % 8))
-            share_sizes.append(len(mine))
+            shares.append(len(mine))
             if not mine:
-                slot_lat.append(0.0)
+                lats.append(0.0)
                 continue
             t1 = time.perf_counter()
             # Two pieces: the H2D copy of the second overlaps the kernels of the first.
@@ -764,18 +787,26 @@ def main():
             tk = []
             for piece in (mine[:half], mine[half:]):
                 if piece:
-                    tk += pusch.submit_tbs(acc, [cfg_sets[s % 2][k % B] for k in piece], [host_sets[s % 2][1][k % B] for k in piece])
+                    src = dev_lists[s % 2] if resident else host_sets[s % 2][1]
+                    tk += pusch.submit_tbs(acc, [cfg_sets[s % 2][k % B] for k in piece], [src[k % B] for k in piece],
+                                           device_resident=resident)
             res = pusch.poll_tbs(acc, tk)
-            slot_lat.append((time.perf_counter() - t1) * 1e6)
+            lats.append((time.perf_counter() - t1) * 1e6)
             if not all(r.tb_crc_ok for r in res):
                 raise SystemExit("64-cell slot leg: a transport block failed its CRC")
         barrier()
-    slot_lat = np.array(slot_lat[10:]) if len(slot_lat) > 20 else np.array(slot_lat)
+        return (np.array(lats[10:]) if len(lats) > 20 else np.array(lats)), shares
+
+    slot_lat, share_sizes, slot_lat_res = np.array([]), [], np.array([])
+    if args.slot_latency_slots > 0:
+        slot_lat, share_sizes = slot_leg(False)
+        slot_lat_res, _ = slot_leg(True)
 
     # ---- max over ranks ------------------------------------------------------------------------------------------------
     vals = [step_ms, e2e_s / e2e_steps, -h2d_gbs,
             symbols["sv_ms"] if symbols else 0.0, (symbols["se_s"] / symbols["se_steps"]) if symbols else 0.0,
-            pct(slot_lat, 50) or 0.0, pct(slot_lat, 99) or 0.0, float(slot_lat.max()) if slot_lat.size else 0.0]
+            pct(slot_lat, 50) or 0.0, pct(slot_lat, 99) or 0.0, float(slot_lat.max()) if slot_lat.size else 0.0,
+            pct(slot_lat_res, 50) or 0.0, pct(slot_lat_res, 99) or 0.0, float(slot_lat_res.max()) if slot_lat_res.size else 0.0]
     red = torch.tensor(vals, dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(red, op=dist.ReduceOp.MAX)
@@ -818,6 +849,12 @@ def main():
                                         "min_seconds": args.min_seconds},
                        "timing": f"device stopwatch (CUDA events on the library streams) over all steps, <= {DEPTH} batches in flight; "
                                  "inputs alternate between two sets larger than L2 (no flush needed)"},
+            "value_tbs_left_in_hbm": {
+                "value": n_gpus * B * tbs / (hbm_step_ms * 1e-3) / 1e9, "unit": "Gbit/s", "ms_per_step": hbm_step_ms,
+                "seconds": hbm_s, "steps_run": hbm_steps,
+                "what": "the `value` leg with the decoded transport blocks left in HBM (srsran_cuda_pusch_dec_set_tb_host_copy(0): a "
+                        "consumer on the device side of the link); CRC verdicts and statistics still return and are enforced. The "
+                        "difference to `value` is the cost of returning 10.4 MB of decoded bits per step and GPU over PCIe"},
             "e2e": {"value": e2e, "unit": "Gbit/s", "h2d_bytes_per_step": B * nllr,
                     "d2h_bytes_per_step": B * (tbs // 8 + 3 + 8 + ncb * 16), "seconds": e2e_s, "steps_run": e2e_steps,
                     "pcie_h2d_gbs_measured": h2d_gbs_min, "ceiling_from_h2d": e2e_ceiling,
@@ -863,6 +900,11 @@ def main():
                 "p50": float(red[5]), "p99": float(red[6]), "max": float(red[7]), "n": int(slot_lat.size), "budget_us": 500,
                 "tbs_per_gpu_per_slot_mean": float(np.mean(share_sizes)) if share_sizes else None,
                 "what": "BASELINE config 5: 64 cells x one config-2 TB per slot, sharded by TbDispatcher (sticky HARQ, least-loaded) over the N GPUs, all ranks at once; host LLRs in (two pieces per share), TB results out; max over ranks of each rank's percentile"},
+            "slot_latency_64_cells_resident_us": {
+                "p50": float(red[8]), "p99": float(red[9]), "max": float(red[10]), "n": int(slot_lat_res.size), "budget_us": 500,
+                "what": "the same slot with the soft bits already in HBM (born there by a device-side demodulator, SURVEY 8(f) row 2): "
+                        "descriptors in, TB bytes and results out; what is left of the slot latency when the 1.36 MB of soft bits per "
+                        "TB do not cross the PCIe fabric"},
         }
         if symbols:
             sv = n_gpus * B * tbs / (float(red[3]) * 1e-3) / 1e9

@@ -219,6 +219,15 @@ int srsran_cuda_pusch_dec_tb_cb_outputs(srsran_cuda_pusch_dec_t* handle, int tic
  * bytes, valid until the ticket's batch context is reused, i.e. for at least the next two submissions); NULL if the
  * reference would not have written the TB (a code-block CRC failed). The ticket must have completed (poll_tb returned 1). */
 int srsran_cuda_pusch_dec_tb_data(srsran_cuda_pusch_dec_t* handle, int ticket, const uint8_t** data);
+/* Where the decoded transport blocks go. 1 (default): copied to the library's page-locked result buffer (poll_tb,
+ * tb_data). 0: left in HBM for a consumer on the device side of the link (tb_data_device: a MAC PDU assembler or a NIC
+ * reading GPU memory) - results, statistics and CRC verdicts are still copied; poll_tb then leaves its `tb` argument
+ * untouched. At eight GPUs the return path of the decoded bits (16 GB/s per GPU at 130 Gbit/s) is what the box's PCIe
+ * fabric limits first. Applies to batches submitted after the call. */
+int srsran_cuda_pusch_dec_set_tb_host_copy(srsran_cuda_pusch_dec_t* handle, int enable);
+/* Device address of a completed transport block (valid until its batch context is reused), NULL if the reference would
+ * not have written it. */
+int srsran_cuda_pusch_dec_tb_data_device(srsran_cuda_pusch_dec_t* handle, int ticket, const uint8_t** data);
 
 /* Same as submit_tb for a batch of TBs whose LLRs are ALREADY RESIDENT in device memory (`llrs_dev[i]` points to
  * `nof_llrs[i]` int8 LLRs in HBM); used when the demodulator runs on the device, and by the benchmark's device-resident

@@ -453,14 +453,10 @@ __global__ void __launch_bounds__(ENC_THREADS) pdsch_encode_packed_kernel(const 
     if (i0 < info) {
       const uint32_t s0 = d.tb_mode ? d.src_bit0 + i0 : i0;
       if (!d.tb_mode || s0 + 32 <= tbs) {
-        const uint32_t by = s0 >> 3, sh = s0 & 7U;
-        // (a code block's last byte may be its input's last: the fifth byte is read only when it holds wanted bits)
-        const uint32_t v  = ((uint32_t)__ldg(src + by) << 24) | ((uint32_t)__ldg(src + by + 1) << 16) |
-                           ((uint32_t)__ldg(src + by + 2) << 8) | (uint32_t)__ldg(src + by + 3);
-        msb = v << sh;
-        if (sh != 0) {
-          msb |= (uint32_t)__ldg(src + by + 4) >> (8 - sh);
-        }
+        // Two aligned words (the staged inputs are 16-byte aligned and padded), big-endian, funnel-shifted to the bit.
+        const uint32_t* __restrict__ w32 = reinterpret_cast<const uint32_t*>(src) + (s0 >> 5);
+        const uint32_t a = __byte_perm(__ldg(w32), 0, 0x0123), b = __byte_perm(__ldg(w32 + 1), 0, 0x0123);
+        msb              = __funnelshift_l(b, a, s0 & 31U);
       } else {
         for (uint32_t k = 0; k != 32; ++k) {
           const uint32_t s = s0 + k;
@@ -504,17 +500,24 @@ __global__ void __launch_bounds__(ENC_THREADS) pdsch_encode_packed_kernel(const 
     return __funnelshift_r(colw[c0 + a], colw[c0 + b], s & 31U);
   };
 
-  // ---- core rows ---------------------------------------------------------------------------------------------------------------
-  if (t < (int)(4 * W)) {
-    const uint32_t r = t / W, w = t - r * W;
+  // ---- core rows: four threads share the (up to 19) edges of a (row, word), combined by two shuffles -----------------------------
+  {
+    const uint32_t task = (uint32_t)t >> 2, q = (uint32_t)t & 3U;
     uint32_t       acc = 0;
-    for (uint32_t e = c_row_ptr[bg - 1][r], e1 = c_row_ptr[bg - 1][r + 1]; e != e1; ++e) {
-      const uint2 te = tab[e];
-      if (te.x < Kb * W) {
-        acc ^= rot_word(te.x, te.y, w);
+    if (task < 4 * W) {
+      const uint32_t r = task / W, w = task - r * W;
+      for (uint32_t e = c_row_ptr[bg - 1][r] + q, e1 = c_row_ptr[bg - 1][r + 1]; e < e1; e += 4) {
+        const uint2 te = tab[e];
+        if (te.x < Kb * W) {
+          acc ^= rot_word(te.x, te.y, w);
+        }
       }
     }
-    lamw[t] = acc;
+    acc ^= __shfl_xor_sync(0xffffffffU, acc, 1);
+    acc ^= __shfl_xor_sync(0xffffffffU, acc, 2);
+    if (task < 4 * W && q == 0) {
+      lamw[task] = acc;
+    }
   }
   __syncthreads();
   const enc_core_desc core = c_enc_core[bg - 1][d.ils];
@@ -547,15 +550,24 @@ __global__ void __launch_bounds__(ENC_THREADS) pdsch_encode_packed_kernel(const 
 
   // ---- extension rows ------------------------------------------------------------------------------------------------------------
   if (rows_needed > 4) {
-    const uint32_t ntask = (rows_needed - 4) * W;
-    for (uint32_t i = t; i < ntask; i += ENC_THREADS) {
-      const uint32_t r = 4 + i / W, w = i - (r - 4) * W;
-      uint32_t       acc = 0;
-      for (uint32_t e = c_row_ptr[bg - 1][r], e1 = c_row_ptr[bg - 1][r + 1] - 1; e != e1; ++e) {
-        const uint2 te = tab[e];
-        acc ^= rot_word(te.x, te.y, w);
+    // (same split: four threads per (row, word); the loop bound is uniform, every thread reaches the shuffles)
+    const uint32_t ntask = (rows_needed - 4) * W, q = (uint32_t)t & 3U;
+    for (uint32_t i0 = 0; i0 < ntask; i0 += ENC_THREADS / 4) {
+      const uint32_t i = i0 + ((uint32_t)t >> 2);
+      uint32_t       acc = 0, r = 0, w = 0;
+      if (i < ntask) {
+        r = 4 + i / W;
+        w = i - (r - 4) * W;
+        for (uint32_t e = c_row_ptr[bg - 1][r] + q, e1 = c_row_ptr[bg - 1][r + 1] - 1; e < e1; e += 4) {
+          const uint2 te = tab[e];
+          acc ^= rot_word(te.x, te.y, w);
+        }
       }
-      colw[(Kb + r) * W + w] = acc;
+      acc ^= __shfl_xor_sync(0xffffffffU, acc, 1);
+      acc ^= __shfl_xor_sync(0xffffffffU, acc, 2);
+      if (i < ntask && q == 0) {
+        colw[(Kb + r) * W + w] = acc;
+      }
     }
   }
   __syncthreads();

@@ -159,6 +159,7 @@ struct batch_context {
   pinned_buf<tb_result_dev> h_tbres;
   device_buf<tb_result_dev> d_tbres;
   pinned_buf<uint8_t>       h_tbout;
+  bool                      tb_on_host = true; // this batch's transport blocks were copied to h_tbout
   device_buf<uint8_t>       d_tbout;
   size_t                    tbout_used = 0;
   bool                      want_bits  = false; // per-CB decoded bits are copied back (HAL path, unit-level decode)
@@ -230,6 +231,7 @@ struct srsran_cuda_pusch_dec {
   bool     use_long          = true;  // many-layer code blocks two per CTA with the messages in tensor memory
   bool     use_bulk          = false; // one-CTA-per-SM forms stage their inputs with cp.async.bulk + mbarrier (variant 7):
                                       // measured equal to plain 128-bit loads, kept selectable
+  bool     tb_host_copy      = true;  // decoded transport blocks are copied to the page-locked result buffer
   bool     prefer_long       = false; // A/B: the many-layer pair form also where the shared-memory pair form fits
   int      last_unit_ctx     = -1;    // context of the last unit-level batch (srsran_cuda_pusch_dec_last_unit_timing)
   bool     force_pairs       = false; // groups of two code blocks per CTA (two CTAs per SM) also for large batches
@@ -1264,7 +1266,10 @@ int launch_context(srsran_cuda_pusch_dec* h, int ci)
   }
   if (ntb != 0) {
     CUDA_TRY(h, cudaMemcpyAsync(c.h_tbres.p, c.d_tbres.p, ntb * sizeof(tb_result_dev), cudaMemcpyDeviceToHost, ts));
-    CUDA_TRY(h, cudaMemcpyAsync(c.h_tbout.p, c.d_tbout.p, c.tbout_used, cudaMemcpyDeviceToHost, ts));
+    c.tb_on_host = h->tb_host_copy;
+    if (c.tb_on_host) {
+      CUDA_TRY(h, cudaMemcpyAsync(c.h_tbout.p, c.d_tbout.p, c.tbout_used, cudaMemcpyDeviceToHost, ts));
+    }
   }
   CUDA_TRY(h, cudaEventRecord(c.done, ts));
   // The batch stream joins the tail so that the next use of this context (and stream-ordered waits on it) see it complete.
@@ -2438,7 +2443,7 @@ static int poll_tb_impl(srsran_cuda_pusch_dec_t* h, int ticket, int block, uint8
   }
   tb_host_meta&        m  = c.tb_meta[ti];
   const tb_result_dev& tr = c.h_tbres.p[ti];
-  if (tb != nullptr && tr.written) {
+  if (tb != nullptr && tr.written && c.tb_on_host) {
     std::memcpy(tb, c.h_tbout.p + m.out_offset, m.tbs_bits / 8);
   }
   if (result != nullptr) {
@@ -2520,7 +2525,36 @@ int srsran_cuda_pusch_dec_tb_data(srsran_cuda_pusch_dec_t* h, int ticket, const 
     h->last_error = "stale, unknown or unfinished ticket";
     return SRSRAN_CUDA_ERR_STATE;
   }
-  *data = c.h_tbres.p[ti].written ? c.h_tbout.p + c.tb_meta[ti].out_offset : nullptr;
+  *data = (c.h_tbres.p[ti].written && c.tb_on_host) ? c.h_tbout.p + c.tb_meta[ti].out_offset : nullptr;
+  return SRSRAN_CUDA_OK;
+}
+
+int srsran_cuda_pusch_dec_tb_data_device(srsran_cuda_pusch_dec_t* h, int ticket, const uint8_t** data)
+{
+  if (h == nullptr || ticket < 0 || data == nullptr) {
+    return SRSRAN_CUDA_ERR_INVALID;
+  }
+  int      ci  = (ticket >> 16) & 0xf;
+  uint32_t ti  = static_cast<uint32_t>(ticket) & 0xffff;
+  uint32_t gen = (static_cast<uint32_t>(ticket) >> 20) & 0x3ff;
+  if (ci >= NOF_CONTEXTS) {
+    return SRSRAN_CUDA_ERR_INVALID;
+  }
+  batch_context& c = h->ctx[ci];
+  if ((c.generation & 0x3ff) != gen || ti >= c.tb_meta.size() || !c.in_flight || cudaEventQuery(c.done) != cudaSuccess) {
+    h->last_error = "stale, unknown or unfinished ticket";
+    return SRSRAN_CUDA_ERR_STATE;
+  }
+  *data = c.h_tbres.p[ti].written ? c.d_tbout.p + c.tb_meta[ti].out_offset : nullptr;
+  return SRSRAN_CUDA_OK;
+}
+
+int srsran_cuda_pusch_dec_set_tb_host_copy(srsran_cuda_pusch_dec_t* h, int enable)
+{
+  if (h == nullptr) {
+    return SRSRAN_CUDA_ERR_INVALID;
+  }
+  h->tb_host_copy = enable != 0;
   return SRSRAN_CUDA_OK;
 }
 

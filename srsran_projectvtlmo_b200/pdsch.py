@@ -151,6 +151,25 @@ def encode_tbs(acc: EncoderAccelerator, configs, tbs, want_bits=True, want_packe
     return cws, pks
 
 
+def encode_tbs_resident(acc: EncoderAccelerator, configs, tbs):
+    """Encodes a batch and leaves the code words in device memory (the input of a modulation mapper running on the GPU).
+    Returns (device_address, offsets, nbits): TB i's bits, one per byte, start at device_address + offsets[i]; valid until
+    the next call on the accelerator."""
+    n = len(tbs)
+    cfgs = (PdschEncTbConfig * n)()
+    tb_ptrs = (capi.u8p * n)()
+    keep = []
+    for i, (c, tb) in enumerate(zip(configs, tbs)):
+        tb = np.ascontiguousarray(tb, dtype=np.uint8)
+        keep.append(tb)
+        cfgs[i] = PdschEncTbConfig(tb.size * 8, c.base_graph, c.rv, c.mod, c.Nref, c.nof_layers, c.nof_ch_symbols)
+        tb_ptrs[i] = tb.ctypes.data_as(capi.u8p)
+    dev = capi.u8p()
+    offs = (C.c_uint64 * n)()
+    acc._check(acc._lib.srsran_cuda_pdsch_enc_encode_tbs_resident(acc.h, n, cfgs, tb_ptrs, C.byref(dev), offs), "encode_tbs_resident")
+    return C.cast(dev, C.c_void_p).value, [int(o) for o in offs], [c.nof_ch_symbols * max(c.mod, 1) for c in configs]
+
+
 class pdsch_encoder_cuda:
     """pdsch_encoder over the accelerator: encode(codeword, transport_block, config)."""
 

@@ -94,6 +94,10 @@ class Accelerator:
     def set_decoder_variant(self, variant):
         self._check(self._lib.srsran_cuda_pusch_dec_set_decoder_variant(self.h, variant), "set_decoder_variant")
 
+    def set_tb_host_copy(self, enable):
+        """False: decoded transport blocks stay in HBM (tb_data_device); results and CRC verdicts still come back."""
+        self._check(self._lib.srsran_cuda_pusch_dec_set_tb_host_copy(self.h, int(bool(enable))), "set_tb_host_copy")
+
     def set_combine_flavour(self, simd_block):
         self._check(self._lib.srsran_cuda_pusch_dec_set_combine_flavour(self.h, simd_block), "set_combine_flavour")
 
@@ -362,6 +366,13 @@ def tb_data(acc: Accelerator, ticket, nbytes):
     if not p:
         return None
     return np.ctypeslib.as_array(p, shape=(nbytes,))
+
+
+def tb_data_device(acc: Accelerator, ticket):
+    """Device address (int) of a completed transport block left in HBM (set_tb_host_copy(False)), or None."""
+    p = capi.u8p()
+    acc._check(acc._lib.srsran_cuda_pusch_dec_tb_data_device(acc.h, ticket, C.byref(p)), "tb_data_device")
+    return C.cast(p, C.c_void_p).value
 
 
 def ticket_timing(acc: Accelerator, ticket):

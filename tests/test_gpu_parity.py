@@ -354,6 +354,46 @@ def test_pusch_poll_tbs_whole_batch(acc):
                 assert np.array_equal(outs[i], payload[i])
 
 
+def test_pusch_transport_blocks_left_in_hbm(acc):
+    """set_tb_host_copy(0): the decoded transport blocks stay in device memory (tb_data_device) for a consumer on the device
+    side of the link; results and CRC verdicts still come back, poll_tbs leaves its output buffers untouched."""
+    rng = np.random.default_rng(62)
+    prb, qm, R, nl, bg, nref = 106, 6, 873, 2, 1, 0
+    tbs = synth.tbs_for(prb, qm, R, nl)
+    nllr = prb * 156 * qm * nl
+    nseg = len(pusch.segment(tbs, bg, qm, nl, nllr))
+    ntb = 4
+    payload = [rng.integers(0, 256, tbs // 8, dtype=np.uint8) for _ in range(ntb)]
+    llrs = [awgn_llrs(rng, synth.encode_tb(payload[i], bg, 0, qm, nref, nl, nllr), 16.0) for i in range(ntb)]
+    cfgs = [pusch.TbConfig(tbs, bg, 0, qm, nref, nl, 6, 1, 1, 3000 + i * nseg) for i in range(ntb)]
+    acc.set_tb_host_copy(False)
+    try:
+        tickets = pusch.submit_tbs(acc, cfgs, llrs)
+        acc.synchronize()
+        import ctypes
+
+        cudart = ctypes.CDLL("libcudart.so.12")  # the runtime the library itself is linked against
+        cudart.cudaMemcpy.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int]
+        for i, tk in enumerate(tickets):
+            ptr = pusch.tb_data_device(acc, tk)
+            assert ptr
+            got = np.zeros(tbs // 8, np.uint8)
+            assert cudart.cudaMemcpy(got.ctypes.data, ptr, got.size, 2) == 0  # device -> host
+            assert np.array_equal(got, payload[i]), i
+            assert pusch.tb_data(acc, tk, tbs // 8) is None  # nothing was copied to the host result buffer
+        outs = [np.full(tbs // 8, 0x5A, np.uint8) for _ in range(ntb)]
+        res = pusch.poll_tbs(acc, tickets, outs)
+        assert all(r.tb_crc_ok for r in res)
+        assert all(np.all(o == 0x5A) for o in outs)
+    finally:
+        acc.set_tb_host_copy(True)
+    # back to the default: the next batch is copied out again
+    tickets = pusch.submit_tbs(acc, cfgs, llrs)
+    outs = [np.zeros(tbs // 8, np.uint8) for _ in range(ntb)]
+    res = pusch.poll_tbs(acc, tickets, outs)
+    assert all(r.tb_crc_ok for r in res) and all(np.array_equal(outs[i], payload[i]) for i in range(ntb))
+
+
 # ---------------------------------------------------------------------------------------------------------------------
 # hal::hw_accelerator_pusch_dec call sequence, as driven by pusch_decoder_hw_impl::on_end_softbits (:132-342)
 # ---------------------------------------------------------------------------------------------------------------------

@@ -90,6 +90,28 @@ def test_headline_slot_of_64_tbs_one_launch(enc):
         assert np.array_equal(np.packbits(cws[i]), pks[i]), i
 
 
+def test_code_words_left_in_device_memory(enc):
+    """encode_tbs_resident: the code words stay in HBM (the modulation mapper's input when it runs on the GPU too)."""
+    import ctypes
+
+    rng = np.random.default_rng(519)
+    cases = [(52, 4, 658, 1, 1, 0, 0), (106, 6, 873, 2, 1, 0, 1), (25, 2, 120, 1, 2, 0, 2)]
+    cfgs, tbs, want = [], [], []
+    for prb, qm, R, nl, bg, nref, rv in cases:
+        nbits = prb * 156 * qm * nl
+        tb = rng.integers(0, 256, synth.tbs_for(prb, qm, R, nl) // 8, dtype=np.uint8)
+        cfgs.append(pdsch.pdsch_encoder_configuration(bg, rv, qm, nref, nl, nbits // qm))
+        tbs.append(tb)
+        want.append(_reference_codeword(tb, bg, rv, qm, nref, nl, nbits))
+    dev, offs, nbits = pdsch.encode_tbs_resident(enc, cfgs, tbs)
+    cudart = ctypes.CDLL("libcudart.so.12")  # the runtime the library itself is linked against
+    cudart.cudaMemcpy.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int]
+    for i in range(len(cases)):
+        got = np.zeros(nbits[i], np.uint8)
+        assert cudart.cudaMemcpy(got.ctypes.data, dev + offs[i], got.size, 2) == 0  # device -> host
+        assert np.array_equal(got, want[i]), cases[i]
+
+
 def _hw_config(tb, bg, rv, qm, nref, nl, nbits, cb_mode):
     """What pdsch_encoder_hw_impl::set_hw_enc_tb_configuration (pdsch_encoder_hw_impl.cpp:196-328) fills in."""
     msg, z, kp, nfill, tb_crc = synth.tx_segments(tb, bg)
