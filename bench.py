@@ -188,7 +188,9 @@ def reference_arm(args, rank, world):
             return ob.port().oracle_pusch_bench(tbs // 8, ob._pi(llr), nllr, w["bg"], w["qm"], w["nref"], w["layers"],
                                                 w["max_it"], w["early_stop"], reps, C.byref(ok))
     t1 = run(1)
-    reps = max(1, int(args.ref_seconds / max(t1, 1e-3)))
+    # A step is a bounded sample sized so that the whole --steps K --warmup W run ends within a few minutes (<= 150 s timed).
+    per_step_s = min(args.ref_seconds, 150.0 / max(args.steps, 1))
+    reps = max(1, int(per_step_s / max(t1, 1e-3)))
     for _ in range(args.warmup):
         run(1)
     times = [run(reps) for _ in range(args.steps)]
