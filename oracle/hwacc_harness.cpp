@@ -333,6 +333,122 @@ int main()
     std::printf("ldpc_decoder cuda vs auto: %s\n", same ? "ok" : "MISMATCH");
     failures += same ? 0 : 1;
   }
+  // ---- the same three "cuda" unit factories over a sweep of shapes: both base graphs, lifting sizes of every kernel class
+  // (general, one code block per CTA, packed groups), every modulation order, limited buffers, fillers, rv sequences with
+  // combining, valid code words (reference encoder + rate matcher, AWGN) so that early stop and CRC verdicts are exercised,
+  // with and without a CRC calculator; CRC sizes of crc_calculator_test.cpp incl. bit lengths that are no byte multiple. -----
+  {
+    auto device  = std::make_shared<hal::cuda_pusch_dec_device>(acc_cfg);
+    auto crc_gpu = create_crc_calculator_factory_cuda(device);
+    auto dem_gpu = create_ldpc_rate_dematcher_factory_cuda(device)->create();
+    auto dec_gpu = create_ldpc_decoder_factory_cuda(device)->create();
+    auto dem_cpu = dem_factory->create();
+    auto dec_cpu = dec_factory->create();
+    auto enc     = create_ldpc_encoder_factory_sw("auto")->create();
+    auto rm      = create_ldpc_rate_matcher_factory_sw()->create();
+    unsigned crc_checked = 0, crc_bad = 0;
+    for (crc_generator_poly poly : {crc_generator_poly::CRC24A, crc_generator_poly::CRC24B, crc_generator_poly::CRC16}) {
+      auto g = crc_gpu->create(poly);
+      auto c = crc_factory->create(poly);
+      for (unsigned nbytes : {1U, 2U, 3U, 8U, 16U, 32U, 257U, 997U, 6012U}) {
+        std::vector<uint8_t> msg(nbytes);
+        for (uint8_t& b : msg) {
+          b = static_cast<uint8_t>(rgen());
+        }
+        ++crc_checked;
+        crc_bad += g->calculate_byte(msg) == c->calculate_byte(msg) ? 0 : 1;
+        std::vector<uint8_t> bits(nbytes * 8 - 3); // not a byte multiple
+        for (uint8_t& b : bits) {
+          b = static_cast<uint8_t>(rgen() & 1U);
+        }
+        ++crc_checked;
+        crc_bad += g->calculate_bit(bits) == c->calculate_bit(bits) ? 0 : 1;
+      }
+    }
+    std::printf("crc_calculator cuda vs auto, %u messages: %u mismatches\n", crc_checked, crc_bad);
+    failures += crc_bad;
+
+    struct shape {
+      unsigned bg, Z, Qm, nref_div, nfill, e_num, e_den; // Nref = N * nref_div / 6 (0: unlimited), E = N * e_num / e_den
+      float    amp;
+    };
+    const shape shapes[] = {{1, 384, 8, 0, 16, 1, 2, 9.0F},  {1, 384, 8, 3, 16, 1, 2, 9.0F},  {1, 352, 6, 0, 40, 2, 3, 6.0F},
+                            {1, 256, 4, 4, 0, 1, 1, 3.0F},   {1, 144, 2, 0, 8, 5, 4, 2.0F},   {1, 52, 2, 0, 0, 1, 1, 2.5F},
+                            {1, 36, 4, 5, 4, 3, 4, 4.0F},    {1, 7, 2, 0, 0, 1, 1, 3.0F},     {2, 384, 2, 0, 136, 1, 1, 1.5F},
+                            {2, 208, 2, 0, 136, 6, 5, 1.2F}, {2, 96, 4, 4, 16, 1, 2, 5.0F},   {2, 30, 6, 0, 2, 2, 3, 6.0F},
+                            {2, 15, 1, 0, 0, 1, 1, 2.0F},    {2, 6, 2, 0, 0, 3, 2, 3.0F},     {1, 320, 8, 0, 8, 3, 8, 20.0F},
+                            {2, 352, 8, 2, 24, 1, 3, 12.0F}};
+    std::normal_distribution<float> noise(0.0F, 1.0F);
+    unsigned dm_bad = 0, dec_bad = 0, dec_ok_crc = 0, nshapes = 0;
+    for (const shape& sh : shapes) {
+      ++nshapes;
+      const unsigned Kb = sh.bg == 1 ? 22 : 10, K = Kb * sh.Z, N = (sh.bg == 1 ? 66 : 50) * sh.Z;
+      codeblock_metadata meta;
+      meta.tb_common.base_graph        = sh.bg == 1 ? ldpc_base_graph_type::BG1 : ldpc_base_graph_type::BG2;
+      meta.tb_common.lifting_size      = static_cast<ldpc::lifting_size_t>(sh.Z);
+      meta.tb_common.mod               = static_cast<modulation_scheme>(sh.Qm);
+      meta.tb_common.Nref              = sh.nref_div ? N * sh.nref_div / 6 : 0;
+      meta.cb_specific.nof_filler_bits = sh.nfill;
+      meta.cb_specific.nof_crc_bits    = 24;
+      meta.cb_specific.full_length     = N;
+      unsigned E                       = N * sh.e_num / sh.e_den;
+      E -= E % sh.Qm;
+      meta.cb_specific.rm_length = E;
+      // Message with CRC24B over the first K - F - 24 bits, fillers zero.
+      const unsigned       nb = K - sh.nfill;
+      std::vector<uint8_t> msg_bits(K, 0);
+      for (unsigned i = 0; i + 24 < nb; ++i) {
+        msg_bits[i] = static_cast<uint8_t>(rgen() & 1U);
+      }
+      auto     crc24b = crc_factory->create(crc_generator_poly::CRC24B);
+      unsigned crc    = crc24b->calculate_bit(span<const uint8_t>(msg_bits.data(), nb - 24));
+      for (unsigned b = 0; b != 24; ++b) {
+        msg_bits[nb - 24 + b] = (crc >> (23 - b)) & 1U;
+      }
+      dynamic_bit_buffer msg(K), cw(N), rmd(E);
+      for (unsigned i = 0; i != K; ++i) {
+        msg.insert(msg_bits[i], i, 1);
+      }
+      enc->encode(cw, msg, meta.tb_common);
+      std::vector<log_likelihood_ratio> soft_cpu(N, 0), soft_gpu(N, 0), in(E);
+      for (unsigned rv : {0U, 2U, 3U}) {
+        meta.tb_common.rv = rv;
+        rm->rate_match(rmd, cw, meta);
+        for (unsigned i = 0; i != E; ++i) {
+          float v = (rmd.extract(i, 1) ? -sh.amp : sh.amp) + sh.amp * 0.7F * noise(rgen);
+          in[i]   = log_likelihood_ratio(static_cast<int>(std::max(-120.0F, std::min(120.0F, std::round(4.0F * v)))));
+        }
+        dem_cpu->rate_dematch(soft_cpu, in, rv == 0, meta);
+        dem_gpu->rate_dematch(soft_gpu, in, rv == 0, meta);
+        if (!std::equal(soft_cpu.begin(), soft_cpu.end(), soft_gpu.begin())) {
+          ++dm_bad;
+          std::printf("MISMATCH rate_dematch bg=%u Z=%u Qm=%u Nref=%u F=%u E=%u rv=%u\n", sh.bg, sh.Z, sh.Qm, meta.tb_common.Nref,
+                      sh.nfill, E, rv);
+        }
+        for (bool with_crc : {true, false}) {
+          std::vector<uint8_t> out_cpu((K + 7) / 8 + 8, 0x5A), out_gpu((K + 7) / 8 + 8, 0x5A);
+          bit_buffer bb_cpu = bit_buffer::from_bytes(out_cpu).first(K), bb_gpu = bit_buffer::from_bytes(out_gpu).first(K);
+          ldpc_decoder::configuration dcfg;
+          dcfg.block_conf               = meta;
+          dcfg.algorithm_conf.max_iterations = with_crc ? 6 : 3;
+          auto it_cpu = dec_cpu->decode(bb_cpu, soft_cpu, with_crc ? crc24b.get() : nullptr, dcfg);
+          auto it_gpu = dec_gpu->decode(bb_gpu, soft_gpu, with_crc ? crc24b.get() : nullptr, dcfg);
+          dec_ok_crc += (with_crc && it_cpu.has_value()) ? 1 : 0;
+          if (it_cpu != it_gpu || out_cpu != out_gpu) {
+            ++dec_bad;
+            std::printf("MISMATCH ldpc_decoder bg=%u Z=%u F=%u rv=%u crc=%d\n", sh.bg, sh.Z, sh.nfill, rv, (int)with_crc);
+          }
+        }
+      }
+    }
+    std::printf("ldpc_rate_dematcher / ldpc_decoder cuda vs auto, %u shapes x rv 0,2,3: %u / %u mismatches (%u early stops)\n",
+                nshapes, dm_bad, dec_bad, dec_ok_crc);
+    failures += dm_bad + dec_bad;
+    if (dec_ok_crc < nshapes) {
+      std::printf("too few successful decodes: the early stop is barely exercised\n");
+      ++failures;
+    }
+  }
   std::printf("hwacc_parity: %s (%d mismatches)\n", failures ? "FAILED" : "PASSED", failures);
   return failures ? 1 : 0;
 }

@@ -156,6 +156,9 @@ struct batch_context {
   device_buf<uint8_t>       d_bits;
   pinned_buf<tb_desc>       h_tb;
   device_buf<tb_desc>       d_tb;
+  // Small batches (a single transport block: the latency case) send their group / order / TB descriptors packed in ONE copy.
+  pinned_buf<uint8_t>       h_meta;
+  device_buf<uint8_t>       d_meta;
   pinned_buf<tb_result_dev> h_tbres;
   device_buf<tb_result_dev> d_tbres;
   pinned_buf<uint8_t>       h_tbout;
@@ -1111,16 +1114,45 @@ int launch_context(srsran_cuda_pusch_dec* h, int ci)
     }
   }
   PROF_T(l2);
-  if (ngrp != 0) {
-    CUDA_TRY(h, cudaMemcpyAsync(c.d_grp.p, c.h_grp.p, ngrp * sizeof(grp_desc), cudaMemcpyHostToDevice, s));
-  }
-  CUDA_TRY(h, cudaMemcpyAsync(c.d_desc.p, c.h_desc.p, ncb * sizeof(cb_desc), cudaMemcpyHostToDevice, s));
-  if (pos != 0) {
-    CUDA_TRY(h, cudaMemcpyAsync(c.d_order.p, c.h_order.p, pos * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
-  }
-  if (ntb != 0) {
-    CUDA_TRY(h, cudaMemcpyAsync(c.d_tb.p, c.h_tb.p, ntb * sizeof(tb_desc), cudaMemcpyHostToDevice, s));
-    CUDA_TRY(h, cudaMemcpyAsync(c.d_tbmap.p, c.h_tbmap.p, ncb * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
+  // Device addresses of the small descriptor arrays: their own buffers, or - for a small batch, where every copy is ~5 us of
+  // the latency - one packed region sent with a single copy.
+  const grp_desc* dv_grp   = c.d_grp.p;
+  const uint32_t* dv_order = c.d_order.p;
+  const tb_desc*  dv_tb    = c.d_tb.p;
+  const uint32_t* dv_tbmap = c.d_tbmap.p;
+  {
+    const size_t b_grp = (ngrp * sizeof(grp_desc) + 15) & ~size_t(15), b_ord = (pos * sizeof(uint32_t) + 15) & ~size_t(15);
+    const size_t b_tb  = (ntb * sizeof(tb_desc) + 15) & ~size_t(15);
+    const size_t b_map = (ntb != 0) ? ((ncb * sizeof(uint32_t) + 15) & ~size_t(15)) : 0;
+    const size_t total = b_grp + b_ord + b_tb + b_map;
+    CUDA_TRY(h, cudaMemcpyAsync(c.d_desc.p, c.h_desc.p, ncb * sizeof(cb_desc), cudaMemcpyHostToDevice, s));
+    if (total != 0 && total <= 16384) {
+      CUDA_TRY(h, c.h_meta.reserve(16384));
+      CUDA_TRY(h, c.d_meta.reserve(16384));
+      uint8_t* m = c.h_meta.p;
+      std::memcpy(m, c.h_grp.p, ngrp * sizeof(grp_desc));
+      std::memcpy(m + b_grp, c.h_order.p, pos * sizeof(uint32_t));
+      if (ntb != 0) {
+        std::memcpy(m + b_grp + b_ord, c.h_tb.p, ntb * sizeof(tb_desc));
+        std::memcpy(m + b_grp + b_ord + b_tb, c.h_tbmap.p, ncb * sizeof(uint32_t));
+      }
+      CUDA_TRY(h, cudaMemcpyAsync(c.d_meta.p, m, total, cudaMemcpyHostToDevice, s));
+      dv_grp   = reinterpret_cast<const grp_desc*>(c.d_meta.p);
+      dv_order = reinterpret_cast<const uint32_t*>(c.d_meta.p + b_grp);
+      dv_tb    = reinterpret_cast<const tb_desc*>(c.d_meta.p + b_grp + b_ord);
+      dv_tbmap = reinterpret_cast<const uint32_t*>(c.d_meta.p + b_grp + b_ord + b_tb);
+    } else {
+      if (ngrp != 0) {
+        CUDA_TRY(h, cudaMemcpyAsync(c.d_grp.p, c.h_grp.p, ngrp * sizeof(grp_desc), cudaMemcpyHostToDevice, s));
+      }
+      if (pos != 0) {
+        CUDA_TRY(h, cudaMemcpyAsync(c.d_order.p, c.h_order.p, pos * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
+      }
+      if (ntb != 0) {
+        CUDA_TRY(h, cudaMemcpyAsync(c.d_tb.p, c.h_tb.p, ntb * sizeof(tb_desc), cudaMemcpyHostToDevice, s));
+        CUDA_TRY(h, cudaMemcpyAsync(c.d_tbmap.p, c.h_tbmap.p, ncb * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
+      }
+    }
   }
   CUDA_TRY(h, cudaEventRecord(c.copied, s));
   if (c.wait_for != nullptr) {
@@ -1181,7 +1213,7 @@ int launch_context(srsran_cuda_pusch_dec* h, int ci)
     return st;
   };
   for (const pklass& k : pclasses) {
-    const grp_desc* grp = c.d_grp.p + k.first;
+    const grp_desc* grp = dv_grp + k.first;
     cudaStream_t    st  = class_stream();
     cudaError_t     e;
     if (k.lanes == 2 && k.tm_cols != 0) {
@@ -1204,7 +1236,7 @@ int launch_context(srsran_cuda_pusch_dec* h, int ci)
   pos = 0;
   for (klass& k : classes) {
     uint32_t        n   = static_cast<uint32_t>(k.idx.size());
-    const uint32_t* ord = c.d_order.p + pos;
+    const uint32_t* ord = dv_order + pos;
     cudaStream_t    st  = class_stream();
     cudaError_t     e   = cudaSuccess;
     switch (k.tpc) {
@@ -1229,7 +1261,7 @@ int launch_context(srsran_cuda_pusch_dec* h, int ci)
   }
   for (klass& k : qclasses) {
     uint32_t        n   = static_cast<uint32_t>(k.idx.size());
-    const uint32_t* ord = c.d_order.p + pos;
+    const uint32_t* ord = dv_order + pos;
     cudaStream_t    st  = class_stream();
     cudaError_t     e   = (k.tpc == 32) ? launch_decode_q4<32>(h, st, c.d_desc.p, ord, c.d_res.p, c.bits_base, n, k.smem)
                           : (k.tpc == 64) ? launch_decode_q4<64>(h, st, c.d_desc.p, ord, c.d_res.p, c.bits_base, n, k.smem)
@@ -1250,11 +1282,11 @@ int launch_context(srsran_cuda_pusch_dec* h, int ci)
   CUDA_TRY(h, cudaEventRecord(c.decoded, s));
   CUDA_TRY(h, cudaStreamWaitEvent(ts, c.decoded, 0));
   if (ntb != 0) {
-    tb_gather_kernel<<<(ncb + TBG_WARPS - 1) / TBG_WARPS, TBG_WARPS * 32, 0, ts>>>(c.d_tb.p, c.d_desc.p, c.d_tbmap.p, ncb, h->d_bits.p,
+    tb_gather_kernel<<<(ncb + TBG_WARPS - 1) / TBG_WARPS, TBG_WARPS * 32, 0, ts>>>(dv_tb, c.d_desc.p, dv_tbmap, ncb, h->d_bits.p,
                                                                                   c.d_tbout.p, c.d_tbshare.p);
     ++h->launches;
     CUDA_TRY(h, cudaGetLastError());
-    tb_finalize_kernel<<<(ntb + 7) / 8, 256, 0, ts>>>(c.d_tb.p, c.d_desc.p, ntb, c.d_tbres.p, c.d_tbshare.p, h->d_crc_flags.p);
+    tb_finalize_kernel<<<(ntb + 7) / 8, 256, 0, ts>>>(dv_tb, c.d_desc.p, ntb, c.d_tbres.p, c.d_tbshare.p, h->d_crc_flags.p);
     ++h->launches;
     CUDA_TRY(h, cudaGetLastError());
   }
@@ -1776,6 +1808,8 @@ void srsran_cuda_pusch_dec_destroy(srsran_cuda_pusch_dec_t* h)
     c.d_bits.release();
     c.h_tb.release();
     c.d_tb.release();
+    c.h_meta.release();
+    c.d_meta.release();
     c.h_tbres.release();
     c.d_tbres.release();
     c.h_tbout.release();

@@ -21,7 +21,7 @@ def run(first=0, count=100):
     checked = 0
     for seed in range(first, first + count):
         rng = np.random.default_rng(seed)
-        acc.set_decoder_variant(int(rng.choice([0, 0, 0, 1, 2, 3, 4])))
+        acc.set_decoder_variant(int(rng.choice([0, 0, 0, 1, 2, 3, 4, 5, 6, 6, 7])))
         early_stop = int(rng.random() < 0.8)
         max_it = int(rng.integers(1, 13))
         ops = []

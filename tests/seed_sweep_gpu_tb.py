@@ -31,7 +31,7 @@ def run(first=0, count=40):
         # decoded one after the other into the SAME slots, so that later ones see the stale soft bits of earlier ones.
         acc = pusch.Accelerator(device=0, max_cbs_in_flight=1024, nof_harq_cb_slots=1024)
         port = ob.PortPusch()
-        acc.set_decoder_variant(int(rng.choice([0, 0, 0, 0, 1, 2, 3, 4])))
+        acc.set_decoder_variant(int(rng.choice([0, 0, 0, 0, 1, 2, 3, 4, 5, 6, 6, 7])))
         qm = int(rng.choice([2, 4, 6, 8]))
         nl = int(rng.choice([1, 1, 2, 4]))
         prb = int(rng.choice([1, 2, 5, 13, 24, 52, 79, 106]))
