@@ -2652,7 +2652,7 @@ int srsran_cuda_pusch_dec_submit_tbs_symbols(srsran_cuda_pusch_dec_t* h, uint32_
     }
   }
   uint32_t              total_cbs = 0;
-  size_t                tb_bytes = 0, llr_bytes = 0, in_bytes = 0, scr_words = 0;
+  size_t                tb_bytes = 0, llr_bytes = 0, in_bytes = 0, scr_words = 0, sym_total = 0;
   std::vector<uint32_t> nsym(nof_tbs);
   for (uint32_t i = 0; i != nof_tbs; ++i) {
     nsym[i] = demod_nof_symbols(demod_configs[i]);
@@ -2668,6 +2668,7 @@ int srsran_cuda_pusch_dec_submit_tbs_symbols(srsran_cuda_pusch_dec_t* h, uint32_
     tb_bytes += configs[i].tbs_bits / 8 + 32;
     llr_bytes += (static_cast<size_t>(nsym[i]) * demod_configs[i].modulation + 15) & ~size_t(15);
     in_bytes += (static_cast<size_t>(nsym[i]) * 12 + 15) & ~size_t(15);
+    sym_total += static_cast<size_t>(nsym[i]) * 8;
     scr_words += (static_cast<size_t>(nsym[i]) * demod_configs[i].modulation + 31) / 32 + 1;
   }
   int ci = open_context(h, total_cbs);
@@ -2691,19 +2692,28 @@ int srsran_cuda_pusch_dec_submit_tbs_symbols(srsran_cuda_pusch_dec_t* h, uint32_
     h->last_error = "demodulation staging allocation failed";
     return fail(SRSRAN_CUDA_ERR_NO_MEMORY);
   }
-  size_t llr_off = 0, in_off = 0, scr_off = 0;
+  // Staging layout: all symbols back to back, then all noise variances (both 4-byte units, sym_total is a multiple of 8), so
+  // that the arrays of a slot that lie back to back in host memory leave in ONE copy each instead of two per transport block.
+  size_t llr_off = 0, sym_off = 0, nv_off = sym_total, scr_off = 0;
+  auto   push_raw = [&c](const void* src, size_t dst_off, size_t bytes) {
+    if (!c.raw_copies.empty() && static_cast<const uint8_t*>(c.raw_copies.back().src) + c.raw_copies.back().bytes == src &&
+        c.raw_copies.back().dst_off + c.raw_copies.back().bytes == dst_off) {
+      c.raw_copies.back().bytes += bytes;
+    } else {
+      c.raw_copies.push_back({src, dst_off, bytes});
+    }
+  };
   for (uint32_t i = 0; i != nof_tbs; ++i) {
     const srsran_cuda_pusch_demod_config& d = demod_configs[i];
     const float*                          sym_dev = symbols[i];
     const float*                          nv_dev  = noise_vars[i];
     if (!device_resident) {
-      // One region per TB: symbols (8 B each) then noise variances (4 B each).
       const size_t sym_bytes = static_cast<size_t>(nsym[i]) * 8, nv_bytes = static_cast<size_t>(nsym[i]) * 4;
-      c.raw_copies.push_back({symbols[i], in_off, sym_bytes});
-      c.raw_copies.push_back({noise_vars[i], in_off + sym_bytes, nv_bytes});
-      sym_dev = reinterpret_cast<const float*>(c.d_dm_in.p + in_off);
-      nv_dev  = reinterpret_cast<const float*>(c.d_dm_in.p + in_off + sym_bytes);
-      in_off += (sym_bytes + nv_bytes + 15) & ~size_t(15);
+      push_raw(symbols[i], sym_off, sym_bytes);
+      sym_dev = reinterpret_cast<const float*>(c.d_dm_in.p + sym_off);
+      nv_dev  = reinterpret_cast<const float*>(c.d_dm_in.p + nv_off);
+      sym_off += sym_bytes;
+      nv_off += nv_bytes;
     }
     const uint32_t nllr = nsym[i] * d.modulation;
     add_demod(h, c, d, nsym[i], sym_dev, nv_dev, c.d_llr.p + llr_off, scr_off);
@@ -2714,6 +2724,13 @@ int srsran_cuda_pusch_dec_submit_tbs_symbols(srsran_cuda_pusch_dec_t* h, uint32_
     llr_off += (static_cast<size_t>(nllr) + 15) & ~size_t(15);
     scr_off += (static_cast<size_t>(nllr) + 31) / 32 + 1;
     tickets[i] = make_ticket(ci, static_cast<uint32_t>(c.tb_meta.size() - 1), c.generation);
+  }
+  if (!device_resident) {
+    size_t off = sym_total;
+    for (uint32_t i = 0; i != nof_tbs; ++i) {
+      push_raw(noise_vars[i], off, static_cast<size_t>(nsym[i]) * 4);
+      off += static_cast<size_t>(nsym[i]) * 4;
+    }
   }
   c.llr_used = llr_off;
   return launch_context(h, ci);
