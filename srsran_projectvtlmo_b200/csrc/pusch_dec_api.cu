@@ -36,6 +36,7 @@ thread_local std::string g_create_error;
 
 constexpr int      NOF_CONTEXTS   = 8;
 constexpr uint32_t MAX_TBS_PER_CTX = 1024;
+constexpr size_t   PACKED_OUT_MAX  = 512 * 1024; // results + TB bytes of a small batch that return in one copy
 
 template <typename T>
 struct pinned_buf {
@@ -150,6 +151,7 @@ struct batch_context {
   pinned_buf<uint32_t>      h_tbmap; // per code block: index of its transport block in h_tb, or 0xffffffff
   device_buf<uint32_t>      d_tbmap;
   device_buf<uint32_t>      d_tbshare; // per code block: its share of the TB CRC24A
+  device_buf<uint32_t>      d_tbdone;  // per transport block: code blocks assembled so far (self-resetting counter)
   pinned_buf<cb_result>     h_res;
   device_buf<cb_result>     d_res;
   pinned_buf<uint8_t>       h_bits;
@@ -159,6 +161,14 @@ struct batch_context {
   // Small batches (a single transport block: the latency case) send their group / order / TB descriptors packed in ONE copy.
   pinned_buf<uint8_t>       h_meta;
   device_buf<uint8_t>       d_meta;
+  // ... and bring their results (code-block results, TB verdicts, TB bytes) back packed in ONE copy. The r_* pointers are where
+  // the results of the batch in flight are read: the context's own result buffers or the packed region.
+  pinned_buf<uint8_t>       h_outp;
+  device_buf<uint8_t>       d_outp;
+  const cb_result*          r_res       = nullptr;
+  const tb_result_dev*      r_tbres     = nullptr;
+  const uint8_t*            r_tbout     = nullptr;
+  const uint8_t*            r_tbout_dev = nullptr;
   pinned_buf<tb_result_dev> h_tbres;
   device_buf<tb_result_dev> d_tbres;
   pinned_buf<uint8_t>       h_tbout;
@@ -1154,6 +1164,29 @@ int launch_context(srsran_cuda_pusch_dec* h, int ci)
       }
     }
   }
+  cb_result*     dv_res   = c.d_res.p;
+  tb_result_dev* dv_tbres = c.d_tbres.p;
+  uint8_t*       dv_tbout = c.d_tbout.p;
+  c.r_res                 = c.h_res.p;
+  c.r_tbres               = c.h_tbres.p;
+  c.r_tbout               = c.h_tbout.p;
+  size_t packed_out       = 0; // bytes of the packed result region (0: separate copies)
+  {
+    const size_t b_tbres = (ntb * sizeof(tb_result_dev) + 15) & ~size_t(15), b_res = (ncb * sizeof(cb_result) + 15) & ~size_t(15);
+    const size_t total   = b_tbres + b_res + c.tbout_used;
+    if (ntb != 0 && h->tb_host_copy && !c.want_bits && total <= PACKED_OUT_MAX) {
+      CUDA_TRY(h, c.h_outp.reserve(PACKED_OUT_MAX));
+      CUDA_TRY(h, c.d_outp.reserve(PACKED_OUT_MAX));
+      dv_tbres   = reinterpret_cast<tb_result_dev*>(c.d_outp.p);
+      dv_res     = reinterpret_cast<cb_result*>(c.d_outp.p + b_tbres);
+      dv_tbout   = c.d_outp.p + b_tbres + b_res;
+      c.r_tbres  = reinterpret_cast<const tb_result_dev*>(c.h_outp.p);
+      c.r_res    = reinterpret_cast<const cb_result*>(c.h_outp.p + b_tbres);
+      c.r_tbout  = c.h_outp.p + b_tbres + b_res;
+      packed_out = total;
+    }
+  }
+  c.r_tbout_dev = dv_tbout;
   CUDA_TRY(h, cudaEventRecord(c.copied, s));
   if (c.wait_for != nullptr) {
     CUDA_TRY(h, cudaStreamWaitEvent(s, c.wait_for, 0));
@@ -1218,18 +1251,18 @@ int launch_context(srsran_cuda_pusch_dec* h, int ci)
     cudaError_t     e;
     if (k.lanes == 2 && k.tm_cols != 0) {
       e = (k.tpc == 256)
-              ? launch_decode2t<256>(h, st, c.d_desc.p, grp, c.d_res.p, c.bits_base, k.count, k.smem, k.tm_cols)
-              : launch_decode2t<384>(h, st, c.d_desc.p, grp, c.d_res.p, c.bits_base, k.count, k.smem, k.tm_cols, k.z == 384);
+              ? launch_decode2t<256>(h, st, c.d_desc.p, grp, dv_res, c.bits_base, k.count, k.smem, k.tm_cols)
+              : launch_decode2t<384>(h, st, c.d_desc.p, grp, dv_res, c.bits_base, k.count, k.smem, k.tm_cols, k.z == 384);
     } else if (k.lanes == 2) {
-      e = (k.tpc == 256) ? launch_decode2<256>(h, st, c.d_desc.p, grp, c.d_res.p, c.bits_base, k.count, k.smem)
-                         : launch_decode2<384>(h, st, c.d_desc.p, grp, c.d_res.p, c.bits_base, k.count, k.smem, k.z == 384);
+      e = (k.tpc == 256) ? launch_decode2<256>(h, st, c.d_desc.p, grp, dv_res, c.bits_base, k.count, k.smem)
+                         : launch_decode2<384>(h, st, c.d_desc.p, grp, dv_res, c.bits_base, k.count, k.smem, k.z == 384);
     } else if (k.tm_cols != 0) {
       e = (k.tpc == 256)
-              ? launch_decode4t<256>(h, st, c.d_desc.p, grp, c.d_res.p, c.bits_base, k.count, k.smem, k.tm_cols)
-              : launch_decode4t<384>(h, st, c.d_desc.p, grp, c.d_res.p, c.bits_base, k.count, k.smem, k.tm_cols, k.z == 384);
+              ? launch_decode4t<256>(h, st, c.d_desc.p, grp, dv_res, c.bits_base, k.count, k.smem, k.tm_cols)
+              : launch_decode4t<384>(h, st, c.d_desc.p, grp, dv_res, c.bits_base, k.count, k.smem, k.tm_cols, k.z == 384);
     } else {
-      e = (k.tpc == 256) ? launch_decode4<256>(h, st, c.d_desc.p, grp, c.d_res.p, c.bits_base, k.count, k.smem)
-                         : launch_decode4<384>(h, st, c.d_desc.p, grp, c.d_res.p, c.bits_base, k.count, k.smem, k.z == 384);
+      e = (k.tpc == 256) ? launch_decode4<256>(h, st, c.d_desc.p, grp, dv_res, c.bits_base, k.count, k.smem)
+                         : launch_decode4<384>(h, st, c.d_desc.p, grp, dv_res, c.bits_base, k.count, k.smem, k.z == 384);
     }
     CUDA_TRY(h, e);
   }
@@ -1241,19 +1274,19 @@ int launch_context(srsran_cuda_pusch_dec* h, int ci)
     cudaError_t     e   = cudaSuccess;
     switch (k.tpc) {
       case 0:
-        e = launch_decode<32, 4>(h, st, c.d_desc.p, ord, c.d_res.p, c.bits_base, n, k.smem);
+        e = launch_decode<32, 4>(h, st, c.d_desc.p, ord, dv_res, c.bits_base, n, k.smem);
         break;
       case 1:
-        e = launch_decode<64, 2>(h, st, c.d_desc.p, ord, c.d_res.p, c.bits_base, n, k.smem);
+        e = launch_decode<64, 2>(h, st, c.d_desc.p, ord, dv_res, c.bits_base, n, k.smem);
         break;
       case 2:
-        e = launch_decode<128, 1>(h, st, c.d_desc.p, ord, c.d_res.p, c.bits_base, n, k.smem);
+        e = launch_decode<128, 1>(h, st, c.d_desc.p, ord, dv_res, c.bits_base, n, k.smem);
         break;
       case 3:
-        e = launch_decode<256, 1>(h, st, c.d_desc.p, ord, c.d_res.p, c.bits_base, n, k.smem);
+        e = launch_decode<256, 1>(h, st, c.d_desc.p, ord, dv_res, c.bits_base, n, k.smem);
         break;
       default:
-        e = launch_decode<384, 1>(h, st, c.d_desc.p, ord, c.d_res.p, c.bits_base, n, k.smem);
+        e = launch_decode<384, 1>(h, st, c.d_desc.p, ord, dv_res, c.bits_base, n, k.smem);
         break;
     }
     CUDA_TRY(h, e);
@@ -1263,9 +1296,9 @@ int launch_context(srsran_cuda_pusch_dec* h, int ci)
     uint32_t        n   = static_cast<uint32_t>(k.idx.size());
     const uint32_t* ord = dv_order + pos;
     cudaStream_t    st  = class_stream();
-    cudaError_t     e   = (k.tpc == 32) ? launch_decode_q4<32>(h, st, c.d_desc.p, ord, c.d_res.p, c.bits_base, n, k.smem)
-                          : (k.tpc == 64) ? launch_decode_q4<64>(h, st, c.d_desc.p, ord, c.d_res.p, c.bits_base, n, k.smem)
-                                          : launch_decode_q4<96>(h, st, c.d_desc.p, ord, c.d_res.p, c.bits_base, n, k.smem);
+    cudaError_t     e   = (k.tpc == 32) ? launch_decode_q4<32>(h, st, c.d_desc.p, ord, dv_res, c.bits_base, n, k.smem)
+                          : (k.tpc == 64) ? launch_decode_q4<64>(h, st, c.d_desc.p, ord, dv_res, c.bits_base, n, k.smem)
+                                          : launch_decode_q4<96>(h, st, c.d_desc.p, ord, dv_res, c.bits_base, n, k.smem);
     CUDA_TRY(h, e);
     pos += n;
   }
@@ -1278,20 +1311,25 @@ int launch_context(srsran_cuda_pusch_dec* h, int ci)
   CUDA_TRY(h, cudaEventRecord(c.stage[3], s));
   // The small end-of-batch kernels and the result copies go to a high-priority stream: when the next batch overlaps this
   // one, its decode CTAs must not keep these few CTAs (and with them the completion of this batch) waiting.
-  cudaStream_t ts = c.tail;
+  // A small batch (the latency case) stays on its own stream: the hop to another stream costs more than it saves there.
+  cudaStream_t ts = (packed_out != 0) ? s : c.tail;
   CUDA_TRY(h, cudaEventRecord(c.decoded, s));
-  CUDA_TRY(h, cudaStreamWaitEvent(ts, c.decoded, 0));
+  if (ts != s) {
+    CUDA_TRY(h, cudaStreamWaitEvent(ts, c.decoded, 0));
+  }
   if (ntb != 0) {
-    tb_gather_kernel<<<(ncb + TBG_WARPS - 1) / TBG_WARPS, TBG_WARPS * 32, 0, ts>>>(dv_tb, c.d_desc.p, dv_tbmap, ncb, h->d_bits.p,
-                                                                                  c.d_tbout.p, c.d_tbshare.p);
-    ++h->launches;
-    CUDA_TRY(h, cudaGetLastError());
-    tb_finalize_kernel<<<(ntb + 7) / 8, 256, 0, ts>>>(dv_tb, c.d_desc.p, ntb, c.d_tbres.p, c.d_tbshare.p, h->d_crc_flags.p);
+    // One warp per code block; the last warp of a transport block also finalises it (TB CRC verdict, CRC-flag reset).
+    tb_gather_kernel<<<(ncb + TBG_WARPS - 1) / TBG_WARPS, TBG_WARPS * 32, 0, ts>>>(
+        dv_tb, c.d_desc.p, dv_tbmap, ncb, h->d_bits.p, dv_tbout, c.d_tbshare.p, dv_tbres, h->d_crc_flags.p, c.d_tbdone.p);
     ++h->launches;
     CUDA_TRY(h, cudaGetLastError());
   }
   CUDA_TRY(h, cudaEventRecord(c.kernels, ts));
   // 5. Device -> host.
+  if (packed_out != 0) {
+    c.tb_on_host = true;
+    CUDA_TRY(h, cudaMemcpyAsync(c.h_outp.p, c.d_outp.p, packed_out, cudaMemcpyDeviceToHost, ts));
+  } else {
   CUDA_TRY(h, cudaMemcpyAsync(c.h_res.p, c.d_res.p, ncb * sizeof(cb_result), cudaMemcpyDeviceToHost, ts));
   if (c.want_bits) {
     CUDA_TRY(h, cudaMemcpyAsync(c.h_bits.p, c.d_bits.p, static_cast<size_t>(ncb) * BITS_STRIDE, cudaMemcpyDeviceToHost, ts));
@@ -1303,9 +1341,12 @@ int launch_context(srsran_cuda_pusch_dec* h, int ci)
       CUDA_TRY(h, cudaMemcpyAsync(c.h_tbout.p, c.d_tbout.p, c.tbout_used, cudaMemcpyDeviceToHost, ts));
     }
   }
+  }
   CUDA_TRY(h, cudaEventRecord(c.done, ts));
   // The batch stream joins the tail so that the next use of this context (and stream-ordered waits on it) see it complete.
-  CUDA_TRY(h, cudaStreamWaitEvent(s, c.done, 0));
+  if (ts != s) {
+    CUDA_TRY(h, cudaStreamWaitEvent(s, c.done, 0));
+  }
   PROF_T(l4);
   PROF_ADD(2, l0, l1);
   PROF_ADD(3, l1, l2);
@@ -1470,6 +1511,11 @@ int prepare_tb_buffers(srsran_cuda_pusch_dec* h, batch_context& c, uint32_t nof_
   CUDA_TRY(h, c.h_tb.reserve(MAX_TBS_PER_CTX));
   CUDA_TRY(h, c.d_tb.reserve(MAX_TBS_PER_CTX));
   CUDA_TRY(h, c.h_tbres.reserve(MAX_TBS_PER_CTX));
+  if (c.d_tbdone.p == nullptr) {
+    // Per transport block: code blocks assembled so far (tb_gather_kernel; returns to zero by itself).
+    CUDA_TRY(h, c.d_tbdone.reserve(MAX_TBS_PER_CTX));
+    CUDA_TRY(h, cudaMemset(c.d_tbdone.p, 0, MAX_TBS_PER_CTX * sizeof(uint32_t)));
+  }
   CUDA_TRY(h, c.d_tbres.reserve(MAX_TBS_PER_CTX));
   size_t need = c.tbout_used + tb_bytes_total + 32 * static_cast<size_t>(nof_tbs);
   if (need > c.h_tbout.cap) {
@@ -1810,7 +1856,10 @@ void srsran_cuda_pusch_dec_destroy(srsran_cuda_pusch_dec_t* h)
     c.d_tb.release();
     c.h_meta.release();
     c.d_meta.release();
+    c.h_outp.release();
+    c.d_outp.release();
     c.h_tbres.release();
+    c.d_tbdone.release();
     c.d_tbres.release();
     c.h_tbout.release();
     c.d_tbout.release();
@@ -2102,7 +2151,7 @@ int srsran_cuda_pusch_dec_read_outputs(srsran_cuda_pusch_dec_t* h, uint32_t cb_i
     h->last_error = "read_outputs before completion";
     return SRSRAN_CUDA_ERR_STATE;
   }
-  const cb_result& r = c.h_res.p[op.idx];
+  const cb_result& r = c.r_res[op.idx];
   if (r.status == 1) {
     h->last_error = "internal: shared-memory layer capacity exceeded";
     return SRSRAN_CUDA_ERR_STATE;
@@ -2476,16 +2525,16 @@ static int poll_tb_impl(srsran_cuda_pusch_dec_t* h, int ticket, int block, uint8
     }
   }
   tb_host_meta&        m  = c.tb_meta[ti];
-  const tb_result_dev& tr = c.h_tbres.p[ti];
+  const tb_result_dev& tr = c.r_tbres[ti];
   if (tb != nullptr && tr.written && c.tb_on_host) {
-    std::memcpy(tb, c.h_tbout.p + m.out_offset, m.tbs_bits / 8);
+    std::memcpy(tb, c.r_tbout + m.out_offset, m.tbs_bits / 8);
   }
   if (result != nullptr) {
     // sample_statistics<unsigned>::update (include/srsran/support/stats.h:49-53), code blocks in order.
     uint32_t nobs = 0, imin = 0xffffffffU, imax = 0;
     float    mean = 0;
     for (uint32_t i = 0; i != m.nof_cbs; ++i) {
-      const cb_result& r = c.h_res.p[m.first_cb + i];
+      const cb_result& r = c.r_res[m.first_cb + i];
       if (r.status == 1) {
         h->last_error = "internal: shared-memory layer capacity exceeded";
         return SRSRAN_CUDA_ERR_STATE;
@@ -2559,7 +2608,7 @@ int srsran_cuda_pusch_dec_tb_data(srsran_cuda_pusch_dec_t* h, int ticket, const 
     h->last_error = "stale, unknown or unfinished ticket";
     return SRSRAN_CUDA_ERR_STATE;
   }
-  *data = (c.h_tbres.p[ti].written && c.tb_on_host) ? c.h_tbout.p + c.tb_meta[ti].out_offset : nullptr;
+  *data = (c.r_tbres[ti].written && c.tb_on_host) ? c.r_tbout + c.tb_meta[ti].out_offset : nullptr;
   return SRSRAN_CUDA_OK;
 }
 
@@ -2579,7 +2628,7 @@ int srsran_cuda_pusch_dec_tb_data_device(srsran_cuda_pusch_dec_t* h, int ticket,
     h->last_error = "stale, unknown or unfinished ticket";
     return SRSRAN_CUDA_ERR_STATE;
   }
-  *data = c.h_tbres.p[ti].written ? c.d_tbout.p + c.tb_meta[ti].out_offset : nullptr;
+  *data = c.r_tbres[ti].written ? c.r_tbout_dev + c.tb_meta[ti].out_offset : nullptr;
   return SRSRAN_CUDA_OK;
 }
 
@@ -2615,7 +2664,7 @@ int srsran_cuda_pusch_dec_tb_cb_outputs(srsran_cuda_pusch_dec_t* h, int ticket, 
   }
   bool all_ok = true;
   for (uint32_t i = 0; i != m.nof_cbs; ++i) {
-    const cb_result& r = c.h_res.p[m.first_cb + i];
+    const cb_result& r = c.r_res[m.first_cb + i];
     crc_ok[i]          = r.crc_ok ? 1 : 0;
     all_ok             = all_ok && crc_ok[i];
     if (nof_iterations != nullptr) {
@@ -2623,7 +2672,7 @@ int srsran_cuda_pusch_dec_tb_cb_outputs(srsran_cuda_pusch_dec_t* h, int ticket, 
     }
   }
   // A TB whose code blocks all pass but whose own CRC fails resets every flag (pusch_decoder_impl.cpp:425-428).
-  if (all_ok && m.nof_cbs > 1 && !c.h_tbres.p[ti].tb_crc_ok) {
+  if (all_ok && m.nof_cbs > 1 && !c.r_tbres[ti].tb_crc_ok) {
     std::memset(crc_ok, 0, m.nof_cbs);
   }
   return static_cast<int>(m.nof_cbs);
@@ -3083,7 +3132,7 @@ int srsran_cuda_ldpc_decode_batch(srsran_cuda_pusch_dec_t* h, uint8_t* bits, con
       return r;
     }
     for (uint32_t i = 0; i != n; ++i) {
-      const cb_result& res = c.h_res.p[i];
+      const cb_result& res = c.r_res[i];
       if (res.status == 1) {
         h->last_error = "internal: shared-memory layer capacity exceeded";
         return SRSRAN_CUDA_ERR_STATE;

@@ -933,12 +933,13 @@ __global__ void __launch_bounds__(CRC_THREADS) crc_kernel(const crc_job* __restr
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
-// TB assembly (pusch_decoder_impl.cpp:384-497) in two small kernels so that a transport block of 152 code blocks is
-// handled by 152 warps instead of one CTA:
+// TB assembly (pusch_decoder_impl.cpp:384-497), so that a transport block of 152 code blocks is handled by 152 warps instead of
+// one CTA:
 //   tb_gather_kernel    one WARP per code block: copies its payload bits (dropping CB CRC, filler and zero padding)
 //                       to their bit position in the transport block, and computes its share of the TB CRC24A:
-//                       (payload(x) x^24 mod g) * x^(bits behind it) mod g  (CRCs are linear over GF(2))
-//   tb_finalize_kernel  one WARP per transport block: all code blocks ok? XOR of the shares == 0? result + CRC-flag reset
+//                       (payload(x) x^24 mod g) * x^(bits behind it) mod g  (CRCs are linear over GF(2)).
+//                       The warp that finishes LAST for its transport block (a counter per TB) also finalises it:
+//   tb_finalize_warp    all code blocks ok? XOR of the shares == 0? result + CRC-flag reset (one warp per transport block)
 // ---------------------------------------------------------------------------------------------------------------------
 constexpr int TBG_WARPS = 16;
 
@@ -1028,13 +1029,48 @@ __device__ __forceinline__ uint32_t warp_xpow(uint32_t e, int poly, int lane)
   return f;
 }
 
+/// TB verdict by one warp (all code blocks ok? XOR of their CRC shares zero?), and the CRC-flag reset of a false positive
+/// (pusch_decoder_impl.cpp:417-429).
+__device__ __forceinline__ void tb_finalize_warp(const tb_desc& tb, uint32_t tbi, const cb_desc* __restrict__ descs,
+                                                 tb_result_dev* __restrict__ tb_results, const uint32_t* crc_share,
+                                                 uint32_t* crc_flags, int lane)
+{
+  bool     ok  = true;
+  uint32_t crc = 0;
+  for (uint32_t i = lane; i < tb.nof_cbs; i += 32) {
+    ok = ok && (crc_flags[descs[tb.first_cb + i].slot] != 0);
+    crc ^= crc_share[tb.first_cb + i];
+  }
+  const uint32_t all_ok = __all_sync(0xffffffffU, ok) ? 1U : 0U;
+  crc                   = __reduce_xor_sync(0xffffffffU, crc);
+  if (tb.nof_cbs == 1 || !all_ok) {
+    // Single code block: its CRC is the TB CRC. Otherwise the TB CRC is only checked when every code block is ok.
+    if (lane == 0) {
+      tb_results[tbi] = {all_ok, all_ok};
+    }
+    return;
+  }
+  if (lane == 0) {
+    tb_results[tbi] = {crc == 0 ? 1U : 0U, 1U};
+  }
+  if (crc != 0) {
+    // At least one code block is a false positive: reset them all (pusch_decoder_impl.cpp:425-428).
+    for (uint32_t i = lane; i < tb.nof_cbs; i += 32) {
+      crc_flags[descs[tb.first_cb + i].slot] = 0;
+    }
+  }
+}
+
 __global__ void __launch_bounds__(TBG_WARPS * 32) tb_gather_kernel(const tb_desc* __restrict__ tbs,
                                                                    const cb_desc* __restrict__ descs,
                                                                    const uint32_t* __restrict__ tb_of_cb,
                                                                    uint32_t nof_cbs,
                                                                    const uint8_t* __restrict__ bits_base,
                                                                    uint8_t* __restrict__ tb_out,
-                                                                   uint32_t* __restrict__ crc_share)
+                                                                   uint32_t* crc_share,
+                                                                   tb_result_dev* __restrict__ tb_results,
+                                                                   uint32_t* crc_flags,
+                                                                   uint32_t* tb_done)
 {
   __shared__ uint32_t tabs[1024];
   const int           t = threadIdx.x, lane = t & 31;
@@ -1050,6 +1086,23 @@ __global__ void __launch_bounds__(TBG_WARPS * 32) tb_gather_kernel(const tb_desc
     return;
   }
   const tb_desc   tb   = tbs[tbi];
+  // Called by every warp once its code block is in place: the last one of a transport block finalises it. The counter
+  // returns to zero, so it needs no clearing between batches.
+  auto code_block_done = [&]() {
+    __threadfence(); // this warp's share and TB words before the count
+    uint32_t prev = 0;
+    if (lane == 0) {
+      prev = atomicAdd(&tb_done[tbi], 1U);
+    }
+    prev = __shfl_sync(0xffffffffU, prev, 0);
+    if (prev + 1 == tb.nof_cbs) {
+      __threadfence(); // the other warps' shares after the count
+      if (lane == 0) {
+        tb_done[tbi] = 0;
+      }
+      tb_finalize_warp(tb, tbi, descs, tb_results, crc_share, crc_flags, lane);
+    }
+  };
   const uint32_t  r    = cb - tb.first_cb;
   const uint32_t* src  = reinterpret_cast<const uint32_t*>(bits_base + (size_t)descs[cb].slot * BITS_STRIDE);
   uint32_t*       out  = reinterpret_cast<uint32_t*>(tb_out + tb.out_offset);
@@ -1062,6 +1115,7 @@ __global__ void __launch_bounds__(TBG_WARPS * 32) tb_gather_kernel(const tb_desc
     if (lane == 0) {
       crc_share[cb] = 0;
     }
+    code_block_done();
     return;
   }
   const uint32_t Lp = tb.cb_data_bits;
@@ -1094,45 +1148,7 @@ __global__ void __launch_bounds__(TBG_WARPS * 32) tb_gather_kernel(const tb_desc
     }
     out[m] = __byte_perm(v, 0, 0x0123);
   }
-}
-
-__global__ void __launch_bounds__(256) tb_finalize_kernel(const tb_desc* __restrict__ tbs,
-                                                          const cb_desc* __restrict__ descs,
-                                                          uint32_t nof_tbs,
-                                                          tb_result_dev* __restrict__ tb_results,
-                                                          const uint32_t* __restrict__ crc_share,
-                                                          uint32_t* __restrict__ crc_flags)
-{
-  const int      lane = threadIdx.x & 31;
-  const uint32_t tbi  = blockIdx.x * 8 + (threadIdx.x >> 5);
-  if (tbi >= nof_tbs) {
-    return;
-  }
-  const tb_desc tb  = tbs[tbi];
-  bool          ok  = true;
-  uint32_t      crc = 0;
-  for (uint32_t i = lane; i < tb.nof_cbs; i += 32) {
-    ok = ok && (crc_flags[descs[tb.first_cb + i].slot] != 0);
-    crc ^= crc_share[tb.first_cb + i];
-  }
-  const uint32_t all_ok = __all_sync(0xffffffffU, ok) ? 1U : 0U;
-  crc                   = __reduce_xor_sync(0xffffffffU, crc);
-  if (tb.nof_cbs == 1 || !all_ok) {
-    // Single code block: its CRC is the TB CRC. Otherwise the TB CRC is only checked when every code block is ok.
-    if (lane == 0) {
-      tb_results[tbi] = {all_ok, all_ok};
-    }
-    return;
-  }
-  if (lane == 0) {
-    tb_results[tbi] = {crc == 0 ? 1U : 0U, 1U};
-  }
-  if (crc != 0) {
-    // At least one code block is a false positive: reset them all (pusch_decoder_impl.cpp:425-428).
-    for (uint32_t i = lane; i < tb.nof_cbs; i += 32) {
-      crc_flags[descs[tb.first_cb + i].slot] = 0;
-    }
-  }
+  code_block_done();
 }
 
 } // namespace pusch_dec
