@@ -50,7 +50,12 @@ struct enc_core_desc {
 };
 __constant__ enc_core_desc c_enc_core[2][8];
 
-constexpr int ENC_THREADS = 256;
+#ifndef PDSCH_ENC_THREADS
+#define PDSCH_ENC_THREADS 256
+#endif
+constexpr int ENC_THREADS = PDSCH_ENC_THREADS;
+static_assert(ENC_THREADS % 32 == 0 && ENC_THREADS >= 192,
+              "the core-row phase of the packed encoder gives four threads to each of the 4 * 12 (row, word) pairs of Z = 384");
 
 /// Shared memory of the encoder for a code block of base graph `bg` and lifting size Z.
 __host__ __device__ inline uint32_t enc_smem_bytes(uint32_t bg, uint32_t Z)

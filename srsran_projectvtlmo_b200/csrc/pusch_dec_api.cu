@@ -37,6 +37,7 @@ thread_local std::string g_create_error;
 constexpr int      NOF_CONTEXTS   = 8;
 constexpr uint32_t MAX_TBS_PER_CTX = 1024;
 constexpr size_t   PACKED_OUT_MAX  = 512 * 1024; // results + TB bytes of a small batch that return in one copy
+constexpr size_t   PACKED_META_MAX = 16 * 1024;  // group / order / TB descriptors of a small batch that travel in one copy
 
 template <typename T>
 struct pinned_buf {
@@ -652,6 +653,11 @@ int open_context(srsran_cuda_pusch_dec* h, uint32_t min_cbs)
   CUDA_TRY(h, c.d_tbshare.reserve(ncb));
   CUDA_TRY(h, c.h_res.reserve(ncb));
   CUDA_TRY(h, c.d_res.reserve(ncb));
+  // Packed descriptor / result regions of small batches (allocated here, not at the first small batch: no hiccup there).
+  CUDA_TRY(h, c.h_meta.reserve(PACKED_META_MAX));
+  CUDA_TRY(h, c.d_meta.reserve(PACKED_META_MAX));
+  CUDA_TRY(h, c.h_outp.reserve(PACKED_OUT_MAX));
+  CUDA_TRY(h, c.d_outp.reserve(PACKED_OUT_MAX));
   c.open       = true;
   c.slot_lo    = 0xffffffffU;
   c.slot_hi    = 0;
@@ -1136,9 +1142,7 @@ int launch_context(srsran_cuda_pusch_dec* h, int ci)
     const size_t b_map = (ntb != 0) ? ((ncb * sizeof(uint32_t) + 15) & ~size_t(15)) : 0;
     const size_t total = b_grp + b_ord + b_tb + b_map;
     CUDA_TRY(h, cudaMemcpyAsync(c.d_desc.p, c.h_desc.p, ncb * sizeof(cb_desc), cudaMemcpyHostToDevice, s));
-    if (total != 0 && total <= 16384) {
-      CUDA_TRY(h, c.h_meta.reserve(16384));
-      CUDA_TRY(h, c.d_meta.reserve(16384));
+    if (total != 0 && total <= PACKED_META_MAX) {
       uint8_t* m = c.h_meta.p;
       std::memcpy(m, c.h_grp.p, ngrp * sizeof(grp_desc));
       std::memcpy(m + b_grp, c.h_order.p, pos * sizeof(uint32_t));
@@ -1175,8 +1179,6 @@ int launch_context(srsran_cuda_pusch_dec* h, int ci)
     const size_t b_tbres = (ntb * sizeof(tb_result_dev) + 15) & ~size_t(15), b_res = (ncb * sizeof(cb_result) + 15) & ~size_t(15);
     const size_t total   = b_tbres + b_res + c.tbout_used;
     if (ntb != 0 && h->tb_host_copy && !c.want_bits && total <= PACKED_OUT_MAX) {
-      CUDA_TRY(h, c.h_outp.reserve(PACKED_OUT_MAX));
-      CUDA_TRY(h, c.d_outp.reserve(PACKED_OUT_MAX));
       dv_tbres   = reinterpret_cast<tb_result_dev*>(c.d_outp.p);
       dv_res     = reinterpret_cast<cb_result*>(c.d_outp.p + b_tbres);
       dv_tbout   = c.d_outp.p + b_tbres + b_res;
