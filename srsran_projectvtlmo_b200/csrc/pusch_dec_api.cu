@@ -12,6 +12,7 @@
 #include <cstring>
 #include <new>
 #include <string>
+#include <tuple>
 #include <vector>
 
 using namespace pusch_dec;
@@ -2247,9 +2248,28 @@ static int submit_batch(srsran_cuda_pusch_dec_t* h, uint32_t nof_tbs, const srsr
       return r;
     }
   }
+  // The packed decoders group CONSECUTIVE code blocks of the same shape (four or two per CTA). A slot of many small
+  // transport blocks of mixed shapes (BASELINE config 3) is therefore processed in shape order (stable: a uniform batch keeps
+  // its order); the order inside a batch has no meaning, a ticket names its transport block.
+  thread_local std::vector<uint32_t> order;
+  order.resize(nof_tbs);
+  bool uniform = true;
+  auto shape_key = [&](uint32_t i) {
+    const srsran_cuda_pusch_dec_tb_config& t = configs[i];
+    return std::make_tuple(t.base_graph, t.tbs_bits, t.modulation, t.nof_layers, src[i].nof_llrs, t.Nref, t.rv, t.new_data,
+                           t.nof_ldpc_iterations, t.use_early_stop);
+  };
   for (uint32_t i = 0; i != nof_tbs; ++i) {
-    const int8_t* dev = src[i].device ? src[i].llrs : c.d_llr.p + offs[i];
-    r                 = add_tb(h, c, configs[i], dev, src[i].nof_llrs, src[i].cb_slots, src[i].nof_cb_slots);
+    order[i] = i;
+    uniform  = uniform && (i == 0 || shape_key(i) == shape_key(i - 1));
+  }
+  if (!uniform) {
+    std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return shape_key(a) < shape_key(b); });
+  }
+  for (uint32_t j = 0; j != nof_tbs; ++j) {
+    const uint32_t i   = order[j];
+    const int8_t*  dev = src[i].device ? src[i].llrs : c.d_llr.p + offs[i];
+    r                  = add_tb(h, c, configs[i], dev, src[i].nof_llrs, src[i].cb_slots, src[i].nof_cb_slots);
     if (r != SRSRAN_CUDA_OK) {
       abandon_context(h, c);
       return r;
