@@ -489,7 +489,7 @@ def main():
     ap.add_argument("--no-other-configs", action="store_true", help="skip BASELINE configs 1, 2 (worst case), 3, 4 (N = 1 only)")
     ap.add_argument("--no-symbols", action="store_true", help="skip the legs fed with equalized symbols (device-side demodulation)")
     ap.add_argument("--snr-db", type=float, default=30.5, help="operating point of the symbol-fed legs (256QAM, R = 0.926)")
-    ap.add_argument("--decoder-variant", type=int, default=0, help="0 auto (tensor-memory packed decoder where it applies), 1 general kernel only, 2 packed decoder with the messages in shared memory (round-1 kernel), 3 one code block per CTA packed kernel everywhere, 4 pairs of code blocks per CTA")
+    ap.add_argument("--decoder-variant", type=int, default=0, help="0 auto (tensor-memory packed decoder where it applies), 1 general kernel only, 2 packed decoder with the messages in shared memory (round-1 kernel), 3 one code block per CTA packed kernel everywhere, 4 pairs of code blocks per CTA, 5 without the many-layer pair form, 6 that form for every batch, 7 bulk-copy input staging")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
 

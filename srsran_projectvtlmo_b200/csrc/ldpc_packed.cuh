@@ -15,6 +15,15 @@
 //   c2v    edges * Z x 2 NR bytes: the message bytes c + 128 of the 2 NR code blocks per lifted edge, check order
 //          (thread-private between barriers)
 //   hb     4 x K/32 words of hard decisions, crc byte tables 4 x 256 words, flags / CRC shares, four lane_state records
+//
+// Forms of ldpc_decode4_kernel<TPC, ZT, NR, TM>:
+//   NR = 2, TM = 1   four code blocks per CTA, messages in TENSOR MEMORY (one 32-bit column per lifted edge), v2c parked in the
+//                    soft array, 80 registers: two CTAs per SM with 256 columns each - the headline form; with all 512 columns
+//                    one CTA per SM for groups of up to ~13 layers (HARQ retransmissions)
+//   NR = 1, TM = 1   two code blocks with MANY layers (up to all 46) per CTA, all 512 columns (two edges per column), the last
+//                    layers' messages in shared memory, v2c in registers, one CTA per SM; optional cp.async.bulk input staging
+//   NR = 2, TM = 0   the round-1 form: messages in shared memory, one CTA per SM (also for lifting sizes with Z % 32 != 0)
+//   NR = 1, TM = 0   two code blocks per CTA, messages in shared memory: small batches (latency mode)
 #pragma once
 #include "ldpc_packed_math.h"
 #include <type_traits>
