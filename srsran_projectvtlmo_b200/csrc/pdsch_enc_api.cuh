@@ -33,7 +33,8 @@ struct srsran_cuda_pdsch_enc {
     uint64_t                     nof_bits = 0;
   };
   std::vector<op>       ops;
-  std::vector<uint32_t> pending; // enqueued, not launched yet
+  std::vector<uint32_t> pending;      // enqueued, not launched yet
+  uint32_t              nof_done = 0; // launched and complete, not dequeued yet: their outputs live in h_bits / h_packed
 
   // The batch being built / last launched. Descriptors hold OFFSETS into the staging / output buffers until the launch,
   // because the buffers may still grow.
@@ -136,10 +137,14 @@ cudaError_t enc_grow_pinned(pinned_buf<T>& b, size_t need, size_t keep)
   return cudaSuccess;
 }
 
-/// Starts a new batch (descriptors and outputs; the staged inputs are kept: the hal seam stages them at enqueue time).
+/// Starts a new batch (descriptors and outputs; the staged inputs are kept: the hal seam stages them at enqueue time). The
+/// output regions restart from zero unless results of an earlier launch are still waiting to be dequeued: then the new
+/// batch is appended behind them.
 void enc_begin(srsran_cuda_pdsch_enc* h)
 {
-  h->bits_used = h->packed_used = 0;
+  if (h->nof_done == 0) {
+    h->bits_used = h->packed_used = 0;
+  }
   h->ndesc = h->njobs = 0;
   h->max_z[0] = h->max_z[1] = 0;
   h->n_packed = h->n_bytewise = 0;
@@ -337,6 +342,7 @@ int enc_launch(srsran_cuda_pdsch_enc* h)
 int enc_flush_ops(srsran_cuda_pdsch_enc* h)
 {
   enc_begin(h);
+  const size_t bits0 = h->bits_used, packed0 = h->packed_used; // results not dequeued yet end here
   for (uint32_t i : h->pending) {
     srsran_cuda_pdsch_enc::op&          o = h->ops[i];
     const srsran_cuda_pdsch_enc_config& c = o.cfg;
@@ -360,16 +366,18 @@ int enc_flush_ops(srsran_cuda_pdsch_enc* h)
   if (r != SRSRAN_CUDA_OK) {
     return r;
   }
-  CUDA_TRY(h, h->h_bits.reserve(h->bits_used + 16));
-  CUDA_TRY(h, h->h_packed.reserve(h->packed_used + 16));
-  CUDA_TRY(h, cudaMemcpyAsync(h->h_bits.p, h->d_bits.p, h->bits_used, cudaMemcpyDeviceToHost, h->stream));
-  CUDA_TRY(h, cudaMemcpyAsync(h->h_packed.p, h->d_packed.p, h->packed_used, cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(h, enc_grow_pinned(h->h_bits, h->bits_used + 16, bits0));
+  CUDA_TRY(h, enc_grow_pinned(h->h_packed, h->packed_used + 16, packed0));
+  CUDA_TRY(h, cudaMemcpyAsync(h->h_bits.p + bits0, h->d_bits.p + bits0, h->bits_used - bits0, cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(h, cudaMemcpyAsync(h->h_packed.p + packed0, h->d_packed.p + packed0, h->packed_used - packed0, cudaMemcpyDeviceToHost,
+                              h->stream));
   CUDA_TRY(h, cudaEventRecord(h->ev[3], h->stream));
   CUDA_TRY(h, cudaEventSynchronize(h->ev[3]));
   h->timing_valid = true;
   for (uint32_t i : h->pending) {
     h->ops[i].state = srsran_cuda_pdsch_enc::DONE;
   }
+  h->nof_done += static_cast<uint32_t>(h->pending.size());
   h->pending.clear();
   return SRSRAN_CUDA_OK;
 }
@@ -504,6 +512,9 @@ int srsran_cuda_pdsch_enc_configure(srsran_cuda_pdsch_enc_t* h, uint32_t cb_inde
     h->last_error = "operation reconfigured while enqueued";
     return SRSRAN_CUDA_ERR_STATE;
   }
+  if (o.state == srsran_cuda_pdsch_enc::DONE) {
+    --h->nof_done; // its result is dropped
+  }
   o.cfg   = *config;
   o.state = srsran_cuda_pdsch_enc::CONFIGURED;
   return SRSRAN_CUDA_OK;
@@ -569,6 +580,7 @@ int srsran_cuda_pdsch_enc_dequeue(srsran_cuda_pdsch_enc_t* h, uint32_t cb_index,
     std::memcpy(packed, h->h_packed.p + o.packed_off, (o.nof_bits + 7) / 8);
   }
   o.state = srsran_cuda_pdsch_enc::EMPTY;
+  --h->nof_done;
   return 1;
 }
 
@@ -579,8 +591,8 @@ static int enc_batch_common(srsran_cuda_pdsch_enc_t* h, uint32_t nof_tbs, const 
   if (h == nullptr || configs == nullptr || tbs == nullptr || nof_tbs == 0) {
     return SRSRAN_CUDA_ERR_INVALID;
   }
-  if (!h->pending.empty()) {
-    h->last_error = "operations of the hal seam are pending";
+  if (!h->pending.empty() || h->nof_done != 0) {
+    h->last_error = "operations of the hal seam are pending or not dequeued yet";
     return SRSRAN_CUDA_ERR_STATE;
   }
   enc_begin(h);

@@ -211,6 +211,47 @@ def test_code_blocks_all_lifting_sizes(enc):
             assert np.array_equal(bits, want), (bg, z, nfill, qm, e_len, rv, nref)
 
 
+def test_interleaved_enqueue_and_dequeue(enc):
+    """Results that are complete but not dequeued yet survive the launch of a later batch (a caller that enqueues more code
+    blocks before it has fetched all earlier ones)."""
+    rng = np.random.default_rng(520)
+    hw = pdsch.hw_accelerator_pdsch_enc_cuda(enc, cb_mode=True)
+    ops = []
+    for i, (bg, z, qm, e_len) in enumerate([(1, 384, 8, 8960), (2, 208, 2, 5000), (1, 96, 4, 4096), (1, 384, 6, 17100)]):
+        k = synth.kb(bg) * z
+        msg = rng.integers(0, 2, k, dtype=np.uint8)
+        cfg = pdsch.hw_pdsch_encoder_configuration()
+        cfg.base_graph, cfg.modulation, cfg.nof_segments, cfg.rv, cfg.lifting_size = bg, qm, 1, i % 4, z
+        cfg.Ncb, cfg.Nref, cfg.nof_filler_bits, cfg.rm_length, cfg.cb_mode = synth.ns(bg) * z, 0, 0, e_len, 1
+        want = synth.rate_match(synth.ldpc_encode(msg, bg, z), bg, z, 0, e_len, i % 4, qm, 0)
+        ops.append((cfg, np.packbits(msg), want))
+
+    def put(i):
+        hw.configure_operation(ops[i][0], i)
+        assert hw.enqueue_operation(ops[i][1], None, i)
+
+    def get(i):
+        bits = np.zeros(ops[i][2].size, np.uint8)
+        packed = np.zeros((bits.size + 7) // 8, np.uint8)
+        assert hw.dequeue_operation(bits, packed, i)
+        assert np.array_equal(bits, ops[i][2]), i
+        assert np.array_equal(packed, np.packbits(ops[i][2])), i
+
+    put(0)
+    put(1)
+    get(0)   # launches 0 and 1
+    put(2)   # a new batch while the result of 1 is still waiting
+    put(3)
+    get(3)   # launches 2 and 3: must not disturb the result of 1
+    get(1)
+    get(2)
+    with pytest.raises(Exception):
+        hw.configure_operation(ops[0][0], 0)
+        hw.enqueue_operation(ops[0][1], None, 0)
+        pdsch.encode_tbs(enc, [pdsch.pdsch_encoder_configuration(1, 0, 2, 0, 1, 156)], [np.zeros(8, np.uint8)])  # hal operations pending
+    get(0)
+
+
 def test_queue_full_and_errors(enc):
     hw = pdsch.hw_accelerator_pdsch_enc_cuda(enc, cb_mode=True)
     cfg = pdsch.hw_pdsch_encoder_configuration()
