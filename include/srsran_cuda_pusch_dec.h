@@ -125,8 +125,8 @@ int srsran_cuda_pusch_dec_set_combine_flavour(srsran_cuda_pusch_dec_t* handle, u
  * messages in shared memory instead of tensor memory (the round-1 kernel, one CTA per SM); 3 = intra-code-block packed
  * kernel wherever it fits; 4 = packed groups of TWO code blocks
  * per CTA, two CTAs per SM (what a small batch uses anyway); 5 = without the many-layer form (pairs of code blocks with up
- * to 46 layers per CTA, messages in tensor memory); 6 = the many-layer form for every batch (by default it needs one code
- * block per SM); 7 = the forms that run one CTA per SM stage their inputs with cp.async.bulk + mbarrier instead of
+ * to 46 layers per CTA, messages in tensor memory); 6 = the many-layer form also where the shared-memory pair form of variant 4
+ * fits; 7 = the forms that run one CTA per SM stage their inputs with cp.async.bulk + mbarrier instead of
  * 128-bit loads. 2-7 exist for A/B measurements.
  * Results are identical: all variants are bit-exact to the reference (ldpc_decoder_avx512.cpp). */
 int srsran_cuda_pusch_dec_set_decoder_variant(srsran_cuda_pusch_dec_t* handle, uint32_t variant);

@@ -1048,9 +1048,11 @@ int launch_context(srsran_cuda_pusch_dec* h, int ci)
       nof_long += inc_long;
     }
   }
-  // The many-layer pair form is a throughput form (one CTA of Z threads per SM works on two code blocks): with fewer such
-  // code blocks than SMs, one code block per CTA (four lifted checks per thread) on an SM of its own finishes earlier.
-  const bool long_batch = h->prefer_long || nof_long >= static_cast<uint32_t>(h->nof_sms);
+  // The many-layer pair form is taken wherever two such code blocks of the same shape follow each other (mixed-shape batches
+  // are processed in shape order, see submit_batch): one check per thread instead of four makes a pair finish earlier than
+  // two single-code-block CTAs even on an otherwise idle GPU (BASELINE config 3: 218 -> 148 us per slot, tools/c3_probe.py).
+  // A lone code block still goes to the one-code-block kernel (close_group).
+  const bool long_batch = nof_long != 0;
   const cb_desc* memo_desc  = nullptr;
   uint32_t       memo_lanes = 0;
   bool           memo_tm    = false;

@@ -1,5 +1,7 @@
 """BASELINE config 3 (64 small TBs of eight shapes per slot): decode span of the whole slot and of each shape alone, to see
 which code blocks bound the slot (a never-converging BG1 / Z = 352 block: 6 iterations x 27 layers on one SM). GPU box."""
+import sys
+
 import numpy as np, torch
 from srsran_projectvtlmo_b200 import capi, pusch, synth
 cases = [(52, 2, 120, 1, 2, 0.9), (52, 2, 449, 1, 1, 2.0), (52, 4, 378, 1, 1, 3.0), (52, 4, 658, 1, 1, 6.0),
@@ -7,6 +9,7 @@ cases = [(52, 2, 120, 1, 2, 0.9), (52, 2, 449, 1, 1, 2.0), (52, 4, 378, 1, 1, 3.
 rng = np.random.default_rng(8)
 for sel in [None] + list(range(8)):
     acc = pusch.Accelerator(device=0, max_cbs_in_flight=4096, nof_harq_cb_slots=4096)
+    acc.set_decoder_variant(int(sys.argv[1]) if len(sys.argv) > 1 else 0)
     cfgs, dev, nllrs, slot = [], [], [], 0
     for ue in range(64):
         ci = ue % 8
