@@ -225,6 +225,11 @@ int srsran_cuda_pusch_dec_tb_data(srsran_cuda_pusch_dec_t* handle, int ticket, c
  * untouched. At eight GPUs the return path of the decoded bits (16 GB/s per GPU at 130 Gbit/s) is what the box's PCIe
  * fabric limits first. Applies to batches submitted after the call. */
 int srsran_cuda_pusch_dec_set_tb_host_copy(srsran_cuda_pusch_dec_t* handle, int enable);
+/* Soft bits that arrive in four or more separate page-locked pieces (buffers that are not adjacent in host memory: one per
+ * decoder instance behind the plugin interface, pusch_decoder_buffer::get_next_block_view) are read over the link by a
+ * gather kernel of `nof_ctas` CTAs instead of one copy-engine job per piece. Default 32; 0 = copy-engine jobs only.
+ * Pieces that are adjacent in host memory are merged into one copy before this applies. */
+int srsran_cuda_pusch_dec_set_h2d_gather(srsran_cuda_pusch_dec_t* handle, uint32_t nof_ctas);
 /* Device address of a completed transport block (valid until its batch context is reused), NULL if the reference would
  * not have written it. */
 int srsran_cuda_pusch_dec_tb_data_device(srsran_cuda_pusch_dec_t* handle, int ticket, const uint8_t** data);

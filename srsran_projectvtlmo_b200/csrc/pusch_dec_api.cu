@@ -19,6 +19,11 @@ using namespace pusch_dec;
 
 namespace {
 // Threads per rate-dematcher CTA (one code block): 128 so that a CTA fits beside a packed-decoder CTA on the same SM.
+// From this many separate page-locked pieces on, a batch's soft bits are read by the gather kernel.
+constexpr size_t H2D_GATHER_MIN_PIECES = 4;
+#ifndef H2D_GATHER_DEFAULT
+#define H2D_GATHER_DEFAULT 32 // CTAs of the gather kernel
+#endif
 #ifndef DM_THREADS
 #define DM_THREADS 128
 #endif
@@ -184,11 +189,13 @@ struct batch_context {
   std::vector<cb_host_meta> cb_meta;
   std::vector<tb_host_meta> tb_meta;
   struct copy_job {
-    const int8_t* src;
+    const int8_t* src;     // page-locked caller memory, nullptr: the context's own staging buffer
     size_t        dst_off;
     size_t        bytes;
+    const int8_t* dev_src; // the same memory as the device sees it (mapped page-locked memory), nullptr if unknown
   };
-  std::vector<copy_job> copies;
+  std::vector<copy_job>  copies;
+  pinned_buf<h2d_piece> h_pieces; // descriptors of the gather kernel that replaces many separate copies
 
   // Device-side demodulation (pusch_demod.cuh): equalized symbols + noise variances staged in d_dm_in (host callers),
   // scrambling sequences in d_scr, one descriptor per transport block.
@@ -247,6 +254,7 @@ struct srsran_cuda_pusch_dec {
   bool     use_bulk          = false; // one-CTA-per-SM forms stage their inputs with cp.async.bulk + mbarrier (variant 7):
                                       // measured equal to plain 128-bit loads, kept selectable
   bool     tb_host_copy      = true;  // decoded transport blocks are copied to the page-locked result buffer
+  uint32_t h2d_gather_ctas   = H2D_GATHER_DEFAULT;    // CTAs of the gather kernel that reads many separate page-locked pieces (0: copies only)
   bool     prefer_long       = false; // A/B: the many-layer pair form also where the shared-memory pair form fits
   int      last_unit_ctx     = -1;    // context of the last unit-level batch (srsran_cuda_pusch_dec_last_unit_timing)
   bool     force_pairs       = false; // groups of two code blocks per CTA (two CTAs per SM) also for large batches
@@ -580,13 +588,16 @@ int upload_tables(Handle* h)
   return SRSRAN_CUDA_OK;
 }
 
-bool is_pinned(const void* p)
+bool is_pinned(const void* p, const void** dev_ptr = nullptr)
 {
   cudaPointerAttributes attr;
   cudaError_t           e = cudaPointerGetAttributes(&attr, p);
   if (e != cudaSuccess) {
     cudaGetLastError();
     return false;
+  }
+  if (dev_ptr != nullptr) {
+    *dev_ptr = (attr.type == cudaMemoryTypeHost) ? attr.devicePointer : nullptr;
   }
   return attr.type == cudaMemoryTypeHost;
 }
@@ -755,14 +766,15 @@ int stage_llrs(srsran_cuda_pusch_dec* h, batch_context& c, const int8_t* src, si
     }
     c.d_llr = nd;
   }
-  if (is_pinned(src)) {
+  const void* dev_src = nullptr;
+  if (is_pinned(src, &dev_src)) {
     // Caller memory is page-locked: copy straight from it at launch. Pieces that are adjacent on both sides (e.g. the
     // transport blocks of one slot laid out back to back) are merged into one copy.
     if (!c.copies.empty() && c.copies.back().src != nullptr && c.copies.back().src + c.copies.back().bytes == src &&
         c.copies.back().dst_off + c.copies.back().bytes == off) {
       c.copies.back().bytes += bytes;
     } else {
-      c.copies.push_back({src, off, bytes});
+      c.copies.push_back({src, off, bytes, static_cast<const int8_t*>(dev_src)});
     }
   } else {
     // Pageable caller memory: stage through the context's pinned buffer (src == nullptr), merging adjacent pieces. The
@@ -781,7 +793,7 @@ int stage_llrs(srsran_cuda_pusch_dec* h, batch_context& c, const int8_t* src, si
         c.copies.back().dst_off + ((c.copies.back().bytes + 15) & ~size_t(15)) == off) {
       c.copies.back().bytes = off + bytes - c.copies.back().dst_off;
     } else {
-      c.copies.push_back({nullptr, off, bytes});
+      c.copies.push_back({nullptr, off, bytes, nullptr});
     }
   }
   c.llr_used = need;
@@ -897,9 +909,32 @@ int launch_context(srsran_cuda_pusch_dec* h, int ci)
   if (h->last_launched >= 0 && h->last_launched != ci && !c.copies.empty()) {
     CUDA_TRY(h, cudaStreamWaitEvent(s, h->ctx[h->last_launched].copied, 0));
   }
-  for (const batch_context::copy_job& j : c.copies) {
-    const int8_t* src = (j.src != nullptr) ? j.src : c.h_llr.p + j.dst_off;
-    CUDA_TRY(h, cudaMemcpyAsync(c.d_llr.p + j.dst_off, src, j.bytes, cudaMemcpyHostToDevice, s));
+  // Soft bits in many separate page-locked pieces (one buffer per decoder instance behind the plugin interface): one
+  // gather kernel reads them over the link instead of one copy-engine job per piece (h2d_gather_kernel). It runs on the
+  // batch's high-priority stream so that its few CTAs are placed ahead of the previous batch's pending decoder CTAs.
+  bool gathered = h->h2d_gather_ctas != 0 && c.copies.size() >= H2D_GATHER_MIN_PIECES && c.copies.size() <= H2D_MAX_PIECES;
+  for (size_t i = 0; gathered && i != c.copies.size(); ++i) {
+    const batch_context::copy_job& j = c.copies[i];
+    gathered = j.dev_src != nullptr && (reinterpret_cast<uintptr_t>(j.dev_src) % 16) == 0 && (j.dst_off % 16) == 0;
+  }
+  if (gathered) {
+    CUDA_TRY(h, c.h_pieces.reserve(H2D_MAX_PIECES));
+    for (size_t i = 0; i != c.copies.size(); ++i) {
+      const batch_context::copy_job& j = c.copies[i];
+      c.h_pieces.p[i] = {reinterpret_cast<const uint8_t*>(j.dev_src), reinterpret_cast<uint8_t*>(c.d_llr.p + j.dst_off), j.bytes};
+    }
+    CUDA_TRY(h, cudaEventRecord(c.fork, s));
+    CUDA_TRY(h, cudaStreamWaitEvent(c.tail, c.fork, 0));
+    h2d_gather_kernel<<<h->h2d_gather_ctas, H2D_THREADS, 0, c.tail>>>(c.h_pieces.p, static_cast<uint32_t>(c.copies.size()));
+    ++h->launches;
+    CUDA_TRY(h, cudaGetLastError());
+    CUDA_TRY(h, cudaEventRecord(c.join[0], c.tail));
+    CUDA_TRY(h, cudaStreamWaitEvent(s, c.join[0], 0));
+  } else {
+    for (const batch_context::copy_job& j : c.copies) {
+      const int8_t* src = (j.src != nullptr) ? j.src : c.h_llr.p + j.dst_off;
+      CUDA_TRY(h, cudaMemcpyAsync(c.d_llr.p + j.dst_off, src, j.bytes, cudaMemcpyHostToDevice, s));
+    }
   }
   for (const batch_context::raw_copy& j : c.raw_copies) {
     CUDA_TRY(h, cudaMemcpyAsync(c.d_dm_in.p + j.dst_off, j.src, j.bytes, cudaMemcpyHostToDevice, s));
@@ -1843,6 +1878,7 @@ void srsran_cuda_pusch_dec_destroy(srsran_cuda_pusch_dec_t* h)
   }
   for (batch_context& c : h->ctx) {
     c.h_llr.release();
+    c.h_pieces.release();
     c.d_llr.release();
     c.h_desc.release();
     c.d_desc.release();
@@ -2662,6 +2698,15 @@ int srsran_cuda_pusch_dec_set_tb_host_copy(srsran_cuda_pusch_dec_t* h, int enabl
     return SRSRAN_CUDA_ERR_INVALID;
   }
   h->tb_host_copy = enable != 0;
+  return SRSRAN_CUDA_OK;
+}
+
+int srsran_cuda_pusch_dec_set_h2d_gather(srsran_cuda_pusch_dec_t* h, uint32_t nof_ctas)
+{
+  if (h == nullptr || nof_ctas > 4096) {
+    return SRSRAN_CUDA_ERR_INVALID;
+  }
+  h->h2d_gather_ctas = nof_ctas;
   return SRSRAN_CUDA_OK;
 }
 

@@ -98,6 +98,10 @@ class Accelerator:
         """False: decoded transport blocks stay in HBM (tb_data_device); results and CRC verdicts still come back."""
         self._check(self._lib.srsran_cuda_pusch_dec_set_tb_host_copy(self.h, int(bool(enable))), "set_tb_host_copy")
 
+    def set_h2d_gather(self, nof_ctas):
+        """CTAs of the kernel that reads soft bits arriving in many separate page-locked pieces (0: copy-engine jobs only)."""
+        self._check(self._lib.srsran_cuda_pusch_dec_set_h2d_gather(self.h, nof_ctas), "set_h2d_gather")
+
     def set_combine_flavour(self, simd_block):
         self._check(self._lib.srsran_cuda_pusch_dec_set_combine_flavour(self.h, simd_block), "set_combine_flavour")
 

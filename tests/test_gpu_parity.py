@@ -290,6 +290,55 @@ def test_pusch_batch_of_tbs_device_resident_and_host(acc):
             assert np.array_equal(out, tbs_bytes[i])
 
 
+def test_pusch_soft_bits_in_separate_page_locked_buffers(acc):
+    """Soft bits handed over in page-locked buffers that are not adjacent (one per decoder instance behind the plugin
+    interface) are read by the gather kernel (set_h2d_gather): same results as with copy-engine jobs and as the oracle;
+    ragged sizes, one of them not a multiple of 16 bytes."""
+    rng = np.random.default_rng(66)
+    lib = capi.lib()
+    shapes = [(52, 4, 658, 1, 1), (25, 2, 120, 1, 2), (106, 6, 873, 2, 1), (3, 2, 308, 1, 2), (52, 2, 449, 1, 1), (1, 2, 120, 1, 2),
+              (52, 4, 378, 1, 1)]
+    cfgs, bufs, llrs, payloads, ptrs, slot = [], [], [], [], [], 5000
+    for prb, qm, R, nl, bg in shapes:
+        tbs = synth.tbs_for(prb, qm, R, nl)
+        nllr = prb * 156 * qm * nl - (qm * nl if prb == 3 else 0)  # 3 PRB: one symbol fewer -> 930 soft bits
+        tb = rng.integers(0, 256, tbs // 8, dtype=np.uint8)
+        llr = awgn_llrs(rng, synth.encode_tb(tb, bg, 0, qm, 25344, nl, nllr), 3.0)
+        p = lib.srsran_cuda_pusch_dec_host_alloc(nllr)
+        assert p
+        ptrs.append(p)
+        b = np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_int8)), shape=(nllr,))
+        b[...] = llr
+        cfgs.append(pusch.TbConfig(tbs, bg, 0, qm, 25344, nl, 6, 1, 1, slot))
+        slot += len(pusch.segment(tbs, bg, qm, nl, nllr))
+        bufs.append(b); llrs.append(llr); payloads.append(tb)
+    assert any(b.size % 16 for b in bufs)
+    try:
+        results = {}
+        for ctas in (0, 8, 32):
+            acc.set_h2d_gather(ctas)
+            n0 = acc.launch_count
+            tickets = pusch.submit_tbs(acc, cfgs, bufs)
+            launches = acc.launch_count - n0
+            outs = [np.zeros(c.tbs_bits // 8, np.uint8) for c in cfgs]
+            results[ctas] = ([pusch.poll_tb(acc, t, o) for t, o in zip(tickets, outs)], outs, launches)
+        assert results[32][2] == results[0][2] + 1 and results[8][2] == results[0][2] + 1  # the gather kernel did run
+        port = ob.PortPusch()
+        for i, c in enumerate(cfgs):
+            _, res_p = port.decode(i, c.tbs_bits // 8, llrs[i], c.base_graph, 0, c.modulation, 25344, c.nof_layers, 6, True, True)
+            for ctas in results:
+                res, outs, _ = results[ctas]
+                assert res[i].tb_crc_ok == res_p.tb_crc_ok
+                assert (res[i].iter_min, res[i].iter_max) == (res_p.iter_min, res_p.iter_max)
+                if res_p.tb_crc_ok:
+                    assert np.array_equal(outs[i], payloads[i])
+        assert sum(r.tb_crc_ok for r in results[32][0]) >= 4
+    finally:
+        acc.set_h2d_gather(32)
+        for p in ptrs:
+            lib.srsran_cuda_pusch_dec_host_free(p)
+
+
 def test_pusch_streamed_tb_with_scattered_harq_slots(acc):
     """stream_begin / stream_push / stream_submit with non-consecutive HARQ slots (rx_buffer absolute code-block ids):
     same TB result as the oracle over rv0 -> rv2, per-code-block CRC flags and iteration observations included."""
