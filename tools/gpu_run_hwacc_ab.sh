@@ -1,4 +1,5 @@
 # Plugin-interface bench (oracle/hwacc_bench.cpp) with and without the gather kernel for the decoders' separate soft-bit buffers.
+# The copy-engine arm needs: make -C srsran_projectvtlmo_b200/csrc OUT=$PWD/gpurun_variants/lib_nogather.so EXTRA=-DH2D_GATHER_DEFAULT=0
 mkdir -p gpurun_out; export PYTHONPATH=$PWD
 python tools/make_tb_file.py /tmp/c2_tbs.bin 8 18 > /dev/null
 : > gpurun_out/hwacc_ab.txt
