@@ -225,6 +225,13 @@ int srsran_cuda_pusch_dec_tb_data(srsran_cuda_pusch_dec_t* handle, int ticket, c
  * untouched. At eight GPUs the return path of the decoded bits (16 GB/s per GPU at 130 Gbit/s) is what the box's PCIe
  * fabric limits first. Applies to batches submitted after the call. */
 int srsran_cuda_pusch_dec_set_tb_host_copy(srsran_cuda_pusch_dec_t* handle, int enable);
+/* Small batches (the latency case: one transport block, a slot of small ones) cross the link without copy-engine jobs.
+ * direct_in (default 1): when a batch holds at most 4 MB of host soft bits, the rate dematcher reads them from page-locked
+ * host memory itself (the caller's, or the library's staging buffer for pageable memory) instead of a host -> device copy
+ * followed by the dematcher. direct_out (default 1): when results + transport-block bytes of a batch are at most 512 KB,
+ * the kernels write them straight into the page-locked result buffer instead of a device -> host copy. Results are
+ * identical either way; 0 / 0 is the copy-engine path (A/B measurements, tests). */
+int srsran_cuda_pusch_dec_set_direct_io(srsran_cuda_pusch_dec_t* handle, int direct_in, int direct_out);
 /* Soft bits that arrive in four or more separate page-locked pieces (buffers that are not adjacent in host memory: one per
  * decoder instance behind the plugin interface, pusch_decoder_buffer::get_next_block_view) are read over the link by a
  * gather kernel of `nof_ctas` CTAs instead of one copy-engine job per piece. Default 32; 0 = copy-engine jobs only.

@@ -107,6 +107,7 @@ SYMBOLS = {
     "srsran_cuda_pusch_dec_tb_data_device": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(u8p)]),
     "srsran_cuda_pusch_dec_set_tb_host_copy": (C.c_int, [C.c_void_p, C.c_int]),
     "srsran_cuda_pusch_dec_set_h2d_gather": (C.c_int, [C.c_void_p, C.c_uint32]),
+    "srsran_cuda_pusch_dec_set_direct_io": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
     "srsran_cuda_pusch_dec_submit_tbs_device": (C.c_int, [C.c_void_p, C.c_uint32, C.POINTER(TbConfig),
                                                            C.POINTER(C.c_void_p), u32p, intp]),
     "srsran_cuda_pusch_dec_submit_tbs": (C.c_int, [C.c_void_p, C.c_uint32, C.POINTER(TbConfig),

@@ -1070,7 +1070,9 @@ __global__ void __launch_bounds__(TBG_WARPS * 32) tb_gather_kernel(const tb_desc
                                                                    uint32_t* crc_share,
                                                                    tb_result_dev* __restrict__ tb_results,
                                                                    uint32_t* crc_flags,
-                                                                   uint32_t* tb_done)
+                                                                   uint32_t* tb_done,
+                                                                   const cb_result* __restrict__ cb_results,
+                                                                   cb_result* __restrict__ cb_results_host)
 {
   __shared__ uint32_t tabs[1024];
   const int           t = threadIdx.x, lane = t & 31;
@@ -1086,6 +1088,11 @@ __global__ void __launch_bounds__(TBG_WARPS * 32) tb_gather_kernel(const tb_desc
     return;
   }
   const tb_desc   tb   = tbs[tbi];
+  if (cb_results_host != nullptr && lane == 0) {
+    // Small batch: the per-code-block results reach the page-locked result buffer from here (one kernel touches host
+    // memory instead of every decoder CTA, whose completion would wait for the link).
+    cb_results_host[cb] = cb_results[cb];
+  }
   // Called by every warp once its code block is in place: the last one of a transport block finalises it. The counter
   // returns to zero, so it needs no clearing between batches.
   auto code_block_done = [&]() {

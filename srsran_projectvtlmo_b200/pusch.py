@@ -102,6 +102,10 @@ class Accelerator:
         """CTAs of the kernel that reads soft bits arriving in many separate page-locked pieces (0: copy-engine jobs only)."""
         self._check(self._lib.srsran_cuda_pusch_dec_set_h2d_gather(self.h, nof_ctas), "set_h2d_gather")
 
+    def set_direct_io(self, direct_in=True, direct_out=True):
+        """Small batches: soft bits read from / results written to page-locked host memory by the kernels themselves."""
+        self._check(self._lib.srsran_cuda_pusch_dec_set_direct_io(self.h, int(bool(direct_in)), int(bool(direct_out))), "set_direct_io")
+
     def set_combine_flavour(self, simd_block):
         self._check(self._lib.srsran_cuda_pusch_dec_set_combine_flavour(self.h, simd_block), "set_combine_flavour")
 

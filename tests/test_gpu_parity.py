@@ -314,6 +314,7 @@ def test_pusch_soft_bits_in_separate_page_locked_buffers(acc):
         bufs.append(b); llrs.append(llr); payloads.append(tb)
     assert any(b.size % 16 for b in bufs)
     try:
+        acc.set_direct_io(False, True)  # a batch this small would otherwise be read by the dematcher itself
         results = {}
         for ctas in (0, 8, 32):
             acc.set_h2d_gather(ctas)
@@ -333,8 +334,24 @@ def test_pusch_soft_bits_in_separate_page_locked_buffers(acc):
                 if res_p.tb_crc_ok:
                     assert np.array_equal(outs[i], payloads[i])
         assert sum(r.tb_crc_ok for r in results[32][0]) >= 4
+        # ... and the same batch with the dematcher reading the page-locked buffers itself (the default for small batches),
+        # with and without the results written straight to host memory.
+        for din, dout in ((True, True), (True, False), (False, False)):
+            acc.set_direct_io(din, dout)
+            n0 = acc.launch_count
+            tickets = pusch.submit_tbs(acc, cfgs, bufs)
+            assert acc.launch_count - n0 == results[0][2] + (0 if din else 1)
+            for i, t in enumerate(tickets):
+                out = np.zeros(cfgs[i].tbs_bits // 8, np.uint8)
+                res = pusch.poll_tb(acc, t, out)
+                ref = results[0][0][i]
+                assert (res.tb_crc_ok, res.iter_min, res.iter_max, res.nof_observations) == \
+                    (ref.tb_crc_ok, ref.iter_min, ref.iter_max, ref.nof_observations)
+                if ref.tb_crc_ok:
+                    assert np.array_equal(out, payloads[i])
     finally:
         acc.set_h2d_gather(32)
+        acc.set_direct_io(True, True)
         for p in ptrs:
             lib.srsran_cuda_pusch_dec_host_free(p)
 
