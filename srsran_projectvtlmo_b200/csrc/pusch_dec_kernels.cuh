@@ -215,7 +215,15 @@ __global__ void __launch_bounds__(256, DM_MINB) rate_dematch_kernel(const cb_des
                                                            uint32_t combine_block)
 {
   extern __shared__ __align__(16) int8_t dm_sm[];
-  const cb_desc& d = descs[blockIdx.x];
+  // The descriptor is fetched once, by 16 threads: for a small batch it lives in page-locked HOST memory (the dematcher
+  // starts before the descriptors' device copy has arrived), where every separate load would be a trip over the link.
+  __shared__ __align__(16) cb_desc sd;
+  static_assert(sizeof(cb_desc) % 4 == 0 && sizeof(cb_desc) / 4 <= 32, "descriptor fetch");
+  if (threadIdx.x < sizeof(cb_desc) / 4) {
+    reinterpret_cast<uint32_t*>(&sd)[threadIdx.x] = reinterpret_cast<const uint32_t*>(descs + blockIdx.x)[threadIdx.x];
+  }
+  __syncthreads();
+  const cb_desc& d = sd;
   if (!(d.flags & FLAG_DEMATCH) || ((d.E <= DM_STAGE_CAP) != STAGED)) {
     return;
   }
