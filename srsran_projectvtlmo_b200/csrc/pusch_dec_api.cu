@@ -1246,6 +1246,8 @@ int launch_context(srsran_cuda_pusch_dec* h, int ci)
   PROF_T(l2);
   // Device addresses of the small descriptor arrays: their own buffers, or - for a small batch, where every copy is ~5 us of
   // the latency - one packed region sent with a single copy.
+  // Stream of the descriptor copies: with the dematcher already launched (early_dm) they leave the batch stream.
+  cudaStream_t    ds       = early_dm ? c.side[0] : s;
   const grp_desc* dv_grp   = c.d_grp.p;
   const uint32_t* dv_order = c.d_order.p;
   const tb_desc*  dv_tb    = c.d_tb.p;
@@ -1255,11 +1257,7 @@ int launch_context(srsran_cuda_pusch_dec* h, int ci)
     const size_t b_tb  = (ntb * sizeof(tb_desc) + 15) & ~size_t(15);
     const size_t b_map = (ntb != 0) ? ((ncb * sizeof(uint32_t) + 15) & ~size_t(15)) : 0;
     const size_t total = b_grp + b_ord + b_tb + b_map;
-    if (early_dm) {
-      // The descriptor copies leave the batch stream: the dematcher does not wait for them (below).
-      s = c.side[0];
-    }
-    CUDA_TRY(h, cudaMemcpyAsync(c.d_desc.p, c.h_desc.p, ncb * sizeof(cb_desc), cudaMemcpyHostToDevice, s));
+    CUDA_TRY(h, cudaMemcpyAsync(c.d_desc.p, c.h_desc.p, ncb * sizeof(cb_desc), cudaMemcpyHostToDevice, ds));
     if (total != 0 && total <= PACKED_META_MAX) {
       uint8_t* m = c.h_meta.p;
       std::memcpy(m, c.h_grp.p, ngrp * sizeof(grp_desc));
@@ -1268,27 +1266,26 @@ int launch_context(srsran_cuda_pusch_dec* h, int ci)
         std::memcpy(m + b_grp + b_ord, c.h_tb.p, ntb * sizeof(tb_desc));
         std::memcpy(m + b_grp + b_ord + b_tb, c.h_tbmap.p, ncb * sizeof(uint32_t));
       }
-      CUDA_TRY(h, cudaMemcpyAsync(c.d_meta.p, m, total, cudaMemcpyHostToDevice, s));
+      CUDA_TRY(h, cudaMemcpyAsync(c.d_meta.p, m, total, cudaMemcpyHostToDevice, ds));
       dv_grp   = reinterpret_cast<const grp_desc*>(c.d_meta.p);
       dv_order = reinterpret_cast<const uint32_t*>(c.d_meta.p + b_grp);
       dv_tb    = reinterpret_cast<const tb_desc*>(c.d_meta.p + b_grp + b_ord);
       dv_tbmap = reinterpret_cast<const uint32_t*>(c.d_meta.p + b_grp + b_ord + b_tb);
     } else {
       if (ngrp != 0) {
-        CUDA_TRY(h, cudaMemcpyAsync(c.d_grp.p, c.h_grp.p, ngrp * sizeof(grp_desc), cudaMemcpyHostToDevice, s));
+        CUDA_TRY(h, cudaMemcpyAsync(c.d_grp.p, c.h_grp.p, ngrp * sizeof(grp_desc), cudaMemcpyHostToDevice, ds));
       }
       if (pos != 0) {
-        CUDA_TRY(h, cudaMemcpyAsync(c.d_order.p, c.h_order.p, pos * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
+        CUDA_TRY(h, cudaMemcpyAsync(c.d_order.p, c.h_order.p, pos * sizeof(uint32_t), cudaMemcpyHostToDevice, ds));
       }
       if (ntb != 0) {
-        CUDA_TRY(h, cudaMemcpyAsync(c.d_tb.p, c.h_tb.p, ntb * sizeof(tb_desc), cudaMemcpyHostToDevice, s));
-        CUDA_TRY(h, cudaMemcpyAsync(c.d_tbmap.p, c.h_tbmap.p, ncb * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
+        CUDA_TRY(h, cudaMemcpyAsync(c.d_tb.p, c.h_tb.p, ntb * sizeof(tb_desc), cudaMemcpyHostToDevice, ds));
+        CUDA_TRY(h, cudaMemcpyAsync(c.d_tbmap.p, c.h_tbmap.p, ncb * sizeof(uint32_t), cudaMemcpyHostToDevice, ds));
       }
     }
   }
   if (early_dm) {
-    CUDA_TRY(h, cudaEventRecord(c.join[0], s));
-    s = c.stream;
+    CUDA_TRY(h, cudaEventRecord(c.join[0], ds));
   }
   cb_result*     dv_res   = c.d_res.p;
   tb_result_dev* dv_tbres = c.d_tbres.p;
